@@ -1,0 +1,960 @@
+// libnqs_b200.so -- implementation of include/nqs_b200.h.  See DESIGN.md for the data layout and the kernel inventory.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <random>
+#include <sstream>
+
+#include "engine.h"
+#include "sampler_kernels.cuh"
+#include "sr_kernels.cuh"
+
+using namespace nqs;
+
+// ------------------------------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library must load (and the single-GPU path must run) without NCCL present, and inside a
+// PyTorch process it must bind to the libnccl.so.2 that torch already loaded instead of pulling a second copy.
+// ------------------------------------------------------------------------------------------------------------------
+namespace
+{
+typedef struct { char internal[128]; } ncclUniqueIdT;
+typedef int (*ncclGetUniqueId_t)(ncclUniqueIdT *);
+typedef int (*ncclCommInitRank_t)(void **, int, ncclUniqueIdT, int);
+typedef int (*ncclAllReduce_t)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*ncclCommDestroy_t)(void *);
+typedef const char * (*ncclGetErrorString_t)(int);
+struct NcclApi
+{
+  void * lib = nullptr;
+  ncclGetUniqueId_t getUniqueId = nullptr;
+  ncclCommInitRank_t commInitRank = nullptr;
+  ncclAllReduce_t allReduce = nullptr;
+  ncclCommDestroy_t commDestroy = nullptr;
+  ncclGetErrorString_t getErrorString = nullptr;
+  std::string why;
+  bool load()
+  {
+    if (lib) return true;
+    const char * names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char * n : names)
+    {
+      lib = dlopen(n, RTLD_NOW|RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { why = std::string("dlopen(libnccl.so.2) failed: ")+dlerror(); return false; }
+    getUniqueId = (ncclGetUniqueId_t)dlsym(lib, "ncclGetUniqueId");
+    commInitRank = (ncclCommInitRank_t)dlsym(lib, "ncclCommInitRank");
+    allReduce = (ncclAllReduce_t)dlsym(lib, "ncclAllReduce");
+    commDestroy = (ncclCommDestroy_t)dlsym(lib, "ncclCommDestroy");
+    getErrorString = (ncclGetErrorString_t)dlsym(lib, "ncclGetErrorString");
+    if (!getUniqueId || !commInitRank || !allReduce || !commDestroy)
+    { why = "libnccl lacks required symbols"; lib = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8, kNcclSum = 0; // ncclDataType_t / ncclRedOp_t values of NCCL 2.x
+
+thread_local std::string g_create_error;
+
+template <typename F>
+nqs_status guarded(nqs_handle * h, F && f)
+{
+  try { f(); return NQS_OK; }
+  catch (const Error & e) { if (h) h->err = e.what(); else g_create_error = e.what(); return e.code; }
+  catch (const std::bad_alloc &) { if (h) h->err = "host allocation failed"; return NQS_ERR_NOMEM; }
+  catch (const std::exception & e) { if (h) h->err = e.what(); else g_create_error = e.what(); return NQS_ERR_INVALID; }
+}
+
+inline int grid_for(long long n, int threads, int cap)
+{
+  long long g = (n+threads-1)/threads;
+  if (g < 1) g = 1;
+  return (int)std::min<long long>(g, cap);
+}
+
+struct PhaseTimer
+{ // CUDA-event bracket on the handle's stream; no-op unless timing is enabled
+  nqs_handle * h; float * dst; bool on;
+  PhaseTimer(nqs_handle * h_, float * d): h(h_), dst(d), on(h_->timing_on && h_->ev_ok)
+  { if (on) cudaEventRecord(h->ev[0], h->stream); }
+  ~PhaseTimer()
+  {
+    if (!on) return;
+    cudaEventRecord(h->ev[1], h->stream);
+    cudaEventSynchronize(h->ev[1]);
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    *dst += ms;
+  }
+};
+
+void check_launch(nqs_handle * h, const char * what)
+{
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    throw Error(NQS_ERR_CUDA, std::string("launch of ")+what+" failed: "+cudaGetErrorString(e));
+  h->timing.kernel_launches += 1;
+}
+
+int warps_for_smem(const nqs_handle * h, size_t per_warp, size_t fixed)
+{ // as many warps per CTA (<= 8) as fit the opt-in shared memory
+  int w = 8;
+  while (w > 1 && per_warp*w+fixed > h->smem_optin) w >>= 1;
+  NQS_REQUIRE(per_warp*w+fixed <= h->smem_optin, NQS_ERR_UNSUPPORTED, "n_hiddens too large for the shared-memory resident chain state");
+  return w;
+}
+
+template <typename Kern>
+void set_smem(Kern kern, size_t bytes)
+{
+  if (bytes > 48*1024)
+    NQS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+}
+
+// ---- launches ------------------------------------------------------------------------------------------------------
+void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_spins_dev, cd * theta, cd * sa, cd * lnpsi)
+{
+  ThetaArgs a;
+  a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
+  a.spins = spins_dev; a.sa_spins = sa_spins_dev; a.theta = theta; a.sa = sa; a.lnpsi = lnpsi;
+  const size_t npad = (size_t)((h->N+15)/16)*16;
+  const int warps = 8;
+  const size_t smem = npad*warps;
+  const int grid = (int)((h->K+warps-1)/warps);
+  if (h->model == MODEL_RBM) theta_generic_kernel<MODEL_RBM><<<grid, warps*32, smem, h->stream>>>(a);
+  else theta_generic_kernel<MODEL_FFNN><<<grid, warps*32, smem, h->stream>>>(a);
+  check_launch(h, "theta_generic_kernel");
+}
+
+void launch_sweep(nqs_handle * h, long long nsteps)
+{
+  if (nsteps <= 0) return;
+  SweepArgs a;
+  a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
+  a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.order = h->order.p;
+  a.pos0 = h->pos; a.nsteps = nsteps;
+  a.uniforms = nullptr;
+  if (h->u_steps > 0)
+  {
+    NQS_REQUIRE(h->u_used+nsteps <= h->u_steps, NQS_ERR_STATE, "pre-drawn uniform feed exhausted: call nqs_set_uniforms with enough steps");
+    a.uniforms = h->uniforms.p+(size_t)h->u_used*h->K;
+  }
+  a.seed = h->cfg.seed; a.step0 = h->step_counter; a.chain_offset = h->koff;
+  a.acc_log = nullptr;
+  if (h->cfg.flags & NQS_FLAG_ACCEPT_LOG)
+  {
+    if ((long long)h->acc_log.n < nsteps*h->K) h->acc_log.alloc((size_t)nsteps*h->K);
+    a.acc_log = h->acc_log.p;
+    h->acc_log_steps = nsteps;
+  }
+  const size_t npad = (size_t)((h->N+15)/16)*16;
+  const size_t per_warp = (size_t)h->M*sizeof(cd)+npad, fixed = (size_t)h->N*sizeof(int);
+  const int warps = warps_for_smem(h, per_warp, fixed);
+  const size_t smem = per_warp*warps+fixed;
+  const int grid = (int)((h->K+warps-1)/warps);
+  if (h->model == MODEL_RBM)
+  {
+    set_smem(sweep_generic_kernel<MODEL_RBM>, smem);
+    sweep_generic_kernel<MODEL_RBM><<<grid, warps*32, smem, h->stream>>>(a);
+  }
+  else
+  {
+    set_smem(sweep_generic_kernel<MODEL_FFNN>, smem);
+    sweep_generic_kernel<MODEL_FFNN><<<grid, warps*32, smem, h->stream>>>(a);
+  }
+  check_launch(h, "sweep_generic_kernel");
+  h->pos = (int)((h->pos+nsteps)%h->N);
+  if (h->u_steps > 0) h->u_used += nsteps;
+  h->step_counter += (unsigned long long)nsteps;
+}
+
+void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
+{
+  ElocArgs a;
+  a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p; a.spins = h->spins.p;
+  a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.Jmat = h->Jmat.p; a.hfield = h->cfg.h;
+  a.htilda = h->htilda.p; a.lnpsi1 = lnpsi1; a.single_site = single_site;
+  const size_t npad = (size_t)((h->N+15)/16)*16;
+  const size_t per_warp = (size_t)h->M*sizeof(cd)+npad;
+  const int warps = warps_for_smem(h, per_warp, 0);
+  const size_t smem = per_warp*warps;
+  const int grid = (int)((h->K+warps-1)/warps);
+  if (h->model == MODEL_RBM)
+  {
+    set_smem(eloc_generic_kernel<MODEL_RBM>, smem);
+    eloc_generic_kernel<MODEL_RBM><<<grid, warps*32, smem, h->stream>>>(a);
+  }
+  else
+  {
+    set_smem(eloc_generic_kernel<MODEL_FFNN>, smem);
+    eloc_generic_kernel<MODEL_FFNN><<<grid, warps*32, smem, h->stream>>>(a);
+  }
+  check_launch(h, "eloc_generic_kernel");
+}
+
+void launch_oderiv(nqs_handle * h)
+{
+  const size_t smem = (size_t)(h->model == MODEL_FFNN ? 2 : 1)*h->M*sizeof(cd)+(size_t)h->N*sizeof(double);
+  NQS_REQUIRE(smem <= h->smem_optin, NQS_ERR_UNSUPPORTED, "n_hiddens too large for oderiv_kernel shared memory");
+  if (h->model == MODEL_RBM)
+  {
+    set_smem(oderiv_kernel<MODEL_RBM>, smem);
+    oderiv_kernel<MODEL_RBM><<<(unsigned)h->K, 256, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
+  }
+  else
+  {
+    set_smem(oderiv_kernel<MODEL_FFNN>, smem);
+    oderiv_kernel<MODEL_FFNN><<<(unsigned)h->K, 256, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
+  }
+  check_launch(h, "oderiv_kernel");
+}
+
+void allreduce_sum(nqs_handle * h, double * buf, size_t count)
+{
+  if (h->comm == nullptr) return;
+  const int rc = g_nccl.allReduce(buf, buf, count, kNcclFloat64, kNcclSum, h->comm, h->stream);
+  if (rc != 0)
+    throw Error(NQS_ERR_NCCL, std::string("ncclAllReduce failed: ")+(g_nccl.getErrorString ? g_nccl.getErrorString(rc) : "?"));
+}
+
+// <O>, F, diag from ONE pass over O (+ one all-reduce of 5P+3 doubles across ranks)
+void sr_setup(nqs_handle * h, bool want_F)
+{
+  const long long P = h->P, K = h->K;
+  htilda_sums_kernel<<<1, 1024, 0, h->stream>>>(K, h->htilda.p, h->sums.p+5*P);
+  check_launch(h, "htilda_sums_kernel");
+  dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
+  setup_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->htilda.p, h->part.p, h->rows_per_block);
+  check_launch(h, "setup_partial_kernel");
+  colsum_reduce_kernel<<<grid_for(5*P, 256, 148*8), 256, 0, h->stream>>>(P, 5, h->nrb, h->part.p, h->sums.p, nullptr);
+  check_launch(h, "colsum_reduce_kernel");
+  allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
+  setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
+    want_F ? h->F.p : nullptr, h->diag.p);
+  check_launch(h, "setup_finalize_kernel");
+}
+
+// traw = sum_k conj(O_kp) (O_k . v): the two streaming passes over O (+ all-reduce of 2P doubles)
+void matvec_passes(nqs_handle * h, const cd * v, const int * done)
+{
+  const long long P = h->P, K = h->K;
+  const unsigned gr = (unsigned)((K+NQS_ROWS_PER_CTA-1)/NQS_ROWS_PER_CTA);
+  matvec_rows_kernel<<<gr, NQS_ROW_THREADS, 0, h->stream>>>(K, P, h->O.p, v, h->zk.p, done);
+  check_launch(h, "matvec_rows_kernel");
+  dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
+  matvec_cols_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->zk.p, h->part.p, h->rows_per_block, done);
+  check_launch(h, "matvec_cols_partial_kernel");
+  colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, h->nrb, h->part.p, h->traw.p, done);
+  check_launch(h, "colsum_reduce_kernel");
+  allreduce_sum(h, h->traw.p, (size_t)(2*P));
+}
+
+int vec_ctas(const nqs_handle * h)
+{
+  return std::max(1, std::min<int>(NQS_VEC_MAX_CTAS, (int)((h->P+NQS_VEC_THREADS*4-1)/(NQS_VEC_THREADS*4))));
+}
+
+CgScalars read_scalars(nqs_handle * h)
+{
+  NQS_CUDA(cudaMemcpyAsync(h->pinned, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  CgScalars s;
+  std::memcpy(&s, h->pinned, sizeof(CgScalars));
+  return s;
+}
+
+// ref: ConjugateGradient::solve(SMatrixFunctor_, F, dx), conjugate_gradient.cuh:29-74, warm start in dx
+void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters, nqs_sr_stats * st)
+{
+  const long long P = h->P;
+  const double inv_k = 1.0/(double)h->Ktot;
+  const int ctas = vec_ctas(h);
+  CgScalars init;
+  std::memset(&init, 0, sizeof(init));
+  init.tol2 = tol*tol;
+  init.fixed = fixed_iters > 0 ? 1 : 0;
+  std::memcpy(h->pinned, &init, sizeof(init));
+  NQS_CUDA(cudaMemcpyAsync(h->scal.p, h->pinned, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream)); // pinned area is reused for read-backs
+  int * done = &h->scal.p->done;
+  cg_aov_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->aO.p, h->dx.p, h->scal.p, h->slots.p);
+  check_launch(h, "cg_aov_kernel");
+  matvec_passes(h, h->dx.p, nullptr);
+  cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, inv_k, lambda, h->traw.p, h->aO.p, h->diag.p, h->dx.p, h->t.p,
+    h->F.p, h->r.p, h->pvec.p, h->scal.p, h->slots.p, 1);
+  check_launch(h, "cg_phase1_kernel");
+  CgScalars s = read_scalars(h);
+  if (s.zero_rhs)
+  {
+    NQS_CUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(cd)*P, h->stream));
+  }
+  else if (!s.done)
+  {
+    const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
+    const int check_every = fixed_iters > 0 ? n_max : 4;
+    for (int it = 0; it < n_max; ++it)
+    {
+      matvec_passes(h, h->pvec.p, done);
+      cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, inv_k, lambda, h->traw.p, h->aO.p, h->diag.p, h->pvec.p, h->t.p,
+        nullptr, nullptr, nullptr, h->scal.p, h->slots.p, 0);
+      check_launch(h, "cg_phase1_kernel");
+      cg_phase2_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, lambda, h->aO.p, h->diag.p, h->pvec.p, h->t.p, h->dx.p, h->r.p,
+        h->z.p, h->scal.p, h->slots.p);
+      check_launch(h, "cg_phase2_kernel");
+      cg_phase3_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->z.p, h->pvec.p, h->scal.p);
+      check_launch(h, "cg_phase3_kernel");
+      h->timing.matvec_count += 1;
+      if ((it+1)%check_every == 0 || it+1 == n_max)
+      {
+        s = read_scalars(h);
+        if (s.done) break;
+      }
+    }
+    s = read_scalars(h);
+  }
+  if (st)
+  {
+    st->cg_iters = s.iters;
+    st->cg_res2 = s.res2;
+    st->cg_rhs2 = s.rhs2;
+  }
+}
+
+void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
+{
+  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
+  check_launch(h, "update_params_kernel");
+  // ref update_variables tail (:161-169): theta and sa re-derived for the current spins; lnpsi0 is NOT refreshed
+  launch_theta(h, h->spins.p, h->spins.p, h->theta.p, h->sa.p, nullptr);
+}
+
+void do_sweeps(nqs_handle * h, int n_sweeps)
+{
+  NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_do_mcmc_steps before nqs_initialize / nqs_warm_up");
+  NQS_REQUIRE(n_sweeps >= 0, NQS_ERR_INVALID, "n_sweeps < 0");
+  const long long nsteps = (long long)n_sweeps*h->N;
+  if (nsteps == 0) return;
+  std::vector<int> ord(h->N);
+  launch_sweep(h, nsteps);
+  // the machine's index_ is the last visited site
+  NQS_CUDA(cudaMemcpyAsync(ord.data(), h->order.p, sizeof(int)*h->N, cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  h->flip_index = ord[(h->pos+h->N-1)%h->N];
+}
+
+void do_initialize(nqs_handle * h, const int8_t * spins_host)
+{
+  std::vector<int8_t> s((size_t)h->K*h->N, 1);
+  if (spins_host) std::memcpy(s.data(), spins_host, s.size());
+  else if (h->cfg.J > 0) // Neel, ref impl_hamiltonians.cuh:196-201
+    for (long long k = 0; k < h->K; ++k)
+      for (int i = 0; i < h->N; ++i)
+        s[(size_t)k*h->N+i] = (i%2 == 0) ? 1 : -1;
+  NQS_CUDA(cudaMemcpyAsync(h->spins.p, s.data(), s.size(), cudaMemcpyHostToDevice, h->stream));
+  launch_theta(h, h->spins.p, h->spins.p, h->theta.p, h->sa.p, h->lnpsi0.p);
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  h->initialized = true;
+}
+
+void build_order(nqs_handle * h)
+{
+  std::vector<int> ring;
+  const int N = h->N;
+  if (h->cfg.order == NQS_ORDER_CHECKERBOARD)
+  { // ring 0 -> evens -> odds -> 0, pointer advanced before use (ref impl_hamiltonians.cuh:163-180,209-210)
+    for (int i = 0; i < N; i += 2) ring.push_back(i);
+    for (int i = 1; i < N; i += 2) ring.push_back(i);
+  }
+  else
+    for (int i = 0; i < N; ++i) ring.push_back(i);
+  std::vector<int> ord(N);
+  for (int t = 0; t < N; ++t) ord[t] = ring[(t+1)%N];
+  NQS_CUDA(cudaMemcpy(h->order.p, ord.data(), sizeof(int)*N, cudaMemcpyHostToDevice));
+}
+
+void build_J(nqs_handle * h)
+{ // ref impl_hamiltonians.cuh:136-161
+  const int L = h->N;
+  std::vector<double> Jm((size_t)L*L, 0.0);
+  for (int i = 0; i < L; ++i)
+    for (int j = i+1; j < L; ++j)
+    {
+      double dist = (double)(j-i);
+      if (h->cfg.pbc) dist = ((j-i) < L/2) ? (double)(j-i) : (double)(L-(j-i));
+      Jm[(size_t)i*L+j] = h->cfg.J*std::pow(dist, -h->cfg.alpha);
+      Jm[(size_t)j*L+i] = Jm[(size_t)i*L+j];
+    }
+  NQS_CUDA(cudaMemcpy(h->Jmat.p, Jm.data(), sizeof(double)*Jm.size(), cudaMemcpyHostToDevice));
+}
+
+void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
+{
+  NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+}
+std::vector<std::complex<double> > download_params(nqs_handle * h)
+{
+  std::vector<std::complex<double> > v((size_t)h->P);
+  NQS_CUDA(cudaMemcpyAsync(v.data(), h->params.p, sizeof(cd)*v.size(), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  return v;
+}
+
+struct ParamFile { const char * suffix; long long off, count, row; const char * name; };
+std::vector<ParamFile> param_files(const nqs_handle * h)
+{ // ref save/load: RBM Dw/Da/Db (:225-232,281-286); FFNN Dw1/Dw2(=w1o)/Db1 (:931-937,985-991)
+  const long long NM = (long long)h->N*h->M;
+  if (h->model == MODEL_RBM)
+    return {{"Dw.dat", 0, NM, h->M, "w"}, {"Da.dat", NM, h->N, h->N, "a"}, {"Db.dat", NM+h->N, h->M, h->M, "b"}};
+  return {{"Dw1.dat", 0, NM, h->M, "w1"}, {"Dw2.dat", NM+h->M, h->M, h->M, "w2"}, {"Db1.dat", NM, h->M, h->M, "b1"}};
+}
+} // namespace
+
+// =====================================================================================================================
+extern "C"
+{
+int32_t nqs_abi_version(void) { return NQS_B200_ABI_VERSION; }
+
+const char * nqs_last_error(const nqs_handle * h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+nqs_status nqs_sr_options_default(nqs_sr_options * o)
+{
+  if (!o) return NQS_ERR_INVALID;
+  o->lr = 1e-2;        // ref default -lr, gpu/src/LICH-train_rbm.cu:36
+  o->tol = 1e-5;       // gpu/include/impl_optimizer.cuh:60
+  o->max_iter = 1000;  // gpu/include/conjugate_gradient.cuh:19
+  o->fixed_iters = 0;
+  o->lambda = -1.0;
+  o->n_mc_steps = 1;   // ref default -nms
+  o->apply_update = 1;
+  return NQS_OK;
+}
+
+nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
+{
+  if (out) *out = nullptr;
+  nqs_handle * h = nullptr;
+  nqs_status rc = guarded(nullptr, [&]()
+  {
+    NQS_REQUIRE(cfg && out, NQS_ERR_INVALID, "nqs_create: null argument");
+    NQS_REQUIRE(cfg->abi_version == NQS_B200_ABI_VERSION, NQS_ERR_INVALID, "nqs_create: abi_version mismatch");
+    NQS_REQUIRE(cfg->model == NQS_MODEL_RBM || cfg->model == NQS_MODEL_FFNN, NQS_ERR_INVALID, "nqs_create: unknown model");
+    NQS_REQUIRE(cfg->n_inputs >= 1 && cfg->n_hiddens >= 1 && cfg->n_chains >= 1, NQS_ERR_INVALID, "nqs_create: sizes must be >= 1");
+    NQS_REQUIRE(!(cfg->pbc && cfg->n_inputs%2 == 1), NQS_ERR_INVALID, "kL%2 == 1 (set \"isPBC\" to \"false\".)"); // ref :141-142
+    NQS_REQUIRE(cfg->order == NQS_ORDER_CHECKERBOARD || cfg->order == NQS_ORDER_SEQUENTIAL, NQS_ERR_INVALID, "nqs_create: unknown order");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(NQS_ERR_CUDA, std::string("no CUDA device (libnqs_b200 has no CPU fallback): ")+cudaGetErrorString(e));
+    NQS_REQUIRE(cfg->device >= 0 && cfg->device < ndev, NQS_ERR_INVALID, "# error ---> dev >= nDevice"); // ref LICH-train_rbm.cu:66-70
+    NQS_CUDA(cudaSetDevice(cfg->device));
+    h = new nqs_handle();
+    h->cfg = *cfg;
+    h->N = cfg->n_inputs; h->M = cfg->n_hiddens; h->model = cfg->model;
+    h->K = cfg->n_chains; h->Ktot = cfg->n_chains_total > 0 ? cfg->n_chains_total : cfg->n_chains; h->koff = cfg->chain_offset;
+    NQS_REQUIRE(h->Ktot >= h->K, NQS_ERR_INVALID, "n_chains_total < n_chains");
+    h->P = (h->model == MODEL_RBM) ? (long long)h->N*h->M+h->N+h->M : (long long)h->N*h->M+2*h->M;
+    std::memset(&h->timing, 0, sizeof(h->timing));
+    cudaDeviceProp prop;
+    NQS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    NQS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) NQS_CUDA(cudaEventCreate(&h->ev[i]));
+    h->ev_ok = true;
+    NQS_CUDA(cudaMallocHost(&h->pinned, 4096));
+    const size_t KM = (size_t)h->K*h->M, KN = (size_t)h->K*h->N;
+    h->params.alloc(h->P); h->theta.alloc(KM); h->tmp_theta.alloc(0);
+    h->lnpsi0.alloc(h->K); h->lnpsi1.alloc(h->K); h->sa.alloc(h->K); h->htilda.alloc(h->K);
+    h->spins.alloc(KN); h->tmp_spins.alloc(KN);
+    h->Jmat.alloc((size_t)h->N*h->N); h->order.alloc(h->N);
+    NQS_CUDA(cudaMemset(h->params.p, 0, sizeof(cd)*h->P));
+    NQS_CUDA(cudaMemset(h->spins.p, 0, KN));   // like the reference's zero-initialised spinStates_dev_
+    NQS_CUDA(cudaMemset(h->theta.p, 0, sizeof(cd)*KM));
+    NQS_CUDA(cudaMemset(h->lnpsi0.p, 0, sizeof(cd)*h->K));
+    NQS_CUDA(cudaMemset(h->sa.p, 0, sizeof(cd)*h->K));
+    NQS_CUDA(cudaMemset(h->htilda.p, 0, sizeof(cd)*h->K));
+    if (cfg->max_predrawn_steps > 0) h->uniforms.alloc((size_t)cfg->max_predrawn_steps*h->K);
+    if (!(cfg->flags & NQS_FLAG_NO_SR))
+    {
+      const size_t KP = (size_t)h->K*(size_t)h->P;
+      h->O.alloc(KP);
+      h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
+      h->zk.alloc(h->K); h->diag.alloc(h->P);
+      const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
+      long long nrb = (2LL*16*h->sm_count+ctiles-1)/ctiles;
+      nrb = std::max<long long>(1, std::min<long long>(nrb, std::min<long long>(64, (h->K+63)/64)));
+      h->nrb = (int)nrb;
+      h->rows_per_block = (h->K+nrb-1)/nrb;
+      h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
+      h->part.alloc((size_t)h->nrb*5*h->P);
+      h->sums.alloc((size_t)5*h->P+3);
+      h->traw.alloc((size_t)2*h->P);
+      h->slots.alloc((size_t)5*NQS_VEC_MAX_CTAS);
+      h->scal.alloc(1);
+      NQS_CUDA(cudaMemset(h->scal.p, 0, sizeof(CgScalars)));
+      NQS_CUDA(cudaMemset(h->dx.p, 0, sizeof(cd)*h->P)); // CG warm start is zero only at construction (ref impl_optimizer.cuh:55)
+    }
+    build_order(h);
+    build_J(h);
+    NQS_CUDA(cudaDeviceSynchronize());
+    *out = h;
+  });
+  if (rc != NQS_OK && h) { nqs_destroy(h); }
+  return rc;
+}
+
+void nqs_destroy(nqs_handle * h)
+{
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  if (h->comm && g_nccl.commDestroy) g_nccl.commDestroy(h->comm);
+  if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  delete h;
+}
+
+nqs_status nqs_sync(nqs_handle * h)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]() { NQS_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+nqs_status nqs_n_variables(const nqs_handle * h, int64_t * P)
+{
+  if (!h || !P) return NQS_ERR_INVALID;
+  *P = h->P;
+  return NQS_OK;
+}
+
+nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(params && P == h->P, NQS_ERR_INVALID, "nqs_set_params: P mismatch");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_get_params(nqs_handle * h, nqs_cdouble * params, int64_t P)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(params && P == h->P, NQS_ERR_INVALID, "nqs_get_params: P mismatch");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(params, h->params.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_init_params_random(nqs_handle * h, uint64_t seed)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    std::mt19937_64 ran(seed);
+    const int N = h->N, M = h->M;
+    std::vector<std::complex<double> > v((size_t)h->P);
+    const long long NM = (long long)N*M;
+    if (h->model == MODEL_RBM)
+    { // ref ctor impl_neural_quantum_state.cuh:30-48
+      std::normal_distribution<double> randw(0, std::sqrt(1.0/(N+M))), randb(0, std::sqrt(1.0/M));
+      for (long long i = 0; i < NM; ++i) { const double re = 1e-1*randw(ran), im = 1e-1*randw(ran); v[i] = {re, im}; }
+      for (int i = 0; i < N; ++i) v[NM+i] = {0.0, 0.0};
+      for (int j = 0; j < M; ++j) { const double re = 1e-1*randb(ran), im = 1e-1*randb(ran); v[NM+N+j] = {re, im}; }
+    }
+    else
+    { // ref ctor :766-783
+      std::normal_distribution<double> randwi1(0, std::sqrt(1.0/(N+M))), randw1o(0, std::sqrt(1.0/M));
+      for (long long i = 0; i < NM; ++i) { const double re = randwi1(ran), im = 1e-1*randwi1(ran); v[i] = {re, im}; }
+      for (int j = 0; j < M; ++j) v[NM+j] = {0.0, 0.0};
+      for (int j = 0; j < M; ++j) { const double re = randw1o(ran), im = 1e-1*randw1o(ran); v[NM+M+j] = {re, im}; }
+    }
+    upload_params(h, v);
+  });
+}
+
+nqs_status nqs_load_params(nqs_handle * h, const char * prefix)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(prefix, NQS_ERR_INVALID, "nqs_load_params: null prefix");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    std::vector<std::complex<double> > v = download_params(h);
+    for (const ParamFile & f : param_files(h))
+    {
+      const std::string path = std::string(prefix)+f.suffix;
+      std::ifstream reader(path);
+      if (!reader.is_open())
+      { // ref :247-251 -- not an error
+        std::cout << "# --- file-path: " << path << " is not exist..." << std::endl;
+        continue;
+      }
+      std::vector<std::complex<double> > raw;
+      std::complex<double> temp;
+      while (reader >> temp) raw.push_back(temp);
+      if ((long long)raw.size() == f.count)
+        std::copy(raw.begin(), raw.end(), v.begin()+f.off);
+      else
+        std::cout << "# check '" << f.name << "' size... " << std::endl; // ref :258-259
+    }
+    upload_params(h, v);
+  });
+}
+
+nqs_status nqs_save_params(nqs_handle * h, const char * prefix, int32_t precision)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(prefix, NQS_ERR_INVALID, "nqs_save_params: null prefix");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    const std::vector<std::complex<double> > v = download_params(h);
+    int idx = 0;
+    for (const ParamFile & f : param_files(h))
+    {
+      std::ofstream writer(std::string(prefix)+f.suffix);
+      NQS_REQUIRE(writer.is_open(), NQS_ERR_IO, std::string("cannot write ")+prefix+f.suffix);
+      writer << std::setprecision(precision);
+      for (long long n = 0; n < f.count; ++n)
+      {
+        writer << v[f.off+n] << " ";
+        if (idx == 0 && (n+1)%f.row == 0) writer << std::endl; // W: one row per line
+      }
+      if (idx == 1) writer << std::endl;                        // a / w1o: trailing newline; b / b1: none
+      ++idx;
+    }
+  });
+}
+
+nqs_status nqs_initialize(nqs_handle * h, const int8_t * spins)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]() { NQS_CUDA(cudaSetDevice(h->cfg.device)); do_initialize(h, spins); });
+}
+
+nqs_status nqs_warm_up(nqs_handle * h, int32_t n_sweeps, const int8_t * spins)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    do_initialize(h, spins);
+    // the all-true accept_next_state_ quirk (ref impl_mcmc_sampler.cuh:21-22): flips site index_ everywhere, lnpsi0 stays stale
+    const int site = h->flip_index;
+    flip_site_all_kernel<<<grid_for(h->K*(long long)h->M, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->K, h->model, h->params.p,
+      h->spins.p, h->theta.p, h->sa.p, site);
+    check_launch(h, "flip_site_all_kernel");
+    flip_site_all_finish_kernel<<<grid_for(h->K, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->K, h->model, h->params.p,
+      h->spins.p, h->sa.p, site);
+    check_launch(h, "flip_site_all_finish_kernel");
+    do_sweeps(h, n_sweeps);
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_do_mcmc_steps(nqs_handle * h, int32_t n_sweeps)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    h->timing.sweep_ms = 0;
+    { PhaseTimer t(h, &h->timing.sweep_ms); do_sweeps(h, n_sweeps); }
+  });
+}
+
+nqs_status nqs_set_uniforms(nqs_handle * h, const double * u, int64_t steps)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    if (u == nullptr) { h->u_steps = 0; h->u_used = 0; return; }
+    NQS_REQUIRE(steps > 0, NQS_ERR_INVALID, "nqs_set_uniforms: steps <= 0");
+    NQS_REQUIRE((size_t)steps*h->K <= h->uniforms.n, NQS_ERR_INVALID, "nqs_set_uniforms: steps exceed nqs_config.max_predrawn_steps");
+    NQS_CUDA(cudaMemcpyAsync(h->uniforms.p, u, sizeof(double)*(size_t)steps*h->K, cudaMemcpyHostToDevice, h->stream));
+    h->u_steps = steps; h->u_used = 0;
+  });
+}
+
+nqs_status nqs_get_spins(nqs_handle * h, int8_t * spins)
+{
+  if (!h || !spins) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(spins, h->spins.p, (size_t)h->K*h->N, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_get_lnpsi(nqs_handle * h, nqs_cdouble * lnpsi)
+{
+  if (!h || !lnpsi) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(lnpsi, h->lnpsi0.p, sizeof(cd)*h->K, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_get_theta(nqs_handle * h, nqs_cdouble * theta)
+{
+  if (!h || !theta) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(theta, h->theta.p, sizeof(cd)*(size_t)h->K*h->M, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_get_accept_log(nqs_handle * h, uint8_t * acc, int64_t steps)
+{
+  if (!h || !acc) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->cfg.flags & NQS_FLAG_ACCEPT_LOG, NQS_ERR_STATE, "handle created without NQS_FLAG_ACCEPT_LOG");
+    NQS_REQUIRE(steps == h->acc_log_steps, NQS_ERR_INVALID, "nqs_get_accept_log: steps != proposals of the last sweep call");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(acc, h->acc_log.p, (size_t)steps*h->K, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_forward_flip(nqs_handle * h, int32_t site, nqs_cdouble * lnpsi1)
+{
+  if (!h || !lnpsi1) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(site >= 0 && site < h->N, NQS_ERR_INVALID, "nqs_forward_flip: site out of range");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    launch_eloc(h, h->lnpsi1.p, site);
+    h->flip_index = site;
+    NQS_CUDA(cudaMemcpyAsync(lnpsi1, h->lnpsi1.p, sizeof(cd)*h->K, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_lnpsi_fixed_spins(nqs_handle * h, const int8_t * spins, nqs_cdouble * lnpsi)
+{
+  if (!h || !spins || !lnpsi) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaMemcpyAsync(h->tmp_spins.p, spins, (size_t)h->K*h->N, cudaMemcpyHostToDevice, h->stream));
+    // ref forward(spins, lnpsi, false): theta from the argument, sa from the MEMBER spins (:119-120); chain state untouched here
+    launch_theta(h, h->tmp_spins.p, h->spins.p, nullptr, nullptr, h->lnpsi1.p);
+    NQS_CUDA(cudaMemcpyAsync(lnpsi, h->lnpsi1.p, sizeof(cd)*h->K, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_local_energy(nqs_handle * h, nqs_cdouble * htilda)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_local_energy before nqs_initialize / nqs_warm_up");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    h->timing.eloc_ms = 0;
+    { PhaseTimer t(h, &h->timing.eloc_ms); launch_eloc(h, nullptr, 0); }
+    h->flip_index = h->N-1; // the reference's loop ends with forward(L-1)
+    if (htilda)
+    {
+      NQS_CUDA(cudaMemcpyAsync(htilda, h->htilda.p, sizeof(cd)*h->K, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
+
+nqs_status nqs_log_derivs(nqs_handle * h, nqs_cdouble * O_host)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_log_derivs before nqs_initialize / nqs_warm_up");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    h->timing.oderiv_ms = 0;
+    { PhaseTimer t(h, &h->timing.oderiv_ms); launch_oderiv(h); }
+    if (O_host)
+    {
+      NQS_CUDA(cudaMemcpyAsync(O_host, h->O.p, sizeof(cd)*(size_t)h->K*(size_t)h->P, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
+
+nqs_status nqs_smatrix_dot(nqs_handle * h, double lambda, const nqs_cdouble * v, nqs_cdouble * Sv, nqs_cdouble * aO, double * diag)
+{
+  if (!h || !v || !Sv) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    const long long P = h->P;
+    sr_setup(h, false);
+    NQS_CUDA(cudaMemcpyAsync(h->pvec.p, v, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
+    CgScalars init; std::memset(&init, 0, sizeof(init));
+    std::memcpy(h->pinned, &init, sizeof(init));
+    NQS_CUDA(cudaMemcpyAsync(h->scal.p, h->pinned, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+    const int ctas = vec_ctas(h);
+    cg_aov_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->aO.p, h->pvec.p, h->scal.p, h->slots.p);
+    check_launch(h, "cg_aov_kernel");
+    matvec_passes(h, h->pvec.p, nullptr);
+    cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, 1.0/(double)h->Ktot, lambda, h->traw.p, h->aO.p, h->diag.p, h->pvec.p,
+      h->t.p, nullptr, nullptr, nullptr, h->scal.p, h->slots.p, 0);
+    check_launch(h, "cg_phase1_kernel");
+    NQS_CUDA(cudaMemcpyAsync(Sv, h->t.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
+    if (aO) NQS_CUDA(cudaMemcpyAsync(aO, h->aO.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
+    if (diag) NQS_CUDA(cudaMemcpyAsync(diag, h->diag.p, sizeof(double)*P, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats * st)
+{
+  if (!h || !opt) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_sr_step before nqs_warm_up");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    nqs_timing & tm = h->timing;
+    tm.sweep_ms = tm.eloc_ms = tm.oderiv_ms = tm.setup_ms = tm.cg_ms = tm.update_ms = tm.matvec_ms = 0;
+    tm.matvec_count = 0;
+    nqs_sr_stats s;
+    std::memset(&s, 0, sizeof(s));
+    { PhaseTimer t(h, &tm.sweep_ms); do_sweeps(h, opt->n_mc_steps); }
+    { PhaseTimer t(h, &tm.eloc_ms); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
+    { PhaseTimer t(h, &tm.oderiv_ms); launch_oderiv(h); }
+    double hs[3];
+    {
+      PhaseTimer t(h, &tm.setup_ms);
+      sr_setup(h, true);
+      NQS_CUDA(cudaMemcpyAsync(h->pinned, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaStreamSynchronize(h->stream));
+      std::memcpy(hs, h->pinned, sizeof(hs));
+    }
+    const double invk = 1.0/(double)h->Ktot;
+    s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
+    s.finite = std::isfinite(s.e_re) ? 1 : 0;
+    if (!s.finite)
+    { // ref optimizer.cuh:134-138: print and stop; here: report and leave the state untouched
+      if (st) *st = s;
+      return;
+    }
+    if (opt->lambda < 0)
+    { // ref schedular_, impl_optimizer.cuh:72-78
+      h->bp *= 0.9;
+      const double lam = 100.0*h->bp;
+      s.lambda = (lam > 1e-2) ? lam : 1e-2;
+    }
+    else s.lambda = opt->lambda;
+    { PhaseTimer t(h, &tm.cg_ms); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
+    if (opt->apply_update)
+    { PhaseTimer t(h, &tm.update_ms); do_evolve(h, h->dx.p, opt->lr); }
+    NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
+    const double n2 = s.e_re*s.e_re+s.e_im*s.e_im;
+    s.rsd = std::sqrt((hs[2]*invk-n2)/n2);
+    if (st) *st = s;
+  });
+}
+
+nqs_status nqs_get_sr_vectors(nqs_handle * h, nqs_cdouble * F, nqs_cdouble * dx)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    if (F) NQS_CUDA(cudaMemcpyAsync(F, h->F.p, sizeof(cd)*h->P, cudaMemcpyDeviceToHost, h->stream));
+    if (dx) NQS_CUDA(cudaMemcpyAsync(dx, h->dx.p, sizeof(cd)*h->P, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_evolve(nqs_handle * h, const nqs_cdouble * dx, double lr)
+{
+  if (!h || !dx) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    cd * buf = h->pvec.p;
+    DevBuf<cd> tmp;
+    if (!buf) { tmp.alloc(h->P); buf = tmp.p; }
+    NQS_CUDA(cudaMemcpyAsync(buf, dx, sizeof(cd)*h->P, cudaMemcpyHostToDevice, h->stream));
+    do_evolve(h, buf, lr);
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_comm_get_unique_id(char id[NQS_UNIQUE_ID_BYTES])
+{
+  if (!id) return NQS_ERR_INVALID;
+  if (!g_nccl.load()) { g_create_error = g_nccl.why; return NQS_ERR_NCCL; }
+  ncclUniqueIdT u;
+  const int rc = g_nccl.getUniqueId(&u);
+  if (rc != 0) { g_create_error = "ncclGetUniqueId failed"; return NQS_ERR_NCCL; }
+  std::memcpy(id, u.internal, NQS_UNIQUE_ID_BYTES);
+  return NQS_OK;
+}
+
+nqs_status nqs_comm_init(nqs_handle * h, int32_t n_ranks, int32_t rank, const char id[NQS_UNIQUE_ID_BYTES])
+{
+  if (!h || !id) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, NQS_ERR_INVALID, "nqs_comm_init: bad rank");
+    if (!g_nccl.load()) throw Error(NQS_ERR_NCCL, g_nccl.why);
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    ncclUniqueIdT u;
+    std::memcpy(u.internal, id, NQS_UNIQUE_ID_BYTES);
+    void * comm = nullptr;
+    const int rc = g_nccl.commInitRank(&comm, n_ranks, u, rank);
+    if (rc != 0)
+      throw Error(NQS_ERR_NCCL, std::string("ncclCommInitRank failed: ")+(g_nccl.getErrorString ? g_nccl.getErrorString(rc) : "?"));
+    h->comm = comm; h->n_ranks = n_ranks; h->rank = rank;
+  });
+}
+
+nqs_status nqs_get_timing(nqs_handle * h, nqs_timing * t)
+{
+  if (!h || !t) return NQS_ERR_INVALID;
+  *t = h->timing;
+  return NQS_OK;
+}
+
+nqs_status nqs_set_timing(nqs_handle * h, int32_t enabled)
+{
+  if (!h) return NQS_ERR_INVALID;
+  h->timing_on = enabled != 0;
+  return NQS_OK;
+}
+
+const char * nqs_kernel_variant(const nqs_handle * h, const char * stage)
+{
+  if (!h || !stage) return "";
+  if (!std::strcmp(stage, "sweep")) return h->variant_sweep.c_str();
+  if (!std::strcmp(stage, "eloc")) return h->variant_eloc.c_str();
+  if (!std::strcmp(stage, "theta")) return h->variant_theta.c_str();
+  return "";
+}
+} // extern "C"

@@ -1,0 +1,87 @@
+// Host-side engine behind the C ABI of include/nqs_b200.h.  One nqs_handle owns the chains of one GPU: parameters,
+// chain state (spins, theta, lnpsi0, sa), the O matrix and the CG vectors, all resident in HBM for the life of the handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/nqs_b200.h"
+#include "device_math.cuh"
+
+namespace nqs
+{
+struct Error: public std::runtime_error
+{
+  nqs_status code;
+  Error(nqs_status c, const std::string & m): std::runtime_error(m), code(c) {}
+};
+
+#define NQS_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+  throw nqs::Error(NQS_ERR_CUDA, std::string(#call)+": "+cudaGetErrorString(e_)+" ("+__FILE__+":"+std::to_string(__LINE__)+")"); } while (0)
+#define NQS_REQUIRE(cond, code, msg) do { if (!(cond)) throw nqs::Error(code, msg); } while (0)
+
+struct CgScalars;
+
+template <typename T>
+struct DevBuf
+{
+  T * p = nullptr;
+  size_t n = 0;
+  void alloc(size_t count)
+  {
+    free();
+    if (count == 0) return;
+    cudaError_t e = cudaMalloc(&p, count*sizeof(T));
+    if (e != cudaSuccess)
+      throw Error(NQS_ERR_NOMEM, "cudaMalloc of "+std::to_string(count*sizeof(T))+" bytes failed: "+cudaGetErrorString(e));
+    n = count;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { free(); }
+};
+} // namespace nqs
+
+struct nqs_handle
+{
+  nqs_config cfg;
+  int N = 0, M = 0, model = 0;
+  long long K = 0, Ktot = 0, koff = 0, P = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+
+  // model + chain state
+  nqs::DevBuf<nqs::cd> params, theta, lnpsi0, lnpsi1, sa, htilda, tmp_theta;
+  nqs::DevBuf<int8_t> spins, tmp_spins;
+  nqs::DevBuf<double> Jmat, uniforms;
+  nqs::DevBuf<int> order;
+  nqs::DevBuf<unsigned char> acc_log;
+  long long u_steps = 0, u_used = 0;      // pre-drawn feed: proposals available / consumed
+  long long acc_log_steps = 0;
+  int pos = 0;                            // next position in the site ring
+  int flip_index = 0;                     // the machine's index_ (ref impl_neural_quantum_state.cuh:19)
+  unsigned long long step_counter = 0;    // proposals done so far (RNG counter)
+  bool initialized = false;
+
+  // SR
+  nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
+  nqs::DevBuf<double> diag, part, sums, traw, slots;
+  nqs::DevBuf<nqs::CgScalars> scal;
+  double bp = 1.0;                        // lambda schedule state (ref bp_, optimizer.cuh:176)
+  int nrb = 1;                            // row blocks of the column passes
+  long long rows_per_block = 0;
+  void * pinned = nullptr;                // small pinned staging area for scalar read-backs
+
+  // multi-GPU
+  void * comm = nullptr;                  // ncclComm_t
+  int n_ranks = 1, rank = 0;
+
+  // bookkeeping
+  std::string err;
+  bool timing_on = false;
+  nqs_timing timing;
+  cudaEvent_t ev[8];
+  bool ev_ok = false;
+  std::string variant_sweep = "generic", variant_eloc = "generic", variant_theta = "generic";
+};

@@ -1,0 +1,328 @@
+// Generic ("direct log cosh") kernels of the sampler side of the path: theta GEMV-style init, Metropolis sweep with the
+// chain state resident in shared memory, local energy, single-flip forward.  They accept any N, M and both ansaetze and
+// follow the reference arithmetic literally; the specialised register-resident kernels live in fast_kernels.cuh.
+//
+// Mapping: ONE WARP PER CHAIN.  theta_k (M complex) and s_k (N int8) of the warp's chain sit in shared memory for the
+// whole launch, W rows are read with coalesced 16-byte loads (W is [N][M] row-major, so the "column of W^T" needed by
+// a flip of site i is the contiguous row i), sum_j is a strided per-lane sum followed by a shuffle butterfly.
+#pragma once
+#include "device_math.cuh"
+
+namespace nqs
+{
+enum { MODEL_RBM = 0, MODEL_FFNN = 1 };
+
+struct ModelPtrs
+{
+  const cd * W;    // [N][M]
+  const cd * a;    // RBM: visible bias [N]; FFNN: unused
+  const cd * b;    // hidden bias [M]
+  const cd * w1o;  // FFNN: output weights [M]; RBM: unused
+};
+
+__host__ __device__ inline ModelPtrs model_ptrs(int model, const cd * params, int N, int M)
+{
+  ModelPtrs p;
+  p.W = params;
+  if (model == MODEL_RBM) { p.a = params+(size_t)N*M; p.b = p.a+N; p.w1o = nullptr; }
+  else { p.a = nullptr; p.b = params+(size_t)N*M; p.w1o = p.b+M; }
+  return p;
+}
+
+// sum_j f_j(theta_j - two_s*W_ij): the body of ref k3 (impl_neural_quantum_state.cuh:1264-1278) + c1 (:102 / :828),
+// warp-reduced.  f = logcosh (RBM) or w1o_j*logcosh (FFNN).
+template <int MODEL>
+__device__ __forceinline__ cd flip_sum(const cd * th, const cd * __restrict__ Wrow, const cd * __restrict__ w1o,
+  const int M, const double two_s, const int lane)
+{
+  cd acc = cmake(0.0, 0.0);
+  for (int j = lane; j < M; j += 32)
+  {
+    const cd w = Wrow[j], t = th[j];
+    const cd lc = c_logcosh(cmake(t.x-w.x*two_s, t.y-w.y*two_s));
+    if (MODEL == MODEL_RBM) acc = cadd(acc, lc);
+    else acc = cadd(acc, cmul(w1o[j], lc));
+  }
+  return warp_sum(acc);
+}
+
+struct SweepArgs
+{
+  int N, M, model;
+  long long K;
+  const cd * params;
+  int8_t * spins;      // [K][N]
+  cd * theta;          // [K][M]
+  cd * lnpsi0;         // [K]
+  cd * sa;             // [K] (RBM)
+  const int * order;   // [N]
+  int pos0;            // index into order of the first site to visit
+  long long nsteps;    // proposals per chain in this launch
+  const double * uniforms; // pre-drawn [nsteps][K] (already offset to the first step) or nullptr
+  unsigned long long seed, step0;
+  long long chain_offset;
+  unsigned char * acc_log; // [nsteps][K] or nullptr
+};
+
+inline size_t sweep_smem_bytes(int N, int M, int warps)
+{
+  const size_t npad = (size_t)((N+15)/16)*16;
+  return (size_t)warps*M*sizeof(cd)+(size_t)warps*npad+(size_t)N*sizeof(int);
+}
+
+// ref: BaseParallelSampler::do_mcmc_steps (impl_mcmc_sampler.cuh:28-39) with sampling_/accept_next_state_ of LITFIChain
+// (impl_hamiltonians.cuh:207-218) -- the reference's 7 launches per proposal (k3,k4,c1,k5,k6,k7,k8,k9) fused into one launch
+// per call, chain state resident on chip.
+template <int MODEL>
+__global__ void __launch_bounds__(256) sweep_generic_kernel(const SweepArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int N = a.N, M = a.M;
+  const int npad = ((N+15)/16)*16;
+  cd * th = reinterpret_cast<cd*>(smem_raw)+(size_t)w*M;
+  int8_t * sp = reinterpret_cast<int8_t*>(reinterpret_cast<cd*>(smem_raw)+(size_t)warps*M)+(size_t)w*npad;
+  int * ord = reinterpret_cast<int*>(reinterpret_cast<int8_t*>(reinterpret_cast<cd*>(smem_raw)+(size_t)warps*M)+(size_t)warps*npad);
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    ord[i] = a.order[i];
+  __syncthreads();
+  const long long k = (long long)blockIdx.x*warps+w;
+  if (k >= a.K) return;
+  const ModelPtrs mp = model_ptrs(MODEL, a.params, N, M);
+  for (int j = lane; j < M; j += 32) th[j] = a.theta[k*M+j];
+  for (int i = lane; i < N; i += 32) sp[i] = a.spins[k*N+i];
+  cd ln0 = a.lnpsi0[k];
+  cd sa = (MODEL == MODEL_RBM) ? a.sa[k] : cmake(0.0, 0.0);
+  __syncwarp();
+  int pos = a.pos0;
+  double ubuf = 0.0;
+  for (long long t = 0; t < a.nsteps; ++t)
+  {
+    if ((t&31) == 0)
+    { // each lane fetches the uniform of one of the next 32 proposals
+      const long long tt = t+lane;
+      if (tt < a.nsteps)
+        ubuf = a.uniforms ? a.uniforms[tt*a.K+k] : philox_uniform(a.seed, (unsigned long long)(a.chain_offset+k), a.step0+(unsigned long long)tt);
+    }
+    const double u = __shfl_sync(0xffffffffu, ubuf, (int)(t&31));
+    const int site = ord[pos];
+    pos = (pos+1 == N) ? 0 : pos+1;
+    const double sig = (double)sp[site], two_s = 2.0*sig;
+    const cd * Wrow = mp.W+(size_t)site*M;
+    cd ln1 = flip_sum<MODEL>(th, Wrow, mp.w1o, M, two_s, lane);
+    cd da = cmake(0.0, 0.0);
+    if (MODEL == MODEL_RBM)
+    { // ref k4 RBM__sadot__ (:1391-1404): lnpsi' = sa - 2 s a_i, then += sum_j
+      const cd ai = mp.a[site];
+      da = cmake(two_s*ai.x, two_s*ai.y);
+      ln1 = cadd(csub(sa, da), ln1);
+    }
+    // ref k6 Sampler__ParallelMetropolisUpdate__ (impl_mcmc_sampler.cuh:75-102)
+    const double d = ln1.x-ln0.x;
+    const double ratio = exp(2.0*((d < 0) ? 1.0 : 0.0)*d);
+    const bool acc = (u < ratio);
+    const double delta = acc ? 1.0 : 0.0;
+    ln0 = cmake(ln0.x+delta*(ln1.x-ln0.x), ln0.y+delta*(ln1.y-ln0.y));
+    if (a.acc_log && lane == 0) a.acc_log[t*a.K+k] = acc ? 1 : 0;
+    if (acc)
+    { // ref k7 conditional_y_update (:1314-1329), k8 RBM__saUpdate__ (:1451-1465), k9 conditional_spin_update (:1353-1368)
+      for (int j = lane; j < M; j += 32)
+      {
+        const cd wv = Wrow[j];
+        cd tv = th[j];
+        tv.x -= wv.x*two_s; tv.y -= wv.y*two_s;
+        th[j] = tv;
+      }
+      sa = csub(sa, da);
+      if (lane == 0) sp[site] = (int8_t)(-sp[site]);
+    }
+    __syncwarp();
+  }
+  for (int j = lane; j < M; j += 32) a.theta[k*M+j] = th[j];
+  for (int i = lane; i < N; i += 32) a.spins[k*N+i] = sp[i];
+  if (lane == 0)
+  {
+    a.lnpsi0[k] = ln0;
+    if (MODEL == MODEL_RBM) a.sa[k] = sa;
+  }
+}
+
+struct ElocArgs
+{
+  int N, M, model;
+  long long K;
+  const cd * params;
+  const int8_t * spins;
+  const cd * theta;
+  const cd * lnpsi0;
+  const cd * sa;
+  const double * Jmat; // [N][N]
+  double hfield;
+  cd * htilda;         // [K]
+  cd * lnpsi1;         // optional [K]: lnpsi' of flipping `single_site` (forward(int) for tests); nullptr in E_loc mode
+  int single_site;
+};
+
+// ref: LITFIChain::get_htilda_ (impl_hamiltonians.cuh:220-241): c5 Zgemm SJ = J s, k10 diag, N x (forward(i) + k11), k12 -- one launch.
+// With lnpsi1 != nullptr the kernel instead evaluates a single forward(int) (ref :93-104).
+template <int MODEL>
+__global__ void __launch_bounds__(256) eloc_generic_kernel(const ElocArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int N = a.N, M = a.M;
+  const int npad = ((N+15)/16)*16;
+  cd * th = reinterpret_cast<cd*>(smem_raw)+(size_t)w*M;
+  int8_t * sp = reinterpret_cast<int8_t*>(reinterpret_cast<cd*>(smem_raw)+(size_t)warps*M)+(size_t)w*npad;
+  const long long k = (long long)blockIdx.x*warps+w;
+  if (k >= a.K) return;
+  const ModelPtrs mp = model_ptrs(MODEL, a.params, N, M);
+  for (int j = lane; j < M; j += 32) th[j] = a.theta[k*M+j];
+  for (int i = lane; i < N; i += 32) sp[i] = a.spins[k*N+i];
+  const cd ln0 = a.lnpsi0[k];
+  const cd sa = (MODEL == MODEL_RBM) ? a.sa[k] : cmake(0.0, 0.0);
+  __syncwarp();
+  if (a.lnpsi1 != nullptr)
+  {
+    const int site = a.single_site;
+    const double two_s = 2.0*(double)sp[site];
+    cd ln1 = flip_sum<MODEL>(th, mp.W+(size_t)site*M, mp.w1o, M, two_s, lane);
+    if (MODEL == MODEL_RBM)
+    {
+      const cd ai = mp.a[site];
+      ln1 = cadd(csub(sa, cmake(two_s*ai.x, two_s*ai.y)), ln1);
+    }
+    if (lane == 0) a.lnpsi1[k] = ln1;
+    return;
+  }
+  // 1/2 sum_ij s_i J_ij s_j: lanes over i
+  double diag = 0.0;
+  for (int i = lane; i < N; i += 32)
+  {
+    const double * Jrow = a.Jmat+(size_t)i*N;
+    double sj = 0.0;
+    for (int j = 0; j < N; ++j)
+      sj = fma(Jrow[j], (double)sp[j], sj);
+    diag = fma(sj, (double)sp[i], diag);
+  }
+  diag = 0.5*warp_sum(diag);
+  cd hsum = cmake(diag, 0.0);
+  for (int site = 0; site < N; ++site)
+  {
+    const double two_s = 2.0*(double)sp[site];
+    cd ln1 = flip_sum<MODEL>(th, mp.W+(size_t)site*M, mp.w1o, M, two_s, lane);
+    if (MODEL == MODEL_RBM)
+    {
+      const cd ai = mp.a[site];
+      ln1 = cadd(csub(sa, cmake(two_s*ai.x, two_s*ai.y)), ln1);
+    }
+    // ref k11 TFI__GetOffDiagElem__ (:857-869): htilda += h exp(lnpsi1 - lnpsi0)
+    const cd e = c_exp(csub(ln1, ln0));
+    hsum.x = fma(a.hfield, e.x, hsum.x);
+    hsum.y = fma(a.hfield, e.y, hsum.y);
+  }
+  if (lane == 0) a.htilda[k] = cscale(hsum, 1.0/(double)N); // ref k12 (:240)
+}
+
+struct ThetaArgs
+{
+  int N, M, model;
+  long long K;
+  const cd * params;
+  const int8_t * spins;     // spins the amplitudes are evaluated on [K][N]
+  const int8_t * sa_spins;  // spins used for the visible-bias term (member spins; see the forward(spins) quirk, ref :119-120)
+  cd * theta;               // out [K][M] (may be nullptr)
+  cd * sa;                  // out [K] (RBM; may be nullptr)
+  cd * lnpsi;               // out [K] (may be nullptr)
+};
+
+// ref: RBM::initialize / forward(spins) / tail of update_variables (impl_neural_quantum_state.cuh:67-91,107-129,161-169):
+// theta = W^T s + b (c2+c3), sa = a.s (c4), lnpsi = sum_j logcosh(theta_j) + sa (k2 + c1).  FFNN :799-847.
+// Generic version: one warp per chain, lanes over j, W read row by row (coalesced).  Spins are +-1 (or 0), so the "GEMM" is
+// signed accumulation of W rows.
+template <int MODEL>
+__global__ void __launch_bounds__(256) theta_generic_kernel(const ThetaArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int N = a.N, M = a.M;
+  const int npad = ((N+15)/16)*16;
+  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*npad;
+  const long long k = (long long)blockIdx.x*warps+w;
+  if (k >= a.K) return;
+  const ModelPtrs mp = model_ptrs(MODEL, a.params, N, M);
+  for (int i = lane; i < N; i += 32) sp[i] = a.spins[k*N+i];
+  __syncwarp();
+  cd lsum = cmake(0.0, 0.0);
+  for (int j = lane; j < M; j += 32)
+  {
+    cd acc = mp.b[j];
+    for (int i = 0; i < N; ++i)
+    {
+      const cd wv = mp.W[(size_t)i*M+j];
+      const double s = (double)sp[i];
+      acc.x = fma(s, wv.x, acc.x);
+      acc.y = fma(s, wv.y, acc.y);
+    }
+    if (a.theta) a.theta[k*M+j] = acc;
+    if (a.lnpsi)
+    {
+      const cd lc = c_logcosh(acc);
+      if (MODEL == MODEL_RBM) lsum = cadd(lsum, lc);
+      else lsum = cadd(lsum, cmul(mp.w1o[j], lc));
+    }
+  }
+  cd sa = cmake(0.0, 0.0);
+  if (MODEL == MODEL_RBM)
+  {
+    for (int i = lane; i < N; i += 32)
+    {
+      const double s = (double)a.sa_spins[k*N+i];
+      const cd ai = mp.a[i];
+      sa.x = fma(s, ai.x, sa.x);
+      sa.y = fma(s, ai.y, sa.y);
+    }
+    sa = warp_sum(sa);
+    if (a.sa && lane == 0) a.sa[k] = sa;
+  }
+  if (a.lnpsi)
+  {
+    lsum = warp_sum(lsum);
+    if (lane == 0) a.lnpsi[k] = cadd(lsum, sa);
+  }
+}
+
+// ref: the all-true accept_next_state_ of warm_up (impl_mcmc_sampler.cuh:21-22) -> Ansatz::spin_flip(all, index_) (:172-182):
+// theta -= 2 s W_i, sa -= 2 s a_i, s_i = -s_i on every chain; lnpsi0 untouched.
+__global__ void flip_site_all_kernel(const int N, const int M, const long long K, const int model, const cd * params,
+  int8_t * spins, cd * theta, cd * sa, const int site)
+{
+  const ModelPtrs mp = model_ptrs(model, params, N, M);
+  const long long total = K*(long long)M;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x)
+  {
+    const long long k = idx/M;
+    const int j = (int)(idx-k*M);
+    const double two_s = 2.0*(double)spins[k*N+site];
+    const cd wv = mp.W[(size_t)site*M+j];
+    cd t = theta[idx];
+    t.x -= wv.x*two_s; t.y -= wv.y*two_s;
+    theta[idx] = t;
+  }
+}
+__global__ void flip_site_all_finish_kernel(const int N, const int M, const long long K, const int model, const cd * params,
+  int8_t * spins, cd * sa, const int site)
+{
+  const ModelPtrs mp = model_ptrs(model, params, N, M);
+  for (long long k = (long long)blockIdx.x*blockDim.x+threadIdx.x; k < K; k += (long long)gridDim.x*blockDim.x)
+  {
+    const double two_s = 2.0*(double)spins[k*N+site];
+    if (model == MODEL_RBM)
+    {
+      const cd ai = mp.a[site];
+      sa[k] = cmake(sa[k].x-two_s*ai.x, sa[k].y-two_s*ai.y);
+    }
+    spins[k*N+site] = (int8_t)(-spins[k*N+site]);
+  }
+}
+} // namespace nqs

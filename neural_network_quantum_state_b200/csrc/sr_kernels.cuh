@@ -1,0 +1,506 @@
+// Stochastic-reconfiguration side of the path: O writer, single-pass SR setup sums, the two streaming passes over O that make
+// one S*v product, and the preconditioned-CG vector phases with device-resident scalars (no host sync inside an iteration).
+// O is [K_loc][P] row-major complex fp64 exactly like the reference's lnpsiGradients (k*P + p); all indices are 64-bit
+// (ref int32 overflow at cfg5).  Every reduction is two-stage with a fixed order -> run-to-run deterministic.
+#pragma once
+#include "device_math.cuh"
+#include "sampler_kernels.cuh"
+
+namespace nqs
+{
+// streaming (evict-first) 16-byte accesses for the O matrix: it is read once per pass and never fits L2
+__device__ __forceinline__ cd ld_stream(const cd * p)
+{
+  cd v;
+  asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(cd * p, const cd v)
+{
+  asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" :: "l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// O writer.  ref: RBM__GetGradientsOfParameters__ (impl_neural_quantum_state.cuh:1426-1449) + the K*P D2D copy (:152);
+// FFNN__GetGradientsOfParameters__ + FFNN__GetlnpsiGradients__ (:1622-1663, W block transposed to j*N+i).
+// One CTA per chain: tanh(theta_kj) is evaluated ONCE per (k,j) into shared memory (the reference recomputes it N times),
+// then the row O_k is streamed out with coalesced 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(256) oderiv_kernel(const int N, const int M, const long long K, const cd * params,
+  const int8_t * __restrict__ spins, const cd * __restrict__ theta, cd * __restrict__ O)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cd * T = reinterpret_cast<cd*>(smem_raw);            // [M]  RBM: tanh(theta_j); FFNN: tanh(theta_j)*w1o_j
+  cd * L = T+M;                                        // [M]  FFNN only: logcosh(theta_j)
+  double * s = reinterpret_cast<double*>(T+(MODEL == MODEL_FFNN ? 2*M : M)); // [N]
+  const long long k = blockIdx.x;
+  const ModelPtrs mp = model_ptrs(MODEL, params, N, M);
+  for (int j = threadIdx.x; j < M; j += blockDim.x)
+  {
+    const cd th = theta[k*M+j];
+    const cd t = c_tanh(th);
+    if (MODEL == MODEL_RBM) T[j] = t;
+    else { T[j] = cmul(t, mp.w1o[j]); L[j] = c_logcosh(th); }
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    s[i] = (double)spins[k*N+i];
+  __syncthreads();
+  const long long P = (MODEL == MODEL_RBM) ? (long long)N*M+N+M : (long long)N*M+2*M;
+  cd * row = O+k*P;
+  const int NM = N*M;
+  if (MODEL == MODEL_RBM)
+  {
+    for (int p = threadIdx.x; p < NM; p += blockDim.x)
+    {
+      const int i = p/M, j = p-i*M;
+      st_stream(row+p, cscale(T[j], s[i]));
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) st_stream(row+NM+i, cmake(s[i], 0.0));
+    for (int j = threadIdx.x; j < M; j += blockDim.x) st_stream(row+NM+N+j, T[j]);
+  }
+  else
+  {
+    for (int p = threadIdx.x; p < NM; p += blockDim.x)
+    {
+      const int j = p/N, i = p-j*N;
+      st_stream(row+p, cscale(T[j], s[i]));
+    }
+    for (int j = threadIdx.x; j < M; j += blockDim.x) st_stream(row+NM+j, T[j]);
+    for (int j = threadIdx.x; j < M; j += blockDim.x) st_stream(row+NM+M+j, L[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Column-direction passes over O.  Grid = (column tiles, row blocks); one thread owns ONE column p of its tile and walks the
+// rows of its row block, so a warp reads 32 consecutive complex numbers (512 B) per row: fully coalesced.  Row-block
+// partials go to part[rb][...][P] and are summed in fixed order by colsum_reduce_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+#define NQS_COL_THREADS 128
+#define NQS_COL_UNROLL 8
+
+// SR setup sums in ONE pass (the reference takes four: c6 x2, c7, k19; optimizer.cuh:140-143, functor_for_CG.cuh:99-102):
+//   part[rb][0..1][p] = sum_k O_kp ; part[rb][2..3][p] = sum_k O_kp conj(h_k) ; part[rb][4][p] = sum_k |O_kp|^2
+__global__ void __launch_bounds__(NQS_COL_THREADS) setup_partial_kernel(const long long K, const long long P,
+  const cd * __restrict__ O, const cd * __restrict__ htilda, double * __restrict__ part, const long long rows_per_block)
+{
+  const long long p = (long long)blockIdx.x*NQS_COL_THREADS+threadIdx.x;
+  const long long k0 = (long long)blockIdx.y*rows_per_block;
+  const long long k1 = (k0+rows_per_block < K) ? k0+rows_per_block : K;
+  if (p >= P) return;
+  double so_x = 0, so_y = 0, sh_x = 0, sh_y = 0, s2 = 0;
+  long long k = k0;
+  for (; k+NQS_COL_UNROLL <= k1; k += NQS_COL_UNROLL)
+  {
+    cd o[NQS_COL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NQS_COL_UNROLL; ++u) o[u] = ld_stream(O+(k+u)*P+p);
+#pragma unroll
+    for (int u = 0; u < NQS_COL_UNROLL; ++u)
+    {
+      const cd h = htilda[k+u];
+      so_x += o[u].x; so_y += o[u].y;
+      sh_x += o[u].x*h.x+o[u].y*h.y;     // O * conj(h)
+      sh_y += o[u].y*h.x-o[u].x*h.y;
+      s2 += o[u].x*o[u].x+o[u].y*o[u].y;
+    }
+  }
+  for (; k < k1; ++k)
+  {
+    const cd o = ld_stream(O+k*P+p), h = htilda[k];
+    so_x += o.x; so_y += o.y;
+    sh_x += o.x*h.x+o.y*h.y;
+    sh_y += o.y*h.x-o.x*h.y;
+    s2 += o.x*o.x+o.y*o.y;
+  }
+  double * base = part+(size_t)blockIdx.y*5*P;
+  base[p] = so_x; base[P+p] = so_y; base[2*P+p] = sh_x; base[3*P+p] = sh_y; base[4*P+p] = s2;
+}
+
+// second pass of S*v:  part[rb][0..1][p] = sum_{k in rb} conj(O_kp) z_k      (ref c9 Zgemv + conj tricks, functor_for_CG.cuh:113-124)
+__global__ void __launch_bounds__(NQS_COL_THREADS) matvec_cols_partial_kernel(const long long K, const long long P,
+  const cd * __restrict__ O, const cd * __restrict__ zk, double * __restrict__ part, const long long rows_per_block,
+  const int * __restrict__ done)
+{
+  if (done != nullptr && *done) return;
+  const long long p = (long long)blockIdx.x*NQS_COL_THREADS+threadIdx.x;
+  const long long k0 = (long long)blockIdx.y*rows_per_block;
+  const long long k1 = (k0+rows_per_block < K) ? k0+rows_per_block : K;
+  if (p >= P) return;
+  double ax = 0, ay = 0;
+  long long k = k0;
+  for (; k+NQS_COL_UNROLL <= k1; k += NQS_COL_UNROLL)
+  {
+    cd o[NQS_COL_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NQS_COL_UNROLL; ++u) o[u] = ld_stream(O+(k+u)*P+p);
+#pragma unroll
+    for (int u = 0; u < NQS_COL_UNROLL; ++u)
+    {
+      const cd z = zk[k+u];
+      ax += o[u].x*z.x+o[u].y*z.y;   // conj(O) * z
+      ay += o[u].x*z.y-o[u].y*z.x;
+    }
+  }
+  for (; k < k1; ++k)
+  {
+    const cd o = ld_stream(O+k*P+p), z = zk[k];
+    ax += o.x*z.x+o.y*z.y;
+    ay += o.x*z.y-o.y*z.x;
+  }
+  double * base = part+(size_t)blockIdx.y*2*P;
+  base[p] = ax; base[P+p] = ay;
+}
+
+// out[c][p] = sum_rb part[rb][c][p], fixed order.  ncomp = 5 (setup) or 2 (matvec)
+__global__ void colsum_reduce_kernel(const long long P, const int ncomp, const int nrb, const double * __restrict__ part,
+  double * __restrict__ out, const int * __restrict__ done)
+{
+  if (done != nullptr && *done) return;
+  const long long total = (long long)ncomp*P;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x)
+  {
+    double s = 0;
+    for (int rb = 0; rb < nrb; ++rb)
+      s += part[(size_t)rb*total+idx];
+    out[idx] = s;
+  }
+}
+
+// sum_k h_k and sum_k |h_k|^2 -> hs[0..2]   (ref t1 thrust::reduce, optimizer.cuh:133; l2_norm :156); single CTA, deterministic
+__global__ void __launch_bounds__(1024) htilda_sums_kernel(const long long K, const cd * __restrict__ htilda, double * __restrict__ hs)
+{
+  __shared__ double sh[3][32];
+  double a = 0, b = 0, c = 0;
+  for (long long k = threadIdx.x; k < K; k += blockDim.x)
+  {
+    const cd h = htilda[k];
+    a += h.x; b += h.y; c += h.x*h.x+h.y*h.y;
+  }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int w = threadIdx.x>>5, lane = threadIdx.x&31;
+  if (lane == 0) { sh[0][w] = a; sh[1][w] = b; sh[2][w] = c; }
+  __syncthreads();
+  if (w == 0)
+  {
+    const int nw = blockDim.x>>5;
+    a = (lane < nw) ? sh[0][lane] : 0; b = (lane < nw) ? sh[1][lane] : 0; c = (lane < nw) ? sh[2][lane] : 0;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { hs[0] = a; hs[1] = b; hs[2] = c; }
+  }
+}
+
+// sums = [sum O (re P | im P) | sum O conj(h) (re P | im P) | sum |O|^2 (P) | sum h (2) | sum |h|^2 (1)]  (all-reduced over ranks before)
+//   aO = sumO/K ; F = conj( sumOh/K - conj(<h>) aO )  (ref SR__FStep2__, impl_optimizer.cuh:82-96) ; diag = sumO2/K - |aO|^2 (ref k19)
+__global__ void setup_finalize_kernel(const long long P, const double inv_ktot, const double * __restrict__ sums,
+  cd * __restrict__ aO, cd * __restrict__ F, double * __restrict__ diag)
+{
+  const double * hs = sums+5*P;
+  const cd conj_havg = cmake(hs[0]*inv_ktot, -hs[1]*inv_ktot);
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    const cd ao = cmake(sums[p]*inv_ktot, sums[P+p]*inv_ktot);
+    if (aO) aO[p] = ao;
+    if (F)
+    {
+      const cd fr = cmake(sums[2*P+p]*inv_ktot, sums[3*P+p]*inv_ktot);
+      F[p] = cconj(csub(fr, cmul(conj_havg, ao)));
+    }
+    if (diag) diag[p] = sums[4*P+p]*inv_ktot-cnorm(ao);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// first pass of S*v:  z_k = sum_p O_kp v_p   (ref c8 Zgemm 1xKxP, functor_for_CG.cuh:110).  One CTA per group of
+// NQS_ROWS_PER_CTA rows so each v_p fetched (L2-resident, P*16 B) is reused for several rows.
+// ---------------------------------------------------------------------------------------------------------------------
+#define NQS_ROW_THREADS 256
+#define NQS_ROWS_PER_CTA 4
+#define NQS_ROW_UNROLL 2
+
+__global__ void __launch_bounds__(NQS_ROW_THREADS) matvec_rows_kernel(const long long K, const long long P,
+  const cd * __restrict__ O, const cd * __restrict__ v, cd * __restrict__ zk, const int * __restrict__ done)
+{
+  if (done != nullptr && *done) return;
+  __shared__ double sh[NQS_ROWS_PER_CTA][2][NQS_ROW_THREADS/32];
+  const long long k0 = (long long)blockIdx.x*NQS_ROWS_PER_CTA;
+  double ax[NQS_ROWS_PER_CTA], ay[NQS_ROWS_PER_CTA];
+#pragma unroll
+  for (int r = 0; r < NQS_ROWS_PER_CTA; ++r) { ax[r] = 0; ay[r] = 0; }
+  const int nrows = (int)((K-k0 < NQS_ROWS_PER_CTA) ? K-k0 : NQS_ROWS_PER_CTA);
+  if (nrows == NQS_ROWS_PER_CTA)
+  {
+    long long p = threadIdx.x;
+    for (; p+(NQS_ROW_UNROLL-1)*NQS_ROW_THREADS < P; p += NQS_ROW_UNROLL*NQS_ROW_THREADS)
+    {
+      cd o[NQS_ROW_UNROLL][NQS_ROWS_PER_CTA], vv[NQS_ROW_UNROLL];
+#pragma unroll
+      for (int u = 0; u < NQS_ROW_UNROLL; ++u)
+      {
+        vv[u] = v[p+u*NQS_ROW_THREADS];
+#pragma unroll
+        for (int r = 0; r < NQS_ROWS_PER_CTA; ++r) o[u][r] = ld_stream(O+(k0+r)*P+p+u*NQS_ROW_THREADS);
+      }
+#pragma unroll
+      for (int u = 0; u < NQS_ROW_UNROLL; ++u)
+#pragma unroll
+        for (int r = 0; r < NQS_ROWS_PER_CTA; ++r)
+        {
+          ax[r] += o[u][r].x*vv[u].x-o[u][r].y*vv[u].y;
+          ay[r] += o[u][r].x*vv[u].y+o[u][r].y*vv[u].x;
+        }
+    }
+    for (; p < P; p += NQS_ROW_THREADS)
+    {
+      const cd vv = v[p];
+#pragma unroll
+      for (int r = 0; r < NQS_ROWS_PER_CTA; ++r)
+      {
+        const cd o = ld_stream(O+(k0+r)*P+p);
+        ax[r] += o.x*vv.x-o.y*vv.y;
+        ay[r] += o.x*vv.y+o.y*vv.x;
+      }
+    }
+  }
+  else
+  {
+    for (long long p = threadIdx.x; p < P; p += NQS_ROW_THREADS)
+    {
+      const cd vv = v[p];
+      for (int r = 0; r < nrows; ++r)
+      {
+        const cd o = ld_stream(O+(k0+r)*P+p);
+        ax[r] += o.x*vv.x-o.y*vv.y;
+        ay[r] += o.x*vv.y+o.y*vv.x;
+      }
+    }
+  }
+  const int w = threadIdx.x>>5, lane = threadIdx.x&31;
+#pragma unroll
+  for (int r = 0; r < NQS_ROWS_PER_CTA; ++r)
+  {
+    const double sx = warp_sum(ax[r]), sy = warp_sum(ay[r]);
+    if (lane == 0) { sh[r][0][w] = sx; sh[r][1][w] = sy; }
+  }
+  __syncthreads();
+  if (threadIdx.x < NQS_ROWS_PER_CTA && threadIdx.x < nrows)
+  {
+    double sx = 0, sy = 0;
+    for (int ww = 0; ww < NQS_ROW_THREADS/32; ++ww) { sx += sh[threadIdx.x][0][ww]; sy += sh[threadIdx.x][1][ww]; }
+    zk[k0+threadIdx.x] = cmake(sx, sy);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// PCG vector phases (ref ConjugateGradient::solve, conjugate_gradient.cuh:29-74, and SMatrixForCG::dot/applyPrecond tails,
+// functor_for_CG.cuh:115-135).  All scalars live in `CgScalars` on the device; a grid of CTAs computes per-CTA partial sums
+// into slots and the LAST CTA to finish (atomic ticket) folds them in slot order, so there is no host round trip per
+// iteration (the reference has four).
+// ---------------------------------------------------------------------------------------------------------------------
+struct CgScalars
+{
+  double rho, rho_old, alpha, beta, res2, thr, rhs2, tp;
+  double aov_x, aov_y;     // <O> . v for the direction currently held in p (or x during init)
+  double tol2;
+  int done, iters, zero_rhs, fixed;
+  unsigned int ticket[4];
+};
+
+#define NQS_VEC_THREADS 256
+#define NQS_VEC_MAX_CTAS 64
+
+__device__ __forceinline__ double block_sum_256(double v, double * sh)
+{ // sh: >= 8 doubles; all threads must call
+  v = warp_sum(v);
+  const int w = threadIdx.x>>5, lane = threadIdx.x&31;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double s = 0;
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NQS_VEC_THREADS/32; ++i) s += sh[i];
+  return s; // valid on thread 0
+}
+
+// returns true on thread 0 of the last CTA to arrive; slots then hold every CTA's partials
+__device__ __forceinline__ bool last_block_arrives(unsigned int * ticket)
+{
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x-1);
+    if (is_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last && threadIdx.x == 0;
+}
+
+// aov = sum_p aO_p v_p   (ref t2 thrust::inner_product, functor_for_CG.cuh:115) -- used once for the warm-start vector x
+__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_aov_kernel(const long long P, const cd * __restrict__ aO,
+  const cd * __restrict__ v, CgScalars * sc, double * slots)
+{
+  __shared__ double sh[8];
+  double sx = 0, sy = 0;
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    const cd a = aO[p], b = v[p];
+    sx += a.x*b.x-a.y*b.y; sy += a.x*b.y+a.y*b.x;
+  }
+  sx = block_sum_256(sx, sh); sy = block_sum_256(sy, sh);
+  if (threadIdx.x == 0) { slots[2*blockIdx.x] = sx; slots[2*blockIdx.x+1] = sy; }
+  if (last_block_arrives(&sc->ticket[0]))
+  {
+    double ax = 0, ay = 0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) { ax += slots[2*b]; ay += slots[2*b+1]; }
+    sc->aov_x = ax; sc->aov_y = ay;
+  }
+}
+
+// t = traw/K - conj(aO) (aO.v) + lambda diag v          (functor_for_CG.cuh:118-126)
+// init != 0 (v = x):  r = F - t ; rhs2 = |F|^2 ; res2 = |r|^2 ; p = M^-1 r ; rho = Re<p,r> ; aov = aO.p ; thr ; done   (conjugate_gradient.cuh:33-48)
+// init == 0 (v = p):  tp = Re<t,p> ; alpha = rho/tp                                                                  (:52-54)
+__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase1_kernel(const long long P, const double inv_ktot, const double lambda,
+  const double * __restrict__ traw, const cd * __restrict__ aO, const double * __restrict__ diag, const cd * __restrict__ v,
+  cd * __restrict__ t, const cd * __restrict__ F, cd * __restrict__ r, cd * __restrict__ pvec, CgScalars * sc, double * slots, const int init)
+{
+  if (!init && sc->done) return;
+  __shared__ double sh[8];
+  const cd aov = cmake(sc->aov_x, sc->aov_y);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+  const double pre = 1.0+lambda;
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    const cd ao = aO[p], vv = v[p];
+    const double dg = diag[p];
+    const cd corr = cmul(cconj(ao), aov);
+    cd tv = cmake(traw[p]*inv_ktot-corr.x, traw[P+p]*inv_ktot-corr.y);
+    tv.x += lambda*dg*vv.x; tv.y += lambda*dg*vv.y;
+    t[p] = tv;
+    if (init)
+    {
+      const cd f = F[p];
+      const cd rv = csub(f, tv);
+      r[p] = rv;
+      const double den = pre*dg;
+      const cd pv = cmake(rv.x/den, rv.y/den);
+      pvec[p] = pv;
+      s0 += cnorm(f); s1 += cnorm(rv);
+      s2 += pv.x*rv.x+pv.y*rv.y;                 // Re(p conj(r))
+      s3 += ao.x*pv.x-ao.y*pv.y; s4 += ao.x*pv.y+ao.y*pv.x;
+    }
+    else
+      s0 += tv.x*vv.x+tv.y*vv.y;                 // Re(t conj(p))
+  }
+  const int ns = init ? 5 : 1;
+  double part[5] = {s0, s1, s2, s3, s4};
+  for (int i = 0; i < ns; ++i)
+  {
+    const double s = block_sum_256(part[i], sh);
+    if (threadIdx.x == 0) slots[5*blockIdx.x+i] = s;
+  }
+  if (last_block_arrives(&sc->ticket[1]))
+  {
+    double tot[5] = {0, 0, 0, 0, 0};
+    for (unsigned int b = 0; b < gridDim.x; ++b)
+      for (int i = 0; i < ns; ++i) tot[i] += slots[5*b+i];
+    if (init)
+    {
+      sc->rhs2 = tot[0]; sc->res2 = tot[1]; sc->rho = tot[2]; sc->aov_x = tot[3]; sc->aov_y = tot[4];
+      sc->zero_rhs = (tot[0] == 0.0) ? 1 : 0;
+      const double thr = fmax(sc->tol2*tot[0], 2.2250738585072014e-308); // std::numeric_limits<double>::min()
+      sc->thr = thr;
+      sc->iters = 0;
+      sc->done = (sc->zero_rhs || (!sc->fixed && tot[1] < thr)) ? 1 : 0;
+    }
+    else
+    {
+      sc->tp = tot[0];
+      sc->alpha = sc->rho/tot[0];
+    }
+  }
+}
+
+// x += alpha p ; r -= alpha t ; res2 = |r|^2 ; [break] ; z = M^-1 r ; rho' = Re<z,r> ; beta = rho'/rho   (conjugate_gradient.cuh:56-69)
+__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase2_kernel(const long long P, const double lambda,
+  const cd * __restrict__ aO, const double * __restrict__ diag, const cd * __restrict__ pvec, const cd * __restrict__ t,
+  cd * __restrict__ x, cd * __restrict__ r, cd * __restrict__ z, CgScalars * sc, double * slots)
+{
+  if (sc->done) return;
+  __shared__ double sh[8];
+  const double alpha = sc->alpha, pre = 1.0+lambda;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    const cd pv = pvec[p], tv = t[p], ao = aO[p];
+    cd xv = x[p], rv = r[p];
+    xv.x += alpha*pv.x; xv.y += alpha*pv.y;
+    rv.x -= alpha*tv.x; rv.y -= alpha*tv.y;
+    x[p] = xv; r[p] = rv;
+    const double den = pre*diag[p];
+    const cd zv = cmake(rv.x/den, rv.y/den);
+    z[p] = zv;
+    s0 += cnorm(rv);
+    s1 += zv.x*rv.x+zv.y*rv.y;
+    s2 += ao.x*zv.x-ao.y*zv.y; s3 += ao.x*zv.y+ao.y*zv.x;
+  }
+  double part[4] = {s0, s1, s2, s3};
+  for (int i = 0; i < 4; ++i)
+  {
+    const double s = block_sum_256(part[i], sh);
+    if (threadIdx.x == 0) slots[5*blockIdx.x+i] = s;
+  }
+  if (last_block_arrives(&sc->ticket[2]))
+  {
+    double tot[4] = {0, 0, 0, 0};
+    for (unsigned int b = 0; b < gridDim.x; ++b)
+      for (int i = 0; i < 4; ++i) tot[i] += slots[5*b+i];
+    sc->res2 = tot[0];
+    sc->iters += 1;
+    sc->rho_old = sc->rho;
+    sc->rho = tot[1];
+    const double beta = tot[1]/sc->rho_old;
+    sc->beta = beta;
+    // aO.(z + beta p) by linearity: saves a pass over p
+    const double ox = sc->aov_x, oy = sc->aov_y;
+    sc->aov_x = tot[2]+beta*ox; sc->aov_y = tot[3]+beta*oy;
+    if (!sc->fixed && tot[0] < sc->thr) sc->done = 1;
+  }
+}
+
+// p = z + beta p   (conjugate_gradient.cuh:71); skipped once converged (the reference breaks before it)
+__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase3_kernel(const long long P, const cd * __restrict__ z, cd * __restrict__ pvec,
+  const CgScalars * sc)
+{
+  if (sc->done) return;
+  const double beta = sc->beta;
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    const cd zv = z[p], pv = pvec[p];
+    pvec[p] = cmake(zv.x+beta*pv.x, zv.y+beta*pv.y);
+  }
+}
+
+// ref: update_parameters (impl_neural_quantum_state.cuh:1300-1312) / FFNN__UpdateParameters__ (:1665-1690, un-transposes the W block)
+__global__ void update_params_kernel(const int N, const int M, const int model, const long long P, const cd * __restrict__ dx,
+  const double lr, cd * __restrict__ params)
+{
+  const long long NM = (long long)N*M;
+  for (long long q = (long long)blockIdx.x*blockDim.x+threadIdx.x; q < P; q += (long long)gridDim.x*blockDim.x)
+  {
+    long long dst = q;
+    if (model == MODEL_FFNN && q < NM)
+    { // dx index q = j*N+i  ->  W1[i*M+j]
+      const long long j = q/N, i = q-j*N;
+      dst = i*M+j;
+    }
+    const cd d = dx[q];
+    cd v = params[dst];
+    v.x -= lr*d.x; v.y -= lr*d.y;
+    params[dst] = v;
+  }
+}
+} // namespace nqs

@@ -1,0 +1,250 @@
+"""GPU parity tests proper: the CUDA engine (through the C ABI, via ctypes) against
+  (1) the golden vectors produced by the reference's own CPU code (tests/golden/*.npz), and
+  (2) the numpy oracle on seeded inputs at sizes the oracle finishes in seconds.
+Bars (north star / SURVEY 8c): fp64 quantities rel 1e-10 (abs 1e-12 near zero); accept/reject decisions EXACT given the same
+uniforms; dx after a converged-to-1e-5 CG rel 1e-6 (iteration count must match here).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, ffnn_cpu_to_gpu_layout
+from oracle import nqs_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(*a, **kw):
+    from neural_network_quantum_state_b200 import Engine
+    return Engine(*a, **kw)
+
+
+def to_gpu(g, v):
+    return ffnn_cpu_to_gpu_layout(v, g["N"], g["M"]) if g["model"] == "ffnn" else v
+
+
+def engine_from_golden(g, **kw):
+    e = _engine(g["model"], g["N"], g["M"], g["K"], g["h"], g["J"], g["alpha"], pbc=bool(g["pbc"]), order=g["order"],
+                max_predrawn_steps=g["uniforms"].shape[0], accept_log=True, **kw)
+    e.set_params(g["params"])
+    e.set_uniforms(g["uniforms"])
+    return e
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_golden_sampler_energy_gradients(golden, force_generic):
+    g = golden
+    e = engine_from_golden(g, force_generic=force_generic)
+    e.warm_up(g["n_warm"], g.get("init_spins"))
+    assert np.array_equal(e.get_spinStates(), g["warm_spins"]), "accept/reject decisions differ from the reference"
+    assert_close(e.get_theta(), g["warm_y"], what="theta")
+    assert_close(e.get_lnpsi(), g["warm_lnpsi"], what="lnpsi0")
+    for i in range(g["N"]):
+        assert_close(e.forward_flip(i), g["flip_lnpsi"][i], what="forward(flip %d)" % i)
+    assert_close(e.get_htilda(), g["htilda"], what="htilda")
+    O = e.get_lnpsiGradients()
+    assert_close(O, to_gpu(g, g["O"]), what="O")
+    Sv, aO, diag = e.smatrix_dot(g["sm_lambda"], to_gpu(g, g["sm_v"]))
+    assert_close(aO, to_gpu(g, g["sm_aO"]), what="<O>")
+    assert_close(diag, to_gpu(g, g["sm_diag"]), what="diag S")
+    assert_close(Sv, to_gpu(g, g["sm_Sv"]), what="S v")
+    e.close()
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_golden_sr_trajectory(golden, force_generic):
+    g = golden
+    e = engine_from_golden(g, force_generic=force_generic)
+    e.warm_up(g["n_warm"], g.get("init_spins"))
+    for it in range(g["n_sr"]):
+        st = e.sr_step(n_mc_steps=1, lr=g["lr"])
+        assert st.finite
+        assert_close(st.e_mean, g["sr_E"][it], what="<H> it %d" % it)
+        assert abs(st.rsd - g["sr_rsd"][it]) < 1e-10
+        assert st.lam == pytest.approx(g["sr_lambda"][it], rel=1e-14)
+        assert st.cg_iters == int(g["sr_cg_iters"][it])
+        F, dx = e.get_sr_vectors()
+        assert_close(F, to_gpu(g, g["sr_F"][it]), what="F it %d" % it)
+        assert_close(dx, to_gpu(g, g["sr_dx"][it]), rtol=1e-6, what="dx it %d" % it)
+    assert_close(e.get_params(), g["final_params"], rtol=1e-8, what="params")
+    assert np.array_equal(e.get_spinStates(), g["final_spins"])
+    assert_close(e.get_theta(), g["final_y"], rtol=1e-8, what="final theta")
+    assert_close(e.get_lnpsi(), g["final_lnpsi"], rtol=1e-8, what="final lnpsi0")
+    e.close()
+
+
+def test_golden_param_files(golden, tmp_path):
+    g = golden
+    e = _engine(g["model"], g["N"], g["M"], 4, g["h"], g["J"], g["alpha"], sampler_only=True)
+    prefix = os.path.join(os.path.dirname(__file__), "golden", "files", g["name"] + "_")
+    e.load(prefix)
+    assert_close(e.get_params(), g["params"], rtol=2e-10, what="loaded params")
+    e.set_params(g["params"])
+    out = str(tmp_path / "y_")
+    e.save(out, 10)
+    sufs = ("Dw.dat", "Da.dat", "Db.dat") if g["model"] == "rbm" else ("Dw1.dat", "Dw2.dat", "Db1.dat")
+    for suf in sufs:
+        assert open(out + suf).read() == open(prefix + suf).read(), suf
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# engine vs numpy oracle on seeded inputs (ragged sizes: M not a multiple of 32, odd N, K not a multiple of the CTA size)
+# ---------------------------------------------------------------------------------------------------------------------
+H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
+
+
+def synth(model, N, M, rng, scale=1.0):
+    sw = math.sqrt(1.0 / (N + M))
+    if model == "rbm":
+        W = scale * 0.8 * (rng.normal(0, sw, (N, M)) + 1j * rng.normal(0, sw, (N, M)))
+        a = 0.3 * (rng.normal(size=N) + 1j * rng.normal(size=N))
+        b = 0.5 * math.sqrt(1.0 / M) * (rng.normal(size=M) + 1j * rng.normal(size=M))
+        return np.concatenate([W.ravel(), a, b])
+    W = scale * (rng.normal(0, sw, (N, M)) + 0.1j * rng.normal(0, sw, (N, M)))
+    b1 = 0.3 * (rng.normal(size=M) + 1j * rng.normal(size=M))
+    w1o = rng.normal(0, math.sqrt(1.0 / M), M) + 0.1j * rng.normal(0, math.sqrt(1.0 / M), M)
+    return np.concatenate([W.ravel(), b1, w1o])
+
+
+CASES = [
+    ("rbm", 16, 16, 512, False),     # cfg1 shape
+    ("rbm", 24, 40, 200, True),      # M not multiple of 32, PBC
+    ("rbm", 33, 64, 130, False),     # odd N
+    ("rbm", 32, 128, 96, False),
+    ("rbm", 20, 256, 64, False),     # M = 256 (cfg3 hidden width)
+    ("ffnn", 16, 48, 200, False),
+    ("ffnn", 21, 70, 77, False),
+]
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+@pytest.mark.parametrize("model,N,M,K,pbc", CASES)
+def test_sweep_matches_oracle_step_by_step(model, N, M, K, pbc, force_generic):
+    rng = np.random.default_rng(N * 1000 + M)
+    params = synth(model, N, M, rng)
+    n_warm, n_more = 5, 3
+    U = rng.random(((n_warm + n_more) * N, K))
+    m = o.make_ansatz(model, N, M, K)
+    m.variables = params.copy()
+    s = o.LITFIChainSampler(m, H, J, ALPHA, pbc, o.UniformSource(K, predrawn=U))
+    s.record = True
+    e = _engine(model, N, M, K, H, J, ALPHA, pbc=pbc, max_predrawn_steps=U.shape[0], accept_log=True,
+                force_generic=force_generic)
+    e.set_params(params)
+    e.set_uniforms(U)
+    s.warm_up(n_warm)
+    e.warm_up(n_warm)
+    acc_ref = np.array(s.accept_log)
+    acc = e.get_accept_log()
+    mism = np.argwhere(acc != acc_ref)
+    assert mism.size == 0, "first accept mismatch at (step, chain) %s" % (mism[0],)
+    assert np.array_equal(e.get_spinStates(), m.spins.astype(np.int8))
+    assert_close(e.get_theta(), m.y, what="theta")
+    assert_close(e.get_lnpsi(), s.lnpsi0, what="lnpsi0")
+    s.accept_log = []
+    s.do_mcmc_steps(n_more)
+    e.do_mcmc_steps(n_more)
+    assert np.array_equal(e.get_accept_log(), np.array(s.accept_log))
+    assert_close(e.get_lnpsi(), s.lnpsi0, what="lnpsi0 after more sweeps")
+    assert_close(e.get_htilda(), s.get_htilda(), what="htilda")
+    assert_close(e.get_lnpsiGradients(), s.get_lnpsiGradients(), what="O")
+    e.close()
+
+
+@pytest.mark.parametrize("model,N,M,K,pbc", CASES[:3] + CASES[5:6])
+def test_internal_philox_stream_matches_oracle(model, N, M, K, pbc):
+    rng = np.random.default_rng(7)
+    params = synth(model, N, M, rng)
+    seed, koff = 0x1234567890ABCDEF, 1000
+    m = o.make_ansatz(model, N, M, K)
+    m.variables = params.copy()
+    s = o.LITFIChainSampler(m, H, J, ALPHA, pbc, o.UniformSource(K, seed=seed, chain_offset=koff))
+    e = _engine(model, N, M, K, H, J, ALPHA, pbc=pbc, seed=seed, chain_offset=koff, n_chains_total=K + koff)
+    e.set_params(params)
+    s.warm_up(4)
+    e.warm_up(4)
+    s.do_mcmc_steps(2)
+    e.do_mcmc_steps(2)
+    assert np.array_equal(e.get_spinStates(), m.spins.astype(np.int8))
+    assert_close(e.get_lnpsi(), s.lnpsi0, what="lnpsi0")
+    e.close()
+
+
+@pytest.mark.parametrize("model,N,M,K,pbc", [CASES[1], CASES[3], CASES[6]])
+def test_sr_matches_oracle_fixed_cg_iterations(model, N, M, K, pbc):
+    """Fixed CG iteration count on both sides -> dx agrees to 1e-10-ish (no dependence on the stopping rule)."""
+    rng = np.random.default_rng(11)
+    params = synth(model, N, M, rng)
+    U = rng.random((12 * N, K))
+    m = o.make_ansatz(model, N, M, K)
+    m.variables = params.copy()
+    s = o.LITFIChainSampler(m, H, J, ALPHA, pbc, o.UniformSource(K, predrawn=U))
+    e = _engine(model, N, M, K, H, J, ALPHA, pbc=pbc, max_predrawn_steps=U.shape[0])
+    e.set_params(params)
+    e.set_uniforms(U)
+    s.warm_up(8)
+    e.warm_up(8)
+    sr = o.StochasticReconfigurationCG(K, m.P)
+    for it in range(3):
+        st_o = sr.step(s, 1, 0.03, fixed_cg_iters=7, lam=0.5)
+        st = e.sr_step(n_mc_steps=1, lr=0.03, fixed_iters=7, lam=0.5)
+        assert st.cg_iters == 7
+        assert_close(st.e_mean, st_o.e_mean, what="<H>")
+        F, dx = e.get_sr_vectors()
+        assert_close(F, st_o.F, what="F")
+        assert_close(dx, st_o.dx, rtol=1e-9, what="dx (7 CG its)")
+    assert_close(e.get_params(), m.variables, rtol=1e-9, what="params")
+    e.close()
+
+
+def test_identities_flip_and_rank1_update():
+    """oracle-independent: forward(i) == full forward of the flipped configuration; rank-1 updated theta == recomputed."""
+    model, N, M, K = "rbm", 18, 50, 64
+    rng = np.random.default_rng(3)
+    params = synth(model, N, M, rng)
+    params[N * M:N * M + N] = 0.0  # a = 0 so that the forward(spins) visible-bias quirk does not enter
+    e = _engine(model, N, M, K, H, J, ALPHA, seed=5)
+    e.set_params(params)
+    e.warm_up(6)
+    spins = e.get_spinStates()
+    for i in (0, 7, N - 1):
+        flipped = spins.copy()
+        flipped[:, i] *= -1
+        assert_close(e.forward_flip(i), e.get_lnpsi_for_fixed_spins(flipped), what="flip identity %d" % i)
+    th = e.get_theta()
+    e.evolve(np.zeros(e.P, dtype=np.complex128), 0.0)  # re-derives theta from the spins
+    assert_close(e.get_theta(), th, what="rank-1 theta vs recomputed")
+    e.close()
+
+
+def test_error_behaviour():
+    from neural_network_quantum_state_b200 import NQSError
+    from neural_network_quantum_state_b200 import _lib as L
+    e = _engine("rbm", 8, 8, 16, H, J, ALPHA, max_predrawn_steps=8)
+    with pytest.raises(NQSError) as ei:
+        e.do_mcmc_steps(1)
+    assert ei.value.status == L.ERR_STATE
+    e.set_uniforms(np.random.default_rng(0).random((8, 16)))
+    e.warm_up(1)
+    with pytest.raises(NQSError) as ei:
+        e.do_mcmc_steps(1)          # feed exhausted
+    assert ei.value.status == L.ERR_STATE
+    with pytest.raises(NQSError):
+        e.set_params(np.zeros(3, dtype=np.complex128))
+    with pytest.raises(NQSError):
+        _engine("rbm", 7, 8, 16, H, J, ALPHA, pbc=True)   # odd L with PBC (ref: invalid_argument)
+    e.close()
+
+
+def test_zero_chains_edge_and_single_chain():
+    from neural_network_quantum_state_b200 import NQSError
+    with pytest.raises(NQSError):
+        _engine("rbm", 8, 8, 0, H, J, ALPHA)
+    e = _engine("rbm", 5, 3, 1, H, J, ALPHA, seed=1, sampler_only=True)
+    e.init_params_random(3)
+    e.warm_up(3)
+    assert e.get_spinStates().shape == (1, 5)
+    e.close()
