@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- the VMC hot path on the workload BASELINE.json's metric is quoted on.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository's CUDA engine (one process per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation (oracle/_ref), rank 0 only
+
+One "step" = one iteration of the reference's StochasticReconfigurationCG::propagate (gpu/include/optimizer.cuh:127-165):
+nms=1 Metropolis sweep (N proposals per chain) -> local energy -> O -> SR setup -> preconditioned CG to tol 1e-5 with the
+reference's lambda schedule -> parameter update.  Workload = cfg3 of BASELINE.json: complex RBM alpha=2 (M=2N), long-range TFI
+chain N=128 (alpha_LR=2, theta=pi/4, OBC), 16384 chains in total, sharded over the ranks (strong scaling; RNG keyed by global
+chain id).  Parameters: the reference init law from a fixed numpy seed ("synthetic"), chains warmed up before timing.
+
+value = VMC samples/s = (chains processed by all ranks per step) / (device time per step, max over ranks, CUDA events on the
+engine's stream).  The O matrix alone is 8.7 GB (>> 126 MB L2), so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (model, N, M, K_total)
+    "cfg1": ("rbm", 16, 16, 512),
+    "cfg2": ("rbm", 64, 128, 4096),
+    "cfg3": ("rbm", 128, 256, 16384),
+    "cfg4": ("ffnn", 128, 512, 8192),
+}
+THETA_H = math.pi / 4
+H_FIELD, J_COUP, ALPHA_LR = -math.cos(THETA_H), math.sin(THETA_H), 2.0
+METRIC = "vmc_samples_per_s"
+UNIT = "samples/s"
+
+
+def synthetic_params(model: str, N: int, M: int, cfg_id: int) -> np.ndarray:
+    """Reference init law (gpu/include/impl_neural_quantum_state.cuh:30-48 / :766-783) from numpy seed 20261018+cfg."""
+    from oracle import nqs_oracle as o   # only the parameter initialiser is used here (input generation, not compute)
+    rng = np.random.default_rng(20261018 + cfg_id)
+    m = o.make_ansatz(model, N, M, 1, rng)
+    return m.variables.copy()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def committed_traffic(kernel: str):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), else None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kernel)
+        except Exception:
+            return None
+    return None
+
+
+# =====================================================================================================================
+# reference arm / cpu baseline: the reference's own CPU implementation (oracle/_ref/libnqs_ref.so) on a bounded sample
+# =====================================================================================================================
+def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_warm_sweeps: int):
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(os.cpu_count() or 1))
+    from oracle import ref_cpu
+    model, N, M, _ = CONFIGS[cfg_name]
+    cfg_id = int(cfg_name[3:])
+    params = synthetic_params(model, N, M, cfg_id)
+    cores = os.cpu_count() or 1
+    lib = ref_cpu.lib()
+
+    def make(threads):
+        lib.ref_set_threads(threads)
+        r = ref_cpu.RefSampler(model, N, M, k_sample, H_FIELD, J_COUP, ALPHA_LR, False)
+        r.set_params(params)
+        rng = np.random.default_rng(99)
+        U = rng.random(((n_warm_sweeps + warmup + steps + 1) * N, k_sample))
+        r.set_uniforms(U)
+        r.warm_up(n_warm_sweeps)
+        return r
+
+    # the reference's OpenMP loops do not always scale: probe 1 thread vs all threads on one sweep
+    best_threads, best_t = 1, None
+    for th in sorted({1, cores}):
+        r = make(th)
+        t0 = time.perf_counter()
+        r.do_mcmc_steps(1)
+        dt = time.perf_counter() - t0
+        r.close()
+        if best_t is None or dt < best_t:
+            best_threads, best_t = th, dt
+    r = make(best_threads)
+    cg = []
+    for _ in range(warmup):
+        r.sr_step(1, 1e-2)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cg.append(r.sr_step(1, 1e-2)["cg_iters"])
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    r.close()
+    return {"value": k_sample / dt, "ms_per_step": dt * 1e3, "cores": best_threads, "host_cores": cores,
+            "cg_iters": cg, "sweep_s_probe": best_t,
+            "sample": "%d of %d chains, same N=%d M=%d, %d warm-up sweeps, %d warm-up + %d timed SR steps; reference CPU "
+                      "headers + OpenBLAS 0.3.15 (MKL/TRNG4 unavailable offline), long-range Hamiltonian shim" %
+                      (k_sample, CONFIGS[cfg_name][3], N, M, n_warm_sweeps, warmup, steps)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--nwarm", type=int, default=100, help="warm-up sweeps before the benchmark (reference default -nwarm)")
+    ap.add_argument("--lr", type=float, default=1e-2)
+    ap.add_argument("--cpu-sample-chains", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--force-generic", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    model, N, M, K_total = CONFIGS[args.config]
+    cfg_id = int(args.config[3:])
+    P = N * M + N + M if model == "rbm" else N * M + 2 * M
+    config = {"workload": "%s: complex %s M=%d, long-range TFI chain N=%d (alpha=2, theta=pi/4, OBC), %d chains total, "
+                          "step = sweep(nms=1) + E_loc + O + SR setup + PCG(tol 1e-5, reference lambda schedule) + update"
+                          % (args.config, model.upper(), M, N, K_total),
+              "N": N, "M": M, "K_total": K_total, "P": P, "sharding": "chains/%d" % world,
+              "l2": "working set (O = %.2f GB per rank) >> 126 MB L2: no flush needed" % (K_total / world * P * 16 / 1e9),
+              "nwarm_sweeps": args.nwarm, "lr": args.lr, "rng": "in-kernel Philox4x32-10 (value) / pre-drawn host uniforms (e2e)"}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from oracle import ref_cpu
+        if not ref_cpu.available():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnqs_ref.so missing (run make -C oracle)"}))
+            return 0
+        res = run_reference_cpu(args.config, args.steps, args.warmup, args.cpu_sample_chains, n_warm_sweeps=10)
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                                 "sample": res["sample"], "host_cores": res["host_cores"]},
+                "cg_iters_per_step": res["cg_iters"],
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # --------------------------------------------------------------------------------------------------- native arm
+    import torch
+    import torch.distributed as dist
+    from neural_network_quantum_state_b200 import Engine
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: the engine has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert K_total % world == 0
+    K_loc = K_total // world
+    e = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
+               n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic)
+    e.set_params(synthetic_params(model, N, M, cfg_id))
+    if world > 1:
+        ids = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        e.comm_init(world, rank, ids[0])
+    e.warm_up(args.nwarm)
+
+    def barrier():
+        e.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return e.sr_step(n_mc_steps=1, lr=args.lr)
+
+    for _ in range(args.warmup):
+        step()
+    e.set_timing(True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = e.get_timing()["kernel_launches"]
+    phase = {k: 0.0 for k in ("sweep_ms", "eloc_ms", "oderiv_ms", "setup_ms", "cg_ms", "update_ms", "rows_ms", "cols_ms")}
+    counts = {"rows_count": 0, "cols_count": 0}
+    cg_iters, energies = [], []
+    e.event_record(0)
+    for _ in range(args.steps):
+        st = step()
+        cg_iters.append(st.cg_iters)
+        energies.append(st.e_mean.real)
+        t = e.get_timing()
+        for k in phase:
+            phase[k] += t[k]
+        for k in counts:
+            counts[k] += t[k]
+    e.event_record(1)
+    barrier()
+    ms_total = e.event_elapsed_ms(0, 1)
+    clock_info = clocks.stop()
+    launches = e.get_timing()["kernel_launches"] - launches0
+    e.set_timing(False)
+    if world > 1:
+        tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = K_total / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API with HOST buffers: pinned uniforms H2D every step, spins + lnpsi + stats D2H
+    e2e = None
+    if not args.no_e2e:
+        rng = np.random.default_rng(1234 + rank)
+        u_pinned = torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True)
+        u_np = u_pinned.numpy()
+        n_e2e = max(3, min(args.steps, 10))
+        draws = [rng.random((N, K_loc)) for _ in range(n_e2e)]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            u_np[...] = draws[i]          # the host produces this step's uniforms (as the reference's host-side RNG seeding would)
+            e.set_uniforms(u_np)          # H2D inside the timed region
+            st = step()
+            spins = e.get_spinStates()    # D2H: what a pynqs user reads back
+            lnpsi = e.get_lnpsi()
+        barrier()
+        dt = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e.set_uniforms(None)
+        e2e = {"value": K_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(u_np.nbytes) * world,
+               "d2h_bytes_per_step": int(spins.nbytes + lnpsi.nbytes + 56) * world, "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "api": "Engine.set_uniforms + Engine.sr_step + get_spinStates + get_lnpsi (C ABI, host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel pair: the two streaming passes over O inside every CG iteration
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = K_loc * P * 16.0
+    dom = "matvec_cols_partial_kernel" if phase["cols_ms"] >= phase["rows_ms"] else "matvec_rows_kernel"
+    dom_ms = (phase["cols_ms"] / max(counts["cols_count"], 1)) if dom.startswith("matvec_cols") else \
+             (phase["rows_ms"] / max(counts["rows_count"], 1))
+    achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": peak_src, "traffic": committed_traffic(dom),
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms,
+                "launches_timed": counts["cols_count"] if dom.startswith("matvec_cols") else counts["rows_count"],
+                "other_pass": {"kernel": "matvec_rows_kernel" if dom.startswith("matvec_cols") else "matvec_cols_partial_kernel",
+                               "avg_launch_ms": (phase["rows_ms"] / max(counts["rows_count"], 1)) if dom.startswith("matvec_cols")
+                               else (phase["cols_ms"] / max(counts["cols_count"], 1))}}
+    sweep_ms = phase["sweep_ms"] / args.steps
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config, "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline,
+            "sr_step_ms": ms_per_step - sweep_ms,
+            "sweep": {"ms": sweep_ms, "samples_per_s": K_total / (sweep_ms * 1e-3) if sweep_ms > 0 else None,
+                      "proposals_per_s": K_total * N / (sweep_ms * 1e-3) if sweep_ms > 0 else None,
+                      "kernel": e.kernel_variant("sweep")},
+            "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+            "cg_iters_per_step": cg_iters,
+            "cg_ms_per_iter": (phase["cg_ms"] / max(sum(cg_iters) + len(cg_iters), 1)),
+            "energy_per_site": energies}
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=10)
+            line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
+                                    "sample": res["sample"], "host_cores": res["host_cores"], "ms_per_step": res["ms_per_step"]}
+        except Exception as ex:  # the checker being absent must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -164,13 +164,16 @@ nqs_status nqs_comm_init(nqs_handle * h, int32_t n_ranks, int32_t rank, const ch
 
 /* ---- introspection for benchmarks ----------------------------------------------------------------------------------- */
 typedef struct nqs_timing {
-  float sweep_ms, eloc_ms, oderiv_ms, setup_ms, cg_ms, update_ms; /* CUDA-event times of the phases of the last nqs_sr_step */
-  float matvec_ms;          /* sum over CG iterations of the two O passes (rows + columns) */
-  int32_t matvec_count;
+  float sweep_ms, eloc_ms, oderiv_ms, setup_ms, cg_ms, update_ms; /* CUDA-event times of the phases of the last timed call */
+  float rows_ms, cols_ms;   /* sums over CG iterations of the per-launch durations of the two O passes (O.v rows / O^H z columns) */
+  int32_t rows_count, cols_count;
   int64_t kernel_launches;  /* kernels launched by this handle since creation */
 } nqs_timing;
 nqs_status nqs_get_timing(nqs_handle * h, nqs_timing * t);
 nqs_status nqs_set_timing(nqs_handle * h, int32_t enabled);
+/* CUDA events on the handle's stream for callers that time several calls as one region (slot 0..7) */
+nqs_status nqs_event_record(nqs_handle * h, int32_t slot);
+nqs_status nqs_event_elapsed_ms(nqs_handle * h, int32_t slot_begin, int32_t slot_end, float * ms); /* synchronises slot_end */
 /* name of the sweep kernel variant in use ("generic", "rbm_regs", ...) */
 const char * nqs_kernel_variant(const nqs_handle * h, const char * stage);
 

@@ -37,8 +37,8 @@ class SROptions(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("sweep_ms", C.c_float), ("eloc_ms", C.c_float), ("oderiv_ms", C.c_float), ("setup_ms", C.c_float),
-                ("cg_ms", C.c_float), ("update_ms", C.c_float), ("matvec_ms", C.c_float), ("matvec_count", C.c_int32),
-                ("kernel_launches", C.c_int64)]
+                ("cg_ms", C.c_float), ("update_ms", C.c_float), ("rows_ms", C.c_float), ("cols_ms", C.c_float),
+                ("rows_count", C.c_int32), ("cols_count", C.c_int32), ("kernel_launches", C.c_int64)]
 
 
 # every symbol include/nqs_b200.h declares: name -> (restype, argtypes)
@@ -76,6 +76,8 @@ SYMBOLS = {
     "nqs_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
     "nqs_get_timing": (_i32, [_vp, C.POINTER(Timing)]),
     "nqs_set_timing": (_i32, [_vp, _i32]),
+    "nqs_event_record": (_i32, [_vp, _i32]),
+    "nqs_event_elapsed_ms": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_float)]),
     "nqs_kernel_variant": (_cp, [_vp, _cp]),
 }
 

@@ -80,20 +80,76 @@ inline int grid_for(long long n, int threads, int cap)
   return (int)std::min<long long>(g, cap);
 }
 
-struct PhaseTimer
-{ // CUDA-event bracket on the handle's stream; no-op unless timing is enabled
-  nqs_handle * h; float * dst; bool on;
-  PhaseTimer(nqs_handle * h_, float * d): h(h_), dst(d), on(h_->timing_on && h_->ev_ok)
-  { if (on) cudaEventRecord(h->ev[0], h->stream); }
-  ~PhaseTimer()
+enum { TAG_SWEEP = 0, TAG_ELOC, TAG_ODERIV, TAG_SETUP, TAG_CG, TAG_UPDATE, TAG_ROWS, TAG_COLS };
+
+int ev_next(nqs_handle * h)
+{
+  if (h->ev_used == h->evpool.size())
+  {
+    cudaEvent_t e;
+    NQS_CUDA(cudaEventCreate(&e));
+    h->evpool.push_back(e);
+  }
+  return (int)h->ev_used++;
+}
+
+struct Span
+{ // CUDA-event bracket on the handle's stream, recorded without any synchronisation; resolve_spans() reads them later
+  nqs_handle * h; int tag, b; bool on;
+  Span(nqs_handle * h_, int tag_): h(h_), tag(tag_), b(-1), on(h_->timing_on)
+  { if (on) { b = ev_next(h); cudaEventRecord(h->evpool[b], h->stream); } }
+  ~Span()
   {
     if (!on) return;
-    cudaEventRecord(h->ev[1], h->stream);
-    cudaEventSynchronize(h->ev[1]);
-    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
-    *dst += ms;
+    const int e = ev_next(h);
+    cudaEventRecord(h->evpool[e], h->stream);
+    h->spans.push_back({tag, b, e});
   }
 };
+
+void reset_phase_times(nqs_handle * h)
+{
+  nqs_timing & t = h->timing;
+  t.sweep_ms = t.eloc_ms = t.oderiv_ms = t.setup_ms = t.cg_ms = t.update_ms = t.rows_ms = t.cols_ms = 0;
+  t.rows_count = t.cols_count = 0;
+}
+
+void resolve_spans(nqs_handle * h)
+{
+  if (h->spans.empty()) { h->ev_used = 0; return; }
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  nqs_timing & t = h->timing;
+  std::vector<float> ms_of(h->spans.size());
+  float max_rows = 0, max_cols = 0;
+  for (size_t i = 0; i < h->spans.size(); ++i)
+  {
+    const nqs_handle::Span & sp = h->spans[i];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->evpool[sp.b], h->evpool[sp.e]);
+    ms_of[i] = ms;
+    if (sp.tag == TAG_ROWS) max_rows = std::max(max_rows, ms);
+    if (sp.tag == TAG_COLS) max_cols = std::max(max_cols, ms);
+  }
+  for (size_t i = 0; i < h->spans.size(); ++i)
+  {
+    const nqs_handle::Span & sp = h->spans[i];
+    const float ms = ms_of[i];
+    switch (sp.tag)
+    {
+      case TAG_SWEEP: t.sweep_ms += ms; break;
+      case TAG_ELOC: t.eloc_ms += ms; break;
+      case TAG_ODERIV: t.oderiv_ms += ms; break;
+      case TAG_SETUP: t.setup_ms += ms; break;
+      case TAG_CG: t.cg_ms += ms; break;
+      case TAG_UPDATE: t.update_ms += ms; break;
+      // launches issued after the CG converged return immediately (device-side `done` flag): they are not O passes
+      case TAG_ROWS: if (ms >= 0.25f*max_rows) { t.rows_ms += ms; t.rows_count += 1; } break;
+      case TAG_COLS: if (ms >= 0.25f*max_cols) { t.cols_ms += ms; t.cols_count += 1; } break;
+    }
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
 
 void check_launch(nqs_handle * h, const char * what)
 {
@@ -246,11 +302,17 @@ void matvec_passes(nqs_handle * h, const cd * v, const int * done)
 {
   const long long P = h->P, K = h->K;
   const unsigned gr = (unsigned)((K+NQS_ROWS_PER_CTA-1)/NQS_ROWS_PER_CTA);
-  matvec_rows_kernel<<<gr, NQS_ROW_THREADS, 0, h->stream>>>(K, P, h->O.p, v, h->zk.p, done);
-  check_launch(h, "matvec_rows_kernel");
+  {
+    Span sp(h, TAG_ROWS);
+    matvec_rows_kernel<<<gr, NQS_ROW_THREADS, 0, h->stream>>>(K, P, h->O.p, v, h->zk.p, done);
+    check_launch(h, "matvec_rows_kernel");
+  }
   dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
-  matvec_cols_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->zk.p, h->part.p, h->rows_per_block, done);
-  check_launch(h, "matvec_cols_partial_kernel");
+  {
+    Span sp(h, TAG_COLS);
+    matvec_cols_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->zk.p, h->part.p, h->rows_per_block, done);
+    check_launch(h, "matvec_cols_partial_kernel");
+  }
   colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, h->nrb, h->part.p, h->traw.p, done);
   check_launch(h, "colsum_reduce_kernel");
   allreduce_sum(h, h->traw.p, (size_t)(2*P));
@@ -310,7 +372,6 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
       check_launch(h, "cg_phase2_kernel");
       cg_phase3_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->z.p, h->pvec.p, h->scal.p);
       check_launch(h, "cg_phase3_kernel");
-      h->timing.matvec_count += 1;
       if ((it+1)%check_every == 0 || it+1 == n_max)
       {
         s = read_scalars(h);
@@ -518,6 +579,7 @@ void nqs_destroy(nqs_handle * h)
   if (h->comm && g_nccl.commDestroy) g_nccl.commDestroy(h->comm);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+  for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
 }
@@ -673,8 +735,9 @@ nqs_status nqs_do_mcmc_steps(nqs_handle * h, int32_t n_sweeps)
   return guarded(h, [&]()
   {
     NQS_CUDA(cudaSetDevice(h->cfg.device));
-    h->timing.sweep_ms = 0;
-    { PhaseTimer t(h, &h->timing.sweep_ms); do_sweeps(h, n_sweeps); }
+    reset_phase_times(h);
+    { Span t(h, TAG_SWEEP); do_sweeps(h, n_sweeps); }
+    resolve_spans(h);
   });
 }
 
@@ -773,8 +836,9 @@ nqs_status nqs_local_energy(nqs_handle * h, nqs_cdouble * htilda)
   {
     NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_local_energy before nqs_initialize / nqs_warm_up");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
-    h->timing.eloc_ms = 0;
-    { PhaseTimer t(h, &h->timing.eloc_ms); launch_eloc(h, nullptr, 0); }
+    reset_phase_times(h);
+    { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); }
+    resolve_spans(h);
     h->flip_index = h->N-1; // the reference's loop ends with forward(L-1)
     if (htilda)
     {
@@ -792,8 +856,9 @@ nqs_status nqs_log_derivs(nqs_handle * h, nqs_cdouble * O_host)
     NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_log_derivs before nqs_initialize / nqs_warm_up");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
-    h->timing.oderiv_ms = 0;
-    { PhaseTimer t(h, &h->timing.oderiv_ms); launch_oderiv(h); }
+    reset_phase_times(h);
+    { Span t(h, TAG_ODERIV); launch_oderiv(h); }
+    resolve_spans(h);
     if (O_host)
     {
       NQS_CUDA(cudaMemcpyAsync(O_host, h->O.p, sizeof(cd)*(size_t)h->K*(size_t)h->P, cudaMemcpyDeviceToHost, h->stream));
@@ -837,18 +902,15 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_sr_step before nqs_warm_up");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
-    nqs_timing & tm = h->timing;
-    tm.sweep_ms = tm.eloc_ms = tm.oderiv_ms = tm.setup_ms = tm.cg_ms = tm.update_ms = tm.matvec_ms = 0;
-    tm.matvec_count = 0;
+    reset_phase_times(h);
     nqs_sr_stats s;
     std::memset(&s, 0, sizeof(s));
-    { PhaseTimer t(h, &tm.sweep_ms); do_sweeps(h, opt->n_mc_steps); }
-    { PhaseTimer t(h, &tm.eloc_ms); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
-    { PhaseTimer t(h, &tm.oderiv_ms); launch_oderiv(h); }
+    { Span t(h, TAG_SWEEP); do_sweeps(h, opt->n_mc_steps); }
+    { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
+    { Span t(h, TAG_ODERIV); launch_oderiv(h); }
     double hs[3];
     {
-      PhaseTimer t(h, &tm.setup_ms);
-      sr_setup(h, true);
+      { Span t(h, TAG_SETUP); sr_setup(h, true); }
       NQS_CUDA(cudaMemcpyAsync(h->pinned, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
       NQS_CUDA(cudaStreamSynchronize(h->stream));
       std::memcpy(hs, h->pinned, sizeof(hs));
@@ -859,6 +921,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     if (!s.finite)
     { // ref optimizer.cuh:134-138: print and stop; here: report and leave the state untouched
       if (st) *st = s;
+      resolve_spans(h);
       return;
     }
     if (opt->lambda < 0)
@@ -868,10 +931,11 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       s.lambda = (lam > 1e-2) ? lam : 1e-2;
     }
     else s.lambda = opt->lambda;
-    { PhaseTimer t(h, &tm.cg_ms); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
+    { Span t(h, TAG_CG); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
     if (opt->apply_update)
-    { PhaseTimer t(h, &tm.update_ms); do_evolve(h, h->dx.p, opt->lr); }
+    { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr); }
     NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
+    resolve_spans(h);
     const double n2 = s.e_re*s.e_re+s.e_im*s.e_im;
     s.rsd = std::sqrt((hs[2]*invk-n2)/n2);
     if (st) *st = s;
@@ -947,6 +1011,23 @@ nqs_status nqs_set_timing(nqs_handle * h, int32_t enabled)
   if (!h) return NQS_ERR_INVALID;
   h->timing_on = enabled != 0;
   return NQS_OK;
+}
+
+nqs_status nqs_event_record(nqs_handle * h, int32_t slot)
+{
+  if (!h || slot < 0 || slot >= 8) return NQS_ERR_INVALID;
+  return guarded(h, [&]() { NQS_CUDA(cudaSetDevice(h->cfg.device)); NQS_CUDA(cudaEventRecord(h->ev[slot], h->stream)); });
+}
+
+nqs_status nqs_event_elapsed_ms(nqs_handle * h, int32_t a, int32_t b, float * ms)
+{
+  if (!h || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaEventSynchronize(h->ev[b]));
+    NQS_CUDA(cudaEventElapsedTime(ms, h->ev[a], h->ev[b]));
+  });
 }
 
 const char * nqs_kernel_variant(const nqs_handle * h, const char * stage)

@@ -81,7 +81,11 @@ struct nqs_handle
   std::string err;
   bool timing_on = false;
   nqs_timing timing;
-  cudaEvent_t ev[8];
+  cudaEvent_t ev[8];                      // user slots of nqs_event_record
   bool ev_ok = false;
+  struct Span { int tag, b, e; };
+  std::vector<cudaEvent_t> evpool;        // events of the timed spans, resolved after the call's final sync
+  size_t ev_used = 0;
+  std::vector<Span> spans;
   std::string variant_sweep = "generic", variant_eloc = "generic", variant_theta = "generic";
 };

@@ -228,5 +228,13 @@ class Engine:
         self._chk(self.lib.nqs_get_timing(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in L.Timing._fields_}
 
+    def event_record(self, slot: int):
+        self._chk(self.lib.nqs_event_record(self._h, int(slot)))
+
+    def event_elapsed_ms(self, slot_begin: int, slot_end: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.nqs_event_elapsed_ms(self._h, int(slot_begin), int(slot_end), C.byref(ms)))
+        return float(ms.value)
+
     def kernel_variant(self, stage: str) -> str:
         return (self.lib.nqs_kernel_variant(self._h, stage.encode()) or b"").decode()
