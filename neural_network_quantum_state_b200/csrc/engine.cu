@@ -189,12 +189,72 @@ void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_sp
   check_launch(h, "theta_generic_kernel");
 }
 
+
+// ---- specialised RBM path (fast_kernels.cuh) -------------------------------------------------------------------------
+void ensure_tables(nqs_handle * h)
+{
+  if (h->tables_valid || h->jpl == 0) return;
+  build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
+    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->w2.p, h->afac.p, h->aexp.p);
+  check_launch(h, "build_fast_tables_kernel");
+  theta_bound_kernel<<<1, 256, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
+  check_launch(h, "theta_bound_kernel");
+  NQS_CUDA(cudaMemcpyAsync(h->pinned, h->bound.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(&h->theta_bound, h->pinned, sizeof(double));
+  h->tables_valid = true;
+}
+
+bool fast_path_ok(nqs_handle * h)
+{ // product form is overflow-free while JPL * 2 max|Re theta| stays far below log(DBL_MAX)
+  if (h->jpl == 0) return false;
+  ensure_tables(h);
+  return std::isfinite(h->theta_bound) && h->theta_bound < 300.0/h->jpl;
+}
+
+template <int JPL, int C>
+void launch_sweep_fast_t(nqs_handle * h, const FastSweepArgs & a)
+{
+  const int warps = 4;
+  const size_t smem = fast_sweep_smem_bytes(h->N, C, warps);
+  set_smem(rbm_sweep_fast_kernel<JPL, C>, smem);
+  const long long per_cta = (long long)warps*C;
+  rbm_sweep_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
+}
+
+template <int JPL, int C>
+void launch_eloc_fast_t(nqs_handle * h, const FastElocArgs & a)
+{
+  const int warps = 4;
+  const size_t npad = (size_t)((h->N+15)/16)*16;
+  const size_t smem = (size_t)warps*C*npad;
+  const long long per_cta = (long long)warps*C;
+  rbm_eloc_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
+}
+
+void launch_eloc_fast(nqs_handle * h)
+{
+  FastElocArgs a;
+  a.N = h->N; a.M = h->M; a.Mpad = h->mpad; a.K = h->K; a.ctab_a = h->ctab_a.p; a.ctab_b = h->ctab_b.p; a.aexp = h->aexp.p; a.spins = h->spins.p;
+  a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.Jmat = h->Jmat.p; a.hfield = h->cfg.h;
+  a.htilda = h->htilda.p;
+  switch (h->jpl)
+  {
+    case 1: launch_eloc_fast_t<1, 4>(h, a); break;
+    case 2: launch_eloc_fast_t<2, 4>(h, a); break;
+    case 4: launch_eloc_fast_t<4, 4>(h, a); break;
+    case 8: launch_eloc_fast_t<8, 2>(h, a); break;
+    default: launch_eloc_fast_t<16, 1>(h, a); break;
+  }
+  check_launch(h, "rbm_eloc_fast_kernel");
+}
+
 void launch_sweep(nqs_handle * h, long long nsteps)
 {
   if (nsteps <= 0) return;
   SweepArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
-  a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.order = h->order.p;
+  a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.order = h->order.p;
   a.pos0 = h->pos; a.nsteps = nsteps;
   a.uniforms = nullptr;
   if (h->u_steps > 0)
@@ -210,6 +270,29 @@ void launch_sweep(nqs_handle * h, long long nsteps)
     a.acc_log = h->acc_log.p;
     h->acc_log_steps = nsteps;
   }
+  if (fast_path_ok(h) && nsteps%h->N == 0)
+  {
+    FastSweepArgs f;
+    f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ftab_a = h->ftab_a.p; f.ftab_b = h->ftab_b.p; f.w2 = h->w2.p; f.afac = h->afac.p;
+    f.spins = h->spins.p; f.theta = h->theta.p; f.lnpsi0 = h->lnpsi0.p; f.sa = h->sa.p; f.fresh = h->fresh.p; f.order = h->order.p;
+    f.pos0 = h->pos; f.nsweeps = (int)(nsteps/h->N); f.uniforms = a.uniforms; f.seed = a.seed; f.step0 = a.step0;
+    f.chain_offset = a.chain_offset; f.acc_log = a.acc_log;
+    switch (h->jpl)
+    {
+      case 1: launch_sweep_fast_t<1, 4>(h, f); break;
+      case 2: launch_sweep_fast_t<2, 4>(h, f); break;
+      case 4: launch_sweep_fast_t<4, 4>(h, f); break;
+      case 8: launch_sweep_fast_t<8, 2>(h, f); break;
+      default: launch_sweep_fast_t<16, 1>(h, f); break;
+    }
+    check_launch(h, "rbm_sweep_fast_kernel");
+    h->variant_sweep = "rbm_regs_j"+std::to_string(h->jpl);
+    h->pos = (int)((h->pos+nsteps)%h->N);
+    if (h->u_steps > 0) h->u_used += nsteps;
+    h->step_counter += (unsigned long long)nsteps;
+    return;
+  }
+  h->variant_sweep = "generic";
   const size_t npad = (size_t)((h->N+15)/16)*16;
   const size_t per_warp = (size_t)h->M*sizeof(cd)+npad, fixed = (size_t)h->N*sizeof(int);
   const int warps = warps_for_smem(h, per_warp, fixed);
@@ -233,6 +316,13 @@ void launch_sweep(nqs_handle * h, long long nsteps)
 
 void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
 {
+  if (lnpsi1 == nullptr && fast_path_ok(h))
+  {
+    launch_eloc_fast(h);
+    h->variant_eloc = "rbm_regs_j"+std::to_string(h->jpl);
+    return;
+  }
+  if (lnpsi1 == nullptr) h->variant_eloc = "generic";
   ElocArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p; a.spins = h->spins.p;
   a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.Jmat = h->Jmat.p; a.hfield = h->cfg.h;
@@ -392,6 +482,8 @@ void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
 {
   update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
   check_launch(h, "update_params_kernel");
+  h->tables_valid = false;
+  NQS_CUDA(cudaMemsetAsync(h->fresh.p, 0, (size_t)h->K, h->stream)); // lnpsi0 is now the pre-update value (ref keeps it)
   // ref update_variables tail (:161-169): theta and sa re-derived for the current spins; lnpsi0 is NOT refreshed
   launch_theta(h, h->spins.p, h->spins.p, h->theta.p, h->sa.p, nullptr);
 }
@@ -420,6 +512,7 @@ void do_initialize(nqs_handle * h, const int8_t * spins_host)
         s[(size_t)k*h->N+i] = (i%2 == 0) ? 1 : -1;
   NQS_CUDA(cudaMemcpyAsync(h->spins.p, s.data(), s.size(), cudaMemcpyHostToDevice, h->stream));
   launch_theta(h, h->spins.p, h->spins.p, h->theta.p, h->sa.p, h->lnpsi0.p);
+  NQS_CUDA(cudaMemsetAsync(h->fresh.p, 1, (size_t)h->K, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
   h->initialized = true;
 }
@@ -457,6 +550,7 @@ void build_J(nqs_handle * h)
 
 void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
+  h->tables_valid = false;
   NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
 }
@@ -536,6 +630,16 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     h->lnpsi0.alloc(h->K); h->lnpsi1.alloc(h->K); h->sa.alloc(h->K); h->htilda.alloc(h->K);
     h->spins.alloc(KN); h->tmp_spins.alloc(KN);
     h->Jmat.alloc((size_t)h->N*h->N); h->order.alloc(h->N);
+    h->fresh.alloc(h->K);
+    NQS_CUDA(cudaMemset(h->fresh.p, 0, (size_t)h->K));
+    if (h->model == MODEL_RBM && !(cfg->flags & NQS_FLAG_FORCE_GENERIC) && h->M <= 512)
+    {
+      int jpl = 1;
+      while (32*jpl < h->M) jpl <<= 1;
+      h->jpl = jpl; h->mpad = 32*jpl;
+      const size_t nm = (size_t)h->N*h->mpad;
+      h->ftab_a.alloc(nm); h->ftab_b.alloc(nm); h->ctab_a.alloc(nm); h->ctab_b.alloc(nm); h->w2.alloc(nm); h->afac.alloc((size_t)2*h->N); h->aexp.alloc((size_t)2*h->N); h->bound.alloc(1);
+    }
     NQS_CUDA(cudaMemset(h->params.p, 0, sizeof(cd)*h->P));
     NQS_CUDA(cudaMemset(h->spins.p, 0, KN));   // like the reference's zero-initialised spinStates_dev_
     NQS_CUDA(cudaMemset(h->theta.p, 0, sizeof(cd)*KM));
@@ -606,6 +710,7 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
+    h->tables_valid = false;
   });
 }
 
@@ -724,6 +829,7 @@ nqs_status nqs_warm_up(nqs_handle * h, int32_t n_sweeps, const int8_t * spins)
     flip_site_all_finish_kernel<<<grid_for(h->K, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->K, h->model, h->params.p,
       h->spins.p, h->sa.p, site);
     check_launch(h, "flip_site_all_finish_kernel");
+    NQS_CUDA(cudaMemsetAsync(h->fresh.p, 0, (size_t)h->K, h->stream)); // lnpsi0 still holds the un-flipped state's value
     do_sweeps(h, n_sweeps);
     NQS_CUDA(cudaStreamSynchronize(h->stream));
   });

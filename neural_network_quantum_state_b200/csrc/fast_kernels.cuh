@@ -1,0 +1,505 @@
+// Register-resident, transcendental-free kernels for the complex RBM (the configuration the headline metric is quoted on).
+//
+// Observation: for the RBM,  |psi(s^(i))/psi(s)|^2 = prod_j |cosh(theta_j - 2 s_i W_ij)|^2 / |cosh(theta_j)|^2 * exp(-4 s_i Re a_i)
+// and |cosh(x+iy)|^2 = sinh^2 x + cos^2 y.  Keeping (e^x/2, e^-x/2, cos y, sin y) per (chain, hidden unit) in REGISTERS and
+// tabulating (e^{-+2 Re W_ij}, cos 2 Im W_ij, sin 2 Im W_ij) once per parameter update turns every Metropolis proposal into
+// 7 fp64 multiply-adds per hidden unit -- no exp / sincos / log inside the sweep (the generic kernel spends ~250 fp64
+// instructions per hidden unit per proposal on them).  The accept test  u < |psi'/psi0|^2  is evaluated on the products
+// themselves in (mantissa, exponent) form, so it needs no log/exp either.  theta itself is NOT carried through the sweep:
+// the accepted flips of a sweep are recorded and replayed afterwards on the exact fp64 theta in the reference's order
+// (theta -= 2 s W_i, ref conditional_y_update, impl_neural_quantum_state.cuh:1314-1329), so theta stays bit-identical to the
+// generic kernel's and the (e^x, cos y, ..) registers are rebuilt from it at every sweep (no drift).
+// lnpsi0 is recomputed from the final theta for chains that accepted at least once (it equals the lnpsi' of their last
+// accepted proposal up to rounding); chains that never accepted keep their tracked -- possibly stale -- value, which is
+// exactly the reference's behaviour.
+//
+// One warp owns C chains and ALL M hidden units (JPL = ceil(M/32) per lane), so every table entry fetched from L1 is used
+// for C chains and the only cross-lane traffic is one shuffle butterfly per proposal.
+#pragma once
+#include "device_math.cuh"
+#include "sampler_kernels.cuh"
+
+namespace nqs
+{
+// Tables are split into 16-byte halves so that a warp's access is one fully coalesced LDG.128 per half (a 32-byte struct
+// read with 8-byte loads costs 4x the L1 wavefronts -- measured, profiles/r1b_fast_kernels.md).
+//   ftab_a = (e^{-2 Re W}, e^{+2 Re W})   ftab_b = (cos 2 Im W, sin 2 Im W)      [sigma = +1]
+//   ctab_a = cosh(2W)                      ctab_b = sinh(2W)
+typedef double2 FlipTab;
+typedef double2 CoshTab;
+__device__ __forceinline__ double2 ld_tab(const double2 * p) { return __ldg(p); }
+
+// tables [N][Mpad] (Mpad = 32*JPL, neutral padding), rebuilt after every parameter change
+__global__ void build_fast_tables_kernel(const int N, const int M, const int Mpad, const cd * __restrict__ params,
+  FlipTab * __restrict__ ftab_a, FlipTab * __restrict__ ftab_b, CoshTab * __restrict__ ctab_a, CoshTab * __restrict__ ctab_b,
+  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp)
+{
+  const cd * W = params;
+  const cd * a = params+(size_t)N*M;
+  const long long total = (long long)N*Mpad;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x)
+  {
+    const int i = (int)(idx/Mpad), j = (int)(idx-(long long)i*Mpad);
+    cd w = cmake(0.0, 0.0);
+    if (j < M) w = W[(size_t)i*M+j];
+    const double ex = exp(2.0*w.x), emx = exp(-2.0*w.x);
+    double s, co;
+    sincos(2.0*w.y, &s, &co);
+    const double ch = 0.5*(ex+emx), sh = 0.5*(ex-emx);
+    ftab_a[idx] = make_double2(emx, ex); ftab_b[idx] = make_double2(co, s);
+    ctab_a[idx] = make_double2(ch*co, sh*s); ctab_b[idx] = make_double2(sh*co, ch*s);
+    w2[idx] = cmake(2.0*w.x, 2.0*w.y);
+  }
+  for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < N; i += gridDim.x*blockDim.x)
+  {
+    const cd ai = a[i];
+    afac[2*i] = exp(-4.0*ai.x);   // sigma = +1
+    afac[2*i+1] = exp(4.0*ai.x);  // sigma = -1
+    aexp[2*i] = c_exp(cmake(-2.0*ai.x, -2.0*ai.y));
+    aexp[2*i+1] = c_exp(cmake(2.0*ai.x, 2.0*ai.y));
+  }
+}
+
+// bound[0] = max_j (|Re b_j| + sum_i |Re W_ij|) >= max |Re theta|: decides whether the product form cannot overflow
+__global__ void theta_bound_kernel(const int N, const int M, const cd * __restrict__ params, double * __restrict__ bound)
+{
+  __shared__ double sh[32];
+  const cd * W = params;
+  const cd * b = params+(size_t)N*M+N;
+  double mx = 0.0;
+  for (int j = threadIdx.x; j < M; j += blockDim.x)
+  {
+    double s = fabs(b[j].x);
+    for (int i = 0; i < N; ++i) s += fabs(W[(size_t)i*M+j].x);
+    mx = fmax(mx, s);
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x&31) == 0) sh[threadIdx.x>>5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double m2 = 0.0;
+    for (int w = 0; w < (int)(blockDim.x>>5); ++w) m2 = fmax(m2, sh[w]);
+    bound[0] = m2;
+  }
+}
+
+// split a positive finite double into mantissa in [1,2) and exponent
+__device__ __forceinline__ void split_me(const double p, double & m, int & e)
+{
+  const int hi = __double2hiint(p);
+  e = ((hi>>20)&0x7ff)-1023;
+  m = __hiloint2double((hi&0x800fffff)|0x3ff00000, __double2loint(p));
+}
+
+struct FastSweepArgs
+{
+  int N, M, Mpad;
+  long long K;
+  const cd * params;
+  const FlipTab * ftab_a;
+  const FlipTab * ftab_b;
+  const cd * w2;
+  const double * afac;
+  int8_t * spins;
+  cd * theta;
+  cd * lnpsi0;
+  cd * sa;
+  unsigned char * fresh;   // [K] 1 = lnpsi0 equals lnpsi(current theta) (set here when the chain accepted at least once)
+  const int * order;
+  int pos0;
+  int nsweeps;
+  const double * uniforms;
+  unsigned long long seed, step0;
+  long long chain_offset;
+  unsigned char * acc_log;
+};
+
+inline size_t fast_sweep_smem_bytes(int N, int C, int warps)
+{
+  const size_t npad = (size_t)((N+15)/16)*16;
+  return (size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int);
+}
+
+template <int JPL, int C>
+__global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int N = a.N, M = a.M, Mpad = a.Mpad;
+  const int npad = ((N+15)/16)*16;
+  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*C*npad;                         // [C][npad]
+  int8_t * rec = reinterpret_cast<int8_t*>(smem_raw)+(size_t)warps*C*npad+(size_t)w*C*N;      // [N][C]: 0 rejected, +-1 = accepted flip of a spin that was +-1
+  int * ord = reinterpret_cast<int*>(smem_raw+(size_t)warps*C*npad+(size_t)warps*C*N);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) ord[i] = a.order[i];
+  __syncthreads();
+  const long long kbase = ((long long)blockIdx.x*warps+w)*C;
+  if (kbase >= a.K) return;
+  const cd * avis = a.params+(size_t)N*M;
+  bool valid[C];
+  cd ln0[C], sa[C];
+  double r0m[C]; int r0e[C];
+  bool any_acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+  {
+    valid[c] = (kbase+c < a.K);
+    const long long k = valid[c] ? kbase+c : kbase;
+    for (int i = lane; i < N; i += 32) sp[c*npad+i] = a.spins[k*N+i];
+    ln0[c] = a.lnpsi0[k]; sa[c] = a.sa[k];
+    // R0 = exp(2 (Re lnpsi0 - Re sa)) as m * 2^e
+    const double v = 2.0*(ln0[c].x-sa[c].x)*1.4426950408889634;
+    const double fl = floor(v);
+    r0m[c] = exp2(v-fl);
+    r0e[c] = (int)fmax(fmin(fl, 100000.0), -100000.0);
+    any_acc[c] = false;
+  }
+  __syncwarp();
+  int pos = a.pos0;
+  long long t_glob = 0;
+  double ubuf[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) ubuf[c] = 0.0;
+
+  for (int sweep = 0; sweep < a.nsweeps; ++sweep)
+  {
+    // ---- (1) rebuild the multiplicative state from the exact theta
+    double h1[C][JPL], h2[C][JPL], cy[C][JPL], sy[C][JPL];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+    {
+      const long long k = valid[c] ? kbase+c : kbase;
+#pragma unroll
+      for (int jj = 0; jj < JPL; ++jj)
+      {
+        const int j = lane+32*jj;
+        cd th = cmake(0.0, 0.0);
+        if (j < M) th = a.theta[k*M+j];
+        const double ex = exp(th.x);
+        h1[c][jj] = 0.5*ex; h2[c][jj] = 0.25/h1[c][jj];
+        sincos(th.y, &sy[c][jj], &cy[c][jj]);
+      }
+    }
+    const int pos_sweep0 = pos;
+    // ---- (2) N proposals
+    for (int t = 0; t < N; ++t, ++t_glob)
+    {
+      if ((t_glob&31) == 0)
+      {
+        const long long tt = t_glob+lane;
+        if (tt < (long long)a.nsweeps*N)
+        {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+          {
+            const long long k = valid[c] ? kbase+c : kbase;
+            ubuf[c] = a.uniforms ? a.uniforms[tt*a.K+k]
+                                 : philox_uniform(a.seed, (unsigned long long)(a.chain_offset+k), a.step0+(unsigned long long)tt);
+          }
+        }
+      }
+      const int site = ord[pos];
+      pos = (pos+1 == N) ? 0 : pos+1;
+      const FlipTab * trow_a = a.ftab_a+(size_t)site*Mpad;
+      const FlipTab * trow_b = a.ftab_b+(size_t)site*Mpad;
+      double sig[C], prod[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { sig[c] = (double)sp[c*npad+site]; prod[c] = 1.0; }
+#pragma unroll
+      for (int jj = 0; jj < JPL; ++jj)
+      {
+        const double2 Ta = ld_tab(trow_a+lane+32*jj), Tb = ld_tab(trow_b+lane+32*jj);
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+        {
+          const bool up = sig[c] > 0.0;
+          const double a1 = up ? Ta.x : Ta.y, a2 = up ? Ta.y : Ta.x, sst = up ? Tb.y : -Tb.y;
+          const double n1 = h1[c][jj]*a1, n2 = h2[c][jj]*a2;
+          const double nc = fma(sy[c][jj], sst, cy[c][jj]*Tb.x);
+          const double d = n1-n2;
+          prod[c] *= fma(d, d, nc*nc);
+        }
+      }
+      bool acc[C];
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+      {
+        double m; int e;
+        split_me(fmax(prod[c], 1e-300), m, e);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          m *= __shfl_xor_sync(0xffffffffu, m, o);
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        // accept  <=>  u < P' A / R0   (== u < exp(2 (Re lnpsi' - Re lnpsi0)), ref impl_mcmc_sampler.cuh:75-99)
+        const double u = __shfl_sync(0xffffffffu, ubuf[c], (int)(t_glob&31));
+        const double A = a.afac[2*site+(sig[c] > 0.0 ? 0 : 1)];
+        int de = e-r0e[c];
+        de = max(-2000, min(2000, de));
+        const double rhs = scalbn(m*A, de);
+        acc[c] = valid[c] && (u*r0m[c] < rhs);
+        if (a.acc_log && lane == 0 && valid[c]) a.acc_log[t_glob*a.K+kbase+c] = acc[c] ? 1 : 0;
+        if (lane == 0) rec[t*C+c] = acc[c] ? (int8_t)(sig[c] > 0.0 ? 1 : -1) : (int8_t)0;
+        if (acc[c])
+        {
+          // renormalise (m in [1, 2^32)) and adopt as the new reference product
+          double m2; int e2;
+          split_me(m, m2, e2);
+          r0m[c] = m2; r0e[c] = e+e2;
+          const cd ai = avis[site];
+          sa[c] = cmake(sa[c].x-2.0*sig[c]*ai.x, sa[c].y-2.0*sig[c]*ai.y);
+          any_acc[c] = true;
+          any = true;
+          if (lane == 0) sp[c*npad+site] = (int8_t)(-sp[c*npad+site]);
+        }
+      }
+      if (any)
+      {
+#pragma unroll
+        for (int jj = 0; jj < JPL; ++jj)
+        {
+          const double2 Ta = ld_tab(trow_a+lane+32*jj), Tb = ld_tab(trow_b+lane+32*jj);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+          {
+            if (acc[c])
+            {
+              const bool up = sig[c] > 0.0;
+              const double a1 = up ? Ta.x : Ta.y, a2 = up ? Ta.y : Ta.x, sst = up ? Tb.y : -Tb.y;
+              h1[c][jj] *= a1; h2[c][jj] *= a2;
+              const double nc = fma(sy[c][jj], sst, cy[c][jj]*Tb.x);
+              const double ns = fma(-cy[c][jj], sst, sy[c][jj]*Tb.x);
+              cy[c][jj] = nc; sy[c][jj] = ns;
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // ---- (3) replay the accepted flips of this sweep on the exact theta, in order (bit-identical to the generic kernel)
+    {
+      cd th[C][JPL];
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+      {
+        const long long k = valid[c] ? kbase+c : kbase;
+#pragma unroll
+        for (int jj = 0; jj < JPL; ++jj)
+        {
+          const int j = lane+32*jj;
+          th[c][jj] = (j < M) ? a.theta[k*M+j] : cmake(0.0, 0.0);
+        }
+      }
+      int rp = pos_sweep0;
+      for (int t = 0; t < N; ++t)
+      {
+        const int site = ord[rp];
+        rp = (rp+1 == N) ? 0 : rp+1;
+        int r[C];
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { r[c] = rec[t*C+c]; any = any || (r[c] != 0); }
+        if (!any) continue;
+        const cd * wrow = a.w2+(size_t)site*Mpad;
+#pragma unroll
+        for (int jj = 0; jj < JPL; ++jj)
+        {
+          const cd wv = ld_tab(wrow+lane+32*jj);
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+          {
+            if (r[c] != 0)
+            { // theta -= W * (2 sigma): w2 = 2W is exact, so this equals the reference's y - w*(2*s) bit for bit
+              const double s = (double)r[c];
+              th[c][jj].x -= wv.x*s; th[c][jj].y -= wv.y*s;
+            }
+          }
+        }
+      }
+      const bool last = (sweep+1 == a.nsweeps);
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+      {
+        if (!valid[c]) continue;
+        const long long k = kbase+c;
+        cd lsum = cmake(0.0, 0.0);
+#pragma unroll
+        for (int jj = 0; jj < JPL; ++jj)
+        {
+          const int j = lane+32*jj;
+          if (j < M)
+          {
+            a.theta[k*M+j] = th[c][jj];
+            if (last && any_acc[c]) lsum = cadd(lsum, c_logcosh(th[c][jj]));
+          }
+        }
+        if (last && any_acc[c])
+        {
+          lsum = warp_sum(lsum);
+          ln0[c] = cadd(lsum, sa[c]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+  {
+    if (!valid[c]) continue;
+    const long long k = kbase+c;
+    for (int i = lane; i < N; i += 32) a.spins[k*N+i] = sp[c*npad+i];
+    if (lane == 0)
+    {
+      a.lnpsi0[k] = ln0[c];
+      a.sa[k] = sa[c];
+      if (any_acc[c]) a.fresh[k] = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Local energy, RBM:  psi(s^(i))/psi(s) = prod_j [cosh(2W_ij) - s_i tanh(theta_j) sinh(2W_ij)] * exp(-2 s_i a_i)
+// (cosh(t - 2sW) = cosh t cosh 2W - s sinh t sinh 2W).  tanh(theta_j) is computed once per (chain, j) and stays in
+// registers; each of the N ratios costs 8 fp64 FMAs per hidden unit.  The reference evaluates N full forward(i) passes
+// (k3+k4+c1) + k11 per call (impl_hamiltonians.cuh:233-238).  The tracked lnpsi0 enters as in the reference:
+// exp(lnpsi' - lnpsi0) = ratio * exp(lnpsi(theta) - lnpsi0); the second factor is 1 for chains flagged fresh and is
+// evaluated explicitly (M log cosh) only for stale ones.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FastElocArgs
+{
+  int N, M, Mpad;
+  long long K;
+  const CoshTab * ctab_a;
+  const CoshTab * ctab_b;
+  const cd * aexp;
+  const int8_t * spins;
+  const cd * theta;
+  const cd * lnpsi0;
+  const cd * sa;
+  const unsigned char * fresh;
+  const double * Jmat;
+  double hfield;
+  cd * htilda;
+};
+
+template <int JPL, int C>
+__global__ void __launch_bounds__(128) rbm_eloc_fast_kernel(const FastElocArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int N = a.N, M = a.M, Mpad = a.Mpad;
+  const int npad = ((N+15)/16)*16;
+  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*C*npad;
+  const long long kbase = ((long long)blockIdx.x*warps+w)*C;
+  if (kbase >= a.K) return;
+  bool valid[C];
+  cd T[C][JPL];
+  cd corr[C];
+  bool stale = false;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+  {
+    valid[c] = (kbase+c < a.K);
+    const long long k = valid[c] ? kbase+c : kbase;
+    for (int i = lane; i < N; i += 32) sp[c*npad+i] = a.spins[k*N+i];
+    stale = stale || (a.fresh[k] == 0);
+    corr[c] = cmake(1.0, 0.0);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+  {
+    const long long k = valid[c] ? kbase+c : kbase;
+    cd lsum = cmake(0.0, 0.0);
+#pragma unroll
+    for (int jj = 0; jj < JPL; ++jj)
+    {
+      const int j = lane+32*jj;
+      cd th = cmake(0.0, 0.0);
+      if (j < M) th = a.theta[k*M+j];
+      T[c][jj] = c_tanh(th);
+      if (stale && j < M) lsum = cadd(lsum, c_logcosh(th));
+    }
+    if (stale)
+    { // exp(lnpsi(theta) - lnpsi0_tracked): != 1 only right after warm_up's quirk flip or a parameter update
+      lsum = warp_sum(lsum);
+      const cd l0 = a.lnpsi0[k], s0 = a.sa[k];
+      corr[c] = c_exp(cmake(lsum.x+s0.x-l0.x, lsum.y+s0.y-l0.y));
+    }
+  }
+  __syncwarp();
+  // 1/2 sum_ij s_i J_ij s_j   (ref c5 + k10, impl_hamiltonians.cuh:226-231,871-887)
+  double diag[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) diag[c] = 0.0;
+  for (int i = lane; i < N; i += 32)
+  {
+    const double * Jrow = a.Jmat+(size_t)i*N;
+    double sj[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) sj[c] = 0.0;
+    for (int j = 0; j < N; ++j)
+    {
+      const double Jv = Jrow[j];
+#pragma unroll
+      for (int c = 0; c < C; ++c) sj[c] = fma(Jv, (double)sp[c*npad+j], sj[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) diag[c] = fma(sj[c], (double)sp[c*npad+i], diag[c]);
+  }
+  cd hsum[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) hsum[c] = cmake(0.0, 0.0);
+  for (int site = 0; site < N; ++site)
+  {
+    const CoshTab * crow_a = a.ctab_a+(size_t)site*Mpad;
+    const CoshTab * crow_b = a.ctab_b+(size_t)site*Mpad;
+    cd pr[C];
+    double sig[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { pr[c] = cmake(1.0, 0.0); sig[c] = (double)sp[c*npad+site]; }
+#pragma unroll
+    for (int jj = 0; jj < JPL; ++jj)
+    {
+      const double2 cc = ld_tab(crow_a+lane+32*jj), ss = ld_tab(crow_b+lane+32*jj);
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+      {
+        const double tr = sig[c]*T[c][jj].x, ti = sig[c]*T[c][jj].y;
+        // f = cosh2W - (s tanh) sinh2W
+        const double fr = fma(ti, ss.y, fma(-tr, ss.x, cc.x));
+        const double fi = fma(-ti, ss.x, fma(-tr, ss.y, cc.y));
+        const double nr = fma(pr[c].x, fr, -pr[c].y*fi);
+        const double ni = fma(pr[c].x, fi, pr[c].y*fr);
+        pr[c].x = nr; pr[c].y = ni;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        const double orr = __shfl_xor_sync(0xffffffffu, pr[c].x, o), oi = __shfl_xor_sync(0xffffffffu, pr[c].y, o);
+        const double nr = fma(pr[c].x, orr, -pr[c].y*oi);
+        const double ni = fma(pr[c].x, oi, pr[c].y*orr);
+        pr[c].x = nr; pr[c].y = ni;
+      }
+      const cd ae = a.aexp[2*site+(sig[c] > 0.0 ? 0 : 1)];
+      const cd ratio = cmul(pr[c], ae);
+      hsum[c] = cadd(hsum[c], ratio);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+  {
+    const double dg = 0.5*warp_sum(diag[c]);
+    if (lane == 0 && valid[c])
+    {
+      const cd off = cmul(hsum[c], corr[c]);
+      a.htilda[kbase+c] = cmake((dg+a.hfield*off.x)/(double)N, (a.hfield*off.y)/(double)N);
+    }
+  }
+}
+} // namespace nqs

@@ -55,6 +55,7 @@ struct SweepArgs
   cd * theta;          // [K][M]
   cd * lnpsi0;         // [K]
   cd * sa;             // [K] (RBM)
+  unsigned char * fresh; // [K] set to 1 when the chain accepted at least once (lnpsi0 then equals lnpsi(theta))
   const int * order;   // [N]
   int pos0;            // index into order of the first site to visit
   long long nsteps;    // proposals per chain in this launch
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const SweepArgs a)
   __syncwarp();
   int pos = a.pos0;
   double ubuf = 0.0;
+  bool any_acc = false;
   for (long long t = 0; t < a.nsteps; ++t)
   {
     if ((t&31) == 0)
@@ -134,6 +136,7 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const SweepArgs a)
         th[j] = tv;
       }
       sa = csub(sa, da);
+      any_acc = true;
       if (lane == 0) sp[site] = (int8_t)(-sp[site]);
     }
     __syncwarp();
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) sweep_generic_kernel(const SweepArgs a)
   {
     a.lnpsi0[k] = ln0;
     if (MODEL == MODEL_RBM) a.sa[k] = sa;
+    if (any_acc) a.fresh[k] = 1;
   }
 }
 

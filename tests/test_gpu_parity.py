@@ -137,6 +137,8 @@ def test_sweep_matches_oracle_step_by_step(model, N, M, K, pbc, force_generic):
     e.set_uniforms(U)
     s.warm_up(n_warm)
     e.warm_up(n_warm)
+    expect = "generic" if (force_generic or model != "rbm") else "rbm_regs"
+    assert e.kernel_variant("sweep").startswith(expect), e.kernel_variant("sweep")
     acc_ref = np.array(s.accept_log)
     acc = e.get_accept_log()
     mism = np.argwhere(acc != acc_ref)
@@ -198,6 +200,50 @@ def test_sr_matches_oracle_fixed_cg_iterations(model, N, M, K, pbc):
         assert_close(dx, st_o.dx, rtol=1e-9, what="dx (7 CG its)")
     assert_close(e.get_params(), m.variables, rtol=1e-9, what="params")
     e.close()
+
+
+def test_large_theta_falls_back_to_generic_kernels():
+    """The product-form kernels are only used while they cannot overflow; a network with huge |Re theta| must take the
+    generic path and still match the oracle."""
+    model, N, M, K = "rbm", 12, 32, 40
+    rng = np.random.default_rng(21)
+    params = synth(model, N, M, rng)
+    params[:N * M] = params[:N * M].real * 600.0 + 1j * params[:N * M].imag
+    U = rng.random((4 * N, K))
+    m = o.make_ansatz(model, N, M, K)
+    m.variables = params.copy()
+    s = o.LITFIChainSampler(m, H, J, ALPHA, False, o.UniformSource(K, predrawn=U))
+    e = _engine(model, N, M, K, H, J, ALPHA, max_predrawn_steps=U.shape[0])
+    e.set_params(params)
+    e.set_uniforms(U)
+    s.warm_up(3)
+    e.warm_up(3)
+    assert e.kernel_variant("sweep") == "generic"
+    assert np.array_equal(e.get_spinStates(), m.spins.astype(np.int8))
+    assert_close(e.get_lnpsi(), s.lnpsi0, what="lnpsi0")
+    assert_close(e.get_htilda(), s.get_htilda(), what="htilda")
+    e.close()
+
+
+def test_fast_and_generic_kernels_agree_bitwise_on_theta():
+    """The specialised sweep replays accepted flips on the exact theta in the reference order: theta and spins must be
+    bit-identical to the generic kernel's; lnpsi0 / htilda agree to rounding."""
+    model, N, M, K = "rbm", 32, 256, 70
+    rng = np.random.default_rng(9)
+    params = synth(model, N, M, rng)
+    outs = []
+    for fg in (False, True):
+        e = _engine(model, N, M, K, H, J, ALPHA, seed=99, force_generic=fg)
+        e.set_params(params)
+        e.warm_up(7)
+        e.do_mcmc_steps(3)
+        outs.append((e.get_spinStates(), e.get_theta(), e.get_lnpsi(), e.get_htilda(), e.kernel_variant("sweep")))
+        e.close()
+    assert outs[0][4].startswith("rbm_regs") and outs[1][4] == "generic"
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert_close(outs[0][2], outs[1][2], what="lnpsi0 fast vs generic")
+    assert_close(outs[0][3], outs[1][3], what="htilda fast vs generic")
 
 
 def test_identities_flip_and_rank1_update():
