@@ -195,7 +195,7 @@ void ensure_tables(nqs_handle * h)
 {
   if (h->tables_valid || h->jpl == 0) return;
   build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
-    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->w2.p, h->afac.p, h->aexp.p);
+    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p);
   check_launch(h, "build_fast_tables_kernel");
   theta_bound_kernel<<<1, 256, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
   check_launch(h, "theta_bound_kernel");
@@ -222,31 +222,23 @@ void launch_sweep_fast_t(nqs_handle * h, const FastSweepArgs & a)
   rbm_sweep_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
 }
 
-template <int JPL, int C>
-void launch_eloc_fast_t(nqs_handle * h, const FastElocArgs & a)
+template <int C>
+void launch_eloc_sites_t(nqs_handle * h, const FastElocArgs & a)
 {
-  const int warps = 4;
-  const size_t npad = (size_t)((h->N+15)/16)*16;
-  const size_t smem = (size_t)warps*C*npad;
-  const long long per_cta = (long long)warps*C;
-  rbm_eloc_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
+  const int nwarps = std::max(1, std::min(8, (h->N+31)/32));
+  const size_t smem = fast_eloc_smem_bytes(h->N, h->M, C);
+  set_smem(rbm_eloc_sites_kernel<C>, smem);
+  rbm_eloc_sites_kernel<C><<<(unsigned)((h->K+C-1)/C), nwarps*32, smem, h->stream>>>(a);
 }
 
 void launch_eloc_fast(nqs_handle * h)
 {
   FastElocArgs a;
-  a.N = h->N; a.M = h->M; a.Mpad = h->mpad; a.K = h->K; a.ctab_a = h->ctab_a.p; a.ctab_b = h->ctab_b.p; a.aexp = h->aexp.p; a.spins = h->spins.p;
-  a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.Jmat = h->Jmat.p; a.hfield = h->cfg.h;
-  a.htilda = h->htilda.p;
-  switch (h->jpl)
-  {
-    case 1: launch_eloc_fast_t<1, 4>(h, a); break;
-    case 2: launch_eloc_fast_t<2, 4>(h, a); break;
-    case 4: launch_eloc_fast_t<4, 4>(h, a); break;
-    case 8: launch_eloc_fast_t<8, 2>(h, a); break;
-    default: launch_eloc_fast_t<16, 1>(h, a); break;
-  }
-  check_launch(h, "rbm_eloc_fast_kernel");
+  a.N = h->N; a.M = h->M; a.Npad = h->npad32; a.K = h->K; a.ctabT_a = h->ctabT_a.p; a.ctabT_b = h->ctabT_b.p; a.aexp = h->aexp.p;
+  a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.Jmat = h->Jmat.p;
+  a.hfield = h->cfg.h; a.htilda = h->htilda.p;
+  launch_eloc_sites_t<4>(h, a);
+  check_launch(h, "rbm_eloc_sites_kernel");
 }
 
 void launch_sweep(nqs_handle * h, long long nsteps)
@@ -319,7 +311,7 @@ void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
   if (lnpsi1 == nullptr && fast_path_ok(h))
   {
     launch_eloc_fast(h);
-    h->variant_eloc = "rbm_regs_j"+std::to_string(h->jpl);
+    h->variant_eloc = "rbm_sites_c4";
     return;
   }
   if (lnpsi1 == nullptr) h->variant_eloc = "generic";
@@ -638,7 +630,9 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
       while (32*jpl < h->M) jpl <<= 1;
       h->jpl = jpl; h->mpad = 32*jpl;
       const size_t nm = (size_t)h->N*h->mpad;
-      h->ftab_a.alloc(nm); h->ftab_b.alloc(nm); h->ctab_a.alloc(nm); h->ctab_b.alloc(nm); h->w2.alloc(nm); h->afac.alloc((size_t)2*h->N); h->aexp.alloc((size_t)2*h->N); h->bound.alloc(1);
+      h->ftab_a.alloc(nm); h->ftab_b.alloc(nm); h->ctab_a.alloc(nm); h->ctab_b.alloc(nm);
+      h->npad32 = ((h->N+31)/32)*32;
+      h->ctabT_a.alloc((size_t)h->M*h->npad32); h->ctabT_b.alloc((size_t)h->M*h->npad32); h->w2.alloc(nm); h->afac.alloc((size_t)2*h->N); h->aexp.alloc((size_t)2*h->N); h->bound.alloc(1);
     }
     NQS_CUDA(cudaMemset(h->params.p, 0, sizeof(cd)*h->P));
     NQS_CUDA(cudaMemset(h->spins.p, 0, KN));   // like the reference's zero-initialised spinStates_dev_

@@ -60,12 +60,12 @@ struct nqs_handle
   nqs::DevBuf<unsigned char> acc_log, fresh;
   // specialised RBM path: flip tables rebuilt after every parameter change (fast_kernels.cuh)
   nqs::DevBuf<nqs::FlipTab> ftab_a, ftab_b;
-  nqs::DevBuf<nqs::CoshTab> ctab_a, ctab_b;
+  nqs::DevBuf<nqs::CoshTab> ctab_a, ctab_b, ctabT_a, ctabT_b;
   nqs::DevBuf<nqs::cd> w2, aexp;
   nqs::DevBuf<double> afac, bound;
   bool tables_valid = false;
   double theta_bound = 0.0;
-  int jpl = 0, mpad = 0;
+  int jpl = 0, mpad = 0, npad32 = 0;
   long long u_steps = 0, u_used = 0;      // pre-drawn feed: proposals available / consumed
   long long acc_log_steps = 0;
   int pos = 0;                            // next position in the site ring

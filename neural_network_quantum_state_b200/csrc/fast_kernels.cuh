@@ -32,6 +32,7 @@ __device__ __forceinline__ double2 ld_tab(const double2 * p) { return __ldg(p); 
 // tables [N][Mpad] (Mpad = 32*JPL, neutral padding), rebuilt after every parameter change
 __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpad, const cd * __restrict__ params,
   FlipTab * __restrict__ ftab_a, FlipTab * __restrict__ ftab_b, CoshTab * __restrict__ ctab_a, CoshTab * __restrict__ ctab_b,
+  CoshTab * __restrict__ ctabT_a, CoshTab * __restrict__ ctabT_b, const int Npad,
   cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp)
 {
   const cd * W = params;
@@ -49,6 +50,18 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     ftab_a[idx] = make_double2(emx, ex); ftab_b[idx] = make_double2(co, s);
     ctab_a[idx] = make_double2(ch*co, sh*s); ctab_b[idx] = make_double2(sh*co, ch*s);
     w2[idx] = cmake(2.0*w.x, 2.0*w.y);
+    if (j < M)
+    {
+      ctabT_a[(size_t)j*Npad+i] = make_double2(ch*co, sh*s);
+      ctabT_b[(size_t)j*Npad+i] = make_double2(sh*co, ch*s);
+    }
+  }
+  // neutral padding of the transposed tables (sites N..Npad-1): cosh = 1, sinh = 0
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < (long long)M*(Npad-N); idx += (long long)gridDim.x*blockDim.x)
+  {
+    const int j = (int)(idx/(Npad-N)), i = N+(int)(idx-(long long)j*(Npad-N));
+    ctabT_a[(size_t)j*Npad+i] = make_double2(1.0, 0.0);
+    ctabT_b[(size_t)j*Npad+i] = make_double2(0.0, 0.0);
   }
   for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < N; i += gridDim.x*blockDim.x)
   {
@@ -361,19 +374,22 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Local energy, RBM:  psi(s^(i))/psi(s) = prod_j [cosh(2W_ij) - s_i tanh(theta_j) sinh(2W_ij)] * exp(-2 s_i a_i)
-// (cosh(t - 2sW) = cosh t cosh 2W - s sinh t sinh 2W).  tanh(theta_j) is computed once per (chain, j) and stays in
-// registers; each of the N ratios costs 8 fp64 FMAs per hidden unit.  The reference evaluates N full forward(i) passes
-// (k3+k4+c1) + k11 per call (impl_hamiltonians.cuh:233-238).  The tracked lnpsi0 enters as in the reference:
-// exp(lnpsi' - lnpsi0) = ratio * exp(lnpsi(theta) - lnpsi0); the second factor is 1 for chains flagged fresh and is
-// evaluated explicitly (M log cosh) only for stale ones.
+// (cosh(t - 2sW) = cosh t cosh 2W - s sinh t sinh 2W).  The N flips of a configuration are independent, so LANES RUN OVER
+// SITES: lane l of a warp owns site i = 32*block + l and walks all hidden units j serially, multiplying its own complex
+// product -- no cross-lane reduction per flip at all.  tanh(theta_j) of the CTA's C chains sits in shared memory (one
+// broadcast LDS per (j, chain)); the table is stored TRANSPOSED ([j][i], i contiguous) so that each (j, 32 sites) access is a
+// coalesced LDG.128 shared by the C chains.  8 fp64 FMAs per (site, hidden unit, chain).  The reference evaluates N full
+// forward(i) passes (k3+k4+c1) + k11 per call (impl_hamiltonians.cuh:233-238).  The tracked lnpsi0 enters as in the
+// reference: exp(lnpsi' - lnpsi0) = ratio * exp(lnpsi(theta) - lnpsi0); the second factor is 1 for chains flagged fresh and
+// is evaluated explicitly (M log cosh) only for stale ones.
 // ---------------------------------------------------------------------------------------------------------------------
 struct FastElocArgs
 {
-  int N, M, Mpad;
+  int N, M, Npad;            // Npad = N rounded up to 32 (neutral table padding)
   long long K;
-  const CoshTab * ctab_a;
-  const CoshTab * ctab_b;
-  const cd * aexp;
+  const CoshTab * ctabT_a;   // [M][Npad] cosh(2 W_ij)
+  const CoshTab * ctabT_b;   // [M][Npad] sinh(2 W_ij)
+  const cd * aexp;           // [N][2] exp(-+2 a_i)
   const int8_t * spins;
   const cd * theta;
   const cd * lnpsi0;
@@ -384,56 +400,57 @@ struct FastElocArgs
   cd * htilda;
 };
 
-template <int JPL, int C>
-__global__ void __launch_bounds__(128) rbm_eloc_fast_kernel(const FastElocArgs a)
+inline size_t fast_eloc_smem_bytes(int N, int M, int C)
+{
+  const size_t npad = (size_t)((N+15)/16)*16;
+  return (size_t)C*M*sizeof(cd)+(size_t)C*npad+(size_t)C*8*6*sizeof(double)+16;
+}
+
+__device__ __forceinline__ double flip_sign(const double v, const int mask)
+{ // v * (+-1) as one integer XOR on the sign bit
+  return __hiloint2double(__double2hiint(v)^mask, __double2loint(v));
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
-  const int N = a.N, M = a.M, Mpad = a.Mpad;
+  const int N = a.N, M = a.M, Npad = a.Npad;
   const int npad = ((N+15)/16)*16;
-  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*C*npad;
-  const long long kbase = ((long long)blockIdx.x*warps+w)*C;
-  if (kbase >= a.K) return;
-  bool valid[C];
-  cd T[C][JPL];
-  cd corr[C];
+  const int nwarps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  cd * Tsh = reinterpret_cast<cd*>(smem_raw);                                   // [C][M] tanh(theta)
+  int8_t * sp = reinterpret_cast<int8_t*>(Tsh+(size_t)C*M);                     // [C][npad]
+  double * red = reinterpret_cast<double*>(smem_raw+(size_t)C*M*sizeof(cd)+(size_t)C*npad); // [C][8 warps][4]
+  const long long kbase = (long long)blockIdx.x*C;
+  // ---- phase 0: tanh(theta), spins, staleness
   bool stale = false;
 #pragma unroll
   for (int c = 0; c < C; ++c)
   {
-    valid[c] = (kbase+c < a.K);
-    const long long k = valid[c] ? kbase+c : kbase;
-    for (int i = lane; i < N; i += 32) sp[c*npad+i] = a.spins[k*N+i];
+    const long long k = (kbase+c < a.K) ? kbase+c : kbase;
     stale = stale || (a.fresh[k] == 0);
-    corr[c] = cmake(1.0, 0.0);
   }
+  double ls_x[C], ls_y[C];
 #pragma unroll
   for (int c = 0; c < C; ++c)
   {
-    const long long k = valid[c] ? kbase+c : kbase;
-    cd lsum = cmake(0.0, 0.0);
-#pragma unroll
-    for (int jj = 0; jj < JPL; ++jj)
+    const long long k = (kbase+c < a.K) ? kbase+c : kbase;
+    ls_x[c] = 0.0; ls_y[c] = 0.0;
+    for (int j = threadIdx.x; j < M; j += blockDim.x)
     {
-      const int j = lane+32*jj;
-      cd th = cmake(0.0, 0.0);
-      if (j < M) th = a.theta[k*M+j];
-      T[c][jj] = c_tanh(th);
-      if (stale && j < M) lsum = cadd(lsum, c_logcosh(th));
+      const cd th = a.theta[k*M+j];
+      Tsh[c*M+j] = c_tanh(th);
+      if (stale) { const cd lc = c_logcosh(th); ls_x[c] += lc.x; ls_y[c] += lc.y; }
     }
-    if (stale)
-    { // exp(lnpsi(theta) - lnpsi0_tracked): != 1 only right after warm_up's quirk flip or a parameter update
-      lsum = warp_sum(lsum);
-      const cd l0 = a.lnpsi0[k], s0 = a.sa[k];
-      corr[c] = c_exp(cmake(lsum.x+s0.x-l0.x, lsum.y+s0.y-l0.y));
-    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sp[c*npad+i] = a.spins[k*N+i];
   }
-  __syncwarp();
-  // 1/2 sum_ij s_i J_ij s_j   (ref c5 + k10, impl_hamiltonians.cuh:226-231,871-887)
-  double diag[C];
+  __syncthreads();
+  // ---- phase 1: per-thread partial sums: [0] diag, [1..2] sum_i ratio_i, and (stale only) [3..] log cosh sums
+  double part_d[C], part_x[C], part_y[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) diag[c] = 0.0;
-  for (int i = lane; i < N; i += 32)
+  for (int c = 0; c < C; ++c) { part_d[c] = 0.0; part_x[c] = 0.0; part_y[c] = 0.0; }
+  // 1/2 sum_ij s_i J_ij s_j  (ref c5 + k10, impl_hamiltonians.cuh:226-231,871-887): threads over i
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
   {
     const double * Jrow = a.Jmat+(size_t)i*N;
     double sj[C];
@@ -441,65 +458,109 @@ __global__ void __launch_bounds__(128) rbm_eloc_fast_kernel(const FastElocArgs a
     for (int c = 0; c < C; ++c) sj[c] = 0.0;
     for (int j = 0; j < N; ++j)
     {
-      const double Jv = Jrow[j];
+      const double Jv = __ldg(Jrow+j);
 #pragma unroll
       for (int c = 0; c < C; ++c) sj[c] = fma(Jv, (double)sp[c*npad+j], sj[c]);
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) diag[c] = fma(sj[c], (double)sp[c*npad+i], diag[c]);
+    for (int c = 0; c < C; ++c) part_d[c] = fma(sj[c], (double)sp[c*npad+i], part_d[c]);
   }
-  cd hsum[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) hsum[c] = cmake(0.0, 0.0);
-  for (int site = 0; site < N; ++site)
+  // N single-flip ratios: warp w takes site blocks w, w+nwarps, ...
+  for (int sb = w; sb*32 < N; sb += nwarps)
   {
-    const CoshTab * crow_a = a.ctab_a+(size_t)site*Mpad;
-    const CoshTab * crow_b = a.ctab_b+(size_t)site*Mpad;
-    cd pr[C];
-    double sig[C];
+    const int i = sb*32+lane;
+    const bool ok = (i < N);
+    int smask[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { pr[c] = cmake(1.0, 0.0); sig[c] = (double)sp[c*npad+site]; }
+    for (int c = 0; c < C; ++c) smask[c] = (ok && sp[c*npad+i] < 0) ? (int)0x80000000 : 0;
+    double p0x[C], p0y[C], p1x[C], p1y[C];
 #pragma unroll
-    for (int jj = 0; jj < JPL; ++jj)
+    for (int c = 0; c < C; ++c) { p0x[c] = 1.0; p0y[c] = 0.0; p1x[c] = 1.0; p1y[c] = 0.0; }
+    const CoshTab * ca = a.ctabT_a+sb*32+lane;
+    const CoshTab * cb = a.ctabT_b+sb*32+lane;
+    int j = 0;
+    for (; j+1 < M; j += 2)
     {
-      const double2 cc = ld_tab(crow_a+lane+32*jj), ss = ld_tab(crow_b+lane+32*jj);
+      const double2 c0 = ld_tab(ca+(size_t)j*Npad), s0 = ld_tab(cb+(size_t)j*Npad);
+      const double2 c1 = ld_tab(ca+(size_t)(j+1)*Npad), s1 = ld_tab(cb+(size_t)(j+1)*Npad);
 #pragma unroll
       for (int c = 0; c < C; ++c)
       {
-        const double tr = sig[c]*T[c][jj].x, ti = sig[c]*T[c][jj].y;
-        // f = cosh2W - (s tanh) sinh2W
-        const double fr = fma(ti, ss.y, fma(-tr, ss.x, cc.x));
-        const double fi = fma(-ti, ss.x, fma(-tr, ss.y, cc.y));
-        const double nr = fma(pr[c].x, fr, -pr[c].y*fi);
-        const double ni = fma(pr[c].x, fi, pr[c].y*fr);
-        pr[c].x = nr; pr[c].y = ni;
+        const cd t0 = Tsh[c*M+j], t1 = Tsh[c*M+j+1];
+        { // f = cosh2W - (s tanh) sinh2W ; p0 *= f
+          const double tr = flip_sign(t0.x, smask[c]), ti = flip_sign(t0.y, smask[c]);
+          const double fr = fma(ti, s0.y, fma(-tr, s0.x, c0.x));
+          const double fi = fma(-ti, s0.x, fma(-tr, s0.y, c0.y));
+          const double nr = fma(p0x[c], fr, -p0y[c]*fi), ni = fma(p0x[c], fi, p0y[c]*fr);
+          p0x[c] = nr; p0y[c] = ni;
+        }
+        {
+          const double tr = flip_sign(t1.x, smask[c]), ti = flip_sign(t1.y, smask[c]);
+          const double fr = fma(ti, s1.y, fma(-tr, s1.x, c1.x));
+          const double fi = fma(-ti, s1.x, fma(-tr, s1.y, c1.y));
+          const double nr = fma(p1x[c], fr, -p1y[c]*fi), ni = fma(p1x[c], fi, p1y[c]*fr);
+          p1x[c] = nr; p1y[c] = ni;
+        }
       }
     }
+    if (j < M)
+    {
+      const double2 c0 = ld_tab(ca+(size_t)j*Npad), s0 = ld_tab(cb+(size_t)j*Npad);
 #pragma unroll
-    for (int c = 0; c < C; ++c)
+      for (int c = 0; c < C; ++c)
+      {
+        const cd t0 = Tsh[c*M+j];
+        const double tr = flip_sign(t0.x, smask[c]), ti = flip_sign(t0.y, smask[c]);
+        const double fr = fma(ti, s0.y, fma(-tr, s0.x, c0.x));
+        const double fi = fma(-ti, s0.x, fma(-tr, s0.y, c0.y));
+        const double nr = fma(p0x[c], fr, -p0y[c]*fi), ni = fma(p0x[c], fi, p0y[c]*fr);
+        p0x[c] = nr; p0y[c] = ni;
+      }
+    }
+    if (ok)
     {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
+      for (int c = 0; c < C; ++c)
       {
-        const double orr = __shfl_xor_sync(0xffffffffu, pr[c].x, o), oi = __shfl_xor_sync(0xffffffffu, pr[c].y, o);
-        const double nr = fma(pr[c].x, orr, -pr[c].y*oi);
-        const double ni = fma(pr[c].x, oi, pr[c].y*orr);
-        pr[c].x = nr; pr[c].y = ni;
+        const cd pr = cmul(cmake(p0x[c], p0y[c]), cmake(p1x[c], p1y[c]));
+        const cd ae = a.aexp[2*i+(smask[c] ? 1 : 0)];
+        const cd ratio = cmul(pr, ae);
+        part_x[c] += ratio.x; part_y[c] += ratio.y;
       }
-      const cd ae = a.aexp[2*site+(sig[c] > 0.0 ? 0 : 1)];
-      const cd ratio = cmul(pr[c], ae);
-      hsum[c] = cadd(hsum[c], ratio);
     }
   }
+  // ---- phase 2: block reduction (fixed order) and output
 #pragma unroll
   for (int c = 0; c < C; ++c)
   {
-    const double dg = 0.5*warp_sum(diag[c]);
-    if (lane == 0 && valid[c])
+    const double d = warp_sum(part_d[c]), x = warp_sum(part_x[c]), y = warp_sum(part_y[c]);
+    const double lx = stale ? warp_sum(ls_x[c]) : 0.0, ly = stale ? warp_sum(ls_y[c]) : 0.0;
+    if (lane == 0)
     {
-      const cd off = cmul(hsum[c], corr[c]);
-      a.htilda[kbase+c] = cmake((dg+a.hfield*off.x)/(double)N, (a.hfield*off.y)/(double)N);
+      double * r = red+((size_t)c*8+w)*4;
+      r[0] = d; r[1] = x; r[2] = y;
+      red[(size_t)C*8*4+((size_t)c*8+w)*2] = lx; red[(size_t)C*8*4+((size_t)c*8+w)*2+1] = ly;
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < C && kbase+threadIdx.x < a.K)
+  {
+    const int c = threadIdx.x;
+    double d = 0, x = 0, y = 0, lx = 0, ly = 0;
+    for (int ww = 0; ww < nwarps; ++ww)
+    {
+      const double * r = red+((size_t)c*8+ww)*4;
+      d += r[0]; x += r[1]; y += r[2];
+      lx += red[(size_t)C*8*4+((size_t)c*8+ww)*2]; ly += red[(size_t)C*8*4+((size_t)c*8+ww)*2+1];
+    }
+    cd off = cmake(x, y);
+    if (stale)
+    { // exp(lnpsi(theta) - lnpsi0_tracked): != 1 only right after warm_up's quirk flip or a parameter update
+      const long long k = kbase+c;
+      const cd l0 = a.lnpsi0[k], s0 = a.sa[k];
+      off = cmul(off, c_exp(cmake(lx+s0.x-l0.x, ly+s0.y-l0.y)));
+    }
+    a.htilda[kbase+c] = cmake((0.5*d+a.hfield*off.x)/(double)N, (a.hfield*off.y)/(double)N);
   }
 }
 } // namespace nqs
