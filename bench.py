@@ -45,10 +45,8 @@ UNIT = "samples/s"
 
 def synthetic_params(model: str, N: int, M: int, cfg_id: int) -> np.ndarray:
     """Reference init law (gpu/include/impl_neural_quantum_state.cuh:30-48 / :766-783) from numpy seed 20261018+cfg."""
-    from oracle import nqs_oracle as o   # only the parameter initialiser is used here (input generation, not compute)
-    rng = np.random.default_rng(20261018 + cfg_id)
-    m = o.make_ansatz(model, N, M, 1, rng)
-    return m.variables.copy()
+    from neural_network_quantum_state_b200.init import reference_init
+    return reference_init(model, N, M, np.random.default_rng(20261018 + cfg_id))
 
 
 class ClockSampler:
@@ -184,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
+    ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
 
@@ -231,7 +230,8 @@ def main():
     assert K_total % world == 0
     K_loc = K_total // world
     e = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
-               n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic)
+               n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic,
+               two_pass_sv=args.two_pass_sv)
     e.set_params(synthetic_params(model, N, M, cfg_id))
     if world > 1:
         ids = [Engine.comm_unique_id() if rank == 0 else None]
@@ -313,20 +313,30 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel pair: the two streaming passes over O inside every CG iteration
+    # ---- roofline of the dominant kernel: the pass(es) over O inside every CG iteration (HBM-bound)
     peak, peak_src = measured_peak_gbs()
-    bytes_per_launch = K_loc * P * 16.0
-    dom = "matvec_cols_partial_kernel" if phase["cols_ms"] >= phase["rows_ms"] else "matvec_rows_kernel"
-    dom_ms = (phase["cols_ms"] / max(counts["cols_count"], 1)) if dom.startswith("matvec_cols") else \
-             (phase["rows_ms"] / max(counts["rows_count"], 1))
+    bytes_per_launch = K_loc * P * 16.0     # one read of this rank's O [K_loc][P] complex fp64
+    sv_variant = e.kernel_variant("sv")
+    if sv_variant.startswith("fused"):
+        # one-pass cluster kernel: O is read from HBM once per S*v (the reference and the two-pass kernels read it twice)
+        dom, dom_ms, n_timed = "sv_fused_kernel", phase["rows_ms"] / max(counts["rows_count"], 1), counts["rows_count"]
+        other = None
+    else:
+        dom = "matvec_cols_partial_kernel" if phase["cols_ms"] >= phase["rows_ms"] else "matvec_rows_kernel"
+        is_cols = dom.startswith("matvec_cols")
+        dom_ms = (phase["cols_ms"] / max(counts["cols_count"], 1)) if is_cols else (phase["rows_ms"] / max(counts["rows_count"], 1))
+        n_timed = counts["cols_count"] if is_cols else counts["rows_count"]
+        other = {"kernel": "matvec_rows_kernel" if is_cols else "matvec_cols_partial_kernel",
+                 "avg_launch_ms": (phase["rows_ms"] / max(counts["rows_count"], 1)) if is_cols
+                 else (phase["cols_ms"] / max(counts["cols_count"], 1))}
     achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": committed_traffic(dom),
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms,
-                "launches_timed": counts["cols_count"] if dom.startswith("matvec_cols") else counts["rows_count"],
-                "other_pass": {"kernel": "matvec_rows_kernel" if dom.startswith("matvec_cols") else "matvec_cols_partial_kernel",
-                               "avg_launch_ms": (phase["rows_ms"] / max(counts["rows_count"], 1)) if dom.startswith("matvec_cols")
-                               else (phase["cols_ms"] / max(counts["cols_count"], 1))}}
+    roofline = {"bound": "hbm", "kernel": dom, "variant": sv_variant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": committed_traffic(dom),
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms, "launches_timed": n_timed,
+                "note": "achieved = K_loc*P*16 B (O read once) / CUDA-event duration of the launch; SURVEY 8d's two-pass figure "
+                        "B_cg = 2*K_loc*P*16 per S*v is met with %s pass(es) over O" % ("1" if other is None else "2")}
+    if other is not None:
+        roofline["other_pass"] = other
     sweep_ms = phase["sweep_ms"] / args.steps
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",

@@ -77,6 +77,7 @@ typedef struct nqs_config {
 #define NQS_FLAG_NO_SR        1  /* sampler only (pynqs use): do not allocate O [K][P] nor the CG vectors */
 #define NQS_FLAG_ACCEPT_LOG   2  /* keep accept masks of the most recent nqs_do_mcmc_steps/nqs_warm_up call (tests) */
 #define NQS_FLAG_FORCE_GENERIC 4 /* use the generic (direct log cosh) kernels even where a specialised one exists */
+#define NQS_FLAG_TWO_PASS_SV  8  /* S*v as two streaming passes over O (reference structure) instead of the one-pass cluster kernel */
 
 /* statistics of one SR iteration.  ref: the row printed by propagate, gpu/include/optimizer.cuh:156-159 */
 typedef struct nqs_sr_stats {
@@ -106,6 +107,18 @@ void nqs_destroy(nqs_handle * h);
 const char * nqs_last_error(const nqs_handle * h);
 int32_t nqs_abi_version(void);
 nqs_status nqs_sync(nqs_handle * h); /* cudaStreamSynchronize of the handle's stream */
+/* The reference builds the ansatz first and hands it to the Hamiltonian/sampler and to the optimizer later
+ * (gpu/src/LICH-train_rbm.cu:90-101); these three let a host mirror that order on one handle:
+ *   nqs_set_hamiltonian  ref: LITFIChain ctor (h, J, alpha, isPBC) gpu/include/impl_hamiltonians.cuh:118-183 (J matrix, site ring)
+ *   nqs_set_seed         ref: seedNumber of BaseParallelSampler (impl_mcmc_sampler.cuh:6-15); restarts the proposal counter
+ *   nqs_enable_sr        ref: StochasticReconfigurationCG ctor (impl_optimizer.cuh:45-64): allocates O [K][P] + CG vectors on a
+ *                        handle created with NQS_FLAG_NO_SR (no-op otherwise) */
+nqs_status nqs_set_hamiltonian(nqs_handle * h, double hfield, double J, double alpha, int32_t pbc, int32_t order);
+nqs_status nqs_set_seed(nqs_handle * h, uint64_t seed);
+nqs_status nqs_enable_sr(nqs_handle * h);
+/* a NEW optimizer object in the reference starts with bp_ = 1 (lambda schedule) and dx = 0 (CG warm start),
+ * gpu/include/impl_optimizer.cuh:45-64 */
+nqs_status nqs_sr_reset(nqs_handle * h);
 
 /* ---- parameters.  Layout = reference `variables_`: RBM [W (i*M+j) | a | b]  (gpu/include/impl_neural_quantum_state.cuh:33-38),
  *      FFNN [W1 (i*M+j) | b1 | w1o] (:772-776).  P = N*M+N+M resp. N*M+2M. ------------------------------------------------ */
@@ -174,7 +187,7 @@ nqs_status nqs_set_timing(nqs_handle * h, int32_t enabled);
 /* CUDA events on the handle's stream for callers that time several calls as one region (slot 0..7) */
 nqs_status nqs_event_record(nqs_handle * h, int32_t slot);
 nqs_status nqs_event_elapsed_ms(nqs_handle * h, int32_t slot_begin, int32_t slot_end, float * ms); /* synchronises slot_end */
-/* name of the sweep kernel variant in use ("generic", "rbm_regs", ...) */
+/* name of the kernel variant in use for stage "sweep" | "eloc" | "theta" | "sv" ("generic", "rbm_regs_j8", "fused_cs8_cpt8", ...) */
 const char * nqs_kernel_variant(const nqs_handle * h, const char * stage);
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ STATUS_NAMES = ["NQS_OK", "NQS_ERR_INVALID", "NQS_ERR_CUDA", "NQS_ERR_NOMEM", "N
                 "NQS_ERR_NCCL", "NQS_ERR_NONFINITE", "NQS_ERR_UNSUPPORTED"]
 MODEL_RBM, MODEL_FFNN = 0, 1
 ORDER_CHECKERBOARD, ORDER_SEQUENTIAL = 0, 1
-FLAG_NO_SR, FLAG_ACCEPT_LOG, FLAG_FORCE_GENERIC = 1, 2, 4
+FLAG_NO_SR, FLAG_ACCEPT_LOG, FLAG_FORCE_GENERIC, FLAG_TWO_PASS_SV = 1, 2, 4, 8
 
 
 class Config(C.Structure):
@@ -49,6 +49,10 @@ SYMBOLS = {
     "nqs_last_error": (_cp, [_vp]),
     "nqs_abi_version": (_i32, []),
     "nqs_sync": (_i32, [_vp]),
+    "nqs_set_hamiltonian": (_i32, [_vp, _dbl, _dbl, _dbl, _i32, _i32]),
+    "nqs_set_seed": (_i32, [_vp, C.c_uint64]),
+    "nqs_enable_sr": (_i32, [_vp]),
+    "nqs_sr_reset": (_i32, [_vp]),
     "nqs_n_variables": (_i32, [_vp, C.POINTER(_i64)]),
     "nqs_set_params": (_i32, [_vp, _vp, _i64]),
     "nqs_get_params": (_i32, [_vp, _vp, _i64]),

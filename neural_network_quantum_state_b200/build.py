@@ -42,6 +42,43 @@ def _source_digest() -> str:
     return h.hexdigest()
 
 
+HOST = os.path.join(PKG_DIR, "host")
+BIN_DIR = os.path.join(PKG_DIR, "bin")
+# reference-compatible command-line programs (C++ host over the C ABI; ref gpu/src/LICH-train_rbm.cu)
+HOST_PROGRAMS = {
+    "LICH-train_rbm-gpu": ("LICH-train_rbm.cpp", []),
+    "LICH-train_ffnn-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_FFNN"]),
+}
+
+
+def _gxx() -> str:
+    for cand in ("/usr/bin/g++", shutil.which("g++")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("g++ not found (needed to build the host programs)")
+
+
+def build_host(force: bool = False) -> list:
+    """Compile the C++ host programs against libnqs_b200.so (rpath $ORIGIN/.. so they run from the tree on the GPU box)."""
+    os.makedirs(BIN_DIR, exist_ok=True)
+    out = []
+    for name, (src, defs) in HOST_PROGRAMS.items():
+        exe = os.path.join(BIN_DIR, name)
+        srcs = [os.path.join(HOST, f) for f in os.listdir(HOST)] + [LIB_PATH]
+        if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(f) for f in srcs):
+            out.append(exe)
+            continue
+        cmd = [_gxx(), "-O2", "-std=c++17", "-Wall"] + defs + ["-o", exe, os.path.join(HOST, src), "-L" + PKG_DIR, "-lnqs_b200",
+               "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath-link," + PKG_DIR]
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if proc.returncode != 0:
+            raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
+        out.append(exe)
+    return out
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB_PATH) or not os.path.exists(STAMP):
         return True
@@ -52,9 +89,10 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into libnqs_b200.so if the sources changed.  Returns the library path."""
     if not force and not needs_build():
+        build_host()
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-Xlinker", "-soname=libnqs_b200.so"]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image exports a wrapper g++ that nvcc must not pick up
     env.pop("CC", None)
@@ -65,6 +103,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stderr[-4000:]))
     with open(STAMP, "w") as f:
         f.write(_source_digest())
+    build_host(force=True)
     return LIB_PATH
 
 

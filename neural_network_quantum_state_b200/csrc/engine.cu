@@ -15,6 +15,7 @@
 #include "engine.h"
 #include "sampler_kernels.cuh"
 #include "sr_kernels.cuh"
+#include "sv_fused.cuh"
 
 using namespace nqs;
 
@@ -354,6 +355,90 @@ void launch_oderiv(nqs_handle * h)
   check_launch(h, "oderiv_kernel");
 }
 
+// ---- one-pass S*v (sv_fused.cuh): cluster launch + plan -------------------------------------------------------------------
+template <int CPT>
+cudaError_t sv_launch_t(const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * query_max_clusters)
+{
+  auto kern = sv_fused_kernel<CPT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cs > 8)
+  {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(cs*nclusters), 1, 1);
+  cfg.blockDim = dim3((unsigned)nt, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (query_max_clusters) return cudaOccupancyMaxActiveClusters(query_max_clusters, kern, &cfg);
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+cudaError_t sv_launch(int cpt, const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * q)
+{
+  switch (cpt)
+  {
+    case 1: return sv_launch_t<1>(a, cs, nclusters, nt, smem, stream, q);
+    case 2: return sv_launch_t<2>(a, cs, nclusters, nt, smem, stream, q);
+    case 3: return sv_launch_t<3>(a, cs, nclusters, nt, smem, stream, q);
+    case 4: return sv_launch_t<4>(a, cs, nclusters, nt, smem, stream, q);
+    case 5: return sv_launch_t<5>(a, cs, nclusters, nt, smem, stream, q);
+    case 6: return sv_launch_t<6>(a, cs, nclusters, nt, smem, stream, q);
+    case 7: return sv_launch_t<7>(a, cs, nclusters, nt, smem, stream, q);
+    case 8: return sv_launch_t<8>(a, cs, nclusters, nt, smem, stream, q);
+    case 9: return sv_launch_t<9>(a, cs, nclusters, nt, smem, stream, q);
+    case 10: return sv_launch_t<10>(a, cs, nclusters, nt, smem, stream, q);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// Pick cluster size / columns per thread / pipeline depth for this (K, P); leaves sv_ok false when the column slice of a
+// 16-CTA cluster still does not fit the register file (very large P: the two-pass kernels take over).
+void plan_sv(nqs_handle * h)
+{
+  h->sv_ok = false;
+  if (h->cfg.flags & NQS_FLAG_TWO_PASS_SV) return;
+  const int cs_try[2] = {8, 16};
+  for (int ci = 0; ci < 2; ++ci)
+  {
+    const int cs = cs_try[ci];
+    const long long pc = (h->P+cs-1)/cs;
+    int cpt = 0, nt = 0;
+    for (int c = 1; c <= NQS_SV_MAX_CPT; ++c)
+    {
+      const long long need = ((pc+c-1)/c+31)/32*32;
+      const int max_t = (c <= 3) ? 1024 : 512;
+      if (need <= max_t) { cpt = c; nt = (int)std::max<long long>(64, need); break; }
+    }
+    if (!cpt) continue;
+    const size_t slot_bytes = (size_t)((pc*(long long)sizeof(cd)+127)/128*128);
+    if (h->smem_optin < NQS_SV_TAIL_BYTES+2*slot_bytes) continue;
+    const int nslot = (int)std::min<size_t>(NQS_SV_MAX_SLOTS, (h->smem_optin-NQS_SV_TAIL_BYTES)/slot_bytes);
+    const size_t smem = (size_t)nslot*slot_bytes+NQS_SV_TAIL_BYTES;
+    SvArgs a;
+    std::memset(&a, 0, sizeof(a));
+    int maxc = 0;
+    cudaError_t e = sv_launch(cpt, a, cs, 1, nt, smem, h->stream, &maxc);
+    if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
+    long long ncl = std::min<long long>(maxc, h->K);
+    const long long rpc = (h->K+ncl-1)/ncl;
+    ncl = (h->K+rpc-1)/rpc;
+    h->sv_cs = cs; h->sv_cpt = cpt; h->sv_nt = nt; h->sv_nslot = nslot; h->sv_nclusters = (int)ncl;
+    h->sv_smem = smem; h->sv_slot_bytes = slot_bytes; h->sv_pc = pc; h->sv_rpc = rpc;
+    h->sv_ok = true;
+    h->variant_sv = "fused_cs"+std::to_string(cs)+"_cpt"+std::to_string(cpt)+"_nt"+std::to_string(nt)+"_slots"+std::to_string(nslot)+
+      "_clusters"+std::to_string(ncl);
+    return;
+  }
+}
+
 void allreduce_sum(nqs_handle * h, double * buf, size_t count)
 {
   if (h->comm == nullptr) return;
@@ -379,10 +464,25 @@ void sr_setup(nqs_handle * h, bool want_F)
   check_launch(h, "setup_finalize_kernel");
 }
 
-// traw = sum_k conj(O_kp) (O_k . v): the two streaming passes over O (+ all-reduce of 2P doubles)
+// traw = sum_k conj(O_kp) (O_k . v) (+ all-reduce of 2P doubles): one pass over O with the cluster kernel, else two passes
 void matvec_passes(nqs_handle * h, const cd * v, const int * done)
 {
   const long long P = h->P, K = h->K;
+  if (h->sv_ok)
+  {
+    SvArgs a;
+    a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
+    a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes;
+    {
+      Span sp(h, TAG_ROWS);
+      NQS_CUDA(sv_launch(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
+      check_launch(h, "sv_fused_kernel");
+    }
+    colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, h->sv_nclusters, h->part.p, h->traw.p, done);
+    check_launch(h, "colsum_reduce_kernel");
+    allreduce_sum(h, h->traw.p, (size_t)(2*P));
+    return;
+  }
   const unsigned gr = (unsigned)((K+NQS_ROWS_PER_CTA-1)/NQS_ROWS_PER_CTA);
   {
     Span sp(h, TAG_ROWS);
@@ -554,6 +654,30 @@ std::vector<std::complex<double> > download_params(nqs_handle * h)
   return v;
 }
 
+// O [K][P], the CG vectors and the reduction scratch (skipped for sampler-only handles until nqs_enable_sr)
+void alloc_sr(nqs_handle * h)
+{
+  if (h->O.p != nullptr) return;
+  const size_t KP = (size_t)h->K*(size_t)h->P;
+  h->O.alloc(KP);
+  h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
+  h->zk.alloc(h->K); h->diag.alloc(h->P);
+  const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
+  long long nrb = (2LL*16*h->sm_count+ctiles-1)/ctiles;
+  nrb = std::max<long long>(1, std::min<long long>(nrb, std::min<long long>(64, (h->K+63)/64)));
+  h->nrb = (int)nrb;
+  h->rows_per_block = (h->K+nrb-1)/nrb;
+  h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
+  plan_sv(h);
+  h->part.alloc(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P));
+  h->sums.alloc((size_t)5*h->P+3);
+  h->traw.alloc((size_t)2*h->P);
+  h->slots.alloc((size_t)5*NQS_VEC_MAX_CTAS);
+  h->scal.alloc(1);
+  NQS_CUDA(cudaMemset(h->scal.p, 0, sizeof(CgScalars)));
+  NQS_CUDA(cudaMemset(h->dx.p, 0, sizeof(cd)*h->P)); // CG warm start is zero only at construction (ref impl_optimizer.cuh:55)
+}
+
 struct ParamFile { const char * suffix; long long off, count, row; const char * name; };
 std::vector<ParamFile> param_files(const nqs_handle * h)
 { // ref save/load: RBM Dw/Da/Db (:225-232,281-286); FFNN Dw1/Dw2(=w1o)/Db1 (:931-937,985-991)
@@ -641,26 +765,7 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     NQS_CUDA(cudaMemset(h->sa.p, 0, sizeof(cd)*h->K));
     NQS_CUDA(cudaMemset(h->htilda.p, 0, sizeof(cd)*h->K));
     if (cfg->max_predrawn_steps > 0) h->uniforms.alloc((size_t)cfg->max_predrawn_steps*h->K);
-    if (!(cfg->flags & NQS_FLAG_NO_SR))
-    {
-      const size_t KP = (size_t)h->K*(size_t)h->P;
-      h->O.alloc(KP);
-      h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
-      h->zk.alloc(h->K); h->diag.alloc(h->P);
-      const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
-      long long nrb = (2LL*16*h->sm_count+ctiles-1)/ctiles;
-      nrb = std::max<long long>(1, std::min<long long>(nrb, std::min<long long>(64, (h->K+63)/64)));
-      h->nrb = (int)nrb;
-      h->rows_per_block = (h->K+nrb-1)/nrb;
-      h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
-      h->part.alloc((size_t)h->nrb*5*h->P);
-      h->sums.alloc((size_t)5*h->P+3);
-      h->traw.alloc((size_t)2*h->P);
-      h->slots.alloc((size_t)5*NQS_VEC_MAX_CTAS);
-      h->scal.alloc(1);
-      NQS_CUDA(cudaMemset(h->scal.p, 0, sizeof(CgScalars)));
-      NQS_CUDA(cudaMemset(h->dx.p, 0, sizeof(cd)*h->P)); // CG warm start is zero only at construction (ref impl_optimizer.cuh:55)
-    }
+    if (!(cfg->flags & NQS_FLAG_NO_SR)) alloc_sr(h);
     build_order(h);
     build_J(h);
     NQS_CUDA(cudaDeviceSynchronize());
@@ -1070,6 +1175,49 @@ nqs_status nqs_evolve(nqs_handle * h, const nqs_cdouble * dx, double lr)
   });
 }
 
+nqs_status nqs_enable_sr(nqs_handle * h)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]() { NQS_CUDA(cudaSetDevice(h->cfg.device)); alloc_sr(h); NQS_CUDA(cudaStreamSynchronize(h->stream)); });
+}
+
+nqs_status nqs_set_hamiltonian(nqs_handle * h, double hfield, double J, double alpha, int32_t pbc, int32_t order)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(!(pbc && h->N%2 == 1), NQS_ERR_INVALID, "kL%2 == 1 (set \"isPBC\" to \"false\".)"); // ref impl_hamiltonians.cuh:141-142
+    NQS_REQUIRE(order == NQS_ORDER_CHECKERBOARD || order == NQS_ORDER_SEQUENTIAL, NQS_ERR_INVALID, "nqs_set_hamiltonian: unknown order");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    h->cfg.h = hfield; h->cfg.J = J; h->cfg.alpha = alpha; h->cfg.pbc = pbc; h->cfg.order = order;
+    build_order(h);
+    build_J(h);
+    h->pos = 0;
+  });
+}
+
+nqs_status nqs_sr_reset(nqs_handle * h)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "nqs_sr_reset before nqs_enable_sr");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    h->bp = 1.0;
+    NQS_CUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(cd)*h->P, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+nqs_status nqs_set_seed(nqs_handle * h, uint64_t seed)
+{
+  if (!h) return NQS_ERR_INVALID;
+  h->cfg.seed = seed;
+  h->step_counter = 0;
+  return NQS_OK;
+}
+
 nqs_status nqs_comm_get_unique_id(char id[NQS_UNIQUE_ID_BYTES])
 {
   if (!id) return NQS_ERR_INVALID;
@@ -1136,6 +1284,7 @@ const char * nqs_kernel_variant(const nqs_handle * h, const char * stage)
   if (!std::strcmp(stage, "sweep")) return h->variant_sweep.c_str();
   if (!std::strcmp(stage, "eloc")) return h->variant_eloc.c_str();
   if (!std::strcmp(stage, "theta")) return h->variant_theta.c_str();
+  if (!std::strcmp(stage, "sv")) return h->variant_sv.c_str();
   return "";
 }
 } // extern "C"

@@ -81,6 +81,11 @@ struct nqs_handle
   int nrb = 1;                            // row blocks of the column passes
   long long rows_per_block = 0;
   void * pinned = nullptr;                // small pinned staging area for scalar read-backs
+  // one-pass S*v (sv_fused.cuh): cluster size, columns per thread, threads, TMA slots, clusters, rows per cluster
+  bool sv_ok = false;
+  int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0;
+  size_t sv_smem = 0, sv_slot_bytes = 0;
+  long long sv_pc = 0, sv_rpc = 0;
 
   // multi-GPU
   void * comm = nullptr;                  // ncclComm_t
@@ -96,5 +101,5 @@ struct nqs_handle
   std::vector<cudaEvent_t> evpool;        // events of the timed spans, resolved after the call's final sync
   size_t ev_used = 0;
   std::vector<Span> spans;
-  std::string variant_sweep = "generic", variant_eloc = "generic", variant_theta = "generic";
+  std::string variant_sweep = "generic", variant_eloc = "generic", variant_theta = "generic", variant_sv = "two_pass";
 };

@@ -1,0 +1,209 @@
+// One-pass S*v:  part[q][p] = sum_{k in rows of cluster q} conj(O_kp) (sum_p' O_kp' v_p')   with O read from HBM ONCE.
+//
+// ref: SMatrixForCG::dot, gpu/include/functor_for_CG.cuh:104-127 = c8 Zgemm(1xKxP) z = O v, then c9 Zgemv(PxK) O^H z: two
+// full passes over O (2*K*P*16 B per CG iteration).  z_k needs the WHOLE row k before O^H z can use it, and the column
+// accumulators of a full row (P*16 B = 530 KB at N=128, M=256) do not fit one SM, so a single CTA cannot fuse the two.
+// A thread-block CLUSTER can: the CS CTAs of a cluster split the columns, CTA r owns the slice [r*pc, (r+1)*pc) and keeps
+// its v slice and its column accumulators in REGISTERS (CPT columns per thread) for the whole launch.  For every row of the
+// cluster's row block:
+//   (1) the slice of row k arrives in shared memory by TMA (cp.async.bulk + mbarrier complete_tx), NSLOT rows deep, so the
+//       HBM stream never waits for the math;
+//   (2) every thread pulls its CPT elements of the row into registers and forms its part of O_k . v; warp shuffles + one
+//       __syncthreads give the CTA partial, which lane r of warp 0 sends into CTA r's shared memory over DSMEM with
+//       st.async (the store itself completes bytes on CTA r's mbarrier) -- no cluster-wide barrier in the loop;
+//   (3) after the mbarrier wait every CTA adds the CS partials in rank order (bit-identical z_k in all CTAs, fixed order =>
+//       run-to-run deterministic) and accumulates conj(O_kp) z_k from the registers it still holds.
+// The shared-memory slot is free again right after (2), so the TMA for row k+NSLOT is issued there.
+// HBM traffic: K*P*16 B per S*v instead of 2*K*P*16 B.  Cluster partials go to part[q][{re,im}][P] and are folded in fixed
+// order by colsum_reduce_kernel exactly like the two-pass kernels' row-block partials.
+#pragma once
+#include <cooperative_groups.h>
+#include "device_math.cuh"
+
+namespace nqs
+{
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t * bar, const uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, const uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, const uint32_t parity)
+{
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void * local, const uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+// 16-byte asynchronous store into a peer CTA's shared memory that completes 16 bytes of transaction count on the PEER's
+// mbarrier (st.async): data and signal travel together, so the consumer needs only the ordinary CTA-scope mbarrier wait.
+// (A release-arrive + acquire.cluster wait works too, but every acquire at cluster scope costs an L1 invalidate,
+// CCTL.IVALL, per polling thread -- 46 % of all stall samples in profiles/r1c_sv_fused_v1_summary.md.)
+__device__ __forceinline__ void st_async_remote_cd(const uint32_t remote_addr, const cd v, const uint32_t remote_bar)
+{
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
+    :: "r"(remote_addr), "d"(v.x), "d"(v.y), "r"(remote_bar) : "memory");
+}
+// 1-D TMA bulk copy global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void * dst, const void * src, const uint32_t bytes, uint64_t * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct SvArgs
+{
+  long long K, P;
+  const cd * O;            // [K][P]
+  const cd * v;            // [P]
+  double * part;           // [n_clusters][2][P]
+  const int * done;        // device flag: converged CG -> return immediately (may be nullptr)
+  long long pc;            // columns per CTA slice = ceil(P / cluster size)
+  long long rows_per_cluster;
+  int nslot;               // shared-memory row slots (TMA pipeline depth)
+  unsigned int slot_bytes; // bytes per slot (multiple of 128)
+};
+
+#define NQS_SV_MAX_CLUSTER 16
+#define NQS_SV_MAX_SLOTS 8
+// shared memory after the slots: red[32] | zbuf[2][16] | full[8] | zfull[2]
+#define NQS_SV_TAIL_BYTES (32*16+2*NQS_SV_MAX_CLUSTER*16+NQS_SV_MAX_SLOTS*8+2*8)
+
+// register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 1024 threads (8 warps per sub-partition x 64
+// registers), larger CPT up to 512 threads (4 warps per sub-partition x 128 registers)
+#define NQS_SV_MAX_CPT 10
+template <int CPT> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
+
+template <int CPT>
+__global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs a)
+{
+  if (a.done != nullptr && *a.done) return;   // uniform over the grid
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned int CS = cluster.num_blocks(), crank = cluster.block_rank();
+  const int NT = blockDim.x, tid = threadIdx.x, lane = tid&31, w = tid>>5, nw = NT>>5;
+  const long long cid = blockIdx.x/CS;
+  unsigned char * tail = smem_raw+(size_t)a.nslot*a.slot_bytes;
+  cd * red = reinterpret_cast<cd*>(tail);                                   // [32] warp partials
+  cd * zbuf = red+32;                                                       // [2][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
+  uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+2*NQS_SV_MAX_CLUSTER); // [NQS_SV_MAX_SLOTS] TMA arrival
+  uint64_t * zfull = full+NQS_SV_MAX_SLOTS;                                 // [2] all CS partials of a row arrived (tx bytes)
+
+  const long long c0 = (long long)crank*a.pc;
+  long long nr_ll = a.P-c0;
+  if (nr_ll > a.pc) nr_ll = a.pc;
+  if (nr_ll < 0) nr_ll = 0;
+  const int n_r = (int)nr_ll;                                               // columns of this CTA's slice
+  const long long k0 = cid*a.rows_per_cluster;
+  long long k1 = k0+a.rows_per_cluster;
+  if (k1 > a.K) k1 = a.K;
+  const int nrows = (k1 > k0) ? (int)(k1-k0) : 0;
+  const uint32_t row_bytes = (uint32_t)n_r*(uint32_t)sizeof(cd);
+
+  if (tid == 0)
+  {
+    for (int s = 0; s < a.nslot; ++s) mbar_init(full+s, 1);
+    mbar_init(zfull, 1); mbar_init(zfull+1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster.sync();   // every CTA's barriers exist before anybody arrives on them
+
+  cd vr[CPT], acc[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+  {
+    const int idx = c*NT+tid;
+    vr[c] = (idx < n_r) ? a.v[c0+idx] : cmake(0.0, 0.0);
+    acc[c] = cmake(0.0, 0.0);
+  }
+  const cd * Oslice = a.O+c0;
+  if (tid == 0 && n_r > 0)
+    for (int s = 0; s < a.nslot && s < nrows; ++s)
+    {
+      mbar_expect_tx(full+s, row_bytes);
+      tma_load_1d(smem_raw+(size_t)s*a.slot_bytes, Oslice+(k0+s)*a.P, row_bytes, full+s);
+    }
+
+  int slot = 0;
+  uint32_t full_par = 0;
+  for (int it = 0; it < nrows; ++it)
+  {
+    // ---- (2) row slice -> registers, partial O_k . v
+    cd o[CPT];
+    double px = 0.0, py = 0.0;
+    if (n_r > 0)
+    {
+      mbar_wait(full+slot, full_par);
+      const cd * srow = reinterpret_cast<const cd*>(smem_raw+(size_t)slot*a.slot_bytes);
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+      {
+        const int idx = c*NT+tid;
+        o[c] = (idx < n_r) ? srow[idx] : cmake(0.0, 0.0);
+        px = fma(o[c].x, vr[c].x, px); px = fma(-o[c].y, vr[c].y, px);
+        py = fma(o[c].x, vr[c].y, py); py = fma(o[c].y, vr[c].x, py);
+      }
+    }
+    else
+    {
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) o[c] = cmake(0.0, 0.0);
+    }
+    px = warp_sum(px); py = warp_sum(py);
+    if (lane == 0) red[w] = cmake(px, py);
+    __syncthreads();                 // warp partials visible; everybody is done reading the slot
+    if (tid == 0 && n_r > 0 && it+a.nslot < nrows)
+    {
+      mbar_expect_tx(full+slot, row_bytes);
+      tma_load_1d(smem_raw+(size_t)slot*a.slot_bytes, Oslice+(k0+it+a.nslot)*a.P, row_bytes, full+slot);
+    }
+    const int zp = it&1;
+    if (w == 0)
+    {
+      cd s = (lane < nw) ? red[lane] : cmake(0.0, 0.0);
+      s = warp_sum(s);               // fixed butterfly order
+      if (lane == 0) mbar_expect_tx(zfull+zp, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
+      if (lane < (int)CS)
+        st_async_remote_cd(map_to_rank(zbuf+zp*NQS_SV_MAX_CLUSTER+crank, (uint32_t)lane), s, map_to_rank(zfull+zp, (uint32_t)lane));
+    }
+    // ---- (3) z_k = sum over the cluster in rank order, then conj(O_kp) z_k from registers
+    mbar_wait(zfull+zp, (uint32_t)((it>>1)&1));
+    double zx = 0.0, zy = 0.0;
+    for (unsigned int r = 0; r < CS; ++r)
+    {
+      const cd t = zbuf[zp*NQS_SV_MAX_CLUSTER+r];
+      zx += t.x; zy += t.y;
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+    {
+      acc[c].x = fma(o[c].x, zx, acc[c].x); acc[c].x = fma(o[c].y, zy, acc[c].x);
+      acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
+    }
+    if (++slot == a.nslot) { slot = 0; full_par ^= 1u; }
+  }
+  double * base = a.part+(size_t)cid*2*(size_t)a.P;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+  {
+    const int idx = c*NT+tid;
+    if (idx < n_r) { base[c0+idx] = acc[c].x; base[a.P+c0+idx] = acc[c].y; }
+  }
+  cluster.sync();   // no CTA may exit while a peer can still write into its shared memory
+}
+} // namespace nqs

@@ -1,0 +1,88 @@
+"""`_pynqs_gpu`: the extension-module surface of the reference's Python binding, served by libnqs_b200.so through ctypes.
+
+ref: PYBIND11_MODULE(_pynqs_gpu, m) and PySampler<ansatz, T>, gpu/src/pywrapping_sampler.cu:9-18,29-132.  Each class takes the
+same kwargs dict {nInputs, nHiddens, nChains, seedNumber, seedDistance} and offers load / warm_up / do_mcmc_steps /
+get_spinStates / get_lnpsi / get_lnpsi_for_fixed_spins with the reference's shapes and dtypes.
+
+Like PySampler it holds TWO ansatz instances: nqs0 is sampled by Sampler4SpinHalf (sequential site order 1,2,..,N-1,0,
+gpu/include/impl_meas.cuh:12-21,33-34), nqs1 evaluates given configurations with forward(spins, lnpsi, saveSpinStates=false).
+nqs1's own spin register is never set (all zero, as the reference's zero-initialised device vector), so the plain RBM's
+visible-bias term -- computed from the MEMBER spins, ref impl_neural_quantum_state.cuh:119-120 -- contributes nothing there;
+that reference quirk is kept bit for bit.
+
+In scope natively: dRBMSampler, dFFNNSampler (fp64, the arithmetic type of the engine).  The float32 and symmetric variants
+exist as names and raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ..engine import Engine
+
+
+class _PySampler:
+    _model = "rbm"
+
+    def __init__(self, kwargs: dict):
+        self._N, self._M, self._K = int(kwargs["nInputs"]), int(kwargs["nHiddens"]), int(kwargs["nChains"])
+        self._seed, self._seed_distance = int(kwargs["seedNumber"]), int(kwargs["seedDistance"])
+        dev = int(kwargs.get("device", 0))
+        # Sampler4SpinHalf has no Hamiltonian: h = J = 0; sequential order; O / CG buffers are not allocated
+        mk = lambda: Engine(self._model, self._N, self._M, self._K, 0.0, 0.0, 0.0, order="sequential", seed=self._seed,
+                            device=dev, sampler_only=True)
+        self._nqs0, self._nqs1 = mk(), mk()
+        # the reference ctor draws clock-seeded random parameters for both instances (load() normally overrides them)
+        self._nqs0.init_params_random(self._seed * 2 + 1)
+        self._nqs1.init_params_random(self._seed * 2 + 2)
+
+    def load(self, prefix: str):
+        self._nqs0.load(str(prefix))
+        self._nqs1.set_params(self._nqs0.get_params())          # nqs0.copy_to(nqs1)
+
+    def warm_up(self, nMCSteps: int):
+        # Sampler4SpinHalf::initialize_ -> psi.initialize(lnpsi) with random +-1 spins (the reference seeds them from the clock,
+        # gpu/include/neural_quantum_state.cuh:239-249; here from seedNumber so that runs are reproducible)
+        rng = np.random.default_rng([self._seed, 0x5EED])
+        spins = (2 * rng.integers(0, 2, size=(self._K, self._N)) - 1).astype(np.int8)
+        self._nqs0.warm_up(int(nMCSteps), spins)
+
+    def do_mcmc_steps(self, nMCSteps: int):
+        self._nqs0.do_mcmc_steps(int(nMCSteps))
+
+    def get_spinStates(self) -> np.ndarray:
+        return self._nqs0.get_spinStates().astype(np.float64).reshape(-1)   # flat [K*N] reals like py::array_t<T>(size)
+
+    def get_lnpsi(self) -> np.ndarray:
+        return self._nqs0.get_lnpsi()
+
+    def get_lnpsi_for_fixed_spins(self, spinStates) -> np.ndarray:
+        s = np.asarray(spinStates).reshape(self._K, self._N)
+        return self._nqs1.get_lnpsi_for_fixed_spins(np.rint(s).astype(np.int8))
+
+
+class dRBMSampler(_PySampler):
+    _model = "rbm"
+
+
+class dFFNNSampler(_PySampler):
+    _model = "ffnn"
+
+
+def _unsupported(name: str, why: str):
+    class _U:
+        def __init__(self, *a, **k):
+            raise NotImplementedError("%s: %s" % (name, why))
+    _U.__name__ = name
+    return _U
+
+
+_FP32 = "libnqs_b200 computes in fp64 only (the reference's float32 instantiation is out of scope)"
+_SYMM = "symmetric ansaetze are out of scope of the B200 hot path (SURVEY 8f)"
+sRBMSampler = _unsupported("sRBMSampler", _FP32)
+sFFNNSampler = _unsupported("sFFNNSampler", _FP32)
+sRBMTrSymmSampler = _unsupported("sRBMTrSymmSampler", _SYMM)
+dRBMTrSymmSampler = _unsupported("dRBMTrSymmSampler", _SYMM)
+sRBMZ2PrSymmSampler = _unsupported("sRBMZ2PrSymmSampler", _SYMM)
+dRBMZ2PrSymmSampler = _unsupported("dRBMZ2PrSymmSampler", _SYMM)
+sFFNNTrSymmSampler = _unsupported("sFFNNTrSymmSampler", _SYMM)
+dFFNNTrSymmSampler = _unsupported("dFFNNTrSymmSampler", _SYMM)

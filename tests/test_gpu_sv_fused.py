@@ -1,0 +1,81 @@
+"""One-pass S*v cluster kernel (csrc/sv_fused.cuh) against (1) the dense formula evaluated in numpy on the engine's own O
+and (2) the two-pass kernels, over shapes that exercise every launch plan: cluster size 8 / 16, 1..9 columns per thread,
+ragged last column slice, row counts that do not divide by the number of clusters, fewer rows than clusters.
+
+ref: SMatrixForCG::dot, gpu/include/functor_for_CG.cuh:104-127:  S v = (1/K) O^H (O v) - conj(<O>) (<O> . v) + lambda diag(S) v.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
+
+# (model, N, M, K, expected cluster size, expected columns per thread)
+SHAPES = [
+    ("rbm", 16, 16, 64, 8, 1),      # tiny: P = 288, 36 columns per CTA
+    ("rbm", 6, 1, 40, 8, 1),        # P = 13 < 2*8: trailing CTAs own no column at all
+    ("rbm", 64, 128, 300, 8, 2),    # cfg2 shape, K not a multiple of the cluster count
+    ("rbm", 80, 250, 37, 8, 3),     # P = 20330
+    ("rbm", 100, 260, 50, 8, 7),    # P = 26360
+    ("rbm", 128, 256, 150, 8, 9),   # cfg3 shape (P = 33152)
+    ("ffnn", 128, 512, 40, 16, 9),  # cfg4 shape (P = 66560): 16-CTA clusters
+    ("rbm", 128, 256, 5, 8, 9),     # fewer rows than clusters
+]
+
+
+def dense_sv(O, v, lam):
+    K = O.shape[0]
+    aO = O.mean(axis=0)
+    diag = (np.abs(O) ** 2).mean(axis=0) - np.abs(aO) ** 2
+    z = O @ v
+    return (O.conj().T @ z) / K - aO.conj() * (aO @ v) + lam * diag * v, aO, diag
+
+
+@pytest.mark.parametrize("model,N,M,K,cs,cpt", SHAPES)
+def test_fused_sv_matches_dense_and_two_pass(model, N, M, K, cs, cpt):
+    from neural_network_quantum_state_b200 import Engine
+    rng = np.random.default_rng(N * 1000 + M)
+    out = {}
+    for two_pass in (False, True):
+        e = Engine(model, N, M, K, H, J, ALPHA, seed=7, two_pass_sv=two_pass)
+        e.init_params_random(5)
+        e.warm_up(2)
+        variant = e.kernel_variant("sv")
+        if two_pass:
+            assert variant == "two_pass"
+        else:
+            assert variant.startswith("fused_cs%d_cpt%d_" % (cs, cpt)), variant
+        O = e.get_lnpsiGradients()
+        v = rng.normal(size=e.P) + 1j * rng.normal(size=e.P) if not out else out["v"]
+        Sv, aO, diag = e.smatrix_dot(0.37, v)
+        want, aO_w, diag_w = dense_sv(O, v, 0.37)
+        assert_close(aO, aO_w, what="<O>")
+        assert_close(diag, diag_w, atol=1e-11, what="diag")
+        assert_close(Sv, want, what="S v (%s)" % variant)
+        # twice in a row: the TMA slots / mbarrier phases are re-initialised per launch
+        Sv2, _, _ = e.smatrix_dot(0.37, v)
+        assert np.array_equal(Sv, Sv2), "S v is not run-to-run deterministic"
+        out["v"] = v
+        out[two_pass] = Sv
+        e.close()
+    assert_close(out[False], out[True], rtol=1e-12, what="fused vs two-pass")
+
+
+def test_fused_sv_inside_cg_matches_two_pass_trajectory():
+    """Whole SR steps (CG to tolerance) with the one-pass kernel give the same iteration counts and parameters."""
+    from neural_network_quantum_state_b200 import Engine
+    res = []
+    for two_pass in (False, True):
+        e = Engine("rbm", 32, 64, 256, H, J, ALPHA, seed=3, two_pass_sv=two_pass)
+        e.init_params_random(11)
+        e.warm_up(20)
+        its = [e.sr_step(n_mc_steps=1, lr=0.05).cg_iters for _ in range(4)]
+        res.append((its, e.get_params()))
+        e.close()
+    assert res[0][0] == res[1][0]
+    assert_close(res[0][1], res[1][1], rtol=1e-9, what="params after 4 SR steps")
