@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
+    ap.add_argument("--cg-fixed-iters", type=int, default=0, help="diagnostics: run exactly this many CG iterations per step")
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -246,7 +247,7 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        return e.sr_step(n_mc_steps=1, lr=args.lr)
+        return e.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
 
     for _ in range(args.warmup):
         step()

@@ -370,7 +370,7 @@ cudaError_t sv_launch_t(const SvArgs & a, int cs, int nclusters, int nt, size_t 
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(cs*nclusters), 1, 1);
-  cfg.blockDim = dim3((unsigned)nt, 1, 1);
+  cfg.blockDim = dim3((unsigned)nt+32, 1, 1);   // nt consumer threads + the producer warp
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -414,11 +414,12 @@ void plan_sv(nqs_handle * h)
     for (int c = 1; c <= NQS_SV_MAX_CPT; ++c)
     {
       const long long need = ((pc+c-1)/c+31)/32*32;
-      const int max_t = (c <= 3) ? 1024 : 512;
+      const int max_t = (c <= 3) ? 992 : 480;   // consumer threads; one more warp is the TMA producer
       if (need <= max_t) { cpt = c; nt = (int)std::max<long long>(64, need); break; }
     }
     if (!cpt) continue;
-    const size_t slot_bytes = (size_t)((pc*(long long)sizeof(cd)+127)/128*128);
+    // a slot holds one row slice, padded to CPT * consumer threads elements so the kernel reads it without bounds checks
+    const size_t slot_bytes = (size_t)((std::max<long long>(pc, (long long)cpt*nt)*(long long)sizeof(cd)+127)/128*128);
     if (h->smem_optin < NQS_SV_TAIL_BYTES+2*slot_bytes) continue;
     const int nslot = (int)std::min<size_t>(NQS_SV_MAX_SLOTS, (h->smem_optin-NQS_SV_TAIL_BYTES)/slot_bytes);
     const size_t smem = (size_t)nslot*slot_bytes+NQS_SV_TAIL_BYTES;
@@ -473,6 +474,7 @@ void matvec_passes(nqs_handle * h, const cd * v, const int * done)
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
     a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes;
+    { const char * dbg = std::getenv("NQS_SV_DEBUG"); a.debug = dbg ? std::atoi(dbg) : 0; }
     {
       Span sp(h, TAG_ROWS);
       NQS_CUDA(sv_launch(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));

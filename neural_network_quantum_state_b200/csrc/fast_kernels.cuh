@@ -1,14 +1,14 @@
 // Register-resident, transcendental-free kernels for the complex RBM (the configuration the headline metric is quoted on).
 //
 // Observation: for the RBM,  |psi(s^(i))/psi(s)|^2 = prod_j |cosh(theta_j - 2 s_i W_ij)|^2 / |cosh(theta_j)|^2 * exp(-4 s_i Re a_i)
-// and |cosh(x+iy)|^2 = sinh^2 x + cos^2 y.  Keeping (e^x/2, e^-x/2, cos y, sin y) per (chain, hidden unit) in REGISTERS and
-// tabulating (e^{-+2 Re W_ij}, cos 2 Im W_ij, sin 2 Im W_ij) once per parameter update turns every Metropolis proposal into
-// 7 fp64 multiply-adds per hidden unit -- no exp / sincos / log inside the sweep (the generic kernel spends ~250 fp64
-// instructions per hidden unit per proposal on them).  The accept test  u < |psi'/psi0|^2  is evaluated on the products
+// and |cosh(x+iy)|^2 = sinh^2 x + cos^2 y.  Keeping (sinh x, cosh x, cos y, sin y) per (chain, hidden unit) in REGISTERS and
+// tabulating (cosh 2 Re W_ij, sinh 2 Re W_ij, cos 2 Im W_ij, sin 2 Im W_ij) once per parameter update turns every Metropolis
+// proposal into 7 fp64 multiply-adds per hidden unit (angle-addition formulas, the spin enters as a sign-bit XOR) -- no exp /
+// sincos / log inside the sweep (the generic kernel spends ~250 fp64 instructions per hidden unit per proposal on them).  The accept test  u < |psi'/psi0|^2  is evaluated on the products
 // themselves in (mantissa, exponent) form, so it needs no log/exp either.  theta itself is NOT carried through the sweep:
 // the accepted flips of a sweep are recorded and replayed afterwards on the exact fp64 theta in the reference's order
 // (theta -= 2 s W_i, ref conditional_y_update, impl_neural_quantum_state.cuh:1314-1329), so theta stays bit-identical to the
-// generic kernel's and the (e^x, cos y, ..) registers are rebuilt from it at every sweep (no drift).
+// generic kernel's and the (sinh x, cosh x, cos y, sin y) registers are rebuilt from it at every sweep (no drift).
 // lnpsi0 is recomputed from the final theta for chains that accepted at least once (it equals the lnpsi' of their last
 // accepted proposal up to rounding); chains that never accepted keep their tracked -- possibly stale -- value, which is
 // exactly the reference's behaviour.
@@ -23,7 +23,7 @@ namespace nqs
 {
 // Tables are split into 16-byte halves so that a warp's access is one fully coalesced LDG.128 per half (a 32-byte struct
 // read with 8-byte loads costs 4x the L1 wavefronts -- measured, profiles/r1b_fast_kernels.md).
-//   ftab_a = (e^{-2 Re W}, e^{+2 Re W})   ftab_b = (cos 2 Im W, sin 2 Im W)      [sigma = +1]
+//   ftab_a = (cosh 2 Re W, sinh 2 Re W)   ftab_b = (cos 2 Im W, sin 2 Im W)
 //   ctab_a = cosh(2W)                      ctab_b = sinh(2W)
 typedef double2 FlipTab;
 typedef double2 CoshTab;
@@ -46,8 +46,8 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     const double ex = exp(2.0*w.x), emx = exp(-2.0*w.x);
     double s, co;
     sincos(2.0*w.y, &s, &co);
-    const double ch = 0.5*(ex+emx), sh = 0.5*(ex-emx);
-    ftab_a[idx] = make_double2(emx, ex); ftab_b[idx] = make_double2(co, s);
+    const double ch = 0.5*(ex+emx), sh = sinh(2.0*w.x);
+    ftab_a[idx] = make_double2(ch, sh); ftab_b[idx] = make_double2(co, s);
     ctab_a[idx] = make_double2(ch*co, sh*s); ctab_b[idx] = make_double2(sh*co, ch*s);
     w2[idx] = cmake(2.0*w.x, 2.0*w.y);
     if (j < M)
@@ -105,6 +105,11 @@ __device__ __forceinline__ void split_me(const double p, double & m, int & e)
   m = __hiloint2double((hi&0x800fffff)|0x3ff00000, __double2loint(p));
 }
 
+__device__ __forceinline__ double flip_sign(const double v, const int mask)
+{ // v * (+-1) as one integer XOR on the sign bit
+  return __hiloint2double(__double2hiint(v)^mask, __double2loint(v));
+}
+
 struct FastSweepArgs
 {
   int N, M, Mpad;
@@ -134,10 +139,73 @@ inline size_t fast_sweep_smem_bytes(int N, int C, int warps)
   return (size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int);
 }
 
+// (mantissa, exponent) products of C chains reduced over the 32 lanes with a TRANSPOSING butterfly: after the first
+// log2(C) stages every lane keeps only the chain of its own lane group (32/C consecutive lanes), so a C-chain reduction
+// costs log2(C) + ... + 5 value shuffles instead of 5*C.  On return lane l holds the total of chain l / (32/C).
+template <int C>
+__device__ __forceinline__ void reduce_me_transposed(double (&m)[C], int (&e)[C], const int lane, double & mo, int & eo)
+{
+  static_assert(C == 1 || C == 2 || C == 4, "C must be 1, 2 or 4");
+  double km[2]; int ke[2];
+  if (C == 4)
+  {
+    const bool up = (lane&16) != 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+    {
+      const double sm = up ? m[q] : m[2+q];
+      const int se = up ? e[q] : e[2+q];
+      km[q] = (up ? m[2+q] : m[q])*__shfl_xor_sync(0xffffffffu, sm, 16);
+      ke[q] = (up ? e[2+q] : e[q])+__shfl_xor_sync(0xffffffffu, se, 16);
+    }
+    const bool up8 = (lane&8) != 0;
+    const double sm = up8 ? km[0] : km[1];
+    const int se = up8 ? ke[0] : ke[1];
+    mo = (up8 ? km[1] : km[0])*__shfl_xor_sync(0xffffffffu, sm, 8);
+    eo = (up8 ? ke[1] : ke[0])+__shfl_xor_sync(0xffffffffu, se, 8);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+    {
+      mo *= __shfl_xor_sync(0xffffffffu, mo, o);
+      eo += __shfl_xor_sync(0xffffffffu, eo, o);
+    }
+  }
+  else if (C == 2)
+  {
+    const bool up = (lane&16) != 0;
+    const double sm = up ? m[0] : m[C-1];
+    const int se = up ? e[0] : e[C-1];
+    mo = (up ? m[C-1] : m[0])*__shfl_xor_sync(0xffffffffu, sm, 16);
+    eo = (up ? e[C-1] : e[0])+__shfl_xor_sync(0xffffffffu, se, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+    {
+      mo *= __shfl_xor_sync(0xffffffffu, mo, o);
+      eo += __shfl_xor_sync(0xffffffffu, eo, o);
+    }
+  }
+  else
+  {
+    mo = m[0]; eo = e[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+      mo *= __shfl_xor_sync(0xffffffffu, mo, o);
+      eo += __shfl_xor_sync(0xffffffffu, eo, o);
+    }
+  }
+}
+
+// State per (chain, hidden unit), in registers: (sinh x, cosh x, cos y, sin y) of theta = x + i y.  Table per (site, hidden
+// unit): ftab_a = (cosh 2ReW, sinh 2ReW), ftab_b = (cos 2ImW, sin 2ImW).  A flip of a spin sigma maps theta -> theta - 2 sigma W:
+//   sinh x' = sinh x cosh 2ReW - sigma cosh x sinh 2ReW        cos y' = cos y cos 2ImW + sigma sin y sin 2ImW
+//   |cosh theta'|^2 = sinh^2 x' + cos^2 y'
+// sigma enters as ONE sign-bit XOR per product (no selects): 7 fp64 instructions + 2 integer XORs per (proposal, chain, unit).
 template <int JPL, int C>
 __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int G = 32/C;                      // lanes per chain group (owner lanes of a chain's accept decision)
   const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
   const int N = a.N, M = a.M, Mpad = a.Mpad;
   const int npad = ((N+15)/16)*16;
@@ -149,9 +217,11 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
   const long long kbase = ((long long)blockIdx.x*warps+w)*C;
   if (kbase >= a.K) return;
   const cd * avis = a.params+(size_t)N*M;
+  const int myc = lane/G;                      // the chain this lane decides for
+  const bool my_valid = (kbase+myc < a.K);
+  const long long my_k = my_valid ? kbase+myc : kbase;
   bool valid[C];
   cd ln0[C], sa[C];
-  double r0m[C]; int r0e[C];
   bool any_acc[C];
 #pragma unroll
   for (int c = 0; c < C; ++c)
@@ -160,24 +230,27 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
     const long long k = valid[c] ? kbase+c : kbase;
     for (int i = lane; i < N; i += 32) sp[c*npad+i] = a.spins[k*N+i];
     ln0[c] = a.lnpsi0[k]; sa[c] = a.sa[k];
-    // R0 = exp(2 (Re lnpsi0 - Re sa)) as m * 2^e
-    const double v = 2.0*(ln0[c].x-sa[c].x)*1.4426950408889634;
-    const double fl = floor(v);
-    r0m[c] = exp2(v-fl);
-    r0e[c] = (int)fmax(fmin(fl, 100000.0), -100000.0);
     any_acc[c] = false;
+  }
+  // R0 = exp(2 (Re lnpsi0 - Re sa)) = prod_j |cosh theta_j|^2 of the TRACKED amplitude, as m * 2^e, kept by the owner lanes
+  double r0m; int r0e;
+  {
+    const cd l0 = a.lnpsi0[my_k], s0 = a.sa[my_k];
+    const double v = 2.0*(l0.x-s0.x)*1.4426950408889634;
+    const double fl = floor(v);
+    r0m = exp2(v-fl);
+    r0e = (int)fmax(fmin(fl, 100000.0), -100000.0);
   }
   __syncwarp();
   int pos = a.pos0;
   long long t_glob = 0;
-  double ubuf[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) ubuf[c] = 0.0;
+  const long long t_end = (long long)a.nsweeps*N;
+  double ubuf = 0.0;                           // uniform of proposal (t_glob rounded down to G) + lane%G of chain myc
 
   for (int sweep = 0; sweep < a.nsweeps; ++sweep)
   {
     // ---- (1) rebuild the multiplicative state from the exact theta
-    double h1[C][JPL], h2[C][JPL], cy[C][JPL], sy[C][JPL];
+    double S[C][JPL], Ch[C][JPL], cy[C][JPL], sy[C][JPL];
 #pragma unroll
     for (int c = 0; c < C; ++c)
     {
@@ -188,8 +261,8 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         const int j = lane+32*jj;
         cd th = cmake(0.0, 0.0);
         if (j < M) th = a.theta[k*M+j];
-        const double ex = exp(th.x);
-        h1[c][jj] = 0.5*ex; h2[c][jj] = 0.25/h1[c][jj];
+        const double ex = exp(th.x), emx = 1.0/ex;
+        S[c][jj] = 0.5*(ex-emx); Ch[c][jj] = 0.5*(ex+emx);
         sincos(th.y, &sy[c][jj], &cy[c][jj]);
       }
     }
@@ -197,96 +270,97 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
     // ---- (2) N proposals
     for (int t = 0; t < N; ++t, ++t_glob)
     {
-      if ((t_glob&31) == 0)
+      if ((t_glob&(G-1)) == 0)
       {
-        const long long tt = t_glob+lane;
-        if (tt < (long long)a.nsweeps*N)
-        {
-#pragma unroll
-          for (int c = 0; c < C; ++c)
-          {
-            const long long k = valid[c] ? kbase+c : kbase;
-            ubuf[c] = a.uniforms ? a.uniforms[tt*a.K+k]
-                                 : philox_uniform(a.seed, (unsigned long long)(a.chain_offset+k), a.step0+(unsigned long long)tt);
-          }
-        }
+        const long long tt = t_glob+(lane&(G-1));
+        if (tt < t_end)
+          ubuf = a.uniforms ? a.uniforms[tt*a.K+my_k]
+                            : philox_uniform(a.seed, (unsigned long long)(a.chain_offset+my_k), a.step0+(unsigned long long)tt);
       }
       const int site = ord[pos];
       pos = (pos+1 == N) ? 0 : pos+1;
-      const FlipTab * trow_a = a.ftab_a+(size_t)site*Mpad;
-      const FlipTab * trow_b = a.ftab_b+(size_t)site*Mpad;
-      double sig[C], prod[C];
+      const FlipTab * trow_a = a.ftab_a+(size_t)site*Mpad+lane;
+      const FlipTab * trow_b = a.ftab_b+(size_t)site*Mpad+lane;
+      int smask[C];                              // sign bit of sigma
+      double prod[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { sig[c] = (double)sp[c*npad+site]; prod[c] = 1.0; }
+      for (int c = 0; c < C; ++c) { smask[c] = (sp[c*npad+site] < 0) ? (int)0x80000000 : 0; prod[c] = 1.0; }
 #pragma unroll
       for (int jj = 0; jj < JPL; ++jj)
       {
-        const double2 Ta = ld_tab(trow_a+lane+32*jj), Tb = ld_tab(trow_b+lane+32*jj);
+        const double2 Ta = ld_tab(trow_a+32*jj), Tb = ld_tab(trow_b+32*jj);
 #pragma unroll
         for (int c = 0; c < C; ++c)
         {
-          const bool up = sig[c] > 0.0;
-          const double a1 = up ? Ta.x : Ta.y, a2 = up ? Ta.y : Ta.x, sst = up ? Tb.y : -Tb.y;
-          const double n1 = h1[c][jj]*a1, n2 = h2[c][jj]*a2;
-          const double nc = fma(sy[c][jj], sst, cy[c][jj]*Tb.x);
-          const double d = n1-n2;
-          prod[c] *= fma(d, d, nc*nc);
+          const double shp = fma(-flip_sign(Ch[c][jj], smask[c]), Ta.y, S[c][jj]*Ta.x);
+          const double cyp = fma(flip_sign(sy[c][jj], smask[c]), Tb.y, cy[c][jj]*Tb.x);
+          prod[c] *= fma(shp, shp, cyp*cyp);
         }
       }
+      double pm[C]; int pe[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) split_me(fmax(prod[c], 1e-300), pm[c], pe[c]);
+      double m; int e;
+      reduce_me_transposed<C>(pm, pe, lane, m, e);
+      // accept  <=>  u < P' A / R0   (== u < exp(2 (Re lnpsi' - Re lnpsi0)), ref impl_mcmc_sampler.cuh:75-99), decided by the owner lanes
+      const double u = __shfl_sync(0xffffffffu, ubuf, (lane&~(G-1))|(int)(t_glob&(G-1)));
+      const bool my_up = sp[myc*npad+site] > 0;
+      const double A = a.afac[2*site+(my_up ? 0 : 1)];
+      int de = e-r0e;
+      de = max(-2000, min(2000, de));
+      const bool my_acc = my_valid && (u*r0m < scalbn(m*A, de));
+      const unsigned int bal = __ballot_sync(0xffffffffu, my_acc);
+      if (my_acc)
+      { // renormalise (m in [1, 2^32)) and adopt as the new reference product
+        double m2; int e2;
+        split_me(m, m2, e2);
+        r0m = m2; r0e = e+e2;
+      }
       bool acc[C];
-      bool any = false;
 #pragma unroll
       for (int c = 0; c < C; ++c)
       {
-        double m; int e;
-        split_me(fmax(prod[c], 1e-300), m, e);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        acc[c] = ((bal>>(c*G))&1u) != 0;
+        if (lane == 0)
         {
-          m *= __shfl_xor_sync(0xffffffffu, m, o);
-          e += __shfl_xor_sync(0xffffffffu, e, o);
-        }
-        // accept  <=>  u < P' A / R0   (== u < exp(2 (Re lnpsi' - Re lnpsi0)), ref impl_mcmc_sampler.cuh:75-99)
-        const double u = __shfl_sync(0xffffffffu, ubuf[c], (int)(t_glob&31));
-        const double A = a.afac[2*site+(sig[c] > 0.0 ? 0 : 1)];
-        int de = e-r0e[c];
-        de = max(-2000, min(2000, de));
-        const double rhs = scalbn(m*A, de);
-        acc[c] = valid[c] && (u*r0m[c] < rhs);
-        if (a.acc_log && lane == 0 && valid[c]) a.acc_log[t_glob*a.K+kbase+c] = acc[c] ? 1 : 0;
-        if (lane == 0) rec[t*C+c] = acc[c] ? (int8_t)(sig[c] > 0.0 ? 1 : -1) : (int8_t)0;
-        if (acc[c])
-        {
-          // renormalise (m in [1, 2^32)) and adopt as the new reference product
-          double m2; int e2;
-          split_me(m, m2, e2);
-          r0m[c] = m2; r0e[c] = e+e2;
-          const cd ai = avis[site];
-          sa[c] = cmake(sa[c].x-2.0*sig[c]*ai.x, sa[c].y-2.0*sig[c]*ai.y);
-          any_acc[c] = true;
-          any = true;
-          if (lane == 0) sp[c*npad+site] = (int8_t)(-sp[c*npad+site]);
+          if (a.acc_log && valid[c]) a.acc_log[t_glob*a.K+kbase+c] = acc[c] ? 1 : 0;
+          rec[t*C+c] = acc[c] ? (int8_t)(smask[c] ? -1 : 1) : (int8_t)0;
         }
       }
-      if (any)
+      if (bal != 0u)
       {
+        const cd ai = avis[site];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (acc[c])
+          {
+            const double sg = smask[c] ? -2.0 : 2.0;
+            sa[c] = cmake(sa[c].x-sg*ai.x, sa[c].y-sg*ai.y);
+            any_acc[c] = true;
+          }
 #pragma unroll
         for (int jj = 0; jj < JPL; ++jj)
         {
-          const double2 Ta = ld_tab(trow_a+lane+32*jj), Tb = ld_tab(trow_b+lane+32*jj);
+          const double2 Ta = ld_tab(trow_a+32*jj), Tb = ld_tab(trow_b+32*jj);
 #pragma unroll
           for (int c = 0; c < C; ++c)
           {
             if (acc[c])
             {
-              const bool up = sig[c] > 0.0;
-              const double a1 = up ? Ta.x : Ta.y, a2 = up ? Ta.y : Ta.x, sst = up ? Tb.y : -Tb.y;
-              h1[c][jj] *= a1; h2[c][jj] *= a2;
-              const double nc = fma(sy[c][jj], sst, cy[c][jj]*Tb.x);
-              const double ns = fma(-cy[c][jj], sst, sy[c][jj]*Tb.x);
-              cy[c][jj] = nc; sy[c][jj] = ns;
+              const double s0 = S[c][jj], c0 = Ch[c][jj], y0 = cy[c][jj], y1 = sy[c][jj];
+              S[c][jj] = fma(-flip_sign(c0, smask[c]), Ta.y, s0*Ta.x);
+              Ch[c][jj] = fma(-flip_sign(s0, smask[c]), Ta.y, c0*Ta.x);
+              cy[c][jj] = fma(flip_sign(y1, smask[c]), Tb.y, y0*Tb.x);
+              sy[c][jj] = fma(-flip_sign(y0, smask[c]), Tb.y, y1*Tb.x);
             }
           }
+        }
+        __syncwarp();
+        if (lane == 0)
+        {
+#pragma unroll
+          for (int c = 0; c < C; ++c)
+            if (acc[c]) sp[c*npad+site] = (int8_t)(smask[c] ? 1 : -1);
         }
       }
       __syncwarp();
@@ -404,11 +478,6 @@ inline size_t fast_eloc_smem_bytes(int N, int M, int C)
 {
   const size_t npad = (size_t)((N+15)/16)*16;
   return (size_t)C*M*sizeof(cd)+(size_t)C*npad+(size_t)C*8*6*sizeof(double)+16;
-}
-
-__device__ __forceinline__ double flip_sign(const double v, const int mask)
-{ // v * (+-1) as one integer XOR on the sign bit
-  return __hiloint2double(__double2hiint(v)^mask, __double2loint(v));
 }
 
 template <int C>

@@ -6,14 +6,15 @@
 // A thread-block CLUSTER can: the CS CTAs of a cluster split the columns, CTA r owns the slice [r*pc, (r+1)*pc) and keeps
 // its v slice and its column accumulators in REGISTERS (CPT columns per thread) for the whole launch.  For every row of the
 // cluster's row block:
-//   (1) the slice of row k arrives in shared memory by TMA (cp.async.bulk + mbarrier complete_tx), NSLOT rows deep, so the
-//       HBM stream never waits for the math;
-//   (2) every thread pulls its CPT elements of the row into registers and forms its part of O_k . v; warp shuffles + one
-//       __syncthreads give the CTA partial, which lane r of warp 0 sends into CTA r's shared memory over DSMEM with
-//       st.async (the store itself completes bytes on CTA r's mbarrier) -- no cluster-wide barrier in the loop;
-//   (3) after the mbarrier wait every CTA adds the CS partials in rank order (bit-identical z_k in all CTAs, fixed order =>
+//   (1) a dedicated PRODUCER warp streams the slice of row k into shared memory by TMA (cp.async.bulk + mbarrier
+//       complete_tx), NSLOT rows deep, re-arming a slot as soon as the consumer warps released it (per-slot "empty"
+//       mbarrier), so the HBM stream never waits for the math;
+//   (2) every consumer thread pulls its CPT elements of the row into registers and forms its part of O_k . v; a shuffle
+//       butterfly gives the warp partial, the warp partials meet on a CTA-local mbarrier, and one (rotating) reducer warp
+//       folds them in a fixed order and sends the CTA partial into every CTA of the cluster over DSMEM with st.async (the
+//       store itself completes bytes on the receiver's mbarrier).  No __syncthreads and no cluster barrier in the loop;
+//   (3) after the mbarrier wait every warp adds the CS CTA partials in rank order (bit-identical z_k in all CTAs,
 //       run-to-run deterministic) and accumulates conj(O_kp) z_k from the registers it still holds.
-// The shared-memory slot is free again right after (2), so the TMA for row k+NSLOT is issued there.
 // HBM traffic: K*P*16 B per S*v instead of 2*K*P*16 B.  Cluster partials go to part[q][{re,im}][P] and are folded in fixed
 // order by colsum_reduce_kernel exactly like the two-pass kernels' row-block partials.
 #pragma once
@@ -35,14 +36,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, const uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t * bar, const uint32_t parity)
-{
+{ // try_wait suspends the thread in hardware (up to the time hint) and wakes it when the phase completes: no busy polling
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
   do
   {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
   } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ uint32_t map_to_rank(const void * local, const uint32_t rank)
 {
@@ -76,19 +81,23 @@ struct SvArgs
   long long pc;            // columns per CTA slice = ceil(P / cluster size)
   long long rows_per_cluster;
   int nslot;               // shared-memory row slots (TMA pipeline depth)
-  unsigned int slot_bytes; // bytes per slot (multiple of 128)
+  unsigned int slot_bytes; // bytes per slot: >= CPT * consumer threads * 16 (the tail past the slice stays zero)
+  int debug;               // timing experiments only (env NQS_SV_DEBUG, results are WRONG when != 0): 1 = no DSMEM exchange,
+                           // 2 = no CTA-level reduction either, 4 = no TMA wait (stale shared memory)
 };
 
 #define NQS_SV_MAX_CLUSTER 16
 #define NQS_SV_MAX_SLOTS 8
-// shared memory after the slots: red[32] | zbuf[2][16] | full[8] | zfull[2]
-#define NQS_SV_TAIL_BYTES (32*16+2*NQS_SV_MAX_CLUSTER*16+NQS_SV_MAX_SLOTS*8+2*8)
+#define NQS_SV_MAX_WARPS 32
+// shared memory after the slots: red[2][warps] | zbuf[2][cluster] | full[8] | empty[8] | wfull[2] | zfull[2]
+#define NQS_SV_TAIL_BYTES (2*NQS_SV_MAX_WARPS*16+2*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+4*8)
 
-// register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 1024 threads (8 warps per sub-partition x 64
-// registers), larger CPT up to 512 threads (4 warps per sub-partition x 128 registers)
+// register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 992+32 threads (8 warps per sub-partition x 64
+// registers), larger CPT up to 480+32 threads (4 warps per sub-partition x 128 registers)
 #define NQS_SV_MAX_CPT 10
 template <int CPT> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
 
+// blockDim.x = 32*(NW+1): warps 0..NW-1 consume (NT = 32*NW threads own the columns), warp NW is the TMA producer.
 template <int CPT>
 __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs a)
 {
@@ -96,13 +105,15 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned int CS = cluster.num_blocks(), crank = cluster.block_rank();
-  const int NT = blockDim.x, tid = threadIdx.x, lane = tid&31, w = tid>>5, nw = NT>>5;
+  const int NT = blockDim.x-32, tid = threadIdx.x, lane = tid&31, w = tid>>5, NW = NT>>5;
   const long long cid = blockIdx.x/CS;
   unsigned char * tail = smem_raw+(size_t)a.nslot*a.slot_bytes;
-  cd * red = reinterpret_cast<cd*>(tail);                                   // [32] warp partials
-  cd * zbuf = red+32;                                                       // [2][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
-  uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+2*NQS_SV_MAX_CLUSTER); // [NQS_SV_MAX_SLOTS] TMA arrival
-  uint64_t * zfull = full+NQS_SV_MAX_SLOTS;                                 // [2] all CS partials of a row arrived (tx bytes)
+  cd * red = reinterpret_cast<cd*>(tail);                                   // [2][NQS_SV_MAX_WARPS] warp partials of this CTA
+  cd * zbuf = red+2*NQS_SV_MAX_WARPS;                                       // [2][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
+  uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+2*NQS_SV_MAX_CLUSTER); // [slots] TMA arrival
+  uint64_t * empty = full+NQS_SV_MAX_SLOTS;                                 // [slots] all consumer warps released the slot
+  uint64_t * wfull = empty+NQS_SV_MAX_SLOTS;                                // [2] all NW warp partials of a row are in red[]
+  uint64_t * zfull = wfull+2;                                               // [2] all CS CTA partials of a row arrived (tx bytes)
 
   const long long c0 = (long long)crank*a.pc;
   long long nr_ll = a.P-c0;
@@ -115,94 +126,113 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   const int nrows = (k1 > k0) ? (int)(k1-k0) : 0;
   const uint32_t row_bytes = (uint32_t)n_r*(uint32_t)sizeof(cd);
 
+  // zero the slots once: TMA only ever writes the first row_bytes of a slot, so elements past the slice read as 0 and the
+  // row loop needs no bounds predicate at all
+  {
+    double2 * z = reinterpret_cast<double2*>(smem_raw);
+    const int nz16 = (int)(((size_t)a.nslot*a.slot_bytes)/sizeof(double2));
+    for (int i = tid; i < nz16; i += blockDim.x) z[i] = make_double2(0.0, 0.0);
+  }
   if (tid == 0)
   {
-    for (int s = 0; s < a.nslot; ++s) mbar_init(full+s, 1);
+    for (int s = 0; s < a.nslot; ++s) { mbar_init(full+s, 1); mbar_init(empty+s, (uint32_t)NW); }
+    mbar_init(wfull, (uint32_t)NW); mbar_init(wfull+1, (uint32_t)NW);
     mbar_init(zfull, 1); mbar_init(zfull+1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  cluster.sync();   // every CTA's barriers exist before anybody arrives on them
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA) writes
+  cluster.sync();   // every CTA's barriers exist before anybody signals them
 
-  cd vr[CPT], acc[CPT];
-#pragma unroll
-  for (int c = 0; c < CPT; ++c)
-  {
-    const int idx = c*NT+tid;
-    vr[c] = (idx < n_r) ? a.v[c0+idx] : cmake(0.0, 0.0);
-    acc[c] = cmake(0.0, 0.0);
-  }
-  const cd * Oslice = a.O+c0;
-  if (tid == 0 && n_r > 0)
-    for (int s = 0; s < a.nslot && s < nrows; ++s)
+  if (w == NW)
+  { // ---- (1) producer warp: one lane keeps NSLOT rows of this CTA's column slice in flight
+    if (lane == 0 && n_r > 0)
     {
-      mbar_expect_tx(full+s, row_bytes);
-      tma_load_1d(smem_raw+(size_t)s*a.slot_bytes, Oslice+(k0+s)*a.P, row_bytes, full+s);
-    }
-
-  int slot = 0;
-  uint32_t full_par = 0;
-  for (int it = 0; it < nrows; ++it)
-  {
-    // ---- (2) row slice -> registers, partial O_k . v
-    cd o[CPT];
-    double px = 0.0, py = 0.0;
-    if (n_r > 0)
-    {
-      mbar_wait(full+slot, full_par);
-      const cd * srow = reinterpret_cast<const cd*>(smem_raw+(size_t)slot*a.slot_bytes);
-#pragma unroll
-      for (int c = 0; c < CPT; ++c)
+      const cd * Oslice = a.O+c0;
+      int slot = 0;
+      uint32_t par = 0;
+      for (int it = 0; it < nrows; ++it)
       {
-        const int idx = c*NT+tid;
-        o[c] = (idx < n_r) ? srow[idx] : cmake(0.0, 0.0);
-        px = fma(o[c].x, vr[c].x, px); px = fma(-o[c].y, vr[c].y, px);
-        py = fma(o[c].x, vr[c].y, py); py = fma(o[c].y, vr[c].x, py);
+        if (it >= a.nslot) mbar_wait(empty+slot, par^1u);   // consumers released the row that used this slot before
+        mbar_expect_tx(full+slot, row_bytes);
+        tma_load_1d(smem_raw+(size_t)slot*a.slot_bytes, Oslice+(k0+it)*a.P, row_bytes, full+slot);
+        if (++slot == a.nslot) { slot = 0; par ^= 1u; }
       }
     }
-    else
-    {
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) o[c] = cmake(0.0, 0.0);
-    }
-    px = warp_sum(px); py = warp_sum(py);
-    if (lane == 0) red[w] = cmake(px, py);
-    __syncthreads();                 // warp partials visible; everybody is done reading the slot
-    if (tid == 0 && n_r > 0 && it+a.nslot < nrows)
-    {
-      mbar_expect_tx(full+slot, row_bytes);
-      tma_load_1d(smem_raw+(size_t)slot*a.slot_bytes, Oslice+(k0+it+a.nslot)*a.P, row_bytes, full+slot);
-    }
-    const int zp = it&1;
-    if (w == 0)
-    {
-      cd s = (lane < nw) ? red[lane] : cmake(0.0, 0.0);
-      s = warp_sum(s);               // fixed butterfly order
-      if (lane == 0) mbar_expect_tx(zfull+zp, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
-      if (lane < (int)CS)
-        st_async_remote_cd(map_to_rank(zbuf+zp*NQS_SV_MAX_CLUSTER+crank, (uint32_t)lane), s, map_to_rank(zfull+zp, (uint32_t)lane));
-    }
-    // ---- (3) z_k = sum over the cluster in rank order, then conj(O_kp) z_k from registers
-    mbar_wait(zfull+zp, (uint32_t)((it>>1)&1));
-    double zx = 0.0, zy = 0.0;
-    for (unsigned int r = 0; r < CS; ++r)
-    {
-      const cd t = zbuf[zp*NQS_SV_MAX_CLUSTER+r];
-      zx += t.x; zy += t.y;
-    }
+  }
+  else
+  {
+    cd vr[CPT], acc[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c)
     {
-      acc[c].x = fma(o[c].x, zx, acc[c].x); acc[c].x = fma(o[c].y, zy, acc[c].x);
-      acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
+      const int idx = c*NT+tid;
+      vr[c] = (idx < n_r) ? a.v[c0+idx] : cmake(0.0, 0.0);
+      acc[c] = cmake(0.0, 0.0);
     }
-    if (++slot == a.nslot) { slot = 0; full_par ^= 1u; }
-  }
-  double * base = a.part+(size_t)cid*2*(size_t)a.P;
+    int slot = 0;
+    uint32_t full_par = 0;
+    const cd * srow = reinterpret_cast<const cd*>(smem_raw)+tid;
+    for (int it = 0; it < nrows; ++it)
+    {
+      // ---- (2) row slice -> registers, partial O_k . v
+      cd o[CPT];
+      if (n_r > 0 && !(a.debug&4)) mbar_wait(full+slot, full_par);
 #pragma unroll
-  for (int c = 0; c < CPT; ++c)
-  {
-    const int idx = c*NT+tid;
-    if (idx < n_r) { base[c0+idx] = acc[c].x; base[a.P+c0+idx] = acc[c].y; }
+      for (int c = 0; c < CPT; ++c) o[c] = srow[c*NT];
+      __syncwarp();
+      if (lane == 0 && n_r > 0) mbar_arrive(empty+slot);
+      double pa = 0.0, pb = 0.0, pc_ = 0.0, pd = 0.0;   // four independent chains
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+      {
+        pa = fma(o[c].x, vr[c].x, pa); pb = fma(o[c].y, vr[c].y, pb);
+        pc_ = fma(o[c].x, vr[c].y, pc_); pd = fma(o[c].y, vr[c].x, pd);
+      }
+      const cd wp = warp_sum(cmake(pa-pb, pc_+pd));
+      const int zp = it&1;
+      const uint32_t zpar = (uint32_t)((it>>1)&1);
+      cd * redrow = red+zp*NQS_SV_MAX_WARPS;
+      double zx = 0.0, zy = 0.0;
+      if (a.debug&2) { zx = wp.x; zy = wp.y; }
+      else {
+      if (lane == 0) { redrow[w] = wp; mbar_arrive(wfull+zp); }
+      if (w == it%NW)
+      { // this row's reducer warp: CTA partial = fixed-order fold of the warp partials, sent to every CTA of the cluster
+        mbar_wait(wfull+zp, zpar);
+        const cd s = warp_sum((lane < NW) ? redrow[lane] : cmake(0.0, 0.0));
+        if (a.debug&1) { if (lane == 0) { zbuf[zp*NQS_SV_MAX_CLUSTER] = s; mbar_arrive(zfull+zp); } }
+        else {
+        if (lane == 0) mbar_expect_tx(zfull+zp, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
+        if (lane < (int)CS)
+          st_async_remote_cd(map_to_rank(zbuf+zp*NQS_SV_MAX_CLUSTER+crank, (uint32_t)lane), s, map_to_rank(zfull+zp, (uint32_t)lane));
+        }
+      }
+      // ---- (3) z_k = sum of the CS partials in rank order, then conj(O_kp) z_k from registers
+      mbar_wait(zfull+zp, zpar);
+      const cd * zrow = zbuf+zp*NQS_SV_MAX_CLUSTER;
+      const unsigned int nzr = (a.debug&1) ? 1u : CS;
+      for (unsigned int r = 0; r < nzr; ++r)
+      {
+        const cd t = zrow[r];
+        zx += t.x; zy += t.y;
+      }
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+      {
+        acc[c].x = fma(o[c].x, zx, acc[c].x); acc[c].x = fma(o[c].y, zy, acc[c].x);
+        acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
+      }
+      srow += a.slot_bytes/sizeof(cd);
+      if (++slot == a.nslot) { slot = 0; full_par ^= 1u; srow = reinterpret_cast<const cd*>(smem_raw)+tid; }
+    }
+    double * base = a.part+(size_t)cid*2*(size_t)a.P;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+    {
+      const int idx = c*NT+tid;
+      if (idx < n_r) { base[c0+idx] = acc[c].x; base[a.P+c0+idx] = acc[c].y; }
+    }
   }
   cluster.sync();   // no CTA may exit while a peer can still write into its shared memory
 }

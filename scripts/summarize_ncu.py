@@ -3,6 +3,7 @@
 
   python scripts/summarize_ncu.py launches gpurun_out/launches_X.csv profiles/launches_X_summary.md "<command that was profiled>"
   python scripts/summarize_ncu.py full gpurun_out/prof_X.ncu-rep profiles/prof_X_summary.md
+  python scripts/summarize_ncu.py stalls gpurun_out/prof_X.ncu-rep profiles/prof_X_stalls.md <kernel regex> [launch index]
 """
 import collections
 import csv
@@ -76,8 +77,44 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def stalls(src, dst, kernel, launch="0"):
+    """Per-instruction warp-stall samples (ncu source page) of one launch: stall-reason totals + the hottest SASS lines."""
+    raw = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel, "--launch-skip", launch,
+                          "--launch-count", "1"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    kname = rows[0][1] if rows and len(rows[0]) > 1 else kernel
+    hdr = rows[1]
+    idx = {n: i for i, n in enumerate(hdr)}
+    seen, data = set(), []
+    for r in rows[2:]:          # the csv repeats every SASS row (once per source view): keep the first by address
+        if len(r) == len(hdr) and r[idx["Address"]] not in seen:
+            seen.add(r[idx["Address"]])
+            data.append(r)
+
+    def val(r, n):
+        try:
+            return int(r[idx[n]] or 0)
+        except ValueError:
+            return 0
+    names = [n for n in hdr if n.startswith("stall_") and "Not Issued" not in n]
+    tot = sum(val(r, "# Samples") for r in data) or 1
+    with open(dst, "a") as f:
+        f.write("\n# warp-stall samples per SASS instruction: `%s` (launch %s of `%s`)\n\n" % (kname, launch, src))
+        f.write("total samples %d over %d SASS instructions\n\n| stall reason | samples | share |\n|---|---:|---:|\n" % (tot, len(data)))
+        for n, v in sorted(((n, sum(val(r, n) for r in data)) for n in names), key=lambda x: -x[1])[:8]:
+            f.write("| %s | %d | %.1f%% |\n" % (n, v, 100.0 * v / tot))
+        f.write("\n| samples | share | executed | SASS | top stall |\n|---:|---:|---:|---|---|\n")
+        for r in sorted(data, key=lambda r: -val(r, "# Samples"))[:25]:
+            top = max(names, key=lambda n: val(r, n))
+            f.write("| %d | %.1f%% | %s | `%s` | %s |\n" % (val(r, "# Samples"), 100.0 * val(r, "# Samples") / tot,
+                                                       r[idx["Instructions Executed"]], r[idx["Source"]].strip()[:70], top))
+    print(open(dst).read()[-5000:])
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    elif sys.argv[1] == "stalls":
+        stalls(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "0")
     else:
         full(sys.argv[2], sys.argv[3])
