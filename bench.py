@@ -186,6 +186,15 @@ def main():
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, torchrun notices) are sent
+    # to stderr for the duration of the run and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,7 +215,7 @@ def main():
             return 0
         from oracle import ref_cpu
         if not ref_cpu.available():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnqs_ref.so missing (run make -C oracle)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libnqs_ref.so missing (run make -C oracle)"})
             return 0
         res = run_reference_cpu(args.config, args.steps, args.warmup, args.cpu_sample_chains, n_warm_sweeps=10)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -216,7 +225,7 @@ def main():
                                  "sample": res["sample"], "host_cores": res["host_cores"]},
                 "cg_iters_per_step": res["cg_iters"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # --------------------------------------------------------------------------------------------------- native arm
@@ -358,7 +367,7 @@ def main():
                                     "sample": res["sample"], "host_cores": res["host_cores"], "ms_per_step": res["ms_per_step"]}
         except Exception as ex:  # the checker being absent must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -1,0 +1,223 @@
+// One launch per CG iteration for everything that is not the pass over O.
+//
+// ref: ConjugateGradient::solve (gpu/include/conjugate_gradient.cuh:29-74) + the tails of SMatrixForCG::dot / applyPrecond
+// (gpu/include/functor_for_CG.cuh:115-135).  The reference spends 7 small kernels, 3 thrust reductions and 4 host syncs per
+// iteration there.  Here ONE kernel of <= 64 co-resident CTAs walks the iteration with
+// two software grid barriers; every CTA re-derives the scalars from the same per-CTA partial sums in the same fixed order,
+// so no broadcast is needed and the result is deterministic.  Scalars stay on the device (CgScalars); the host only polls
+// `done` every few iterations, without draining the queue.
+//
+//   MODE_ITER  t = S p ;  alpha = rho / Re<t,p> ;  x += alpha p ;  r -= alpha t ;  |r|^2 < thr -> done
+//              z = M^-1 r ;  rho' = Re<z,r> ;  beta = rho'/rho ;  p = z + beta p ;  <O>.p updated by linearity
+//   MODE_INIT  t = S x0 ;  r = F - t ;  |F|^2 == 0 -> x = 0, done ;  |r|^2 < thr -> done ;  p = M^-1 r ;  rho = Re<p,r> ;  <O>.p
+//   MODE_DOT   t = S v  (nqs_smatrix_dot)
+// with  (S v)_p = traw_p / K - conj(<O>_p) (<O>.v) + lambda diag_p v_p,   traw = sum_k conj(O_kp) (O_k . v)  (all ranks),
+//       M = (1 + lambda) diag(S).
+// traw comes either from the all-reduced buffer (multi-GPU) or, single-GPU, straight from the cluster / row-block partials
+// of the S*v kernel (folded here in fixed order: saves a launch).
+#pragma once
+#include "device_math.cuh"
+#include "sr_kernels.cuh"
+
+namespace nqs
+{
+enum { CG_MODE_ITER = 0, CG_MODE_INIT = 1, CG_MODE_DOT = 2 };
+
+#define NQS_CG_THREADS 256
+#define NQS_CG_MAX_CTAS 64
+#define NQS_CG_NVALS 6
+
+struct CgArgs
+{
+  long long P;
+  int mode;
+  int nparts;              // > 0: traw = sum over parts of part[q][{re,im}][P]; 0: read traw
+  const double * part;
+  const double * traw;     // [2][P]
+  double inv_ktot, lambda;
+  const cd * aO;
+  const double * diag;
+  const cd * F;            // INIT
+  cd * v;                  // ITER: p (updated in place); INIT: x0 (read; zeroed when |F| = 0); DOT: v
+  cd * pvec;               // INIT: p out
+  cd * x;                  // ITER
+  cd * r;                  // ITER (in/out), INIT (out)
+  cd * t;                  // scratch / DOT result
+  CgScalars * sc;
+  double * slots;          // [2][NQS_CG_MAX_CTAS][NQS_CG_NVALS] (successive grid sums alternate between the two halves)
+  unsigned int * barrier;  // zero between launches
+};
+
+// all CTAs of the grid are co-resident (grid <= 64, nothing else runs on the stream): spin barrier on a global counter
+__device__ __forceinline__ void cg_grid_barrier(unsigned int * counter, const unsigned int target)
+{
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int seen;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// CTA partials -> slots; after the grid barrier every CTA folds all slots in the same order.  vals/out: NV doubles.
+template <int NV>
+__device__ __forceinline__ void cg_grid_sum(double (&vals)[NV], const CgArgs & a, double * sh, unsigned int & epoch)
+{
+  const int lane = threadIdx.x&31, w = threadIdx.x>>5;
+  // a CTA can only write the slots of sum k+2 after every CTA finished reading those of sum k (it passed barrier k+1)
+  double * slots = a.slots+(size_t)(epoch&1u)*NQS_CG_MAX_CTAS*NQS_CG_NVALS;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) vals[i] = warp_sum(vals[i]);
+  if (lane == 0)
+  {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) sh[w*NV+i] = vals[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV)
+  {
+    double s = 0.0;
+    for (int ww = 0; ww < NQS_CG_THREADS/32; ++ww) s += sh[ww*NV+threadIdx.x];
+    slots[(size_t)blockIdx.x*NQS_CG_NVALS+threadIdx.x] = s;
+  }
+  ++epoch;
+  cg_grid_barrier(a.barrier, epoch*gridDim.x);
+  // NQS_CG_MAX_CTAS <= 64: lane b and b+32, then a fixed butterfly
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+  {
+    double s = 0.0;
+    if (lane < (int)gridDim.x) s = __ldcg(slots+(size_t)lane*NQS_CG_NVALS+i);
+    if (lane+32 < (int)gridDim.x) s += __ldcg(slots+(size_t)(lane+32)*NQS_CG_NVALS+i);
+    vals[i] = warp_sum(s);
+  }
+}
+
+__global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a)
+{
+  if (a.mode == CG_MODE_ITER && a.sc->done) return;     // uniform over the grid: converged earlier
+  __shared__ double sh[(NQS_CG_THREADS/32)*NQS_CG_NVALS];
+  const long long P = a.P;
+  const long long i0 = (long long)blockIdx.x*blockDim.x+threadIdx.x, stride = (long long)gridDim.x*blockDim.x;
+  unsigned int epoch = 0;
+  const double pre = 1.0+a.lambda;
+
+  // <O>.v: carried by recurrence during the iteration, computed explicitly for x0 / an arbitrary v
+  double aovx, aovy;
+  if (a.mode == CG_MODE_ITER) { aovx = a.sc->aov_x; aovy = a.sc->aov_y; }
+  else
+  {
+    double s[2] = {0.0, 0.0};
+    for (long long p = i0; p < P; p += stride)
+    {
+      const cd ao = a.aO[p], vv = a.v[p];
+      s[0] += ao.x*vv.x-ao.y*vv.y; s[1] += ao.x*vv.y+ao.y*vv.x;
+    }
+    cg_grid_sum<2>(s, a, sh, epoch);
+    aovx = s[0]; aovy = s[1];
+  }
+
+  // ---- t = S v, and the sums that decide the step
+  double s1[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (long long p = i0; p < P; p += stride)
+  {
+    double trx = 0.0, try_ = 0.0;
+    if (a.nparts > 0)
+    {
+      const double * base = a.part+p;
+      for (int q = 0; q < a.nparts; ++q) { trx += __ldcg(base+(size_t)q*2*P); try_ += __ldcg(base+(size_t)q*2*P+P); }
+    }
+    else { trx = a.traw[p]; try_ = a.traw[P+p]; }
+    const cd ao = a.aO[p], vv = a.v[p];
+    const double dg = a.diag[p];
+    // conj(aO) * aov
+    const double cx = ao.x*aovx+ao.y*aovy, cy = ao.x*aovy-ao.y*aovx;
+    cd tv = cmake(trx*a.inv_ktot-cx, try_*a.inv_ktot-cy);
+    tv.x += a.lambda*dg*vv.x; tv.y += a.lambda*dg*vv.y;
+    if (a.mode == CG_MODE_INIT)
+    {
+      const cd f = a.F[p];
+      const cd rv = csub(f, tv);
+      a.r[p] = rv;
+      const double den = pre*dg;
+      const cd pv = cmake(rv.x/den, rv.y/den);
+      a.pvec[p] = pv;
+      s1[0] += cnorm(f); s1[1] += cnorm(rv);
+      s1[2] += pv.x*rv.x+pv.y*rv.y;                            // Re(p conj(r))
+      s1[3] += ao.x*pv.x-ao.y*pv.y; s1[4] += ao.x*pv.y+ao.y*pv.x;
+    }
+    else
+    {
+      a.t[p] = tv;
+      s1[0] += tv.x*vv.x+tv.y*vv.y;                            // Re(t conj(p))
+    }
+  }
+  if (a.mode != CG_MODE_DOT) cg_grid_sum<5>(s1, a, sh, epoch);
+
+  if (a.mode == CG_MODE_DOT) {}
+  else if (a.mode == CG_MODE_INIT)
+  {
+    const double rhs2 = s1[0], res2 = s1[1];
+    const bool zero_rhs = (rhs2 == 0.0);
+    const double thr = fmax(a.sc->tol2*rhs2, 2.2250738585072014e-308);     // std::numeric_limits<double>::min()
+    if (zero_rhs)
+      for (long long p = i0; p < P; p += stride) a.v[p] = cmake(0.0, 0.0);   // conjugate_gradient.cuh:39-43: x = 0
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+      CgScalars * sc = a.sc;
+      sc->rhs2 = rhs2; sc->res2 = res2; sc->rho = s1[2]; sc->aov_x = s1[3]; sc->aov_y = s1[4];
+      sc->zero_rhs = zero_rhs ? 1 : 0; sc->thr = thr; sc->iters = 0;
+      sc->done = (zero_rhs || (!sc->fixed && res2 < thr)) ? 1 : 0;
+    }
+  }
+  else
+  {
+    const double rho = a.sc->rho, thr = a.sc->thr;
+    const int fixed = a.sc->fixed;
+    const double alpha = rho/s1[0];
+    double s2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long p = i0; p < P; p += stride)
+    {
+      const cd pv = a.v[p], tv = a.t[p], ao = a.aO[p];
+      cd xv = a.x[p], rv = a.r[p];
+      xv.x += alpha*pv.x; xv.y += alpha*pv.y;
+      rv.x -= alpha*tv.x; rv.y -= alpha*tv.y;
+      a.x[p] = xv; a.r[p] = rv;
+      const double den = pre*a.diag[p];
+      const cd zv = cmake(rv.x/den, rv.y/den);
+      a.t[p] = zv;                                             // t is dead now: reuse it for z
+      s2[0] += cnorm(rv);
+      s2[1] += zv.x*rv.x+zv.y*rv.y;
+      s2[2] += ao.x*zv.x-ao.y*zv.y; s2[3] += ao.x*zv.y+ao.y*zv.x;
+    }
+    cg_grid_sum<4>(s2, a, sh, epoch);
+    const double beta = s2[1]/rho;
+    const bool done = (!fixed && s2[0] < thr);
+    if (!done)
+      for (long long p = i0; p < P; p += stride)
+      {
+        const cd zv = a.t[p], pv = a.v[p];
+        a.v[p] = cmake(zv.x+beta*pv.x, zv.y+beta*pv.y);        // conjugate_gradient.cuh:71
+      }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+      CgScalars * sc = a.sc;
+      sc->tp = s1[0]; sc->alpha = alpha; sc->res2 = s2[0]; sc->iters += 1; sc->rho_old = rho; sc->rho = s2[1]; sc->beta = beta;
+      sc->aov_x = s2[2]+beta*aovx; sc->aov_y = s2[3]+beta*aovy;   // <O>.(z + beta p) by linearity
+      if (done) sc->done = 1;
+    }
+  }
+  // leave the barrier counter at zero for the next launch: the last CTA to get here resets it
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    const unsigned int n = atomicAdd(a.barrier, 1u);
+    if (n == (epoch+1)*gridDim.x-1) *a.barrier = 0u;
+  }
+}
+} // namespace nqs

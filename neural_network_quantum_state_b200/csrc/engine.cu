@@ -16,6 +16,7 @@
 #include "sampler_kernels.cuh"
 #include "sr_kernels.cuh"
 #include "sv_fused.cuh"
+#include "cg_fused.cuh"
 
 using namespace nqs;
 
@@ -465,105 +466,104 @@ void sr_setup(nqs_handle * h, bool want_F)
   check_launch(h, "setup_finalize_kernel");
 }
 
-// traw = sum_k conj(O_kp) (O_k . v) (+ all-reduce of 2P doubles): one pass over O with the cluster kernel, else two passes
-void matvec_passes(nqs_handle * h, const cd * v, const int * done)
+// The pass(es) over O of one S*v: cluster / row-block partials of sum_k conj(O_kp) (O_k . v) land in h->part.  Multi-GPU: they
+// are folded into traw and all-reduced (2P doubles) here; single GPU: cg_fused_kernel folds them itself.  Returns the number
+// of partials cg_fused_kernel has to fold (0 = read traw).
+int matvec_passes(nqs_handle * h, const cd * v, const int * done)
 {
   const long long P = h->P, K = h->K;
+  int nparts;
   if (h->sv_ok)
   {
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
     a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes;
     { const char * dbg = std::getenv("NQS_SV_DEBUG"); a.debug = dbg ? std::atoi(dbg) : 0; }
+    Span sp(h, TAG_ROWS);
+    NQS_CUDA(sv_launch(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
+    check_launch(h, "sv_fused_kernel");
+    nparts = h->sv_nclusters;
+  }
+  else
+  {
+    const unsigned gr = (unsigned)((K+NQS_ROWS_PER_CTA-1)/NQS_ROWS_PER_CTA);
     {
       Span sp(h, TAG_ROWS);
-      NQS_CUDA(sv_launch(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
-      check_launch(h, "sv_fused_kernel");
+      matvec_rows_kernel<<<gr, NQS_ROW_THREADS, 0, h->stream>>>(K, P, h->O.p, v, h->zk.p, done);
+      check_launch(h, "matvec_rows_kernel");
     }
-    colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, h->sv_nclusters, h->part.p, h->traw.p, done);
-    check_launch(h, "colsum_reduce_kernel");
-    allreduce_sum(h, h->traw.p, (size_t)(2*P));
-    return;
+    dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
+    {
+      Span sp(h, TAG_COLS);
+      matvec_cols_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->zk.p, h->part.p, h->rows_per_block, done);
+      check_launch(h, "matvec_cols_partial_kernel");
+    }
+    nparts = h->nrb;
   }
-  const unsigned gr = (unsigned)((K+NQS_ROWS_PER_CTA-1)/NQS_ROWS_PER_CTA);
-  {
-    Span sp(h, TAG_ROWS);
-    matvec_rows_kernel<<<gr, NQS_ROW_THREADS, 0, h->stream>>>(K, P, h->O.p, v, h->zk.p, done);
-    check_launch(h, "matvec_rows_kernel");
-  }
-  dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
-  {
-    Span sp(h, TAG_COLS);
-    matvec_cols_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->zk.p, h->part.p, h->rows_per_block, done);
-    check_launch(h, "matvec_cols_partial_kernel");
-  }
-  colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, h->nrb, h->part.p, h->traw.p, done);
+  if (h->comm == nullptr) return nparts;
+  colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, nparts, h->part.p, h->traw.p, done);
   check_launch(h, "colsum_reduce_kernel");
   allreduce_sum(h, h->traw.p, (size_t)(2*P));
+  return 0;
 }
 
-int vec_ctas(const nqs_handle * h)
+int cg_ctas(const nqs_handle * h)
 {
-  return std::max(1, std::min<int>(NQS_VEC_MAX_CTAS, (int)((h->P+NQS_VEC_THREADS*4-1)/(NQS_VEC_THREADS*4))));
+  return std::max(1, std::min<int>(NQS_CG_MAX_CTAS, (int)((h->P+NQS_CG_THREADS-1)/NQS_CG_THREADS)));
 }
 
-CgScalars read_scalars(nqs_handle * h)
+void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v)
 {
-  NQS_CUDA(cudaMemcpyAsync(h->pinned, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
-  NQS_CUDA(cudaStreamSynchronize(h->stream));
-  CgScalars s;
-  std::memcpy(&s, h->pinned, sizeof(CgScalars));
-  return s;
+  CgArgs a;
+  a.P = h->P; a.mode = mode; a.nparts = nparts; a.part = h->part.p; a.traw = h->traw.p;
+  a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p;
+  a.v = v; a.pvec = h->pvec.p; a.x = h->dx.p; a.r = h->r.p; a.t = h->t.p; a.sc = h->scal.p; a.slots = h->slots.p; a.barrier = h->cgbar.p;
+  cg_fused_kernel<<<cg_ctas(h), NQS_CG_THREADS, 0, h->stream>>>(a);
+  check_launch(h, "cg_fused_kernel");
 }
 
-// ref: ConjugateGradient::solve(SMatrixFunctor_, F, dx), conjugate_gradient.cuh:29-74, warm start in dx
+// ref: ConjugateGradient::solve(SMatrixFunctor_, F, dx), conjugate_gradient.cuh:29-74, warm start in dx.
+// Two launches per iteration (pass over O + cg_fused_kernel) and no host round trip inside: iterations are enqueued in batches
+// of four, the device-side `done` flag turns the ones past convergence into empty launches, and the host looks at a copy of
+// the scalars one batch behind the queue (the reference synchronises four times per iteration).
 void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters, nqs_sr_stats * st)
 {
-  const long long P = h->P;
-  const double inv_k = 1.0/(double)h->Ktot;
-  const int ctas = vec_ctas(h);
   CgScalars init;
   std::memset(&init, 0, sizeof(init));
   init.tol2 = tol*tol;
   init.fixed = fixed_iters > 0 ? 1 : 0;
+  NQS_CUDA(cudaStreamSynchronize(h->stream)); // pinned area is shared with earlier read-backs
   std::memcpy(h->pinned, &init, sizeof(init));
   NQS_CUDA(cudaMemcpyAsync(h->scal.p, h->pinned, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
-  NQS_CUDA(cudaStreamSynchronize(h->stream)); // pinned area is reused for read-backs
   int * done = &h->scal.p->done;
-  cg_aov_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->aO.p, h->dx.p, h->scal.p, h->slots.p);
-  check_launch(h, "cg_aov_kernel");
-  matvec_passes(h, h->dx.p, nullptr);
-  cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, inv_k, lambda, h->traw.p, h->aO.p, h->diag.p, h->dx.p, h->t.p,
-    h->F.p, h->r.p, h->pvec.p, h->scal.p, h->slots.p, 1);
-  check_launch(h, "cg_phase1_kernel");
-  CgScalars s = read_scalars(h);
-  if (s.zero_rhs)
+  int nparts = matvec_passes(h, h->dx.p, nullptr);
+  launch_cg_fused(h, CG_MODE_INIT, nparts, lambda, h->dx.p);
+  const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
+  const int batch = 4;
+  CgScalars * snap[2] = {reinterpret_cast<CgScalars*>((char*)h->pinned+1024), reinterpret_cast<CgScalars*>((char*)h->pinned+2048)};
+  int nb = 0;
+  bool stop = false;
+  for (int it = 0; it < n_max && !stop; )
   {
-    NQS_CUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(cd)*P, h->stream));
-  }
-  else if (!s.done)
-  {
-    const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
-    const int check_every = fixed_iters > 0 ? n_max : 4;
-    for (int it = 0; it < n_max; ++it)
+    const int n_here = std::min(batch, n_max-it);
+    for (int q = 0; q < n_here; ++q)
     {
-      matvec_passes(h, h->pvec.p, done);
-      cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, inv_k, lambda, h->traw.p, h->aO.p, h->diag.p, h->pvec.p, h->t.p,
-        nullptr, nullptr, nullptr, h->scal.p, h->slots.p, 0);
-      check_launch(h, "cg_phase1_kernel");
-      cg_phase2_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, lambda, h->aO.p, h->diag.p, h->pvec.p, h->t.p, h->dx.p, h->r.p,
-        h->z.p, h->scal.p, h->slots.p);
-      check_launch(h, "cg_phase2_kernel");
-      cg_phase3_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->z.p, h->pvec.p, h->scal.p);
-      check_launch(h, "cg_phase3_kernel");
-      if ((it+1)%check_every == 0 || it+1 == n_max)
-      {
-        s = read_scalars(h);
-        if (s.done) break;
-      }
+      nparts = matvec_passes(h, h->pvec.p, done);
+      launch_cg_fused(h, CG_MODE_ITER, nparts, lambda, h->pvec.p);
     }
-    s = read_scalars(h);
+    it += n_here;
+    NQS_CUDA(cudaMemcpyAsync(snap[nb&1], h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaEventRecord(h->cg_ev[nb&1], h->stream));
+    if (nb >= 1)
+    { // look at the batch before the one just enqueued
+      NQS_CUDA(cudaEventSynchronize(h->cg_ev[(nb-1)&1]));
+      if (snap[(nb-1)&1]->done) stop = true;
+    }
+    ++nb;
   }
+  if (nb == 0) NQS_CUDA(cudaMemcpyAsync(snap[1], h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  const CgScalars s = *snap[(nb+1)&1];
   if (st)
   {
     st->cg_iters = s.iters;
@@ -674,7 +674,9 @@ void alloc_sr(nqs_handle * h)
   h->part.alloc(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->traw.alloc((size_t)2*h->P);
-  h->slots.alloc((size_t)5*NQS_VEC_MAX_CTAS);
+  h->slots.alloc((size_t)2*NQS_CG_MAX_CTAS*NQS_CG_NVALS);
+  h->cgbar.alloc(1);
+  NQS_CUDA(cudaMemset(h->cgbar.p, 0, sizeof(unsigned int)));
   h->scal.alloc(1);
   NQS_CUDA(cudaMemset(h->scal.p, 0, sizeof(CgScalars)));
   NQS_CUDA(cudaMemset(h->dx.p, 0, sizeof(cd)*h->P)); // CG warm start is zero only at construction (ref impl_optimizer.cuh:55)
@@ -741,6 +743,7 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     h->smem_optin = prop.sharedMemPerBlockOptin;
     NQS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) NQS_CUDA(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 2; ++i) NQS_CUDA(cudaEventCreateWithFlags(&h->cg_ev[i], cudaEventDisableTiming));
     h->ev_ok = true;
     NQS_CUDA(cudaMallocHost(&h->pinned, 4096));
     const size_t KM = (size_t)h->K*h->M, KN = (size_t)h->K*h->N;
@@ -784,6 +787,7 @@ void nqs_destroy(nqs_handle * h)
   if (h->comm && g_nccl.commDestroy) g_nccl.commDestroy(h->comm);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 2; ++i) if (h->cg_ev[i]) cudaEventDestroy(h->cg_ev[i]);
   for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
@@ -1084,16 +1088,8 @@ nqs_status nqs_smatrix_dot(nqs_handle * h, double lambda, const nqs_cdouble * v,
     const long long P = h->P;
     sr_setup(h, false);
     NQS_CUDA(cudaMemcpyAsync(h->pvec.p, v, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
-    CgScalars init; std::memset(&init, 0, sizeof(init));
-    std::memcpy(h->pinned, &init, sizeof(init));
-    NQS_CUDA(cudaMemcpyAsync(h->scal.p, h->pinned, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
-    const int ctas = vec_ctas(h);
-    cg_aov_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, h->aO.p, h->pvec.p, h->scal.p, h->slots.p);
-    check_launch(h, "cg_aov_kernel");
-    matvec_passes(h, h->pvec.p, nullptr);
-    cg_phase1_kernel<<<ctas, NQS_VEC_THREADS, 0, h->stream>>>(P, 1.0/(double)h->Ktot, lambda, h->traw.p, h->aO.p, h->diag.p, h->pvec.p,
-      h->t.p, nullptr, nullptr, nullptr, h->scal.p, h->slots.p, 0);
-    check_launch(h, "cg_phase1_kernel");
+    const int nparts = matvec_passes(h, h->pvec.p, nullptr);
+    launch_cg_fused(h, CG_MODE_DOT, nparts, lambda, h->pvec.p);
     NQS_CUDA(cudaMemcpyAsync(Sv, h->t.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
     if (aO) NQS_CUDA(cudaMemcpyAsync(aO, h->aO.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
     if (diag) NQS_CUDA(cudaMemcpyAsync(diag, h->diag.p, sizeof(double)*P, cudaMemcpyDeviceToHost, h->stream));

@@ -77,6 +77,8 @@ struct nqs_handle
   nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
   nqs::DevBuf<double> diag, part, sums, traw, slots;
   nqs::DevBuf<nqs::CgScalars> scal;
+  nqs::DevBuf<unsigned int> cgbar;         // grid-barrier counter of cg_fused_kernel (zero between launches)
+  cudaEvent_t cg_ev[2] = {nullptr, nullptr};
   double bp = 1.0;                        // lambda schedule state (ref bp_, optimizer.cuh:176)
   int nrb = 1;                            // row blocks of the column passes
   long long rows_per_block = 0;

@@ -1,5 +1,5 @@
-// Stochastic-reconfiguration side of the path: O writer, single-pass SR setup sums, the two streaming passes over O that make
-// one S*v product, and the preconditioned-CG vector phases with device-resident scalars (no host sync inside an iteration).
+// Stochastic-reconfiguration side of the path: O writer, single-pass SR setup sums, the two-pass fallback of the S*v product
+// (the one-pass cluster kernel is in sv_fused.cuh, the CG iteration body in cg_fused.cuh) and the parameter update.
 // O is [K_loc][P] row-major complex fp64 exactly like the reference's lnpsiGradients (k*P + p); all indices are 64-bit
 // (ref int32 overflow at cfg5).  Every reduction is two-stage with a fixed order -> run-to-run deterministic.
 #pragma once
@@ -291,198 +291,14 @@ __global__ void __launch_bounds__(NQS_ROW_THREADS) matvec_rows_kernel(const long
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// PCG vector phases (ref ConjugateGradient::solve, conjugate_gradient.cuh:29-74, and SMatrixForCG::dot/applyPrecond tails,
-// functor_for_CG.cuh:115-135).  All scalars live in `CgScalars` on the device; a grid of CTAs computes per-CTA partial sums
-// into slots and the LAST CTA to finish (atomic ticket) folds them in slot order, so there is no host round trip per
-// iteration (the reference has four).
-// ---------------------------------------------------------------------------------------------------------------------
+// Device-resident scalars of the preconditioned CG (csrc/cg_fused.cuh); the host only ever reads a copy.
 struct CgScalars
 {
   double rho, rho_old, alpha, beta, res2, thr, rhs2, tp;
-  double aov_x, aov_y;     // <O> . v for the direction currently held in p (or x during init)
+  double aov_x, aov_y;     // <O> . p for the direction currently held in p
   double tol2;
   int done, iters, zero_rhs, fixed;
-  unsigned int ticket[4];
 };
-
-#define NQS_VEC_THREADS 256
-#define NQS_VEC_MAX_CTAS 64
-
-__device__ __forceinline__ double block_sum_256(double v, double * sh)
-{ // sh: >= 8 doubles; all threads must call
-  v = warp_sum(v);
-  const int w = threadIdx.x>>5, lane = threadIdx.x&31;
-  __syncthreads();
-  if (lane == 0) sh[w] = v;
-  __syncthreads();
-  double s = 0;
-  if (threadIdx.x == 0)
-    for (int i = 0; i < NQS_VEC_THREADS/32; ++i) s += sh[i];
-  return s; // valid on thread 0
-}
-
-// returns true on thread 0 of the last CTA to arrive; slots then hold every CTA's partials
-__device__ __forceinline__ bool last_block_arrives(unsigned int * ticket)
-{
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    const unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x-1);
-    if (is_last) *ticket = 0;
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last && threadIdx.x == 0;
-}
-
-// aov = sum_p aO_p v_p   (ref t2 thrust::inner_product, functor_for_CG.cuh:115) -- used once for the warm-start vector x
-__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_aov_kernel(const long long P, const cd * __restrict__ aO,
-  const cd * __restrict__ v, CgScalars * sc, double * slots)
-{
-  __shared__ double sh[8];
-  double sx = 0, sy = 0;
-  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
-  {
-    const cd a = aO[p], b = v[p];
-    sx += a.x*b.x-a.y*b.y; sy += a.x*b.y+a.y*b.x;
-  }
-  sx = block_sum_256(sx, sh); sy = block_sum_256(sy, sh);
-  if (threadIdx.x == 0) { slots[2*blockIdx.x] = sx; slots[2*blockIdx.x+1] = sy; }
-  if (last_block_arrives(&sc->ticket[0]))
-  {
-    double ax = 0, ay = 0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) { ax += slots[2*b]; ay += slots[2*b+1]; }
-    sc->aov_x = ax; sc->aov_y = ay;
-  }
-}
-
-// t = traw/K - conj(aO) (aO.v) + lambda diag v          (functor_for_CG.cuh:118-126)
-// init != 0 (v = x):  r = F - t ; rhs2 = |F|^2 ; res2 = |r|^2 ; p = M^-1 r ; rho = Re<p,r> ; aov = aO.p ; thr ; done   (conjugate_gradient.cuh:33-48)
-// init == 0 (v = p):  tp = Re<t,p> ; alpha = rho/tp                                                                  (:52-54)
-__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase1_kernel(const long long P, const double inv_ktot, const double lambda,
-  const double * __restrict__ traw, const cd * __restrict__ aO, const double * __restrict__ diag, const cd * __restrict__ v,
-  cd * __restrict__ t, const cd * __restrict__ F, cd * __restrict__ r, cd * __restrict__ pvec, CgScalars * sc, double * slots, const int init)
-{
-  if (!init && sc->done) return;
-  __shared__ double sh[8];
-  const cd aov = cmake(sc->aov_x, sc->aov_y);
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
-  const double pre = 1.0+lambda;
-  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
-  {
-    const cd ao = aO[p], vv = v[p];
-    const double dg = diag[p];
-    const cd corr = cmul(cconj(ao), aov);
-    cd tv = cmake(traw[p]*inv_ktot-corr.x, traw[P+p]*inv_ktot-corr.y);
-    tv.x += lambda*dg*vv.x; tv.y += lambda*dg*vv.y;
-    t[p] = tv;
-    if (init)
-    {
-      const cd f = F[p];
-      const cd rv = csub(f, tv);
-      r[p] = rv;
-      const double den = pre*dg;
-      const cd pv = cmake(rv.x/den, rv.y/den);
-      pvec[p] = pv;
-      s0 += cnorm(f); s1 += cnorm(rv);
-      s2 += pv.x*rv.x+pv.y*rv.y;                 // Re(p conj(r))
-      s3 += ao.x*pv.x-ao.y*pv.y; s4 += ao.x*pv.y+ao.y*pv.x;
-    }
-    else
-      s0 += tv.x*vv.x+tv.y*vv.y;                 // Re(t conj(p))
-  }
-  const int ns = init ? 5 : 1;
-  double part[5] = {s0, s1, s2, s3, s4};
-  for (int i = 0; i < ns; ++i)
-  {
-    const double s = block_sum_256(part[i], sh);
-    if (threadIdx.x == 0) slots[5*blockIdx.x+i] = s;
-  }
-  if (last_block_arrives(&sc->ticket[1]))
-  {
-    double tot[5] = {0, 0, 0, 0, 0};
-    for (unsigned int b = 0; b < gridDim.x; ++b)
-      for (int i = 0; i < ns; ++i) tot[i] += slots[5*b+i];
-    if (init)
-    {
-      sc->rhs2 = tot[0]; sc->res2 = tot[1]; sc->rho = tot[2]; sc->aov_x = tot[3]; sc->aov_y = tot[4];
-      sc->zero_rhs = (tot[0] == 0.0) ? 1 : 0;
-      const double thr = fmax(sc->tol2*tot[0], 2.2250738585072014e-308); // std::numeric_limits<double>::min()
-      sc->thr = thr;
-      sc->iters = 0;
-      sc->done = (sc->zero_rhs || (!sc->fixed && tot[1] < thr)) ? 1 : 0;
-    }
-    else
-    {
-      sc->tp = tot[0];
-      sc->alpha = sc->rho/tot[0];
-    }
-  }
-}
-
-// x += alpha p ; r -= alpha t ; res2 = |r|^2 ; [break] ; z = M^-1 r ; rho' = Re<z,r> ; beta = rho'/rho   (conjugate_gradient.cuh:56-69)
-__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase2_kernel(const long long P, const double lambda,
-  const cd * __restrict__ aO, const double * __restrict__ diag, const cd * __restrict__ pvec, const cd * __restrict__ t,
-  cd * __restrict__ x, cd * __restrict__ r, cd * __restrict__ z, CgScalars * sc, double * slots)
-{
-  if (sc->done) return;
-  __shared__ double sh[8];
-  const double alpha = sc->alpha, pre = 1.0+lambda;
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
-  {
-    const cd pv = pvec[p], tv = t[p], ao = aO[p];
-    cd xv = x[p], rv = r[p];
-    xv.x += alpha*pv.x; xv.y += alpha*pv.y;
-    rv.x -= alpha*tv.x; rv.y -= alpha*tv.y;
-    x[p] = xv; r[p] = rv;
-    const double den = pre*diag[p];
-    const cd zv = cmake(rv.x/den, rv.y/den);
-    z[p] = zv;
-    s0 += cnorm(rv);
-    s1 += zv.x*rv.x+zv.y*rv.y;
-    s2 += ao.x*zv.x-ao.y*zv.y; s3 += ao.x*zv.y+ao.y*zv.x;
-  }
-  double part[4] = {s0, s1, s2, s3};
-  for (int i = 0; i < 4; ++i)
-  {
-    const double s = block_sum_256(part[i], sh);
-    if (threadIdx.x == 0) slots[5*blockIdx.x+i] = s;
-  }
-  if (last_block_arrives(&sc->ticket[2]))
-  {
-    double tot[4] = {0, 0, 0, 0};
-    for (unsigned int b = 0; b < gridDim.x; ++b)
-      for (int i = 0; i < 4; ++i) tot[i] += slots[5*b+i];
-    sc->res2 = tot[0];
-    sc->iters += 1;
-    sc->rho_old = sc->rho;
-    sc->rho = tot[1];
-    const double beta = tot[1]/sc->rho_old;
-    sc->beta = beta;
-    // aO.(z + beta p) by linearity: saves a pass over p
-    const double ox = sc->aov_x, oy = sc->aov_y;
-    sc->aov_x = tot[2]+beta*ox; sc->aov_y = tot[3]+beta*oy;
-    if (!sc->fixed && tot[0] < sc->thr) sc->done = 1;
-  }
-}
-
-// p = z + beta p   (conjugate_gradient.cuh:71); skipped once converged (the reference breaks before it)
-__global__ void __launch_bounds__(NQS_VEC_THREADS) cg_phase3_kernel(const long long P, const cd * __restrict__ z, cd * __restrict__ pvec,
-  const CgScalars * sc)
-{
-  if (sc->done) return;
-  const double beta = sc->beta;
-  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
-  {
-    const cd zv = z[p], pv = pvec[p];
-    pvec[p] = cmake(zv.x+beta*pv.x, zv.y+beta*pv.y);
-  }
-}
 
 // ref: update_parameters (impl_neural_quantum_state.cuh:1300-1312) / FFNN__UpdateParameters__ (:1665-1690, un-transposes the W block)
 __global__ void update_params_kernel(const int N, const int M, const int model, const long long P, const cd * __restrict__ dx,
