@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--cg-fixed-iters", type=int, default=0, help="diagnostics: run exactly this many CG iterations per step")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllReduce per CG iteration instead of the in-kernel exchange")
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
@@ -205,7 +206,7 @@ def main():
     config = {"workload": "%s: complex %s M=%d, long-range TFI chain N=%d (alpha=2, theta=pi/4, OBC), %d chains total, "
                           "step = sweep(nms=1) + E_loc + O + SR setup + PCG(tol 1e-5, reference lambda schedule) + update"
                           % (args.config, model.upper(), M, N, K_total),
-              "N": N, "M": M, "K_total": K_total, "P": P, "sharding": "chains/%d" % world,
+              "N": N, "M": M, "K_total": K_total, "P": P, "sharding": "chains/%d" % world, "cg_exchange": None,
               "l2": "working set (O = %.2f GB per rank) >> 126 MB L2: no flush needed" % (K_total / world * P * 16 / 1e9),
               "nwarm_sweeps": args.nwarm, "lr": args.lr, "rng": "in-kernel Philox4x32-10 (value) / pre-drawn host uniforms (e2e)"}
 
@@ -243,10 +244,12 @@ def main():
                n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic,
                two_pass_sv=args.two_pass_sv)
     e.set_params(synthetic_params(model, N, M, cfg_id))
+    p2p = False
     if world > 1:
-        ids = [Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        e.comm_init(world, rank, ids[0])
+        from neural_network_quantum_state_b200.dist import bootstrap_comm, enable_p2p
+        bootstrap_comm(e, world, rank, p2p=False)          # NCCL communicator (SR-setup all-reduce)
+        if not args.no_p2p:
+            p2p = enable_p2p(e, world)                      # per-CG-iteration exchange inside the CG kernel over NVLink
     e.warm_up(args.nwarm)
 
     def barrier():
@@ -290,6 +293,7 @@ def main():
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
     value = K_total / (ms_per_step * 1e-3)
+    config["cg_exchange"] = "none (1 GPU)" if world == 1 else ("in-kernel all-reduce over NVLink peer memory" if p2p else "ncclAllReduce")
 
     # ---- end-to-end through the public API with HOST buffers: pinned uniforms H2D every step, spins + lnpsi + stats D2H
     e2e = None

@@ -77,6 +77,7 @@ typedef struct nqs_config {
 #define NQS_FLAG_NO_SR        1  /* sampler only (pynqs use): do not allocate O [K][P] nor the CG vectors */
 #define NQS_FLAG_ACCEPT_LOG   2  /* keep accept masks of the most recent nqs_do_mcmc_steps/nqs_warm_up call (tests) */
 #define NQS_FLAG_FORCE_GENERIC 4 /* use the generic (direct log cosh) kernels even where a specialised one exists */
+#define NQS_FLAG_SETUP_FROM_O 16 /* SR setup sums by a pass over O (reference structure) instead of from the factors (spins, tanh theta) */
 #define NQS_FLAG_TWO_PASS_SV  8  /* S*v as two streaming passes over O (reference structure) instead of the one-pass cluster kernel */
 
 /* statistics of one SR iteration.  ref: the row printed by propagate, gpu/include/optimizer.cuh:156-159 */
@@ -174,6 +175,14 @@ nqs_status nqs_evolve(nqs_handle * h, const nqs_cdouble * dx, double lr);
 #define NQS_UNIQUE_ID_BYTES 128
 nqs_status nqs_comm_get_unique_id(char id[NQS_UNIQUE_ID_BYTES]);                      /* rank 0, then broadcast by the host */
 nqs_status nqs_comm_init(nqs_handle * h, int32_t n_ranks, int32_t rank, const char id[NQS_UNIQUE_ID_BYTES]);
+/* Optional fast path for the per-CG-iteration exchange: the all-reduce of O_loc^H (O_loc v) is done inside the CG kernel over
+ * NVLink peer memory.  After nqs_comm_init every rank exports the handle of its receive buffer, the host gathers the handles
+ * of all ranks (rank order, NQS_IPC_HANDLE_BYTES each) and every rank imports them.  If the import fails
+ * (NQS_ERR_UNSUPPORTED: no peer mapping between the processes) the engine keeps using ncclAllReduce. */
+#define NQS_IPC_HANDLE_BYTES 64
+nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BYTES]);
+nqs_status nqs_comm_p2p_import(nqs_handle * h, const char * handles /* [n_ranks][NQS_IPC_HANDLE_BYTES] */);
+nqs_status nqs_comm_p2p_disable(nqs_handle * h); /* back to ncclAllReduce (all ranks must switch together) */
 
 /* ---- introspection for benchmarks ----------------------------------------------------------------------------------- */
 typedef struct nqs_timing {

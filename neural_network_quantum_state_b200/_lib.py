@@ -9,6 +9,7 @@ from . import build as _build
 
 ABI_VERSION = 1
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_NCCL, ERR_NONFINITE, ERR_UNSUPPORTED = range(9)
 STATUS_NAMES = ["NQS_OK", "NQS_ERR_INVALID", "NQS_ERR_CUDA", "NQS_ERR_NOMEM", "NQS_ERR_IO", "NQS_ERR_STATE",
@@ -78,6 +79,9 @@ SYMBOLS = {
     "nqs_evolve": (_i32, [_vp, _vp, _dbl]),
     "nqs_comm_get_unique_id": (_i32, [_vp]),
     "nqs_comm_init": (_i32, [_vp, _i32, _i32, _vp]),
+    "nqs_comm_p2p_export": (_i32, [_vp, _vp]),
+    "nqs_comm_p2p_import": (_i32, [_vp, _vp]),
+    "nqs_comm_p2p_disable": (_i32, [_vp]),
     "nqs_get_timing": (_i32, [_vp, C.POINTER(Timing)]),
     "nqs_set_timing": (_i32, [_vp, _i32]),
     "nqs_event_record": (_i32, [_vp, _i32]),

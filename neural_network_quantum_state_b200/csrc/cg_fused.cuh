@@ -13,8 +13,16 @@
 //   MODE_DOT   t = S v  (nqs_smatrix_dot)
 // with  (S v)_p = traw_p / K - conj(<O>_p) (<O>.v) + lambda diag_p v_p,   traw = sum_k conj(O_kp) (O_k . v)  (all ranks),
 //       M = (1 + lambda) diag(S).
-// traw comes either from the all-reduced buffer (multi-GPU) or, single-GPU, straight from the cluster / row-block partials
-// of the S*v kernel (folded here in fixed order: saves a launch).
+// traw comes straight from the cluster / row-block partials of the S*v kernel (folded here in fixed order: saves a launch).
+//
+// Multi-GPU: the all-reduce of the P complex partial sums that every CG iteration needs is done INSIDE this kernel over
+// NVLink peer memory instead of a separate NCCL launch: every rank stores its folded partial into slot [rank] of a receive
+// buffer that lives on EVERY peer (plain st.global on cudaIpc-mapped peer pointers), publishes a per-(rank, parity) epoch
+// flag with a system-scope release, waits for the flags of all ranks and adds the slots in RANK ORDER -- so the sum is
+// bit-identical on all ranks (the replicated CG state never diverges) and costs one NVLink hop (~P*16 B per peer) instead
+// of a collective launch.  Receive buffers are double-buffered by epoch parity: a rank can only write epoch n+2 after it
+// has seen every peer's flag n+1, which a peer raises after it finished reading epoch n.  (If the peer mapping is not
+// available the engine falls back to colsum_reduce_kernel + ncclAllReduce + traw.)
 #pragma once
 #include "device_math.cuh"
 #include "sr_kernels.cuh"
@@ -26,6 +34,7 @@ enum { CG_MODE_ITER = 0, CG_MODE_INIT = 1, CG_MODE_DOT = 2 };
 #define NQS_CG_THREADS 256
 #define NQS_CG_MAX_CTAS 64
 #define NQS_CG_NVALS 6
+#define NQS_CG_MAX_RANKS 16
 
 struct CgArgs
 {
@@ -46,6 +55,11 @@ struct CgArgs
   CgScalars * sc;
   double * slots;          // [2][NQS_CG_MAX_CTAS][NQS_CG_NVALS] (successive grid sums alternate between the two halves)
   unsigned int * barrier;  // zero between launches
+  // in-kernel all-reduce over peer memory (n_ranks > 1 and the peers are mapped)
+  int n_ranks, rank;
+  unsigned int epoch;      // increases by one per exchange on every rank
+  double * peer_x[NQS_CG_MAX_RANKS];            // peer_x[r]: receive buffer of rank r, [2][n_ranks][2P]
+  unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS]
 };
 
 // all CTAs of the grid are co-resident (grid <= 64, nothing else runs on the stream): spin barrier on a global counter
@@ -97,6 +111,32 @@ __device__ __forceinline__ void cg_grid_sum(double (&vals)[NV], const CgArgs & a
   }
 }
 
+// sum_q part[q][{re,im}][p] in a fixed order with four independent load streams (a serial chain would expose one L2 latency
+// per partial: ~9 us for 15 cluster partials)
+__device__ __forceinline__ void cg_fold_parts(const double * __restrict__ part, const int nparts, const long long P, const long long p,
+  double & rx, double & ry)
+{
+  double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
+  const double * base = part+p;
+  int q = 0;
+  for (; q+4 <= nparts; q += 4)
+  {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+      ax[u] += __ldcg(base+(size_t)(q+u)*2*P);
+      ay[u] += __ldcg(base+(size_t)(q+u)*2*P+P);
+    }
+  }
+  for (int u = 0; q < nparts; ++q, ++u)
+  {
+    ax[u] += __ldcg(base+(size_t)q*2*P);
+    ay[u] += __ldcg(base+(size_t)q*2*P+P);
+  }
+  rx = (ax[0]+ax[1])+(ax[2]+ax[3]);
+  ry = (ay[0]+ay[1])+(ay[2]+ay[3]);
+}
+
 __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a)
 {
   if (a.mode == CG_MODE_ITER && a.sc->done) return;     // uniform over the grid: converged earlier
@@ -121,16 +161,44 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
     aovx = s[0]; aovy = s[1];
   }
 
+  // ---- multi-GPU: push this rank's folded partial to every peer, then wait for everybody's
+  const bool p2p = (a.n_ranks > 1 && a.nparts > 0);
+  const double * xin = nullptr;
+  if (p2p)
+  {
+    const int par = (int)(a.epoch&1u);
+    const size_t slot = ((size_t)par*a.n_ranks+a.rank)*2*(size_t)P;
+    for (long long p = i0; p < P; p += stride)
+    {
+      double trx, try_;
+      cg_fold_parts(a.part, a.nparts, P, p, trx, try_);
+      for (int r = 0; r < a.n_ranks; ++r) { a.peer_x[r][slot+p] = trx; a.peer_x[r][slot+P+p] = try_; }
+    }
+    __threadfence_system();
+    ++epoch;
+    cg_grid_barrier(a.barrier, epoch*gridDim.x);            // every CTA's stores are issued and fenced
+    if (blockIdx.x == 0 && threadIdx.x < a.n_ranks)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.peer_flag[threadIdx.x]+par*NQS_CG_MAX_RANKS+a.rank), "r"(a.epoch) : "memory");
+    if (threadIdx.x < a.n_ranks)
+    {
+      const unsigned int * f = a.peer_flag[a.rank]+par*NQS_CG_MAX_RANKS+threadIdx.x;
+      unsigned int seen;
+      do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory"); } while ((int)(seen-a.epoch) < 0);
+    }
+    __syncthreads();
+    xin = a.peer_x[a.rank]+(size_t)par*a.n_ranks*2*(size_t)P;
+  }
+
   // ---- t = S v, and the sums that decide the step
   double s1[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   for (long long p = i0; p < P; p += stride)
   {
     double trx = 0.0, try_ = 0.0;
-    if (a.nparts > 0)
-    {
-      const double * base = a.part+p;
-      for (int q = 0; q < a.nparts; ++q) { trx += __ldcg(base+(size_t)q*2*P); try_ += __ldcg(base+(size_t)q*2*P+P); }
+    if (p2p)
+    { // rank order: identical bits on every rank
+      for (int r = 0; r < a.n_ranks; ++r) { trx += __ldcv(xin+(size_t)r*2*P+p); try_ += __ldcv(xin+(size_t)r*2*P+P+p); }
     }
+    else if (a.nparts > 0) cg_fold_parts(a.part, a.nparts, P, p, trx, try_);
     else { trx = a.traw[p]; try_ = a.traw[P+p]; }
     const cd ao = a.aO[p], vv = a.v[p];
     const double dg = a.diag[p];

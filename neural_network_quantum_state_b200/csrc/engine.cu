@@ -246,6 +246,7 @@ void launch_eloc_fast(nqs_handle * h)
 void launch_sweep(nqs_handle * h, long long nsteps)
 {
   if (nsteps <= 0) return;
+  h->theta_matches_O = false;
   SweepArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
   a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.order = h->order.p;
@@ -354,13 +355,14 @@ void launch_oderiv(nqs_handle * h)
     oderiv_kernel<MODEL_FFNN><<<(unsigned)h->K, 256, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
   }
   check_launch(h, "oderiv_kernel");
+  h->theta_matches_O = true;   // O was built from the current (spins, theta, params): the setup sums may use the factors
 }
 
 // ---- one-pass S*v (sv_fused.cuh): cluster launch + plan -------------------------------------------------------------------
-template <int CPT>
+template <int CPT, int DEFER>
 cudaError_t sv_launch_t(const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * query_max_clusters)
 {
-  auto kern = sv_fused_kernel<CPT>;
+  auto kern = sv_fused_kernel<CPT, DEFER>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (cs > 8)
@@ -382,20 +384,20 @@ cudaError_t sv_launch_t(const SvArgs & a, int cs, int nclusters, int nt, size_t 
   return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-cudaError_t sv_launch(int cpt, const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * q)
+cudaError_t sv_launch(int cpt, int defer, const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * q)
 {
   switch (cpt)
   {
-    case 1: return sv_launch_t<1>(a, cs, nclusters, nt, smem, stream, q);
-    case 2: return sv_launch_t<2>(a, cs, nclusters, nt, smem, stream, q);
-    case 3: return sv_launch_t<3>(a, cs, nclusters, nt, smem, stream, q);
-    case 4: return sv_launch_t<4>(a, cs, nclusters, nt, smem, stream, q);
-    case 5: return sv_launch_t<5>(a, cs, nclusters, nt, smem, stream, q);
-    case 6: return sv_launch_t<6>(a, cs, nclusters, nt, smem, stream, q);
-    case 7: return sv_launch_t<7>(a, cs, nclusters, nt, smem, stream, q);
-    case 8: return sv_launch_t<8>(a, cs, nclusters, nt, smem, stream, q);
-    case 9: return sv_launch_t<9>(a, cs, nclusters, nt, smem, stream, q);
-    case 10: return sv_launch_t<10>(a, cs, nclusters, nt, smem, stream, q);
+    case 1: return defer ? sv_launch_t<1, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<1, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 2: return defer ? sv_launch_t<2, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<2, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 3: return defer ? sv_launch_t<3, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<3, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 4: return defer ? sv_launch_t<4, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<4, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 5: return defer ? sv_launch_t<5, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<5, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 6: return defer ? sv_launch_t<6, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<6, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 7: return defer ? sv_launch_t<7, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<7, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 8: return defer ? sv_launch_t<8, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<8, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 9: return defer ? sv_launch_t<9, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<9, 0>(a, cs, nclusters, nt, smem, stream, q);
+    case 10: return defer ? sv_launch_t<10, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<10, 0>(a, cs, nclusters, nt, smem, stream, q);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -406,6 +408,8 @@ void plan_sv(nqs_handle * h)
 {
   h->sv_ok = false;
   if (h->cfg.flags & NQS_FLAG_TWO_PASS_SV) return;
+  // software-pipelined variant by default (1.50 ms vs 1.95 ms per S*v at N=128, M=256, K=16384; needs >= 3 row slots)
+  { const char * d = std::getenv("NQS_SV_DEFER"); h->sv_defer = d ? std::atoi(d) : 1; }
   const int cs_try[2] = {8, 16};
   for (int ci = 0; ci < 2; ++ci)
   {
@@ -427,16 +431,17 @@ void plan_sv(nqs_handle * h)
     SvArgs a;
     std::memset(&a, 0, sizeof(a));
     int maxc = 0;
-    cudaError_t e = sv_launch(cpt, a, cs, 1, nt, smem, h->stream, &maxc);
+    cudaError_t e = sv_launch(cpt, h->sv_defer, a, cs, 1, nt, smem, h->stream, &maxc);
     if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
     long long ncl = std::min<long long>(maxc, h->K);
     const long long rpc = (h->K+ncl-1)/ncl;
     ncl = (h->K+rpc-1)/rpc;
+    if (nslot < 3) h->sv_defer = 0;
     h->sv_cs = cs; h->sv_cpt = cpt; h->sv_nt = nt; h->sv_nslot = nslot; h->sv_nclusters = (int)ncl;
     h->sv_smem = smem; h->sv_slot_bytes = slot_bytes; h->sv_pc = pc; h->sv_rpc = rpc;
     h->sv_ok = true;
     h->variant_sv = "fused_cs"+std::to_string(cs)+"_cpt"+std::to_string(cpt)+"_nt"+std::to_string(nt)+"_slots"+std::to_string(nslot)+
-      "_clusters"+std::to_string(ncl);
+      "_clusters"+std::to_string(ncl)+(h->sv_defer ? "_defer" : "");
     return;
   }
 }
@@ -449,15 +454,47 @@ void allreduce_sum(nqs_handle * h, double * buf, size_t count)
     throw Error(NQS_ERR_NCCL, std::string("ncclAllReduce failed: ")+(g_nccl.getErrorString ? g_nccl.getErrorString(rc) : "?"));
 }
 
+template <int MODEL>
+void launch_setup_structured_m(nqs_handle * h, dim3 grid, size_t smem, int ipt)
+{
+#define NQS_SS_CASE(I) setup_structured_kernel<MODEL, I><<<grid, NQS_SS_THREADS, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, \
+    h->spins.p, h->theta.p, h->htilda.p, h->part.p, h->rows_per_block)
+  if (ipt <= 1) NQS_SS_CASE(1);
+  else if (ipt <= 2) NQS_SS_CASE(2);
+  else if (ipt <= 4) NQS_SS_CASE(4);
+  else if (ipt <= 8) NQS_SS_CASE(8);
+  else NQS_SS_CASE(16);
+#undef NQS_SS_CASE
+}
+
+void launch_setup_structured(nqs_handle * h, dim3 grid, size_t smem, int ipt)
+{
+  if (h->model == MODEL_RBM) launch_setup_structured_m<MODEL_RBM>(h, grid, smem, ipt);
+  else launch_setup_structured_m<MODEL_FFNN>(h, grid, smem, ipt);
+}
+
 // <O>, F, diag from ONE pass over O (+ one all-reduce of 5P+3 doubles across ranks)
 void sr_setup(nqs_handle * h, bool want_F)
 {
   const long long P = h->P, K = h->K;
   htilda_sums_kernel<<<1, 1024, 0, h->stream>>>(K, h->htilda.p, h->sums.p+5*P);
   check_launch(h, "htilda_sums_kernel");
-  dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
-  setup_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->htilda.p, h->part.p, h->rows_per_block);
-  check_launch(h, "setup_partial_kernel");
+  const int ipt = (h->N+15)/16;
+  if (ipt <= 16 && h->theta_matches_O && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
+  { // sums from the factors of O (spins, tanh theta): no pass over O
+    dim3 grid((unsigned)((h->M+NQS_SS_JT-1)/NQS_SS_JT), (unsigned)h->nrb);
+    int ipt_t = 1;
+    while (ipt_t < ipt) ipt_t <<= 1;                      // template instantiations: 1, 2, 4, 8, 16 sites per thread
+    const size_t smem = (size_t)NQS_SS_CH*16*ipt_t;
+    launch_setup_structured(h, grid, smem, ipt);
+    check_launch(h, "setup_structured_kernel");
+  }
+  else
+  {
+    dim3 grid((unsigned)((P+NQS_COL_THREADS-1)/NQS_COL_THREADS), (unsigned)h->nrb);
+    setup_partial_kernel<<<grid, NQS_COL_THREADS, 0, h->stream>>>(K, P, h->O.p, h->htilda.p, h->part.p, h->rows_per_block);
+    check_launch(h, "setup_partial_kernel");
+  }
   colsum_reduce_kernel<<<grid_for(5*P, 256, 148*8), 256, 0, h->stream>>>(P, 5, h->nrb, h->part.p, h->sums.p, nullptr);
   check_launch(h, "colsum_reduce_kernel");
   allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
@@ -478,9 +515,8 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
     a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes;
-    { const char * dbg = std::getenv("NQS_SV_DEBUG"); a.debug = dbg ? std::atoi(dbg) : 0; }
     Span sp(h, TAG_ROWS);
-    NQS_CUDA(sv_launch(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
+    NQS_CUDA(sv_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
     check_launch(h, "sv_fused_kernel");
     nparts = h->sv_nclusters;
   }
@@ -500,7 +536,7 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
     }
     nparts = h->nrb;
   }
-  if (h->comm == nullptr) return nparts;
+  if (h->comm == nullptr || h->p2p_ok) return nparts;     // single GPU, or the all-reduce happens inside cg_fused_kernel
   colsum_reduce_kernel<<<grid_for(2*P, 256, 148*8), 256, 0, h->stream>>>(P, 2, nparts, h->part.p, h->traw.p, done);
   check_launch(h, "colsum_reduce_kernel");
   allreduce_sum(h, h->traw.p, (size_t)(2*P));
@@ -518,6 +554,17 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
   a.P = h->P; a.mode = mode; a.nparts = nparts; a.part = h->part.p; a.traw = h->traw.p;
   a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p;
   a.v = v; a.pvec = h->pvec.p; a.x = h->dx.p; a.r = h->r.p; a.t = h->t.p; a.sc = h->scal.p; a.slots = h->slots.p; a.barrier = h->cgbar.p;
+  a.n_ranks = 1; a.rank = 0; a.epoch = 0;
+  for (int r = 0; r < NQS_CG_MAX_RANKS; ++r) { a.peer_x[r] = nullptr; a.peer_flag[r] = nullptr; }
+  if (h->p2p_ok && nparts > 0)
+  {
+    a.n_ranks = h->n_ranks; a.rank = h->rank; a.epoch = ++h->p2p_epoch;
+    for (int r = 0; r < h->n_ranks; ++r)
+    {
+      a.peer_x[r] = reinterpret_cast<double*>(h->peer_base[r]);
+      a.peer_flag[r] = reinterpret_cast<unsigned int*>((char*)h->peer_base[r]+h->xbuf_data_bytes);
+    }
+  }
   cg_fused_kernel<<<cg_ctas(h), NQS_CG_THREADS, 0, h->stream>>>(a);
   check_launch(h, "cg_fused_kernel");
 }
@@ -574,6 +621,7 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
 
 void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
 {
+  h->theta_matches_O = false;
   update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
   check_launch(h, "update_params_kernel");
   h->tables_valid = false;
@@ -598,6 +646,7 @@ void do_sweeps(nqs_handle * h, int n_sweeps)
 
 void do_initialize(nqs_handle * h, const int8_t * spins_host)
 {
+  h->theta_matches_O = false;
   std::vector<int8_t> s((size_t)h->K*h->N, 1);
   if (spins_host) std::memcpy(s.data(), spins_host, s.size());
   else if (h->cfg.J > 0) // Neel, ref impl_hamiltonians.cuh:196-201
@@ -645,6 +694,7 @@ void build_J(nqs_handle * h)
 void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
   h->tables_valid = false;
+  h->theta_matches_O = false;
   NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
 }
@@ -784,6 +834,9 @@ void nqs_destroy(nqs_handle * h)
 {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  for (int r = 0; r < 16; ++r)
+    if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+  if (h->xbuf) cudaFree(h->xbuf);
   if (h->comm && g_nccl.commDestroy) g_nccl.commDestroy(h->comm);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
@@ -816,6 +869,7 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
     NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
     h->tables_valid = false;
+    h->theta_matches_O = false;
   });
 }
 
@@ -1243,6 +1297,64 @@ nqs_status nqs_comm_init(nqs_handle * h, int32_t n_ranks, int32_t rank, const ch
       throw Error(NQS_ERR_NCCL, std::string("ncclCommInitRank failed: ")+(g_nccl.getErrorString ? g_nccl.getErrorString(rc) : "?"));
     h->comm = comm; h->n_ranks = n_ranks; h->rank = rank;
   });
+}
+
+nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BYTES])
+{
+  if (!h || !handle_out) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->n_ranks > 1 && h->n_ranks <= NQS_CG_MAX_RANKS, NQS_ERR_STATE, "nqs_comm_p2p_export: call nqs_comm_init first (2..16 ranks)");
+    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    static_assert(sizeof(cudaIpcMemHandle_t) == NQS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    if (h->xbuf == nullptr)
+    {
+      h->xbuf_data_bytes = (size_t)2*h->n_ranks*2*(size_t)h->P*sizeof(double);
+      const size_t total = h->xbuf_data_bytes+2*NQS_CG_MAX_RANKS*sizeof(unsigned int);
+      cudaError_t e = cudaMalloc(&h->xbuf, total);
+      if (e != cudaSuccess) throw Error(NQS_ERR_NOMEM, std::string("cudaMalloc of the peer exchange buffer failed: ")+cudaGetErrorString(e));
+      NQS_CUDA(cudaMemset(h->xbuf, 0, total));
+      NQS_CUDA(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t ipc;
+    NQS_CUDA(cudaIpcGetMemHandle(&ipc, h->xbuf));
+    std::memcpy(handle_out, &ipc, NQS_IPC_HANDLE_BYTES);
+  });
+}
+
+nqs_status nqs_comm_p2p_import(nqs_handle * h, const char * handles)
+{
+  if (!h || !handles) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->xbuf != nullptr, NQS_ERR_STATE, "nqs_comm_p2p_import before nqs_comm_p2p_export");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    for (int r = 0; r < h->n_ranks; ++r)
+    {
+      if (r == h->rank) { h->peer_base[r] = h->xbuf; continue; }
+      cudaIpcMemHandle_t ipc;
+      std::memcpy(&ipc, handles+(size_t)r*NQS_IPC_HANDLE_BYTES, NQS_IPC_HANDLE_BYTES);
+      void * ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+      {
+        cudaGetLastError();
+        throw Error(NQS_ERR_UNSUPPORTED, std::string("cudaIpcOpenMemHandle(rank ")+std::to_string(r)+") failed: "+cudaGetErrorString(e)+
+          " -- the engine keeps using ncclAllReduce");
+      }
+      h->peer_base[r] = ptr;
+    }
+    h->p2p_ok = true;
+    h->p2p_epoch = 0;
+  });
+}
+
+nqs_status nqs_comm_p2p_disable(nqs_handle * h)
+{
+  if (!h) return NQS_ERR_INVALID;
+  h->p2p_ok = false;
+  return NQS_OK;
 }
 
 nqs_status nqs_get_timing(nqs_handle * h, nqs_timing * t)

@@ -72,6 +72,7 @@ struct nqs_handle
   int flip_index = 0;                     // the machine's index_ (ref impl_neural_quantum_state.cuh:19)
   unsigned long long step_counter = 0;    // proposals done so far (RNG counter)
   bool initialized = false;
+  bool theta_matches_O = false;           // O was written from the current spins / theta / params (structured SR setup allowed)
 
   // SR
   nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
@@ -85,13 +86,20 @@ struct nqs_handle
   void * pinned = nullptr;                // small pinned staging area for scalar read-backs
   // one-pass S*v (sv_fused.cuh): cluster size, columns per thread, threads, TMA slots, clusters, rows per cluster
   bool sv_ok = false;
-  int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0;
+  int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0, sv_defer = 0;
   size_t sv_smem = 0, sv_slot_bytes = 0;
   long long sv_pc = 0, sv_rpc = 0;
 
   // multi-GPU
   void * comm = nullptr;                  // ncclComm_t
   int n_ranks = 1, rank = 0;
+  // in-kernel all-reduce of the CG partials over NVLink peer memory (cg_fused.cuh): receive buffer [2][n_ranks][2P] doubles +
+  // flags [2][16] on every rank, mapped into every peer with cudaIpc
+  void * xbuf = nullptr;
+  size_t xbuf_data_bytes = 0;
+  void * peer_base[16] = {nullptr};
+  bool p2p_ok = false;
+  unsigned int p2p_epoch = 0;
 
   // bookkeeping
   std::string err;

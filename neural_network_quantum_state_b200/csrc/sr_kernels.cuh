@@ -152,6 +152,152 @@ __global__ void __launch_bounds__(NQS_COL_THREADS) matvec_cols_partial_kernel(co
   base[p] = ax; base[P+p] = ay;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// SR setup sums WITHOUT reading O back.  Every row of O is an outer product plus two short blocks,
+//   RBM  O_k = [ s_ki T_kj (i*M+j) | s_ki | T_kj ],  T = tanh(theta)         (ref k13, impl_neural_quantum_state.cuh:1426-1449)
+//   FFNN O_k = [ s_ki T'_kj (j*N+i) | T'_kj | L_kj ], T' = tanh(theta) w1o, L = logcosh(theta)        (ref k15, :1622-1663)
+// so  sum_k O_kp,  sum_k O_kp conj(h_k)  and  sum_k |O_kp|^2  follow from the [K][N] spins and the [K][M] hidden-unit values:
+// the W block is S^T T and S^T (T conj(h)) -- signed accumulation, K*N*M*4 fp64 FMAs -- and |O|^2 of the W block does not
+// depend on i at all.  This replaces the 8.7 GB pass of setup_partial_kernel (1.49 ms at N=128, M=256, K=16384) by
+// ~70 MB of reads; the reference makes FOUR passes over O for the same numbers (optimizer.cuh:140-143, functor_for_CG.cuh:99-102).
+// Grid = (hidden-unit tiles of 16, row blocks); a thread owns hidden unit j = t%16 of the tile and the sites i = t/16 + 16 m.
+// Output layout = setup_partial_kernel's: part[rb][0..1] = sum O, [2..3] = sum O conj(h), [4] = sum |O|^2.
+// ---------------------------------------------------------------------------------------------------------------------
+#define NQS_SS_THREADS 256
+#define NQS_SS_JT 16
+#define NQS_SS_CH 16
+
+template <int MODEL, int IPT>
+__global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const int N, const int M, const long long K,
+  const cd * params, const int8_t * __restrict__ spins, const cd * __restrict__ theta, const cd * __restrict__ htilda,
+  double * __restrict__ part, const long long rows_per_block)
+{
+  __shared__ cd Tsh[NQS_SS_CH][NQS_SS_JT], Thsh[NQS_SS_CH][NQS_SS_JT], Lsh[NQS_SS_CH][NQS_SS_JT];
+  __shared__ cd hsh[NQS_SS_CH];
+  extern __shared__ __align__(16) unsigned char smem_raw[];     // spins chunk [NQS_SS_CH][16*IPT] int8, zero beyond N
+  constexpr int npad = 16*IPT;
+  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw);
+  const int t = threadIdx.x, jl = t%NQS_SS_JT, ig = t/NQS_SS_JT;   // ig = 0..15
+  const int j = blockIdx.x*NQS_SS_JT+jl;
+  const bool jok = (j < M);
+  const ModelPtrs mp = model_ptrs(MODEL, params, N, M);
+  const cd w1o = (MODEL == MODEL_FFNN && jok) ? mp.w1o[j] : cmake(1.0, 0.0);
+  const long long k0 = (long long)blockIdx.y*rows_per_block;
+  const long long k1 = (k0+rows_per_block < K) ? k0+rows_per_block : K;
+  double a1x[IPT], a1y[IPT], a2x[IPT], a2y[IPT];
+#pragma unroll
+  for (int m = 0; m < IPT; ++m) { a1x[m] = 0; a1y[m] = 0; a2x[m] = 0; a2y[m] = 0; }
+  double bT[2] = {0, 0}, bTh[2] = {0, 0}, bT2 = 0;      // hidden-bias block (thread group ig == 0)
+  double bL[2] = {0, 0}, bLh[2] = {0, 0}, bL2 = 0;      // FFNN: logcosh block (ig == 1)
+  double as[IPT], ahx[IPT], ahy[IPT];                   // RBM visible-bias block (tile 0, jl == 0)
+#pragma unroll
+  for (int m = 0; m < IPT; ++m) { as[m] = 0; ahx[m] = 0; ahy[m] = 0; }
+  const bool do_a = (MODEL == MODEL_RBM && blockIdx.x == 0 && jl == 0);
+
+  for (long long kc = k0; kc < k1; kc += NQS_SS_CH)
+  {
+    const int nk = (int)((k1-kc < NQS_SS_CH) ? k1-kc : NQS_SS_CH);
+    __syncthreads();
+    { // one hidden-unit value per thread: chain kc + ig, hidden unit j
+      const int kk = ig;
+      cd T = cmake(0.0, 0.0), Th = T, L = T;
+      if (kk < nk && jok)
+      {
+        const cd th = theta[(kc+kk)*M+j], h = htilda[kc+kk];
+        T = c_tanh(th);
+        if (MODEL == MODEL_FFNN) { T = cmul(T, w1o); L = c_logcosh(th); }
+        Th = cmake(T.x*h.x+T.y*h.y, T.y*h.x-T.x*h.y);      // T conj(h)
+      }
+      Tsh[kk][jl] = T; Thsh[kk][jl] = Th;
+      if (MODEL == MODEL_FFNN) Lsh[kk][jl] = L;
+      if (t < NQS_SS_CH) hsh[t] = (t < nk) ? htilda[kc+t] : cmake(0.0, 0.0);
+    }
+    for (int idx = t; idx < NQS_SS_CH*npad; idx += NQS_SS_THREADS)
+    {
+      const int kk = idx/npad, i = idx-kk*npad;
+      sp[idx] = (kk < nk && i < N) ? spins[(kc+kk)*N+i] : (int8_t)0;
+    }
+    __syncthreads();
+    for (int kk = 0; kk < nk; ++kk)
+    {
+      const cd T = Tsh[kk][jl], Th = Thsh[kk][jl];
+      const int8_t * srow = sp+kk*npad+ig;
+#pragma unroll
+      for (int m = 0; m < IPT; ++m)
+      {
+        const double s = (double)srow[16*m];              // 0 beyond N
+        a1x[m] = fma(s, T.x, a1x[m]); a1y[m] = fma(s, T.y, a1y[m]);
+        a2x[m] = fma(s, Th.x, a2x[m]); a2y[m] = fma(s, Th.y, a2y[m]);
+      }
+      if (ig == 0)
+      {
+        bT[0] += T.x; bT[1] += T.y; bTh[0] += Th.x; bTh[1] += Th.y; bT2 += T.x*T.x+T.y*T.y;
+      }
+      if (MODEL == MODEL_FFNN && ig == 1)
+      {
+        const cd L = Lsh[kk][jl], h = hsh[kk];
+        bL[0] += L.x; bL[1] += L.y; bLh[0] += L.x*h.x+L.y*h.y; bLh[1] += L.y*h.x-L.x*h.y; bL2 += L.x*L.x+L.y*L.y;
+      }
+      if (do_a)
+      {
+        const cd h = hsh[kk];
+#pragma unroll
+        for (int m = 0; m < IPT; ++m)
+        {
+          const double s = (double)srow[16*m];
+          as[m] += s; ahx[m] = fma(s, h.x, ahx[m]); ahy[m] = fma(-s, h.y, ahy[m]);   // s conj(h)
+        }
+      }
+    }
+  }
+  // every thread of row group 0 also needs sum_k |T_kj|^2 for the W block of all its sites: share it through shared memory
+  __syncthreads();
+  double * t2sh = reinterpret_cast<double*>(&Tsh[0][0]);
+  if (ig == 0) t2sh[jl] = bT2;
+  __syncthreads();
+  const double t2 = t2sh[jl];
+  const long long P = (MODEL == MODEL_RBM) ? (long long)N*M+N+M : (long long)N*M+2*M;
+  const long long NM = (long long)N*M;
+  double * base = part+(size_t)blockIdx.y*5*P;
+  if (jok)
+  {
+#pragma unroll
+    for (int m = 0; m < IPT; ++m)
+    {
+      const int i = ig+16*m;
+      if (i < N)
+      {
+        const long long p = (MODEL == MODEL_RBM) ? (long long)i*M+j : (long long)j*N+i;
+        base[p] = a1x[m]; base[P+p] = a1y[m]; base[2*P+p] = a2x[m]; base[3*P+p] = a2y[m]; base[4*P+p] = t2;
+      }
+    }
+    if (ig == 0)
+    {
+      const long long p = (MODEL == MODEL_RBM) ? NM+N+j : NM+j;
+      base[p] = bT[0]; base[P+p] = bT[1]; base[2*P+p] = bTh[0]; base[3*P+p] = bTh[1]; base[4*P+p] = bT2;
+    }
+    if (MODEL == MODEL_FFNN && ig == 1)
+    {
+      const long long p = NM+M+j;
+      base[p] = bL[0]; base[P+p] = bL[1]; base[2*P+p] = bLh[0]; base[3*P+p] = bLh[1]; base[4*P+p] = bL2;
+    }
+  }
+  if (do_a)
+  {
+    const double nrows = (double)(k1 > k0 ? k1-k0 : 0);
+#pragma unroll
+    for (int m = 0; m < IPT; ++m)
+    {
+      const int i = ig+16*m;
+      if (i < N)
+      {
+        const long long p = NM+i;
+        base[p] = as[m]; base[P+p] = 0.0; base[2*P+p] = ahx[m]; base[3*P+p] = ahy[m]; base[4*P+p] = nrows;   // s^2 = 1
+      }
+    }
+  }
+}
+
 // out[c][p] = sum_rb part[rb][c][p], fixed order.  ncomp = 5 (setup) or 2 (matvec)
 __global__ void colsum_reduce_kernel(const long long P, const int ncomp, const int nrb, const double * __restrict__ part,
   double * __restrict__ out, const int * __restrict__ done)

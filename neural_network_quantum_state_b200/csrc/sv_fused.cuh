@@ -14,7 +14,12 @@
 //       folds them in a fixed order and sends the CTA partial into every CTA of the cluster over DSMEM with st.async (the
 //       store itself completes bytes on the receiver's mbarrier).  No __syncthreads and no cluster barrier in the loop;
 //   (3) after the mbarrier wait every warp adds the CS CTA partials in rank order (bit-identical z_k in all CTAs,
-//       run-to-run deterministic) and accumulates conj(O_kp) z_k from the registers it still holds.
+//       run-to-run deterministic) and accumulates conj(O_kp) z_k.
+// The reduction + DSMEM round trip of (2) costs ~0.7 us per row (measured, profiles/r1d_sv_fused_experiments.md), more than
+// half of the 1.2 us the HBM stream needs per row slice.  DEFER = 1 therefore software-pipelines the loop by one row: the
+// z exchange of row k is in flight while the warps already run (2) on row k+1, and (3) for row k re-reads the slice from
+// its shared-memory slot (released only then) instead of holding it in registers.  DEFER = 0 keeps the row in registers and
+// releases the slot right after (2).
 // HBM traffic: K*P*16 B per S*v instead of 2*K*P*16 B.  Cluster partials go to part[q][{re,im}][P] and are folded in fixed
 // order by colsum_reduce_kernel exactly like the two-pass kernels' row-block partials.
 #pragma once
@@ -82,15 +87,14 @@ struct SvArgs
   long long rows_per_cluster;
   int nslot;               // shared-memory row slots (TMA pipeline depth)
   unsigned int slot_bytes; // bytes per slot: >= CPT * consumer threads * 16 (the tail past the slice stays zero)
-  int debug;               // timing experiments only (env NQS_SV_DEBUG, results are WRONG when != 0): 1 = no DSMEM exchange,
-                           // 2 = no CTA-level reduction either, 4 = no TMA wait (stale shared memory)
 };
 
 #define NQS_SV_MAX_CLUSTER 16
 #define NQS_SV_MAX_SLOTS 8
 #define NQS_SV_MAX_WARPS 32
-// shared memory after the slots: red[2][warps] | zbuf[2][cluster] | full[8] | empty[8] | wfull[2] | zfull[2]
-#define NQS_SV_TAIL_BYTES (2*NQS_SV_MAX_WARPS*16+2*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+4*8)
+#define NQS_SV_ZBUFS 4     // z exchange buffers: a peer may run (2) up to two rows ahead of this CTA's (3) when DEFER = 1
+// shared memory after the slots: red[2][warps] | zbuf[ZBUFS][cluster] | full[8] | empty[8] | wfull[2] | zfull[ZBUFS]
+#define NQS_SV_TAIL_BYTES (2*NQS_SV_MAX_WARPS*16+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+2*8+NQS_SV_ZBUFS*8)
 
 // register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 992+32 threads (8 warps per sub-partition x 64
 // registers), larger CPT up to 480+32 threads (4 warps per sub-partition x 128 registers)
@@ -98,7 +102,7 @@ struct SvArgs
 template <int CPT> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
 
 // blockDim.x = 32*(NW+1): warps 0..NW-1 consume (NT = 32*NW threads own the columns), warp NW is the TMA producer.
-template <int CPT>
+template <int CPT, int DEFER>
 __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs a)
 {
   if (a.done != nullptr && *a.done) return;   // uniform over the grid
@@ -109,11 +113,11 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   const long long cid = blockIdx.x/CS;
   unsigned char * tail = smem_raw+(size_t)a.nslot*a.slot_bytes;
   cd * red = reinterpret_cast<cd*>(tail);                                   // [2][NQS_SV_MAX_WARPS] warp partials of this CTA
-  cd * zbuf = red+2*NQS_SV_MAX_WARPS;                                       // [2][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
-  uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+2*NQS_SV_MAX_CLUSTER); // [slots] TMA arrival
+  cd * zbuf = red+2*NQS_SV_MAX_WARPS;                                       // [ZBUFS][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
+  uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER); // [slots] TMA arrival
   uint64_t * empty = full+NQS_SV_MAX_SLOTS;                                 // [slots] all consumer warps released the slot
   uint64_t * wfull = empty+NQS_SV_MAX_SLOTS;                                // [2] all NW warp partials of a row are in red[]
-  uint64_t * zfull = wfull+2;                                               // [2] all CS CTA partials of a row arrived (tx bytes)
+  uint64_t * zfull = wfull+2;                                               // [ZBUFS] all CS CTA partials of a row arrived (tx bytes)
 
   const long long c0 = (long long)crank*a.pc;
   long long nr_ll = a.P-c0;
@@ -137,7 +141,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   {
     for (int s = 0; s < a.nslot; ++s) { mbar_init(full+s, 1); mbar_init(empty+s, (uint32_t)NW); }
     mbar_init(wfull, (uint32_t)NW); mbar_init(wfull+1, (uint32_t)NW);
-    mbar_init(zfull, 1); mbar_init(zfull+1, 1);
+    for (int q = 0; q < NQS_SV_ZBUFS; ++q) mbar_init(zfull+q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy zero fill before async-proxy (TMA) writes
@@ -169,18 +173,38 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       vr[c] = (idx < n_r) ? a.v[c0+idx] : cmake(0.0, 0.0);
       acc[c] = cmake(0.0, 0.0);
     }
-    int slot = 0;
+    const cd * const sbase = reinterpret_cast<const cd*>(smem_raw)+tid;
+    const size_t slot_elems = a.slot_bytes/sizeof(cd);
+
+    // (3) for row jt: z_k = sum of the CS partials in rank order, then acc += conj(O_kp) z_k
+    auto wait_z = [&](const int jt, double & zx, double & zy)
+    {
+      const int zq = jt&(NQS_SV_ZBUFS-1);
+      mbar_wait(zfull+zq, (uint32_t)((jt/NQS_SV_ZBUFS)&1));
+      const cd * zrow = zbuf+zq*NQS_SV_MAX_CLUSTER;
+      zx = 0.0; zy = 0.0;
+      for (unsigned int r = 0; r < CS; ++r)
+      {
+        const cd t = zrow[r];
+        zx += t.x; zy += t.y;
+      }
+    };
+
+    int slot = 0, prev_slot = 0;
     uint32_t full_par = 0;
-    const cd * srow = reinterpret_cast<const cd*>(smem_raw)+tid;
     for (int it = 0; it < nrows; ++it)
     {
       // ---- (2) row slice -> registers, partial O_k . v
       cd o[CPT];
-      if (n_r > 0 && !(a.debug&4)) mbar_wait(full+slot, full_par);
+      const cd * srow = sbase+(size_t)slot*slot_elems;
+      if (n_r > 0) mbar_wait(full+slot, full_par);
 #pragma unroll
       for (int c = 0; c < CPT; ++c) o[c] = srow[c*NT];
-      __syncwarp();
-      if (lane == 0 && n_r > 0) mbar_arrive(empty+slot);
+      if (DEFER == 0)
+      {
+        __syncwarp();
+        if (lane == 0 && n_r > 0) mbar_arrive(empty+slot);
+      }
       double pa = 0.0, pb = 0.0, pc_ = 0.0, pd = 0.0;   // four independent chains
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
@@ -189,42 +213,58 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
         pc_ = fma(o[c].x, vr[c].y, pc_); pd = fma(o[c].y, vr[c].x, pd);
       }
       const cd wp = warp_sum(cmake(pa-pb, pc_+pd));
-      const int zp = it&1;
-      const uint32_t zpar = (uint32_t)((it>>1)&1);
-      cd * redrow = red+zp*NQS_SV_MAX_WARPS;
-      double zx = 0.0, zy = 0.0;
-      if (a.debug&2) { zx = wp.x; zy = wp.y; }
-      else {
-      if (lane == 0) { redrow[w] = wp; mbar_arrive(wfull+zp); }
+      const int rq = it&1, zq = it&(NQS_SV_ZBUFS-1);
+      cd * redrow = red+rq*NQS_SV_MAX_WARPS;
+      if (lane == 0) { redrow[w] = wp; mbar_arrive(wfull+rq); }
       if (w == it%NW)
       { // this row's reducer warp: CTA partial = fixed-order fold of the warp partials, sent to every CTA of the cluster
-        mbar_wait(wfull+zp, zpar);
+        mbar_wait(wfull+rq, (uint32_t)((it>>1)&1));
         const cd s = warp_sum((lane < NW) ? redrow[lane] : cmake(0.0, 0.0));
-        if (a.debug&1) { if (lane == 0) { zbuf[zp*NQS_SV_MAX_CLUSTER] = s; mbar_arrive(zfull+zp); } }
-        else {
-        if (lane == 0) mbar_expect_tx(zfull+zp, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
+        if (lane == 0) mbar_expect_tx(zfull+zq, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
         if (lane < (int)CS)
-          st_async_remote_cd(map_to_rank(zbuf+zp*NQS_SV_MAX_CLUSTER+crank, (uint32_t)lane), s, map_to_rank(zfull+zp, (uint32_t)lane));
+          st_async_remote_cd(map_to_rank(zbuf+zq*NQS_SV_MAX_CLUSTER+crank, (uint32_t)lane), s, map_to_rank(zfull+zq, (uint32_t)lane));
+      }
+      if (DEFER == 0)
+      {
+        double zx, zy;
+        wait_z(it, zx, zy);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+        {
+          acc[c].x = fma(o[c].x, zx, acc[c].x); acc[c].x = fma(o[c].y, zy, acc[c].x);
+          acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
         }
       }
-      // ---- (3) z_k = sum of the CS partials in rank order, then conj(O_kp) z_k from registers
-      mbar_wait(zfull+zp, zpar);
-      const cd * zrow = zbuf+zp*NQS_SV_MAX_CLUSTER;
-      const unsigned int nzr = (a.debug&1) ? 1u : CS;
-      for (unsigned int r = 0; r < nzr; ++r)
-      {
-        const cd t = zrow[r];
-        zx += t.x; zy += t.y;
+      else if (it > 0)
+      { // row it-1: its exchange travelled while this warp worked on row it; the slice is still in its slot
+        double zx, zy;
+        wait_z(it-1, zx, zy);
+        const cd * prow = sbase+(size_t)prev_slot*slot_elems;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+        {
+          const cd q = prow[c*NT];
+          acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
+          acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
+        }
+        __syncwarp();
+        if (lane == 0 && n_r > 0) mbar_arrive(empty+prev_slot);
       }
-      }
+      prev_slot = slot;
+      if (++slot == a.nslot) { slot = 0; full_par ^= 1u; }
+    }
+    if (DEFER != 0 && nrows > 0)
+    {
+      double zx, zy;
+      wait_z(nrows-1, zx, zy);
+      const cd * prow = sbase+(size_t)prev_slot*slot_elems;
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
       {
-        acc[c].x = fma(o[c].x, zx, acc[c].x); acc[c].x = fma(o[c].y, zy, acc[c].x);
-        acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
+        const cd q = prow[c*NT];
+        acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
+        acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
       }
-      srow += a.slot_bytes/sizeof(cd);
-      if (++slot == a.nslot) { slot = 0; full_par ^= 1u; srow = reinterpret_cast<const cd*>(smem_raw)+tid; }
     }
     double * base = a.part+(size_t)cid*2*(size_t)a.P;
 #pragma unroll

@@ -48,7 +48,7 @@ def sr_allreduce_layout(P: int) -> dict:
             "sum_h_re": 5 * P, "sum_h_im": 5 * P + 1, "sum_h2": 5 * P + 2, "count": 5 * P + 3}
 
 
-def bootstrap_comm(engine, world: int, rank: int, group=None) -> None:
+def bootstrap_comm(engine, world: int, rank: int, group=None, p2p: bool = True) -> None:
     """Create the engine's NCCL communicator: rank 0 draws the unique id, torch.distributed broadcasts it."""
     if world == 1:
         return
@@ -57,6 +57,26 @@ def bootstrap_comm(engine, world: int, rank: int, group=None) -> None:
     ids = [Engine.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0, group=group)
     engine.comm_init(world, rank, ids[0])
+    if p2p:
+        enable_p2p(engine, world, group)
+
+
+def enable_p2p(engine, world: int, group=None) -> bool:
+    """Map every rank's CG exchange buffer into every peer (cudaIpc over NVLink) so that the per-iteration all-reduce runs
+    inside the CG kernel.  All ranks must agree: if any rank cannot map its peers, every rank stays on ncclAllReduce."""
+    import torch.distributed as dist
+    handles = [None] * world
+    dist.all_gather_object(handles, engine.comm_p2p_export(), group=group)
+    try:
+        ok = engine.comm_p2p_import(handles)
+    except Exception:
+        ok = False
+    oks = [None] * world
+    dist.all_gather_object(oks, bool(ok), group=group)
+    if not all(oks):
+        engine.comm_p2p_disable()
+        return False
+    return True
 
 
 def make_sharded_engine(model: str, n_inputs: int, n_hiddens: int, n_chains_total: int, h: float, J: float, alpha: float,

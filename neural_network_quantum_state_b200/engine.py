@@ -220,6 +220,24 @@ class Engine:
         buf = C.create_string_buffer(unique_id, L.UNIQUE_ID_BYTES)
         self._chk(self.lib.nqs_comm_init(self._h, int(n_ranks), int(rank), buf))
 
+    def comm_p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+        self._chk(self.lib.nqs_comm_p2p_export(self._h, buf))
+        return buf.raw
+
+    def comm_p2p_import(self, handles) -> bool:
+        """handles: the exported handles of all ranks in rank order.  Returns False (and keeps NCCL) if peers cannot be mapped."""
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        rc = self.lib.nqs_comm_p2p_import(self._h, buf)
+        if rc == L.ERR_UNSUPPORTED:
+            return False
+        self._chk(rc)
+        return True
+
+    def comm_p2p_disable(self):
+        self._chk(self.lib.nqs_comm_p2p_disable(self._h))
+
     # ---- introspection
     def set_timing(self, on: bool = True):
         self._chk(self.lib.nqs_set_timing(self._h, int(on)))
