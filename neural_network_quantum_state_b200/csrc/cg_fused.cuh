@@ -2,7 +2,7 @@
 //
 // ref: ConjugateGradient::solve (gpu/include/conjugate_gradient.cuh:29-74) + the tails of SMatrixForCG::dot / applyPrecond
 // (gpu/include/functor_for_CG.cuh:115-135).  The reference spends 7 small kernels, 3 thrust reductions and 4 host syncs per
-// iteration there.  Here ONE kernel of <= 64 co-resident CTAs walks the iteration with
+// iteration there.  Here ONE kernel of co-resident CTAs (<= 1 per SM) walks the iteration with
 // two software grid barriers; every CTA re-derives the scalars from the same per-CTA partial sums in the same fixed order,
 // so no broadcast is needed and the result is deterministic.  Scalars stay on the device (CgScalars); the host only polls
 // `done` every few iterations, without draining the queue.
@@ -32,7 +32,7 @@ namespace nqs
 enum { CG_MODE_ITER = 0, CG_MODE_INIT = 1, CG_MODE_DOT = 2 };
 
 #define NQS_CG_THREADS 256
-#define NQS_CG_MAX_CTAS 64
+#define NQS_CG_MAX_CTAS 148   // one CTA per SM at most: the software grid barrier needs every CTA resident
 #define NQS_CG_NVALS 6
 #define NQS_CG_MAX_RANKS 16
 
@@ -62,7 +62,7 @@ struct CgArgs
   unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS]
 };
 
-// all CTAs of the grid are co-resident (grid <= 64, nothing else runs on the stream): spin barrier on a global counter
+// all CTAs of the grid are co-resident (grid <= #SMs, nothing else runs on the stream): spin barrier on a global counter
 __device__ __forceinline__ void cg_grid_barrier(unsigned int * counter, const unsigned int target)
 {
   __syncthreads();
@@ -100,41 +100,39 @@ __device__ __forceinline__ void cg_grid_sum(double (&vals)[NV], const CgArgs & a
   }
   ++epoch;
   cg_grid_barrier(a.barrier, epoch*gridDim.x);
-  // NQS_CG_MAX_CTAS <= 64: lane b and b+32, then a fixed butterfly
+  // every warp of every CTA folds the per-CTA partials in the same order: lane-strided, then a fixed butterfly
+  double s[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int i = 0; i < NV; ++i) s[i] = 0.0;
+  for (int b = lane; b < (int)gridDim.x; b += 32)
   {
-    double s = 0.0;
-    if (lane < (int)gridDim.x) s = __ldcg(slots+(size_t)lane*NQS_CG_NVALS+i);
-    if (lane+32 < (int)gridDim.x) s += __ldcg(slots+(size_t)(lane+32)*NQS_CG_NVALS+i);
-    vals[i] = warp_sum(s);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s[i] += __ldcg(slots+(size_t)b*NQS_CG_NVALS+i);
   }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) vals[i] = warp_sum(s[i]);
 }
 
-// sum_q part[q][{re,im}][p] in a fixed order with four independent load streams (a serial chain would expose one L2 latency
-// per partial: ~9 us for 15 cluster partials)
+// sum_q part[q][{re,im}][p] in a fixed order; the loads of up to 8 partials are issued before the first add (a serial chain
+// would expose one L2 round trip per partial: ~9 us for 15 cluster partials)
 __device__ __forceinline__ void cg_fold_parts(const double * __restrict__ part, const int nparts, const long long P, const long long p,
   double & rx, double & ry)
 {
-  double ax[4] = {0.0, 0.0, 0.0, 0.0}, ay[4] = {0.0, 0.0, 0.0, 0.0};
   const double * base = part+p;
-  int q = 0;
-  for (; q+4 <= nparts; q += 4)
+  rx = 0.0; ry = 0.0;
+  for (int q0 = 0; q0 < nparts; q0 += 8)
   {
+    double vx[8], vy[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 8; ++u)
     {
-      ax[u] += __ldcg(base+(size_t)(q+u)*2*P);
-      ay[u] += __ldcg(base+(size_t)(q+u)*2*P+P);
+      const bool ok = (q0+u < nparts);
+      vx[u] = ok ? __ldcg(base+(size_t)(q0+u)*2*P) : 0.0;
+      vy[u] = ok ? __ldcg(base+(size_t)(q0+u)*2*P+P) : 0.0;
     }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { rx += vx[u]; ry += vy[u]; }
   }
-  for (int u = 0; q < nparts; ++q, ++u)
-  {
-    ax[u] += __ldcg(base+(size_t)q*2*P);
-    ay[u] += __ldcg(base+(size_t)q*2*P+P);
-  }
-  rx = (ax[0]+ax[1])+(ax[2]+ax[3]);
-  ry = (ay[0]+ay[1])+(ay[2]+ay[3]);
 }
 
 __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a)

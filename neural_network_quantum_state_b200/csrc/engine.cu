@@ -277,7 +277,7 @@ void launch_sweep(nqs_handle * h, long long nsteps)
       case 1: launch_sweep_fast_t<1, 4>(h, f); break;
       case 2: launch_sweep_fast_t<2, 4>(h, f); break;
       case 4: launch_sweep_fast_t<4, 4>(h, f); break;
-      case 8: launch_sweep_fast_t<8, 2>(h, f); break;
+      case 8: if (std::getenv("NQS_SWEEP_C1")) launch_sweep_fast_t<8, 1>(h, f); else launch_sweep_fast_t<8, 2>(h, f); break;
       default: launch_sweep_fast_t<16, 1>(h, f); break;
     }
     check_launch(h, "rbm_sweep_fast_kernel");
@@ -545,7 +545,7 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
 
 int cg_ctas(const nqs_handle * h)
 {
-  return std::max(1, std::min<int>(NQS_CG_MAX_CTAS, (int)((h->P+NQS_CG_THREADS-1)/NQS_CG_THREADS)));
+  return std::max(1, std::min<int>(std::min(NQS_CG_MAX_CTAS, h->sm_count), (int)((h->P+NQS_CG_THREADS-1)/NQS_CG_THREADS)));
 }
 
 void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v)
