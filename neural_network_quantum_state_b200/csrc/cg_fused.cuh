@@ -17,8 +17,8 @@
 //
 // Multi-GPU: the all-reduce of the P complex partial sums that every CG iteration needs is done INSIDE this kernel over
 // NVLink peer memory instead of a separate NCCL launch: every rank stores its folded partial into slot [rank] of a receive
-// buffer that lives on EVERY peer (plain st.global on cudaIpc-mapped peer pointers), publishes a per-(rank, parity) epoch
-// flag with a system-scope release, waits for the flags of all ranks and adds the slots in RANK ORDER -- so the sum is
+// buffer that lives on EVERY peer (plain st.global on cudaIpc-mapped peer pointers), publishes per-(parity, rank, CTA) epoch
+// flags with a system-scope release, waits for the flags of all ranks and adds the slots in RANK ORDER -- so the sum is
 // bit-identical on all ranks (the replicated CG state never diverges) and costs one NVLink hop (~P*16 B per peer) instead
 // of a collective launch.  Receive buffers are double-buffered by epoch parity: a rank can only write epoch n+2 after it
 // has seen every peer's flag n+1, which a peer raises after it finished reading epoch n.  (If the peer mapping is not
@@ -59,7 +59,7 @@ struct CgArgs
   int n_ranks, rank;
   unsigned int epoch;      // increases by one per exchange on every rank
   double * peer_x[NQS_CG_MAX_RANKS];            // peer_x[r]: receive buffer of rank r, [2][n_ranks][2P]
-  unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS]
+  unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS][NQS_CG_MAX_CTAS]
 };
 
 // all CTAs of the grid are co-resident (grid <= #SMs, nothing else runs on the stream): spin barrier on a global counter
@@ -172,14 +172,16 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
       cg_fold_parts(a.part, a.nparts, P, p, trx, try_);
       for (int r = 0; r < a.n_ranks; ++r) { a.peer_x[r][slot+p] = trx; a.peer_x[r][slot+P+p] = try_; }
     }
-    __threadfence_system();
-    ++epoch;
-    cg_grid_barrier(a.barrier, epoch*gridDim.x);            // every CTA's stores are issued and fenced
-    if (blockIdx.x == 0 && threadIdx.x < a.n_ranks)
-      asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(a.peer_flag[threadIdx.x]+par*NQS_CG_MAX_RANKS+a.rank), "r"(a.epoch) : "memory");
+    // CTA b of every rank owns the same elements p (equal grids), so the hand-shake is per CTA: no grid barrier, and a slow
+    // CTA only delays its own counterparts.  The release store at system scope publishes every store the CTA made before
+    // the barrier (cumulativity); flags are [parity][source rank][CTA].
+    __syncthreads();
+    if (threadIdx.x < a.n_ranks)
+      asm volatile("st.release.sys.global.u32 [%0], %1;"
+        :: "l"(a.peer_flag[threadIdx.x]+((size_t)par*NQS_CG_MAX_RANKS+a.rank)*NQS_CG_MAX_CTAS+blockIdx.x), "r"(a.epoch) : "memory");
     if (threadIdx.x < a.n_ranks)
     {
-      const unsigned int * f = a.peer_flag[a.rank]+par*NQS_CG_MAX_RANKS+threadIdx.x;
+      const unsigned int * f = a.peer_flag[a.rank]+((size_t)par*NQS_CG_MAX_RANKS+threadIdx.x)*NQS_CG_MAX_CTAS+blockIdx.x;
       unsigned int seen;
       do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory"); } while ((int)(seen-a.epoch) < 0);
     }

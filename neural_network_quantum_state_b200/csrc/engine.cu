@@ -182,13 +182,14 @@ void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_sp
   ThetaArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
   a.spins = spins_dev; a.sa_spins = sa_spins_dev; a.theta = theta; a.sa = sa; a.lnpsi = lnpsi;
-  const size_t npad = (size_t)((h->N+15)/16)*16;
-  const int warps = 8;
-  const size_t smem = npad*warps;
-  const int grid = (int)((h->K+warps-1)/warps);
-  if (h->model == MODEL_RBM) theta_generic_kernel<MODEL_RBM><<<grid, warps*32, smem, h->stream>>>(a);
-  else theta_generic_kernel<MODEL_FFNN><<<grid, warps*32, smem, h->stream>>>(a);
-  check_launch(h, "theta_generic_kernel");
+  const size_t smem = (size_t)h->N*NQS_TH_CH*sizeof(double)+(size_t)(NQS_TH_THREADS/32)*NQS_TH_CH*sizeof(cd);
+  const int grid = (int)((h->K+NQS_TH_CH-1)/NQS_TH_CH);
+#define NQS_TH_LAUNCH(MODEL_, LN_) do { set_smem(theta_tiled_kernel<MODEL_, LN_>, smem); \
+    theta_tiled_kernel<MODEL_, LN_><<<grid, NQS_TH_THREADS, smem, h->stream>>>(a); } while (0)
+  if (h->model == MODEL_RBM) { if (lnpsi) NQS_TH_LAUNCH(MODEL_RBM, true); else NQS_TH_LAUNCH(MODEL_RBM, false); }
+  else { if (lnpsi) NQS_TH_LAUNCH(MODEL_FFNN, true); else NQS_TH_LAUNCH(MODEL_FFNN, false); }
+#undef NQS_TH_LAUNCH
+  check_launch(h, "theta_tiled_kernel");
 }
 
 
@@ -277,7 +278,7 @@ void launch_sweep(nqs_handle * h, long long nsteps)
       case 1: launch_sweep_fast_t<1, 4>(h, f); break;
       case 2: launch_sweep_fast_t<2, 4>(h, f); break;
       case 4: launch_sweep_fast_t<4, 4>(h, f); break;
-      case 8: if (std::getenv("NQS_SWEEP_C1")) launch_sweep_fast_t<8, 1>(h, f); else launch_sweep_fast_t<8, 2>(h, f); break;
+      case 8: launch_sweep_fast_t<8, 2>(h, f); break;   // <8, 1> at 128 registers / 16 warps per SM was measured 1.7x slower (spills)
       default: launch_sweep_fast_t<16, 1>(h, f); break;
     }
     check_launch(h, "rbm_sweep_fast_kernel");
@@ -485,7 +486,7 @@ void sr_setup(nqs_handle * h, bool want_F)
     dim3 grid((unsigned)((h->M+NQS_SS_JT-1)/NQS_SS_JT), (unsigned)h->nrb);
     int ipt_t = 1;
     while (ipt_t < ipt) ipt_t <<= 1;                      // template instantiations: 1, 2, 4, 8, 16 sites per thread
-    const size_t smem = (size_t)NQS_SS_CH*16*ipt_t;
+    const size_t smem = (size_t)NQS_SS_CH*16*ipt_t*sizeof(double);
     launch_setup_structured(h, grid, smem, ipt);
     check_launch(h, "setup_structured_kernel");
   }
@@ -1311,7 +1312,7 @@ nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BY
     if (h->xbuf == nullptr)
     {
       h->xbuf_data_bytes = (size_t)2*h->n_ranks*2*(size_t)h->P*sizeof(double);
-      const size_t total = h->xbuf_data_bytes+2*NQS_CG_MAX_RANKS*sizeof(unsigned int);
+      const size_t total = h->xbuf_data_bytes+(size_t)2*NQS_CG_MAX_RANKS*NQS_CG_MAX_CTAS*sizeof(unsigned int);
       cudaError_t e = cudaMalloc(&h->xbuf, total);
       if (e != cudaSuccess) throw Error(NQS_ERR_NOMEM, std::string("cudaMalloc of the peer exchange buffer failed: ")+cudaGetErrorString(e));
       NQS_CUDA(cudaMemset(h->xbuf, 0, total));

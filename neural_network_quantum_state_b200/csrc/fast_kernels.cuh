@@ -201,9 +201,8 @@ __device__ __forceinline__ void reduce_me_transposed(double (&m)[C], int (&e)[C]
 //   sinh x' = sinh x cosh 2ReW - sigma cosh x sinh 2ReW        cos y' = cos y cos 2ImW + sigma sin y sin 2ImW
 //   |cosh theta'|^2 = sinh^2 x' + cos^2 y'
 // sigma enters as ONE sign-bit XOR per product (no selects): 7 fp64 instructions + 2 integer XORs per (proposal, chain, unit).
-// <JPL = 8, C = 1>: 8 state quadruples per thread fit 128 registers -> four CTAs (16 warps) per SM instead of two
 template <int JPL, int C>
-__global__ void __launch_bounds__(128, (C == 1 && JPL == 8) ? 4 : 1) rbm_sweep_fast_kernel(const FastSweepArgs a)
+__global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int G = 32/C;                      // lanes per chain group (owner lanes of a chain's accept decision)

@@ -1,4 +1,4 @@
-// Generic ("direct log cosh") kernels of the sampler side of the path: theta GEMV-style init, Metropolis sweep with the
+// Generic ("direct log cosh") kernels of the sampler side of the path: tiled theta init, Metropolis sweep with the
 // chain state resident in shared memory, local energy, single-flip forward.  They accept any N, M and both ansaetze and
 // follow the reference arithmetic literally; the specialised register-resident kernels live in fast_kernels.cuh.
 //
@@ -242,57 +242,99 @@ struct ThetaArgs
 
 // ref: RBM::initialize / forward(spins) / tail of update_variables (impl_neural_quantum_state.cuh:67-91,107-129,161-169):
 // theta = W^T s + b (c2+c3), sa = a.s (c4), lnpsi = sum_j logcosh(theta_j) + sa (k2 + c1).  FFNN :799-847.
-// Generic version: one warp per chain, lanes over j, W read row by row (coalesced).  Spins are +-1 (or 0), so the "GEMM" is
-// signed accumulation of W rows.
-template <int MODEL>
-__global__ void __launch_bounds__(256) theta_generic_kernel(const ThetaArgs a)
+// The reference runs this as Zgemm on spins stored as complex numbers.  Spins are +-1, so theta is a SIGNED ACCUMULATION of W
+// rows: a CTA takes NQS_TH_CH chains, thread t owns hidden unit j = t (+256, ...) for all of them, so every W_ij fetched (one
+// coalesced 16-byte load per thread) is used for NQS_TH_CH chains and the spins come from shared memory as broadcast doubles;
+// log cosh and the sum over j are fused behind the accumulation (no theta round trip through HBM for lnpsi).
+#define NQS_TH_THREADS 256
+#define NQS_TH_CH 16
+
+template <int MODEL, bool LNPSI>
+__global__ void __launch_bounds__(NQS_TH_THREADS) theta_tiled_kernel(const ThetaArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
   const int N = a.N, M = a.M;
-  const int npad = ((N+15)/16)*16;
-  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*npad;
-  const long long k = (long long)blockIdx.x*warps+w;
-  if (k >= a.K) return;
+  double * sp = reinterpret_cast<double*>(smem_raw);                    // [N][NQS_TH_CH] spins as doubles (0 for missing chains)
+  cd * red = reinterpret_cast<cd*>(sp+(size_t)N*NQS_TH_CH);              // [NQS_TH_THREADS/32][NQS_TH_CH]
+  const int t = threadIdx.x, lane = t&31, w = t>>5;
+  const long long kbase = (long long)blockIdx.x*NQS_TH_CH;
+  const int nk = (int)((a.K-kbase < NQS_TH_CH) ? a.K-kbase : NQS_TH_CH);
   const ModelPtrs mp = model_ptrs(MODEL, a.params, N, M);
-  for (int i = lane; i < N; i += 32) sp[i] = a.spins[k*N+i];
-  __syncwarp();
-  cd lsum = cmake(0.0, 0.0);
-  for (int j = lane; j < M; j += 32)
+  for (int idx = t; idx < N*NQS_TH_CH; idx += NQS_TH_THREADS)
   {
-    cd acc = mp.b[j];
+    const int i = idx/NQS_TH_CH, c = idx-i*NQS_TH_CH;
+    sp[idx] = (c < nk) ? (double)a.spins[(kbase+c)*N+i] : 0.0;
+  }
+  __syncthreads();
+  cd lsum[LNPSI ? NQS_TH_CH : 1];
+#pragma unroll
+  for (int c = 0; c < (LNPSI ? NQS_TH_CH : 1); ++c) lsum[c] = cmake(0.0, 0.0);
+  for (int j = t; j < M; j += NQS_TH_THREADS)
+  {
+    cd acc[NQS_TH_CH];
+    const cd bj = mp.b[j];
+#pragma unroll
+    for (int c = 0; c < NQS_TH_CH; ++c) acc[c] = bj;
     for (int i = 0; i < N; ++i)
     {
       const cd wv = mp.W[(size_t)i*M+j];
-      const double s = (double)sp[i];
-      acc.x = fma(s, wv.x, acc.x);
-      acc.y = fma(s, wv.y, acc.y);
+      const double2 * srow = reinterpret_cast<const double2*>(sp+(size_t)i*NQS_TH_CH);
+#pragma unroll
+      for (int c2 = 0; c2 < NQS_TH_CH/2; ++c2)
+      {
+        const double2 s2 = srow[c2];
+        acc[2*c2].x = fma(s2.x, wv.x, acc[2*c2].x); acc[2*c2].y = fma(s2.x, wv.y, acc[2*c2].y);
+        acc[2*c2+1].x = fma(s2.y, wv.x, acc[2*c2+1].x); acc[2*c2+1].y = fma(s2.y, wv.y, acc[2*c2+1].y);
+      }
     }
-    if (a.theta) a.theta[k*M+j] = acc;
-    if (a.lnpsi)
+    cd wo = cmake(1.0, 0.0);
+    if (MODEL == MODEL_FFNN && LNPSI) wo = mp.w1o[j];
+#pragma unroll
+    for (int c = 0; c < NQS_TH_CH; ++c)
     {
-      const cd lc = c_logcosh(acc);
-      if (MODEL == MODEL_RBM) lsum = cadd(lsum, lc);
-      else lsum = cadd(lsum, cmul(mp.w1o[j], lc));
+      if (c < nk)
+      {
+        if (a.theta) a.theta[(kbase+c)*M+j] = acc[c];
+        if (LNPSI)
+        {
+          const cd lc = c_logcosh(acc[c]);
+          lsum[LNPSI ? c : 0] = cadd(lsum[LNPSI ? c : 0], (MODEL == MODEL_RBM) ? lc : cmul(wo, lc));
+        }
+      }
     }
   }
-  cd sa = cmake(0.0, 0.0);
-  if (MODEL == MODEL_RBM)
+  if (LNPSI)
   {
-    for (int i = lane; i < N; i += 32)
+#pragma unroll
+    for (int c = 0; c < (LNPSI ? NQS_TH_CH : 1); ++c)
     {
-      const double s = (double)a.sa_spins[k*N+i];
-      const cd ai = mp.a[i];
-      sa.x = fma(s, ai.x, sa.x);
-      sa.y = fma(s, ai.y, sa.y);
+      const cd s = warp_sum(lsum[c]);
+      if (lane == 0) red[w*NQS_TH_CH+c] = s;
     }
-    sa = warp_sum(sa);
-    if (a.sa && lane == 0) a.sa[k] = sa;
   }
-  if (a.lnpsi)
+  __syncthreads();
+  // visible-bias term (RBM) from sa_spins, and the final lnpsi: warp w finishes chains w, w+8
+  for (int c = w; c < nk; c += NQS_TH_THREADS/32)
   {
-    lsum = warp_sum(lsum);
-    if (lane == 0) a.lnpsi[k] = cadd(lsum, sa);
+    cd sa = cmake(0.0, 0.0);
+    if (MODEL == MODEL_RBM)
+    {
+      for (int i = lane; i < N; i += 32)
+      {
+        const double s = (double)a.sa_spins[(kbase+c)*N+i];
+        const cd ai = mp.a[i];
+        sa.x = fma(s, ai.x, sa.x);
+        sa.y = fma(s, ai.y, sa.y);
+      }
+      sa = warp_sum(sa);
+      if (a.sa && lane == 0) a.sa[kbase+c] = sa;
+    }
+    if (LNPSI && lane == 0)
+    {
+      cd tot = sa;
+      for (int ww = 0; ww < NQS_TH_THREADS/32; ++ww) tot = cadd(tot, red[ww*NQS_TH_CH+c]);
+      a.lnpsi[kbase+c] = tot;
+    }
   }
 }
 

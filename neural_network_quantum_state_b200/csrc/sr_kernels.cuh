@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NQS_COL_THREADS) matvec_cols_partial_kernel(co
 // the W block is S^T T and S^T (T conj(h)) -- signed accumulation, K*N*M*4 fp64 FMAs -- and |O|^2 of the W block does not
 // depend on i at all.  This replaces the 8.7 GB pass of setup_partial_kernel (1.49 ms at N=128, M=256, K=16384) by
 // ~70 MB of reads; the reference makes FOUR passes over O for the same numbers (optimizer.cuh:140-143, functor_for_CG.cuh:99-102).
-// Grid = (hidden-unit tiles of 16, row blocks); a thread owns hidden unit j = t%16 of the tile and the sites i = t/16 + 16 m.
+// Grid = (hidden-unit tiles of 16, row blocks); a thread owns hidden unit j = t%16 of the tile and IPT consecutive sites.
 // Output layout = setup_partial_kernel's: part[rb][0..1] = sum O, [2..3] = sum O conj(h), [4] = sum |O|^2.
 // ---------------------------------------------------------------------------------------------------------------------
 #define NQS_SS_THREADS 256
@@ -174,10 +174,10 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
 {
   __shared__ cd Tsh[NQS_SS_CH][NQS_SS_JT], Thsh[NQS_SS_CH][NQS_SS_JT], Lsh[NQS_SS_CH][NQS_SS_JT];
   __shared__ cd hsh[NQS_SS_CH];
-  extern __shared__ __align__(16) unsigned char smem_raw[];     // spins chunk [NQS_SS_CH][16*IPT] int8, zero beyond N
+  extern __shared__ __align__(16) unsigned char smem_raw[];     // spins chunk [NQS_SS_CH][16*IPT] as doubles, zero beyond N
   constexpr int npad = 16*IPT;
-  int8_t * sp = reinterpret_cast<int8_t*>(smem_raw);
-  const int t = threadIdx.x, jl = t%NQS_SS_JT, ig = t/NQS_SS_JT;   // ig = 0..15
+  double * sp = reinterpret_cast<double*>(smem_raw);
+  const int t = threadIdx.x, jl = t%NQS_SS_JT, ig = t/NQS_SS_JT;   // ig = 0..15: the thread owns sites ig*IPT .. ig*IPT+IPT-1
   const int j = blockIdx.x*NQS_SS_JT+jl;
   const bool jok = (j < M);
   const ModelPtrs mp = model_ptrs(MODEL, params, N, M);
@@ -189,10 +189,8 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
   for (int m = 0; m < IPT; ++m) { a1x[m] = 0; a1y[m] = 0; a2x[m] = 0; a2y[m] = 0; }
   double bT[2] = {0, 0}, bTh[2] = {0, 0}, bT2 = 0;      // hidden-bias block (thread group ig == 0)
   double bL[2] = {0, 0}, bLh[2] = {0, 0}, bL2 = 0;      // FFNN: logcosh block (ig == 1)
-  double as[IPT], ahx[IPT], ahy[IPT];                   // RBM visible-bias block (tile 0, jl == 0)
-#pragma unroll
-  for (int m = 0; m < IPT; ++m) { as[m] = 0; ahx[m] = 0; ahy[m] = 0; }
-  const bool do_a = (MODEL == MODEL_RBM && blockIdx.x == 0 && jl == 0);
+  const bool do_a = (MODEL == MODEL_RBM && blockIdx.x == 0);    // visible-bias block: hidden-unit tile 0, threads t < N
+  double as = 0, ahx = 0, ahy = 0;
 
   for (long long kc = k0; kc < k1; kc += NQS_SS_CH)
   {
@@ -215,17 +213,17 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
     for (int idx = t; idx < NQS_SS_CH*npad; idx += NQS_SS_THREADS)
     {
       const int kk = idx/npad, i = idx-kk*npad;
-      sp[idx] = (kk < nk && i < N) ? spins[(kc+kk)*N+i] : (int8_t)0;
+      sp[idx] = (kk < nk && i < N) ? (double)spins[(kc+kk)*N+i] : 0.0;
     }
     __syncthreads();
     for (int kk = 0; kk < nk; ++kk)
     {
       const cd T = Tsh[kk][jl], Th = Thsh[kk][jl];
-      const int8_t * srow = sp+kk*npad+ig;
+      const double * srow = sp+kk*npad+ig*IPT;
 #pragma unroll
       for (int m = 0; m < IPT; ++m)
       {
-        const double s = (double)srow[16*m];              // 0 beyond N
+        const double s = srow[m];                          // 0 beyond N
         a1x[m] = fma(s, T.x, a1x[m]); a1y[m] = fma(s, T.y, a1y[m]);
         a2x[m] = fma(s, Th.x, a2x[m]); a2y[m] = fma(s, Th.y, a2y[m]);
       }
@@ -238,19 +236,17 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
         const cd L = Lsh[kk][jl], h = hsh[kk];
         bL[0] += L.x; bL[1] += L.y; bLh[0] += L.x*h.x+L.y*h.y; bLh[1] += L.y*h.x-L.x*h.y; bL2 += L.x*L.x+L.y*L.y;
       }
-      if (do_a)
-      {
-        const cd h = hsh[kk];
-#pragma unroll
-        for (int m = 0; m < IPT; ++m)
-        {
-          const double s = (double)srow[16*m];
-          as[m] += s; ahx[m] = fma(s, h.x, ahx[m]); ahy[m] = fma(-s, h.y, ahy[m]);   // s conj(h)
-        }
-      }
     }
+    if (do_a)
+      for (int i = t; i < N; i += NQS_SS_THREADS)         // at most one site per thread for N <= 256
+        for (int kk = 0; kk < nk; ++kk)
+        {
+          const double s = sp[kk*npad+i];
+          const cd h = hsh[kk];
+          as += s; ahx = fma(s, h.x, ahx); ahy = fma(-s, h.y, ahy);   // s conj(h)
+        }
   }
-  // every thread of row group 0 also needs sum_k |T_kj|^2 for the W block of all its sites: share it through shared memory
+  // sum_k |T_kj|^2 is the |O|^2 sum of every W-block column with this hidden unit: share it through shared memory
   __syncthreads();
   double * t2sh = reinterpret_cast<double*>(&Tsh[0][0]);
   if (ig == 0) t2sh[jl] = bT2;
@@ -264,7 +260,7 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
 #pragma unroll
     for (int m = 0; m < IPT; ++m)
     {
-      const int i = ig+16*m;
+      const int i = ig*IPT+m;
       if (i < N)
       {
         const long long p = (MODEL == MODEL_RBM) ? (long long)i*M+j : (long long)j*N+i;
@@ -285,15 +281,10 @@ __global__ void __launch_bounds__(NQS_SS_THREADS) setup_structured_kernel(const 
   if (do_a)
   {
     const double nrows = (double)(k1 > k0 ? k1-k0 : 0);
-#pragma unroll
-    for (int m = 0; m < IPT; ++m)
+    for (int i = t; i < N; i += NQS_SS_THREADS)
     {
-      const int i = ig+16*m;
-      if (i < N)
-      {
-        const long long p = NM+i;
-        base[p] = as[m]; base[P+p] = 0.0; base[2*P+p] = ahx[m]; base[3*P+p] = ahy[m]; base[4*P+p] = nrows;   // s^2 = 1
-      }
+      const long long p = NM+i;
+      base[p] = as; base[P+p] = 0.0; base[2*P+p] = ahx; base[3*P+p] = ahy; base[4*P+p] = nrows;   // s^2 = 1
     }
   }
 }
