@@ -183,7 +183,15 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
     {
       const unsigned int * f = a.peer_flag[a.rank]+((size_t)par*NQS_CG_MAX_RANKS+threadIdx.x)*NQS_CG_MAX_CTAS+blockIdx.x;
       unsigned int seen;
-      do { asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory"); } while ((int)(seen-a.epoch) < 0);
+      unsigned long long t0 = 0, now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;)
+      {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+        if ((int)(seen-a.epoch) >= 0) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now-t0 > 20000000000ull) { a.sc->peer_timeout = 1; break; }   // a peer died: never hang the GPU (host raises NQS_ERR_NCCL)
+      }
     }
     __syncthreads();
     xin = a.peer_x[a.rank]+(size_t)par*a.n_ranks*2*(size_t)P;

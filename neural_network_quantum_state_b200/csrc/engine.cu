@@ -97,14 +97,14 @@ int ev_next(nqs_handle * h)
 
 struct Span
 { // CUDA-event bracket on the handle's stream, recorded without any synchronisation; resolve_spans() reads them later
-  nqs_handle * h; int tag, b; bool on;
-  Span(nqs_handle * h_, int tag_): h(h_), tag(tag_), b(-1), on(h_->timing_on)
-  { if (on) { b = ev_next(h); cudaEventRecord(h->evpool[b], h->stream); } }
+  nqs_handle * h; int tag, b; bool on; cudaStream_t st;
+  Span(nqs_handle * h_, int tag_, cudaStream_t st_ = nullptr): h(h_), tag(tag_), b(-1), on(h_->timing_on), st(st_ ? st_ : h_->stream)
+  { if (on) { b = ev_next(h); cudaEventRecord(h->evpool[b], st); } }
   ~Span()
   {
     if (!on) return;
     const int e = ev_next(h);
-    cudaEventRecord(h->evpool[e], h->stream);
+    cudaEventRecord(h->evpool[e], st);
     h->spans.push_back({tag, b, e});
   }
 };
@@ -341,19 +341,20 @@ void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
   check_launch(h, "eloc_generic_kernel");
 }
 
-void launch_oderiv(nqs_handle * h)
+void launch_oderiv(nqs_handle * h, cudaStream_t stream = nullptr)
 {
+  if (stream == nullptr) stream = h->stream;
   const size_t smem = (size_t)(h->model == MODEL_FFNN ? 2 : 1)*h->M*sizeof(cd)+(size_t)h->N*sizeof(double);
   NQS_REQUIRE(smem <= h->smem_optin, NQS_ERR_UNSUPPORTED, "n_hiddens too large for oderiv_kernel shared memory");
   if (h->model == MODEL_RBM)
   {
     set_smem(oderiv_kernel<MODEL_RBM>, smem);
-    oderiv_kernel<MODEL_RBM><<<(unsigned)h->K, 256, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
+    oderiv_kernel<MODEL_RBM><<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
   }
   else
   {
     set_smem(oderiv_kernel<MODEL_FFNN>, smem);
-    oderiv_kernel<MODEL_FFNN><<<(unsigned)h->K, 256, smem, h->stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
+    oderiv_kernel<MODEL_FFNN><<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
   }
   check_launch(h, "oderiv_kernel");
   h->theta_matches_O = true;   // O was built from the current (spins, theta, params): the setup sums may use the factors
@@ -410,11 +411,17 @@ void plan_sv(nqs_handle * h)
   h->sv_ok = false;
   if (h->cfg.flags & NQS_FLAG_TWO_PASS_SV) return;
   // software-pipelined variant by default (1.50 ms vs 1.95 ms per S*v at N=128, M=256, K=16384; needs >= 3 row slots)
-  { const char * d = std::getenv("NQS_SV_DEFER"); h->sv_defer = d ? std::atoi(d) : 1; }
-  const int cs_try[2] = {8, 16};
-  for (int ci = 0; ci < 2; ++ci)
+  int want_defer = 1;
+  { const char * d = std::getenv("NQS_SV_DEFER"); if (d) want_defer = std::atoi(d); }
+  // Candidate cluster sizes.  What matters is how many SMs the resident clusters cover: clusters must sit inside one GPC, so
+  // on a B200 15 clusters of 8 cover 120 SMs, 15 clusters of 9 cover 135 (1.39 vs 1.47 ms per S*v at N=128, M=256, K=16384),
+  // 11 clusters of 10 cover 110 and 7 clusters of 16 cover 112 (measured, profiles/r1d_sv_fused_experiments.md).  Sizes above 8
+  // are "non-portable" and need cudaFuncAttributeNonPortableClusterSizeAllowed.  NQS_SV_CS pins the size (tests).
+  std::vector<int> cs_list = {8, 9, 10, 12, 16};
+  { const char * c = std::getenv("NQS_SV_CS"); if (c && std::atoi(c) >= 1 && std::atoi(c) <= NQS_SV_MAX_CLUSTER) cs_list = {std::atoi(c)}; }
+  long long best_score = -1;
+  for (const int cs : cs_list)
   {
-    const int cs = cs_try[ci];
     const long long pc = (h->P+cs-1)/cs;
     int cpt = 0, nt = 0;
     for (int c = 1; c <= NQS_SV_MAX_CPT; ++c)
@@ -429,21 +436,25 @@ void plan_sv(nqs_handle * h)
     if (h->smem_optin < NQS_SV_TAIL_BYTES+2*slot_bytes) continue;
     const int nslot = (int)std::min<size_t>(NQS_SV_MAX_SLOTS, (h->smem_optin-NQS_SV_TAIL_BYTES)/slot_bytes);
     const size_t smem = (size_t)nslot*slot_bytes+NQS_SV_TAIL_BYTES;
+    const int defer = (nslot >= 3) ? want_defer : 0;
     SvArgs a;
     std::memset(&a, 0, sizeof(a));
     int maxc = 0;
-    cudaError_t e = sv_launch(cpt, h->sv_defer, a, cs, 1, nt, smem, h->stream, &maxc);
+    cudaError_t e = sv_launch(cpt, defer, a, cs, 1, nt, smem, h->stream, &maxc);
     if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
     long long ncl = std::min<long long>(maxc, h->K);
     const long long rpc = (h->K+ncl-1)/ncl;
     ncl = (h->K+rpc-1)/rpc;
-    if (nslot < 3) h->sv_defer = 0;
+    // score: SMs kept busy; the pipelined variant (>= 3 slots) beats the in-order one at equal coverage
+    const long long score = ncl*cs*4+(defer ? 2 : 0)+(cpt > 3 ? 1 : 0);
+    if (score <= best_score) continue;
+    best_score = score;
+    h->sv_defer = defer;
     h->sv_cs = cs; h->sv_cpt = cpt; h->sv_nt = nt; h->sv_nslot = nslot; h->sv_nclusters = (int)ncl;
     h->sv_smem = smem; h->sv_slot_bytes = slot_bytes; h->sv_pc = pc; h->sv_rpc = rpc;
     h->sv_ok = true;
     h->variant_sv = "fused_cs"+std::to_string(cs)+"_cpt"+std::to_string(cpt)+"_nt"+std::to_string(nt)+"_slots"+std::to_string(nslot)+
       "_clusters"+std::to_string(ncl)+(h->sv_defer ? "_defer" : "");
-    return;
   }
 }
 
@@ -571,9 +582,8 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
 }
 
 // ref: ConjugateGradient::solve(SMatrixFunctor_, F, dx), conjugate_gradient.cuh:29-74, warm start in dx.
-// Two launches per iteration (pass over O + cg_fused_kernel) and no host round trip inside: iterations are enqueued in batches
-// of four, the device-side `done` flag turns the ones past convergence into empty launches, and the host looks at a copy of
-// the scalars one batch behind the queue (the reference synchronises four times per iteration).
+// Two launches per iteration (pass over O + cg_fused_kernel) and no host round trip inside an iteration (the reference
+// synchronises four times per iteration).
 void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters, nqs_sr_stats * st)
 {
   CgScalars init;
@@ -587,31 +597,31 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
   int nparts = matvec_passes(h, h->dx.p, nullptr);
   launch_cg_fused(h, CG_MODE_INIT, nparts, lambda, h->dx.p);
   const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
-  const int batch = 4;
-  CgScalars * snap[2] = {reinterpret_cast<CgScalars*>((char*)h->pinned+1024), reinterpret_cast<CgScalars*>((char*)h->pinned+2048)};
-  int nb = 0;
-  bool stop = false;
-  for (int it = 0; it < n_max && !stop; )
+  CgScalars * snap = reinterpret_cast<CgScalars*>((char*)h->pinned+1024);
+  // Iterations are enqueued without looking at the result: first as many as the previous solve needed (consecutive SR steps
+  // need almost the same number), then two at a time, each batch followed by one read-back of the scalars.  Iterations past
+  // convergence are skipped on the device (`done`), so the count is exact and a misprediction costs one queue bubble.
+  int enq = 0;
+  CgScalars s;
+  std::memset(&s, 0, sizeof(s));
+  int n_here = fixed_iters > 0 ? n_max : std::max(1, std::min(n_max, h->cg_prev_iters));
+  for (;;)
   {
-    const int n_here = std::min(batch, n_max-it);
     for (int q = 0; q < n_here; ++q)
     {
       nparts = matvec_passes(h, h->pvec.p, done);
       launch_cg_fused(h, CG_MODE_ITER, nparts, lambda, h->pvec.p);
     }
-    it += n_here;
-    NQS_CUDA(cudaMemcpyAsync(snap[nb&1], h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
-    NQS_CUDA(cudaEventRecord(h->cg_ev[nb&1], h->stream));
-    if (nb >= 1)
-    { // look at the batch before the one just enqueued
-      NQS_CUDA(cudaEventSynchronize(h->cg_ev[(nb-1)&1]));
-      if (snap[(nb-1)&1]->done) stop = true;
-    }
-    ++nb;
+    enq += n_here;
+    NQS_CUDA(cudaMemcpyAsync(snap, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    s = *snap;
+    if (s.done || enq >= n_max) break;
+    n_here = std::min(2, n_max-enq);
   }
-  if (nb == 0) NQS_CUDA(cudaMemcpyAsync(snap[1], h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
-  NQS_CUDA(cudaStreamSynchronize(h->stream));
-  const CgScalars s = *snap[(nb+1)&1];
+  if (fixed_iters <= 0) h->cg_prev_iters = std::max(1, s.iters);
+  if (s.peer_timeout)
+    throw Error(NQS_ERR_NCCL, "in-kernel NVLink exchange timed out after 20 s: a peer rank did not reach the same CG iteration");
   if (st)
   {
     st->cg_iters = s.iters;
@@ -793,8 +803,9 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     NQS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
     for (int i = 0; i < 8; ++i) NQS_CUDA(cudaEventCreate(&h->ev[i]));
-    for (int i = 0; i < 2; ++i) NQS_CUDA(cudaEventCreateWithFlags(&h->cg_ev[i], cudaEventDisableTiming));
+
     h->ev_ok = true;
     NQS_CUDA(cudaMallocHost(&h->pinned, 4096));
     const size_t KM = (size_t)h->K*h->M, KN = (size_t)h->K*h->N;
@@ -841,7 +852,7 @@ void nqs_destroy(nqs_handle * h)
   if (h->comm && g_nccl.commDestroy) g_nccl.commDestroy(h->comm);
   if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
   if (h->ev_ok) for (int i = 0; i < 8; ++i) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < 2; ++i) if (h->cg_ev[i]) cudaEventDestroy(h->cg_ev[i]);
+
   for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
   if (h->pinned) cudaFreeHost(h->pinned);
   delete h;
@@ -1164,6 +1175,8 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     nqs_sr_stats s;
     std::memset(&s, 0, sizeof(s));
     { Span t(h, TAG_SWEEP); do_sweeps(h, opt->n_mc_steps); }
+    // (Running the HBM-write-bound O writer on a side stream next to the fp64-bound local energy was tried: the writer's K CTAs
+    // occupy every SM slot, the two kernels serialise anyway and the step time does not change.)
     { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
     { Span t(h, TAG_ODERIV); launch_oderiv(h); }
     double hs[3];

@@ -79,8 +79,8 @@ struct nqs_handle
   nqs::DevBuf<double> diag, part, sums, traw, slots;
   nqs::DevBuf<nqs::CgScalars> scal;
   nqs::DevBuf<unsigned int> cgbar;         // grid-barrier counter of cg_fused_kernel (zero between launches)
-  cudaEvent_t cg_ev[2] = {nullptr, nullptr};
   double bp = 1.0;                        // lambda schedule state (ref bp_, optimizer.cuh:176)
+  int cg_prev_iters = 4;                  // iterations the previous CG solve needed (how many to enqueue before polling)
   int nrb = 1;                            // row blocks of the column passes
   long long rows_per_block = 0;
   void * pinned = nullptr;                // small pinned staging area for scalar read-backs

@@ -435,6 +435,7 @@ struct CgScalars
   double aov_x, aov_y;     // <O> . p for the direction currently held in p
   double tol2;
   int done, iters, zero_rhs, fixed;
+  int peer_timeout;        // multi-GPU: a peer's flag did not arrive within 20 s
 };
 
 // ref: update_parameters (impl_neural_quantum_state.cuh:1300-1312) / FFNN__UpdateParameters__ (:1665-1690, un-transposes the W block)

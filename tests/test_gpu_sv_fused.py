@@ -1,5 +1,5 @@
 """One-pass S*v cluster kernel (csrc/sv_fused.cuh) against (1) the dense formula evaluated in numpy on the engine's own O
-and (2) the two-pass kernels, over shapes that exercise every launch plan: cluster size 8 / 16, 1..9 columns per thread,
+and (2) the two-pass kernels, over shapes that exercise every launch plan: cluster sizes 8 / 9 / 10 / 16, 1..9 columns per thread,
 ragged last column slice, row counts that do not divide by the number of clusters, fewer rows than clusters.
 
 ref: SMatrixForCG::dot, gpu/include/functor_for_CG.cuh:104-127:  S v = (1/K) O^H (O v) - conj(<O>) (<O> . v) + lambda diag(S) v.
@@ -15,16 +15,19 @@ pytestmark = pytest.mark.gpu
 
 H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
 
-# (model, N, M, K, expected cluster size, expected columns per thread)
+# (model, N, M, K, pinned cluster size or None = the engine's own choice, expected cluster size, expected columns per thread)
 SHAPES = [
-    ("rbm", 16, 16, 64, 8, 1),      # tiny: P = 288, 36 columns per CTA
-    ("rbm", 6, 1, 40, 8, 1),        # P = 13 < 2*8: trailing CTAs own no column at all
-    ("rbm", 64, 128, 300, 8, 2),    # cfg2 shape, K not a multiple of the cluster count
-    ("rbm", 80, 250, 37, 8, 3),     # P = 20330
-    ("rbm", 100, 260, 50, 8, 7),    # P = 26360
-    ("rbm", 128, 256, 150, 8, 9),   # cfg3 shape (P = 33152)
-    ("ffnn", 128, 512, 40, 16, 9),  # cfg4 shape (P = 66560): 16-CTA clusters
-    ("rbm", 128, 256, 5, 8, 9),     # fewer rows than clusters
+    ("rbm", 16, 16, 64, 8, 8, 1),       # tiny: P = 288, 36 columns per CTA
+    ("rbm", 6, 1, 40, 8, 8, 1),         # P = 13 < 2*8: trailing CTAs own no column at all
+    ("rbm", 64, 128, 300, 8, 8, 2),     # cfg2 shape, K not a multiple of the cluster count
+    ("rbm", 80, 250, 37, 8, 8, 3),      # P = 20330
+    ("rbm", 100, 260, 50, 8, 8, 7),     # P = 26360
+    ("rbm", 128, 256, 150, 8, 8, 9),    # cfg3 shape (P = 33152), portable cluster size
+    ("rbm", 128, 256, 150, None, 9, 8), # cfg3 shape as shipped: 9-CTA clusters cover 135 SMs
+    ("rbm", 64, 128, 300, None, 9, 1),  # cfg2 shape as shipped
+    ("rbm", 128, 256, 150, 10, 10, 7),
+    ("ffnn", 128, 512, 40, None, 16, 9),# cfg4 shape (P = 66560): 16-CTA clusters
+    ("rbm", 128, 256, 5, None, 16, 3),  # fewer rows than clusters: the widest cluster covers most SMs
 ]
 
 
@@ -36,9 +39,13 @@ def dense_sv(O, v, lam):
     return (O.conj().T @ z) / K - aO.conj() * (aO @ v) + lam * diag * v, aO, diag
 
 
-@pytest.mark.parametrize("model,N,M,K,cs,cpt", SHAPES)
-def test_fused_sv_matches_dense_and_two_pass(model, N, M, K, cs, cpt):
+@pytest.mark.parametrize("model,N,M,K,pin_cs,cs,cpt", SHAPES)
+def test_fused_sv_matches_dense_and_two_pass(model, N, M, K, pin_cs, cs, cpt, monkeypatch):
     from neural_network_quantum_state_b200 import Engine
+    if pin_cs is not None:
+        monkeypatch.setenv("NQS_SV_CS", str(pin_cs))     # read by the engine when it plans the S*v launch (nqs_create / enable_sr)
+    else:
+        monkeypatch.delenv("NQS_SV_CS", raising=False)
     rng = np.random.default_rng(N * 1000 + M)
     out = {}
     for two_pass in (False, True):
