@@ -278,7 +278,7 @@ void launch_sweep(nqs_handle * h, long long nsteps)
       case 1: launch_sweep_fast_t<1, 4>(h, f); break;
       case 2: launch_sweep_fast_t<2, 4>(h, f); break;
       case 4: launch_sweep_fast_t<4, 4>(h, f); break;
-      case 8: launch_sweep_fast_t<8, 2>(h, f); break;   // <8, 1> at 128 registers / 16 warps per SM was measured 1.7x slower (spills)
+      case 8: launch_sweep_fast_t<8, 2>(h, f); break;
       default: launch_sweep_fast_t<16, 1>(h, f); break;
     }
     check_launch(h, "rbm_sweep_fast_kernel");

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         }
       }
       if (bal != 0u)
-      {
+      { // (a warp-uniform branch per accepted chain instead of predication was measured slower: 2.71 vs 2.60 ms)
         const cd ai = avis[site];
 #pragma unroll
         for (int c = 0; c < C; ++c)
