@@ -423,12 +423,18 @@ void plan_sv(nqs_handle * h)
   for (const int cs : cs_list)
   {
     const long long pc = (h->P+cs-1)/cs;
+    // columns per thread / consumer threads: every row costs each WARP a fixed ~150 instructions (reduction, exchange, waits),
+    // so few fat warps beat many thin ones: prefer 8 columns per thread down to 128 threads, then 9-10 columns (register
+    // limit), then whatever fits (tiny slices).  One more warp is the TMA producer.
     int cpt = 0, nt = 0;
-    for (int c = 1; c <= NQS_SV_MAX_CPT; ++c)
+    const int order[NQS_SV_MAX_CPT+3] = {8, 7, 6, 5, 4, 3, 2, 1, 9, 10, 1, 2, 3};
+    for (int q = 0; q < NQS_SV_MAX_CPT+3 && !cpt; ++q)
     {
+      const int c = order[q];
       const long long need = ((pc+c-1)/c+31)/32*32;
-      const int max_t = (c <= 3) ? 992 : 480;   // consumer threads; one more warp is the TMA producer
-      if (need <= max_t) { cpt = c; nt = (int)std::max<long long>(64, need); break; }
+      const int max_t = (c <= 3) ? 992 : 480;
+      const long long min_t = (q < 8) ? 128 : 0;
+      if (need <= max_t && need >= min_t) { cpt = c; nt = (int)std::max<long long>(64, need); }
     }
     if (!cpt) continue;
     // a slot holds one row slice, padded to CPT * consumer threads elements so the kernel reads it without bounds checks
@@ -450,11 +456,13 @@ void plan_sv(nqs_handle * h)
     if (score <= best_score) continue;
     best_score = score;
     h->sv_defer = defer;
+    h->sv_depth = defer ? std::max(1, std::min(NQS_SV_MAX_DEPTH, (nslot-1)/2)) : 0;   // keep >= depth+1 slots for rows in flight
+    { const char * d = std::getenv("NQS_SV_DEPTH"); if (d && defer) h->sv_depth = std::max(1, std::min(std::min(NQS_SV_MAX_DEPTH, nslot-2), std::atoi(d))); }
     h->sv_cs = cs; h->sv_cpt = cpt; h->sv_nt = nt; h->sv_nslot = nslot; h->sv_nclusters = (int)ncl;
     h->sv_smem = smem; h->sv_slot_bytes = slot_bytes; h->sv_pc = pc; h->sv_rpc = rpc;
     h->sv_ok = true;
     h->variant_sv = "fused_cs"+std::to_string(cs)+"_cpt"+std::to_string(cpt)+"_nt"+std::to_string(nt)+"_slots"+std::to_string(nslot)+
-      "_clusters"+std::to_string(ncl)+(h->sv_defer ? "_defer" : "");
+      "_clusters"+std::to_string(ncl)+(h->sv_defer ? "_defer"+std::to_string(h->sv_depth) : "");
   }
 }
 
@@ -526,7 +534,7 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
   {
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
-    a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes;
+    a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
     Span sp(h, TAG_ROWS);
     NQS_CUDA(sv_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
     check_launch(h, "sv_fused_kernel");

@@ -86,7 +86,7 @@ struct nqs_handle
   void * pinned = nullptr;                // small pinned staging area for scalar read-backs
   // one-pass S*v (sv_fused.cuh): cluster size, columns per thread, threads, TMA slots, clusters, rows per cluster
   bool sv_ok = false;
-  int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0, sv_defer = 0;
+  int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0, sv_defer = 0, sv_depth = 0;
   size_t sv_smem = 0, sv_slot_bytes = 0;
   long long sv_pc = 0, sv_rpc = 0;
 

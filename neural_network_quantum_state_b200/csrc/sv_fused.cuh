@@ -17,9 +17,9 @@
 //       run-to-run deterministic) and accumulates conj(O_kp) z_k.
 // The reduction + DSMEM round trip of (2) costs ~0.7 us per row (measured, profiles/r1d_sv_fused_experiments.md), more than
 // half of the 1.2 us the HBM stream needs per row slice.  DEFER = 1 therefore software-pipelines the loop by one row: the
-// z exchange of row k is in flight while the warps already run (2) on row k+1, and (3) for row k re-reads the slice from
-// its shared-memory slot (released only then) instead of holding it in registers.  DEFER = 0 keeps the row in registers and
-// releases the slot right after (2).
+// z exchange of row k is in flight while the warps already run (2) on rows k+1 .. k+depth, and (3) for row k re-reads the
+// slice from its shared-memory slot (released only then) instead of holding it in registers; depth = 1 when only three row
+// slots fit (wide slices), up to 3 for narrow ones.  DEFER = 0 keeps the row in registers and releases the slot right after (2).
 // HBM traffic: K*P*16 B per S*v instead of 2*K*P*16 B.  Cluster partials go to part[q][{re,im}][P] and are folded in fixed
 // order by colsum_reduce_kernel exactly like the two-pass kernels' row-block partials.
 #pragma once
@@ -87,14 +87,17 @@ struct SvArgs
   long long rows_per_cluster;
   int nslot;               // shared-memory row slots (TMA pipeline depth)
   unsigned int slot_bytes; // bytes per slot: >= CPT * consumer threads * 16 (the tail past the slice stays zero)
+  int depth;               // DEFER = 1: pass (3) of row k runs after pass (2) of row k+depth (1..NQS_SV_MAX_DEPTH, <= nslot-2)
 };
 
 #define NQS_SV_MAX_CLUSTER 16
 #define NQS_SV_MAX_SLOTS 8
 #define NQS_SV_MAX_WARPS 32
-#define NQS_SV_ZBUFS 4     // z exchange buffers: a peer may run (2) up to two rows ahead of this CTA's (3) when DEFER = 1
-// shared memory after the slots: red[2][warps] | zbuf[ZBUFS][cluster] | full[8] | empty[8] | wfull[2] | zfull[ZBUFS]
-#define NQS_SV_TAIL_BYTES (2*NQS_SV_MAX_WARPS*16+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+2*8+NQS_SV_ZBUFS*8)
+#define NQS_SV_ZBUFS 8     // z exchange buffers, >= 2*depth+2: a peer may run (2) up to depth+1 rows ahead of this CTA's (3)
+#define NQS_SV_MAX_DEPTH 3
+#define NQS_SV_RBUFS 4     // CTA-level reduction buffers, >= depth+1: a warp may run (2) up to depth rows ahead of a reducer
+// shared memory after the slots: red[RBUFS][warps] | zbuf[ZBUFS][cluster] | full[8] | empty[8] | wfull[RBUFS] | zfull[ZBUFS]
+#define NQS_SV_TAIL_BYTES (NQS_SV_RBUFS*NQS_SV_MAX_WARPS*16+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+NQS_SV_RBUFS*8+NQS_SV_ZBUFS*8)
 
 // register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 992+32 threads (8 warps per sub-partition x 64
 // registers), larger CPT up to 480+32 threads (4 warps per sub-partition x 128 registers)
@@ -112,12 +115,12 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   const int NT = blockDim.x-32, tid = threadIdx.x, lane = tid&31, w = tid>>5, NW = NT>>5;
   const long long cid = blockIdx.x/CS;
   unsigned char * tail = smem_raw+(size_t)a.nslot*a.slot_bytes;
-  cd * red = reinterpret_cast<cd*>(tail);                                   // [2][NQS_SV_MAX_WARPS] warp partials of this CTA
-  cd * zbuf = red+2*NQS_SV_MAX_WARPS;                                       // [ZBUFS][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
+  cd * red = reinterpret_cast<cd*>(tail);                                   // [RBUFS][NQS_SV_MAX_WARPS] warp partials of this CTA
+  cd * zbuf = red+NQS_SV_RBUFS*NQS_SV_MAX_WARPS;                                       // [ZBUFS][NQS_SV_MAX_CLUSTER] CTA partials of the cluster
   uint64_t * full = reinterpret_cast<uint64_t*>(zbuf+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER); // [slots] TMA arrival
   uint64_t * empty = full+NQS_SV_MAX_SLOTS;                                 // [slots] all consumer warps released the slot
-  uint64_t * wfull = empty+NQS_SV_MAX_SLOTS;                                // [2] all NW warp partials of a row are in red[]
-  uint64_t * zfull = wfull+2;                                               // [ZBUFS] all CS CTA partials of a row arrived (tx bytes)
+  uint64_t * wfull = empty+NQS_SV_MAX_SLOTS;                                // [RBUFS] all NW warp partials of a row are in red[]
+  uint64_t * zfull = wfull+NQS_SV_RBUFS;                                               // [ZBUFS] all CS CTA partials of a row arrived (tx bytes)
 
   const long long c0 = (long long)crank*a.pc;
   long long nr_ll = a.P-c0;
@@ -140,7 +143,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
   if (tid == 0)
   {
     for (int s = 0; s < a.nslot; ++s) { mbar_init(full+s, 1); mbar_init(empty+s, (uint32_t)NW); }
-    mbar_init(wfull, (uint32_t)NW); mbar_init(wfull+1, (uint32_t)NW);
+    for (int q = 0; q < NQS_SV_RBUFS; ++q) mbar_init(wfull+q, (uint32_t)NW);
     for (int q = 0; q < NQS_SV_ZBUFS; ++q) mbar_init(zfull+q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -190,7 +193,25 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       }
     };
 
-    int slot = 0, prev_slot = 0;
+    // (3) for row jt held in slot jslot: re-read the slice from shared memory, then release the slot
+    auto pass3_from_slot = [&](const int jt, const int jslot)
+    {
+      double zx, zy;
+      wait_z(jt, zx, zy);
+      const cd * prow = sbase+(size_t)jslot*slot_elems;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+      {
+        const cd q = prow[c*NT];
+        acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
+        acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
+      }
+      __syncwarp();
+      if (lane == 0 && n_r > 0) mbar_arrive(empty+jslot);
+    };
+
+    const int depth = a.depth;
+    int slot = 0, tail_slot = 0;       // tail_slot: slot of row it-depth (the oldest row still waiting for its pass (3))
     uint32_t full_par = 0;
     for (int it = 0; it < nrows; ++it)
     {
@@ -213,12 +234,12 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
         pc_ = fma(o[c].x, vr[c].y, pc_); pd = fma(o[c].y, vr[c].x, pd);
       }
       const cd wp = warp_sum(cmake(pa-pb, pc_+pd));
-      const int rq = it&1, zq = it&(NQS_SV_ZBUFS-1);
+      const int rq = it&(NQS_SV_RBUFS-1), zq = it&(NQS_SV_ZBUFS-1);
       cd * redrow = red+rq*NQS_SV_MAX_WARPS;
       if (lane == 0) { redrow[w] = wp; mbar_arrive(wfull+rq); }
       if (w == it%NW)
       { // this row's reducer warp: CTA partial = fixed-order fold of the warp partials, sent to every CTA of the cluster
-        mbar_wait(wfull+rq, (uint32_t)((it>>1)&1));
+        mbar_wait(wfull+rq, (uint32_t)((it/NQS_SV_RBUFS)&1));
         const cd s = warp_sum((lane < NW) ? redrow[lane] : cmake(0.0, 0.0));
         if (lane == 0) mbar_expect_tx(zfull+zq, CS*(uint32_t)sizeof(cd));   // this row's CS partials land here
         if (lane < (int)CS)
@@ -235,35 +256,19 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
           acc[c].y = fma(o[c].x, zy, acc[c].y); acc[c].y = fma(-o[c].y, zx, acc[c].y);
         }
       }
-      else if (it > 0)
-      { // row it-1: its exchange travelled while this warp worked on row it; the slice is still in its slot
-        double zx, zy;
-        wait_z(it-1, zx, zy);
-        const cd * prow = sbase+(size_t)prev_slot*slot_elems;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-        {
-          const cd q = prow[c*NT];
-          acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
-          acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
-        }
-        __syncwarp();
-        if (lane == 0 && n_r > 0) mbar_arrive(empty+prev_slot);
+      else if (it >= depth)
+      { // row it-depth: its exchange travelled while this warp worked on the rows after it; the slice is still in its slot
+        pass3_from_slot(it-depth, tail_slot);
+        if (++tail_slot == a.nslot) tail_slot = 0;
       }
-      prev_slot = slot;
       if (++slot == a.nslot) { slot = 0; full_par ^= 1u; }
     }
-    if (DEFER != 0 && nrows > 0)
+    if (DEFER != 0)
     {
-      double zx, zy;
-      wait_z(nrows-1, zx, zy);
-      const cd * prow = sbase+(size_t)prev_slot*slot_elems;
-#pragma unroll
-      for (int c = 0; c < CPT; ++c)
+      for (int jt = (nrows > depth ? nrows-depth : 0); jt < nrows; ++jt)
       {
-        const cd q = prow[c*NT];
-        acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
-        acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
+        pass3_from_slot(jt, tail_slot);
+        if (++tail_slot == a.nslot) tail_slot = 0;
       }
     }
     double * base = a.part+(size_t)cid*2*(size_t)a.P;
