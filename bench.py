@@ -39,6 +39,7 @@ CONFIGS = {
 }
 THETA_H = math.pi / 4
 H_FIELD, J_COUP, ALPHA_LR = -math.cos(THETA_H), math.sin(THETA_H), 2.0
+FP64_DMMA_PEAK_TFLOPS = 37.1   # mma.sync m8n8k4 f64, all 148 SMs, measured (scripts/micro/dmma_bench.cu); nominal 37-40
 METRIC = "vmc_samples_per_s"
 UNIT = "samples/s"
 
@@ -188,6 +189,8 @@ def main():
     ap.add_argument("--cg-fixed-iters", type=int, default=0, help="diagnostics: run exactly this many CG iterations per step")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllReduce per CG iteration instead of the in-kernel exchange")
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
+    ap.add_argument("--structured-sv", action="store_true",
+                    help="S*v from the factors of O as two fp64 tensor-core GEMMs (no O matrix); roofline is then the fp64 tensor pipe")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, torchrun notices) are sent
@@ -213,6 +216,10 @@ def main():
               "l2": "working set (O = %.2f GB per rank) >> 126 MB L2: no flush needed" % (K_total / world * P * 16 / 1e9),
               "nwarm_sweeps": args.nwarm, "lr": args.lr, "rng": "in-kernel Philox4x32-10 (value) / pre-drawn host uniforms (e2e)"}
 
+    if args.structured_sv:
+        config["l2"] = ("structured S*v keeps no O: per step theta + T (%.0f MB each per rank) are rewritten and re-read and the "
+                        "GEMM partials (~20 MB) rewritten per product; together > 126 MB L2, no flush" % (K_total / world * M * 16 / 1e6))
+        config["workload"] += "; S*v from the factors of O (NQS_FLAG_STRUCTURED_SV)"
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
@@ -245,7 +252,7 @@ def main():
     K_loc = K_total // world
     e = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
                n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic,
-               two_pass_sv=args.two_pass_sv)
+               two_pass_sv=args.two_pass_sv, structured_sv=args.structured_sv)
     e.set_params(synthetic_params(model, N, M, cfg_id))
     p2p = False
     if world > 1:
@@ -335,7 +342,9 @@ def main():
     peak, peak_src = measured_peak_gbs()
     bytes_per_launch = K_loc * P * 16.0     # one read of this rank's O [K_loc][P] complex fp64
     sv_variant = e.kernel_variant("sv")
-    if sv_variant.startswith("fused"):
+    if sv_variant.startswith("structured"):
+        dom = other = None
+    elif sv_variant.startswith("fused"):
         # one-pass cluster kernel: O is read from HBM once per S*v (the reference and the two-pass kernels read it twice)
         dom, dom_ms, n_timed = "sv_fused_kernel", phase["rows_ms"] / max(counts["rows_count"], 1), counts["rows_count"]
         other = None
@@ -347,12 +356,33 @@ def main():
         other = {"kernel": "matvec_rows_kernel" if is_cols else "matvec_cols_partial_kernel",
                  "avg_launch_ms": (phase["rows_ms"] / max(counts["rows_count"], 1)) if is_cols
                  else (phase["cols_ms"] / max(counts["cols_count"], 1))}
-    achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": dom, "variant": sv_variant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": committed_traffic(dom),
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms, "launches_timed": n_timed,
-                "note": "achieved = K_loc*P*16 B (O read once) / CUDA-event duration of the launch; SURVEY 8d's two-pass figure "
-                        "B_cg = 2*K_loc*P*16 per S*v is met with %s pass(es) over O" % ("1" if other is None else "2")}
+    if dom is None:
+        # structured S*v: the two GEMMs (rows: z = O v, cols: O^H z) are fp64 tensor-core work, 2*K_loc*N*2M flops each
+        flops = 2.0 * K_loc * N * 2 * M
+        r_ms = phase["rows_ms"] / max(counts["rows_count"], 1)
+        c_ms = phase["cols_ms"] / max(counts["cols_count"], 1)
+        dom, dom_ms, n_timed = ("spin_cols_dmma_kernel", c_ms, counts["cols_count"]) if c_ms >= r_ms else \
+                               ("spin_rows_dmma_kernel", r_ms, counts["rows_count"])
+        ach = flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": dom, "variant": sv_variant, "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS,
+                    "unit": "TFLOP/s", "frac": ach / FP64_DMMA_PEAK_TFLOPS,
+                    "peak_source": "fp64 DMMA peak measured on this pool's B200 with scripts/micro/dmma_bench.cu (MEASURED_PEAKS.json "
+                                   "holds only the bf16 figure)",
+                    "traffic": committed_traffic(dom), "algorithmic_flops_per_launch": flops, "avg_launch_ms": dom_ms,
+                    "launches_timed": n_timed,
+                    "other_pass": {"kernel": "spin_rows_dmma_kernel" if dom.startswith("spin_cols") else "spin_cols_dmma_kernel",
+                                   "avg_launch_ms": r_ms if dom.startswith("spin_cols") else c_ms},
+                    "note": "S*v = two real-by-complex GEMMs with the +-1 spin matrix (mma.sync m8n8k4 f64); no pass over O"}
+        other = None
+        achieved = None
+    else:
+        achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    if achieved is not None:
+        roofline = {"bound": "hbm", "kernel": dom, "variant": sv_variant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                  "frac": achieved / peak, "peak_source": peak_src, "traffic": committed_traffic(dom),
+                  "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms, "launches_timed": n_timed,
+                  "note": "achieved = K_loc*P*16 B (O read once) / CUDA-event duration of the launch; SURVEY 8d's two-pass figure "
+                          "B_cg = 2*K_loc*P*16 per S*v is met with %s pass(es) over O" % ("1" if other is None else "2")}
     if other is not None:
         roofline["other_pass"] = other
     sweep_ms = phase["sweep_ms"] / args.steps

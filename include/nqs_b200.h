@@ -79,6 +79,9 @@ typedef struct nqs_config {
 #define NQS_FLAG_FORCE_GENERIC 4 /* use the generic (direct log cosh) kernels even where a specialised one exists */
 #define NQS_FLAG_SETUP_FROM_O 16 /* SR setup sums by a pass over O (reference structure) instead of from the factors (spins, tanh theta) */
 #define NQS_FLAG_TWO_PASS_SV  8  /* S*v as two streaming passes over O (reference structure) instead of the one-pass cluster kernel */
+#define NQS_FLAG_STRUCTURED_SV 32 /* S*v from the factors of O (spins, tanh theta) as two fp64 tensor-core GEMMs; O [K][P] is neither
+                                   * written nor allocated unless nqs_log_derivs asks for it (N <= 256).  Same results to rounding. */
+#define NQS_FLAG_NO_DMMA      64 /* theta = S W + b with the scalar-FMA kernel instead of the fp64 tensor-core GEMM (A/B switch) */
 
 /* statistics of one SR iteration.  ref: the row printed by propagate, gpu/include/optimizer.cuh:156-159 */
 typedef struct nqs_sr_stats {

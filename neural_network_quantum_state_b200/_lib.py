@@ -17,6 +17,7 @@ STATUS_NAMES = ["NQS_OK", "NQS_ERR_INVALID", "NQS_ERR_CUDA", "NQS_ERR_NOMEM", "N
 MODEL_RBM, MODEL_FFNN = 0, 1
 ORDER_CHECKERBOARD, ORDER_SEQUENTIAL = 0, 1
 FLAG_NO_SR, FLAG_ACCEPT_LOG, FLAG_FORCE_GENERIC, FLAG_TWO_PASS_SV = 1, 2, 4, 8
+FLAG_SETUP_FROM_O, FLAG_STRUCTURED_SV, FLAG_NO_DMMA = 16, 32, 64
 
 
 class Config(C.Structure):

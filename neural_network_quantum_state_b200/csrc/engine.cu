@@ -16,6 +16,7 @@
 #include "sampler_kernels.cuh"
 #include "sr_kernels.cuh"
 #include "sv_fused.cuh"
+#include "sv_struct.cuh"
 #include "cg_fused.cuh"
 
 using namespace nqs;
@@ -177,8 +178,51 @@ void set_smem(Kern kern, size_t bytes)
 }
 
 // ---- launches ------------------------------------------------------------------------------------------------------
+// chains per CTA of the rows GEMM: 32, or 16 when that leaves SMs idle (two CTAs per SM are resident)
+int rows_dmma_mt(const nqs_handle * h) { return ((h->K+31)/32 >= 2LL*h->sm_count) ? 4 : 2; }
+
+template <int MODEL, int EPI>
+void launch_rows_dmma(nqs_handle * h, const RowsArgs & a)
+{
+  const int mt = rows_dmma_mt(h);
+  const size_t smem = rows_dmma_smem(h->N, mt);
+  const unsigned grid = (unsigned)((h->K+8*mt-1)/(8*mt));
+  if (mt == 4)
+  {
+    set_smem(spin_rows_dmma_kernel<MODEL, EPI, 4>, smem);
+    spin_rows_dmma_kernel<MODEL, EPI, 4><<<grid, NQS_DR_THREADS, smem, h->stream>>>(a);
+  }
+  else
+  {
+    set_smem(spin_rows_dmma_kernel<MODEL, EPI, 2>, smem);
+    spin_rows_dmma_kernel<MODEL, EPI, 2><<<grid, NQS_DR_THREADS, smem, h->stream>>>(a);
+  }
+  check_launch(h, "spin_rows_dmma_kernel");
+}
+
+bool rows_dmma_ok(const nqs_handle * h)
+{ // the spin tile of 32 chains and one slab of B must fit the shared memory of one CTA (N up to ~600)
+  return !(h->cfg.flags & NQS_FLAG_NO_DMMA) && rows_dmma_smem(h->N, 4) <= h->smem_optin;
+}
+
+// theta = S W + b (+ sa, + lnpsi): fp64 tensor-core GEMM with the log cosh row sum fused into its epilogue (sv_struct.cuh);
+// theta_tiled_kernel (scalar FMAs) for very long chains or on request
 void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_spins_dev, cd * theta, cd * sa, cd * lnpsi)
 {
+  if (rows_dmma_ok(h))
+  {
+    const ModelPtrs mp = model_ptrs(h->model, h->params.p, h->N, h->M);
+    RowsArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.N = h->N; a.M = h->M; a.K = h->K; a.spins = spins_dev; a.B = reinterpret_cast<const double*>(mp.W); a.bias = mp.b;
+    a.theta = theta; a.sa_spins = sa_spins_dev; a.avis = mp.a; a.w1o = mp.w1o; a.sa = sa; a.lnpsi = lnpsi;
+    if (h->model == MODEL_RBM)
+    { if (lnpsi) launch_rows_dmma<MODEL_RBM, ROWS_EPI_LNPSI>(h, a); else launch_rows_dmma<MODEL_RBM, ROWS_EPI_THETA>(h, a); }
+    else
+    { if (lnpsi) launch_rows_dmma<MODEL_FFNN, ROWS_EPI_LNPSI>(h, a); else launch_rows_dmma<MODEL_FFNN, ROWS_EPI_THETA>(h, a); }
+    h->variant_theta = "dmma_rows";
+    return;
+  }
   ThetaArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
   a.spins = spins_dev; a.sa_spins = sa_spins_dev; a.theta = theta; a.sa = sa; a.lnpsi = lnpsi;
@@ -190,6 +234,7 @@ void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_sp
   else { if (lnpsi) NQS_TH_LAUNCH(MODEL_FFNN, true); else NQS_TH_LAUNCH(MODEL_FFNN, false); }
 #undef NQS_TH_LAUNCH
   check_launch(h, "theta_tiled_kernel");
+  h->variant_theta = "tiled_fma";
 }
 
 
@@ -247,7 +292,7 @@ void launch_eloc_fast(nqs_handle * h)
 void launch_sweep(nqs_handle * h, long long nsteps)
 {
   if (nsteps <= 0) return;
-  h->theta_matches_O = false;
+  h->theta_matches_O = false; h->hidden_valid = false;
   SweepArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
   a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.order = h->order.p;
@@ -427,15 +472,17 @@ void plan_sv(nqs_handle * h)
     // so few fat warps beat many thin ones: prefer 8 columns per thread down to 128 threads, then 9-10 columns (register
     // limit), then whatever fits (tiny slices).  One more warp is the TMA producer.
     int cpt = 0, nt = 0;
-    const int order[NQS_SV_MAX_CPT+3] = {8, 7, 6, 5, 4, 3, 2, 1, 9, 10, 1, 2, 3};
-    for (int q = 0; q < NQS_SV_MAX_CPT+3 && !cpt; ++q)
-    {
-      const int c = order[q];
-      const long long need = ((pc+c-1)/c+31)/32*32;
-      const int max_t = (c <= 3) ? 992 : 480;
-      const long long min_t = (q < 8) ? 128 : 0;
-      if (need <= max_t && need >= min_t) { cpt = c; nt = (int)std::max<long long>(64, need); }
-    }
+    static const int fat_order[] = {8, 7, 6, 5, 4, 3, 2, 1, 9, 10}, thin_order[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10};
+    const char * fat_env = std::getenv("NQS_SV_FAT");
+    const bool fat = fat_env ? std::atoi(fat_env) != 0 : true;
+    for (int pass = (fat ? 0 : 1); pass < 2 && !cpt; ++pass)
+      for (int q = 0; q < NQS_SV_MAX_CPT && !cpt; ++q)
+      {
+        const int c = (pass == 0) ? fat_order[q] : thin_order[q];
+        const long long need = ((pc+c-1)/c+31)/32*32;
+        const int max_t = (c <= 3) ? 992 : 480;
+        if (need <= max_t && (pass == 1 || need >= 128)) { cpt = c; nt = (int)std::max<long long>(64, need); }
+      }
     if (!cpt) continue;
     // a slot holds one row slice, padded to CPT * consumer threads elements so the kernel reads it without bounds checks
     const size_t slot_bytes = (size_t)((std::max<long long>(pc, (long long)cpt*nt)*(long long)sizeof(cd)+127)/128*128);
@@ -523,6 +570,96 @@ void sr_setup(nqs_handle * h, bool want_F)
   check_launch(h, "setup_finalize_kernel");
 }
 
+// ---- structured S*v (sv_struct.cuh) ---------------------------------------------------------------------------------------
+void launch_hidden_values(nqs_handle * h)
+{
+  const int grid = grid_for((long long)h->K*h->M, 256, 148*8);
+  if (h->model == MODEL_RBM)
+    hidden_values_kernel<MODEL_RBM><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, nullptr);
+  else
+    hidden_values_kernel<MODEL_FFNN><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, h->Lm.p);
+  check_launch(h, "hidden_values_kernel");
+  h->hidden_valid = true;
+  h->theta_matches_O = true;   // the factors (spins, theta, params) are what S is built from: structured setup sums allowed
+}
+
+// warp grids / tile shapes of spin_cols_dmma_kernel by chain length: {MTW, NTW, WM}
+static const int kColsVariants[5][3] = {{1, 8, 2}, {1, 16, 4}, {1, 16, 8}, {2, 16, 8}, {4, 8, 8}};
+int cols_variant_for(int N) { return N <= 16 ? 0 : N <= 32 ? 1 : N <= 64 ? 2 : N <= 128 ? 3 : 4; }
+
+void plan_struct(nqs_handle * h)
+{
+  NQS_REQUIRE(h->N <= 256, NQS_ERR_UNSUPPORTED, "NQS_FLAG_STRUCTURED_SV supports n_inputs <= 256");
+  NQS_REQUIRE(!(h->cfg.flags & (NQS_FLAG_SETUP_FROM_O | NQS_FLAG_TWO_PASS_SV)), NQS_ERR_INVALID,
+    "NQS_FLAG_STRUCTURED_SV excludes NQS_FLAG_SETUP_FROM_O / NQS_FLAG_TWO_PASS_SV");
+  const int var = cols_variant_for(h->N);
+  const int cw = cols_dmma_cw(kColsVariants[var][1], kColsVariants[var][2]);
+  const int colgroups = (2*h->M+cw-1)/cw;
+  long long nchunks = std::max(1, h->sm_count/colgroups);
+  nchunks = std::min<long long>(nchunks, (h->K+NQS_DC_KC-1)/NQS_DC_KC);
+  long long rpc = (h->K+nchunks-1)/nchunks;
+  rpc = (rpc+NQS_DC_KC-1)/NQS_DC_KC*NQS_DC_KC;
+  h->sc_variant = var; h->sc_colgroups = colgroups; h->sc_rows_per_chunk = rpc; h->sc_nchunks = (int)((h->K+rpc-1)/rpc);
+  h->struct_sv = true;
+  h->variant_sv = "structured_dmma_mtw"+std::to_string(kColsVariants[var][0])+"_ntw"+std::to_string(kColsVariants[var][1])+
+    "_wm"+std::to_string(kColsVariants[var][2])+"_colgroups"+std::to_string(colgroups)+"_chunks"+std::to_string(h->sc_nchunks);
+}
+
+template <int MODEL, int MTW, int NTW, int WM>
+void launch_cols_dmma_t(nqs_handle * h, const ColsArgs & a)
+{
+  const size_t smem = cols_dmma_smem(cols_dmma_nsc(MTW, WM), cols_dmma_cw(NTW, WM));
+  set_smem(spin_cols_dmma_kernel<MODEL, MTW, NTW, WM>, smem);
+  dim3 grid((unsigned)h->sc_colgroups, (unsigned)h->sc_nchunks);
+  spin_cols_dmma_kernel<MODEL, MTW, NTW, WM><<<grid, NQS_DC_THREADS, smem, h->stream>>>(a);
+}
+template <int MODEL>
+void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
+{
+  switch (h->sc_variant)
+  {
+    case 0: launch_cols_dmma_t<MODEL, 1, 8, 2>(h, a); break;
+    case 1: launch_cols_dmma_t<MODEL, 1, 16, 4>(h, a); break;
+    case 2: launch_cols_dmma_t<MODEL, 1, 16, 8>(h, a); break;
+    case 3: launch_cols_dmma_t<MODEL, 2, 16, 8>(h, a); break;
+    default: launch_cols_dmma_t<MODEL, 4, 8, 8>(h, a); break;
+  }
+  check_launch(h, "spin_cols_dmma_kernel");
+}
+
+// z = O v and the chunk partials of O^H z from the factors: two tensor-core GEMMs, no pass over O
+int matvec_structured(nqs_handle * h, const cd * v, const int * done)
+{
+  NQS_REQUIRE(h->hidden_valid, NQS_ERR_STATE, "structured S*v before the hidden-unit factors were computed");
+  const long long NM = (long long)h->N*h->M;
+  RowsArgs r;
+  std::memset(&r, 0, sizeof(r));
+  r.N = h->N; r.M = h->M; r.K = h->K; r.spins = h->spins.p; r.T = h->Tm.p; r.L = h->Lm.p; r.zk = h->zk.p; r.done = done;
+  {
+    Span sp(h, TAG_ROWS);
+    if (h->model == MODEL_RBM)
+    { // v = [V (i*M+j) | a block | b block]
+      r.B = reinterpret_cast<const double*>(v); r.avis = v+NM; r.bias = v+NM+h->N;
+      launch_rows_dmma<MODEL_RBM, ROWS_EPI_Z>(h, r);
+    }
+    else
+    { // v = [V (j*N+i) | b1 block | w1o block]
+      transpose_wblock_kernel<<<grid_for(NM, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, v, h->vnat.p, done);
+      check_launch(h, "transpose_wblock_kernel");
+      r.B = reinterpret_cast<const double*>(h->vnat.p); r.bias = v+NM; r.w1o = v+NM+h->M;
+      launch_rows_dmma<MODEL_FFNN, ROWS_EPI_Z>(h, r);
+    }
+  }
+  ColsArgs c;
+  c.N = h->N; c.M = h->M; c.K = h->K; c.P = h->P; c.spins = h->spins.p; c.T = h->Tm.p; c.L = h->Lm.p; c.zk = h->zk.p;
+  c.part = h->part.p; c.rows_per_chunk = h->sc_rows_per_chunk; c.done = done;
+  {
+    Span sp(h, TAG_COLS);
+    if (h->model == MODEL_RBM) launch_cols_dmma<MODEL_RBM>(h, c); else launch_cols_dmma<MODEL_FFNN>(h, c);
+  }
+  return h->sc_nchunks;
+}
+
 // The pass(es) over O of one S*v: cluster / row-block partials of sum_k conj(O_kp) (O_k . v) land in h->part.  Multi-GPU: they
 // are folded into traw and all-reduced (2P doubles) here; single GPU: cg_fused_kernel folds them itself.  Returns the number
 // of partials cg_fused_kernel has to fold (0 = read traw).
@@ -530,7 +667,8 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
 {
   const long long P = h->P, K = h->K;
   int nparts;
-  if (h->sv_ok)
+  if (h->struct_sv) nparts = matvec_structured(h, v, done);
+  else if (h->sv_ok)
   {
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
@@ -640,7 +778,7 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
 
 void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
 {
-  h->theta_matches_O = false;
+  h->theta_matches_O = false; h->hidden_valid = false;
   update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
   check_launch(h, "update_params_kernel");
   h->tables_valid = false;
@@ -665,7 +803,7 @@ void do_sweeps(nqs_handle * h, int n_sweeps)
 
 void do_initialize(nqs_handle * h, const int8_t * spins_host)
 {
-  h->theta_matches_O = false;
+  h->theta_matches_O = false; h->hidden_valid = false;
   std::vector<int8_t> s((size_t)h->K*h->N, 1);
   if (spins_host) std::memcpy(s.data(), spins_host, s.size());
   else if (h->cfg.J > 0) // Neel, ref impl_hamiltonians.cuh:196-201
@@ -713,7 +851,7 @@ void build_J(nqs_handle * h)
 void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
   h->tables_valid = false;
-  h->theta_matches_O = false;
+  h->theta_matches_O = false; h->hidden_valid = false;
   NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
 }
@@ -728,9 +866,14 @@ std::vector<std::complex<double> > download_params(nqs_handle * h)
 // O [K][P], the CG vectors and the reduction scratch (skipped for sampler-only handles until nqs_enable_sr)
 void alloc_sr(nqs_handle * h)
 {
-  if (h->O.p != nullptr) return;
-  const size_t KP = (size_t)h->K*(size_t)h->P;
-  h->O.alloc(KP);
+  if (h->aO.p != nullptr) return;
+  if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV)
+  { // S*v from the factors: T [K][M] (+ L, FFNN) instead of O [K][P]; O is allocated only if nqs_log_derivs asks for it
+    plan_struct(h);
+    h->Tm.alloc((size_t)h->K*h->M);
+    if (h->model == MODEL_FFNN) { h->Lm.alloc((size_t)h->K*h->M); h->vnat.alloc((size_t)h->N*h->M); }
+  }
+  else h->O.alloc((size_t)h->K*(size_t)h->P);
   h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
   h->zk.alloc(h->K); h->diag.alloc(h->P);
   const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
@@ -739,8 +882,8 @@ void alloc_sr(nqs_handle * h)
   h->nrb = (int)nrb;
   h->rows_per_block = (h->K+nrb-1)/nrb;
   h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
-  plan_sv(h);
-  h->part.alloc(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P));
+  if (!h->struct_sv) plan_sv(h);
+  h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*2*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->traw.alloc((size_t)2*h->P);
   h->slots.alloc((size_t)2*NQS_CG_MAX_CTAS*NQS_CG_NVALS);
@@ -889,7 +1032,7 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
     NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
     h->tables_valid = false;
-    h->theta_matches_O = false;
+    h->theta_matches_O = false; h->hidden_valid = false;
   });
 }
 
@@ -1138,10 +1281,11 @@ nqs_status nqs_log_derivs(nqs_handle * h, nqs_cdouble * O_host)
   if (!h) return NQS_ERR_INVALID;
   return guarded(h, [&]()
   {
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_log_derivs before nqs_initialize / nqs_warm_up");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     reset_phase_times(h);
+    if (h->O.p == nullptr) h->O.alloc((size_t)h->K*(size_t)h->P);   // structured mode keeps no O until somebody asks for it
     { Span t(h, TAG_ODERIV); launch_oderiv(h); }
     resolve_spans(h);
     if (O_host)
@@ -1157,9 +1301,10 @@ nqs_status nqs_smatrix_dot(nqs_handle * h, double lambda, const nqs_cdouble * v,
   if (!h || !v || !Sv) return NQS_ERR_INVALID;
   return guarded(h, [&]()
   {
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     const long long P = h->P;
+    if (h->struct_sv && !h->hidden_valid) launch_hidden_values(h);
     sr_setup(h, false);
     NQS_CUDA(cudaMemcpyAsync(h->pvec.p, v, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     const int nparts = matvec_passes(h, h->pvec.p, nullptr);
@@ -1176,7 +1321,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
   if (!h || !opt) return NQS_ERR_INVALID;
   return guarded(h, [&]()
   {
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_sr_step before nqs_warm_up");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     reset_phase_times(h);
@@ -1186,7 +1331,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     // (Running the HBM-write-bound O writer on a side stream next to the fp64-bound local energy was tried: the writer's K CTAs
     // occupy every SM slot, the two kernels serialise anyway and the step time does not change.)
     { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
-    { Span t(h, TAG_ODERIV); launch_oderiv(h); }
+    { Span t(h, TAG_ODERIV); if (h->struct_sv) launch_hidden_values(h); else launch_oderiv(h); }
     double hs[3];
     {
       { Span t(h, TAG_SETUP); sr_setup(h, true); }
@@ -1226,7 +1371,7 @@ nqs_status nqs_get_sr_vectors(nqs_handle * h, nqs_cdouble * F, nqs_cdouble * dx)
   if (!h) return NQS_ERR_INVALID;
   return guarded(h, [&]()
   {
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     if (F) NQS_CUDA(cudaMemcpyAsync(F, h->F.p, sizeof(cd)*h->P, cudaMemcpyDeviceToHost, h->stream));
     if (dx) NQS_CUDA(cudaMemcpyAsync(dx, h->dx.p, sizeof(cd)*h->P, cudaMemcpyDeviceToHost, h->stream));
@@ -1276,7 +1421,7 @@ nqs_status nqs_sr_reset(nqs_handle * h)
   if (!h) return NQS_ERR_INVALID;
   return guarded(h, [&]()
   {
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "nqs_sr_reset before nqs_enable_sr");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "nqs_sr_reset before nqs_enable_sr");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     h->bp = 1.0;
     NQS_CUDA(cudaMemsetAsync(h->dx.p, 0, sizeof(cd)*h->P, h->stream));
@@ -1327,7 +1472,7 @@ nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BY
   return guarded(h, [&]()
   {
     NQS_REQUIRE(h->n_ranks > 1 && h->n_ranks <= NQS_CG_MAX_RANKS, NQS_ERR_STATE, "nqs_comm_p2p_export: call nqs_comm_init first (2..16 ranks)");
-    NQS_REQUIRE(h->O.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
+    NQS_REQUIRE(h->aO.p != nullptr, NQS_ERR_STATE, "handle created with NQS_FLAG_NO_SR");
     static_assert(sizeof(cudaIpcMemHandle_t) == NQS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     if (h->xbuf == nullptr)

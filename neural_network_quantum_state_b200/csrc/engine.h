@@ -89,6 +89,11 @@ struct nqs_handle
   int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0, sv_defer = 0, sv_depth = 0;
   size_t sv_smem = 0, sv_slot_bytes = 0;
   long long sv_pc = 0, sv_rpc = 0;
+  // structured S*v (sv_struct.cuh, NQS_FLAG_STRUCTURED_SV): hidden-unit factors T (and L, FFNN), chain chunks of the column GEMM
+  bool struct_sv = false, hidden_valid = false;
+  nqs::DevBuf<nqs::cd> Tm, Lm, vnat;
+  int sc_variant = 0, sc_nchunks = 0, sc_colgroups = 0;
+  long long sc_rows_per_chunk = 0;
 
   // multi-GPU
   void * comm = nullptr;                  // ncclComm_t

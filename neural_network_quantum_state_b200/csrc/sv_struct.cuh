@@ -1,24 +1,35 @@
-// Structured S*v (opt-in, NQS_FLAG_STRUCTURED_SV): the same product  traw_p = sum_k conj(O_kp) (O_k . v)  WITHOUT the O matrix.
-//
-// Every row of O is an outer product plus two short blocks (see setup_structured_kernel in sr_kernels.cuh),
+// fp64 tensor-core (DMMA) kernels for the GEMM-shaped pieces of the path.  Every row of O is an outer product of the spin
+// row and the hidden-unit row plus two short blocks (ref RBM__GetGradientsOfParameters__, impl_neural_quantum_state.cuh:1426-1449;
+// FFNN :1622-1690),
 //   RBM   O_k = [ s_ki T_kj (i*M+j) | s_ki | T_kj ],   T = tanh(theta)
 //   FFNN  O_k = [ s_ki T_kj (j*N+i) | T_kj | L_kj ],   T = tanh(theta) w1o,  L = logcosh(theta)
-// so with v = [V | v1 | v2]
-//   z_k = (O v)_k       = sum_j T_kj ( sum_i s_ki V_ij + v2_j ) + s_k . v1              (FFNN: ... + v1_j ..., + sum_j L_kj v2_j)
-//   (O^H z)_ij          = sum_k s_ki conj(T_kj) z_k ,  a-block sum_k s_ki z_k ,  b-block sum_k conj(T_kj) z_k
-// i.e. two signed accumulations of K*N*M complex terms each (2.1 G fp64 FMAs at N=128, M=256, K=16384) that read the
-// [K][N] spins and the [K][M] hidden-unit values (70 MB) instead of streaming the 8.7 GB of O -- the HBM bound of the
-// reference's Zgemm + Zgemv pair (gpu/include/functor_for_CG.cuh:110,121) disappears and O need not exist at all (SURVEY 7,
-// last bullet).  The north star grades the explicit-O formulation, which stays the default; this mode is reported
-// separately by bench.py.
+// so three products are real-by-complex GEMMs with the +-1 spin matrix S [K][N] as one operand:
+//   theta  = S W + b                                              (ref RBM::initialize / forward, Zgemm at :78,:114)
+//   z_k    = (O v)_k   = sum_j T_kj ((S V)_kj + vh_j) + ...       (ref SMatrixForCG::dot, Zgemm 1xKxP, functor_for_CG.cuh:110)
+//   traw   = O^H z     : W block = S^T C,  C_kj = conj(T_kj) z_k  (ref Zgemv PxK, functor_for_CG.cuh:121)
+// A complex [.][M] operand is a real [.][2M] operand (re, im interleaved), and the two doubles a lane holds of a DMMA
+// accumulator tile are exactly (re, im) of one complex element.  Both kernels issue mma.sync.aligned.m8n8k4 f64 (SASS
+// DMMA.8x8x4; measured 37.1 TFLOP/s on B200 = the fp64 peak, scripts/micro/dmma_bench.cu) with operands staged in shared
+// memory at a row pitch of 4 (mod 16) doubles, which makes every fragment load a 2-wavefront (minimal) LDS.64.
+//
+// spin_rows_dmma_kernel   m = chains, n = 2M, k = sites:   theta (+ fused lnpsi = sum_j logcosh theta + a.s epilogue), or z
+// spin_cols_dmma_kernel   m = sites,  n = 2M, k = chains:  split over chain chunks, partials folded in fixed order by
+//                         cg_fused_kernel exactly like the cluster partials of the one-pass kernel
+// With NQS_FLAG_STRUCTURED_SV the CG uses the last two instead of streaming O: 2 x 2.1 GFLOP instead of 8.7 GB per S*v at
+// N=128, M=256, K=16384, and O is never written.  The explicit-O path (sv_fused.cuh) stays the default: it is the
+// formulation the reference and the headline roofline are stated on.
 #pragma once
 #include "device_math.cuh"
 #include "sampler_kernels.cuh"
-#include "sr_kernels.cuh"
 
 namespace nqs
 {
-// T (and, FFNN, L) of the current chain state: one pass over theta
+__device__ __forceinline__ void dmma884(double & c0, double & c1, const double a, const double b)
+{
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// T (and, FFNN, L) of the current chain state: one pass over theta, once per SR step
 template <int MODEL>
 __global__ void hidden_values_kernel(const int N, const int M, const long long K, const cd * params, const cd * __restrict__ theta,
   cd * __restrict__ T, cd * __restrict__ L)
@@ -39,9 +50,10 @@ __global__ void hidden_values_kernel(const int N, const int M, const long long K
   }
 }
 
-// FFNN keeps the W block of v transposed (j*N+i): bring it to the natural i*M+j layout once per product
-__global__ void transpose_wblock_kernel(const int N, const int M, const cd * __restrict__ v, cd * __restrict__ out)
+// FFNN keeps the W block of O / v transposed (j*N+i): bring it to the natural i*M+j layout once per product
+__global__ void transpose_wblock_kernel(const int N, const int M, const cd * __restrict__ v, cd * __restrict__ out, const int * __restrict__ done)
 {
+  if (done != nullptr && *done) return;
   const long long total = (long long)N*M;
   for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < total; idx += (long long)gridDim.x*blockDim.x)
   {
@@ -50,193 +62,354 @@ __global__ void transpose_wblock_kernel(const int N, const int M, const cd * __r
   }
 }
 
-// z_k = O_k . v.  Same tiling as theta_tiled_kernel: a CTA takes NQS_TH_CH chains, thread t owns hidden unit j = t (+256, ..).
-//   Vw: W block of v in i*M+j layout;  vh: the per-hidden-unit block that multiplies T (RBM v2 = b block, FFNN v1 = b1 block);
-//   va: RBM a block (multiplies s), nullptr for FFNN;  vl: FFNN w1o block (multiplies L), nullptr for RBM.
-template <int MODEL>
-__global__ void __launch_bounds__(NQS_TH_THREADS) sv_struct_z_kernel(const int N, const int M, const long long K,
-  const int8_t * __restrict__ spins, const cd * __restrict__ T, const cd * __restrict__ L, const cd * __restrict__ Vw,
-  const cd * __restrict__ vh, const cd * __restrict__ va, const cd * __restrict__ vl, cd * __restrict__ zk, const int * __restrict__ done)
+// ---- rows: C[k][c] = sum_i s_ki B[i][c] ------------------------------------------------------------------------------------
+enum { ROWS_EPI_THETA = 0, ROWS_EPI_LNPSI = 1, ROWS_EPI_Z = 2 };
+#define NQS_DR_THREADS 256
+#define NQS_DR_KC 32        // sites per staged slab of B
+#define NQS_DR_NTW 4        // n-tiles (8 real columns each) per warp
+#define NQS_DR_CW (8*NQS_DR_NTW*8)   // 256 real = 128 complex columns per pass
+
+struct RowsArgs
 {
-  if (done != nullptr && *done) return;
+  int N, M;
+  long long K;
+  const int8_t * spins;      // [K][N]
+  const double * B;          // [N][2M]: W (theta) or the W block of v in natural layout (z)
+  const cd * bias;           // [M]: b (theta) or the hidden-unit block of v that multiplies T (z)
+  // theta / lnpsi
+  cd * theta;                // [K][M] out (may be null)
+  const int8_t * sa_spins;   // RBM visible-bias term taken from these spins (ref forward(spins, lnpsi, false) quirk)
+  const cd * avis;           // [N] RBM a (theta: sa; z: the a block of v)
+  const cd * w1o;            // [M] FFNN output weights (lnpsi) / the w1o block of v (z)
+  cd * sa;                   // [K] out (may be null)
+  cd * lnpsi;                // [K] out (LNPSI)
+  // z
+  const cd * T;              // [K][M]
+  const cd * L;              // [K][M] FFNN
+  cd * zk;                   // [K] out
+  const int * done;
+};
+
+inline size_t rows_dmma_smem(int N, int MT)
+{
+  const int n4 = (N+3)/4*4;
+  return ((size_t)8*MT*(n4+4)+(size_t)NQS_DR_KC*(NQS_DR_CW+4))*sizeof(double)+(size_t)(NQS_DR_THREADS/32)*8*MT*sizeof(cd);
+}
+
+template <int MODEL, int EPI, int MT>
+__global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const RowsArgs a)
+{
+  if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double * sp = reinterpret_cast<double*>(smem_raw);                    // [N][NQS_TH_CH]
-  cd * red = reinterpret_cast<cd*>(sp+(size_t)N*NQS_TH_CH);              // [warps][NQS_TH_CH]
-  const int t = threadIdx.x, lane = t&31, w = t>>5;
-  const long long kbase = (long long)blockIdx.x*NQS_TH_CH;
-  const int nk = (int)((K-kbase < NQS_TH_CH) ? K-kbase : NQS_TH_CH);
-  for (int idx = t; idx < N*NQS_TH_CH; idx += NQS_TH_THREADS)
+  constexpr int RT = 8*MT, NTW = NQS_DR_NTW, CW = NQS_DR_CW, KC = NQS_DR_KC, PB = CW+4;
+  const int N = a.N, M = a.M, n4 = (N+3)/4*4, PA = n4+4, M2 = 2*M;
+  double * As = reinterpret_cast<double*>(smem_raw);            // [RT][PA] spins of the CTA's chains (0 for padding)
+  double * Bs = As+(size_t)RT*PA;                               // [KC][PB] slab of B
+  cd * red = reinterpret_cast<cd*>(Bs+(size_t)KC*PB);           // [warps][RT]
+  const int tid = threadIdx.x, lane = tid&31, w = tid>>5, g = lane>>2, t = lane&3;
+  const long long kbase = (long long)blockIdx.x*RT;
+  for (int idx = tid; idx < RT*n4; idx += NQS_DR_THREADS)
   {
-    const int i = idx/NQS_TH_CH, c = idx-i*NQS_TH_CH;
-    sp[idx] = (c < nk) ? (double)spins[(kbase+c)*N+i] : 0.0;
+    const int r = idx/n4, i = idx-r*n4;
+    As[r*PA+i] = (kbase+r < a.K && i < N) ? (double)a.spins[(kbase+r)*N+i] : 0.0;
+  }
+  cd rsum[MT];
+#pragma unroll
+  for (int m = 0; m < MT; ++m) rsum[m] = cmake(0.0, 0.0);
+
+  for (int c0 = 0; c0 < M2; c0 += CW)
+  {
+    double acc[MT][NTW][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int n = 0; n < NTW; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
+    for (int i0 = 0; i0 < n4; i0 += KC)
+    {
+      __syncthreads();
+      for (int idx = tid; idx < KC*(CW/2); idx += NQS_DR_THREADS)
+      {
+        const int r = idx/(CW/2), c = 2*(idx-r*(CW/2));
+        double2 v = make_double2(0.0, 0.0);
+        if (i0+r < N && c0+c < M2) v = *reinterpret_cast<const double2*>(a.B+(size_t)(i0+r)*M2+c0+c);
+        *reinterpret_cast<double2*>(Bs+r*PB+c) = v;
+      }
+      __syncthreads();
+      const int ksteps = ((n4-i0 < KC) ? n4-i0 : KC)/4;
+      const double * ap = As+g*PA+i0+t;
+      const double * bp = Bs+t*PB+w*NTW*8+g;
+      for (int ks = 0; ks < ksteps; ++ks)
+      {
+        double af[MT], bf[NTW];
+#pragma unroll
+        for (int m = 0; m < MT; ++m) af[m] = ap[m*8*PA+ks*4];
+#pragma unroll
+        for (int n = 0; n < NTW; ++n) bf[n] = bp[ks*4*PB+n*8];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+          for (int n = 0; n < NTW; ++n) dmma884(acc[m][n][0], acc[m][n][1], af[m], bf[n]);
+      }
+    }
+    // epilogue of this column pass: lane holds (re, im) of chain kbase + 8m + g, hidden unit (c0 + (w NTW + n) 8)/2 + t
+#pragma unroll
+    for (int n = 0; n < NTW; ++n)
+    {
+      const int j = (c0+(w*NTW+n)*8)/2+t;
+      if (j >= M) continue;
+      const cd bj = a.bias[j];
+      cd wj = cmake(1.0, 0.0);
+      if (MODEL == MODEL_FFNN && EPI != ROWS_EPI_THETA) wj = a.w1o[j];
+#pragma unroll
+      for (int m = 0; m < MT; ++m)
+      {
+        const long long k = kbase+8*m+g;
+        if (k >= a.K) continue;
+        const cd val = cmake(acc[m][n][0]+bj.x, acc[m][n][1]+bj.y);
+        if (EPI == ROWS_EPI_Z)
+        {
+          cd term = cmul(a.T[k*M+j], val);
+          if (MODEL == MODEL_FFNN) term = cadd(term, cmul(a.L[k*M+j], wj));
+          rsum[m] = cadd(rsum[m], term);
+        }
+        else
+        {
+          if (a.theta) a.theta[k*M+j] = val;
+          if (EPI == ROWS_EPI_LNPSI)
+          {
+            const cd lc = c_logcosh(val);
+            rsum[m] = cadd(rsum[m], (MODEL == MODEL_RBM) ? lc : cmul(wj, lc));
+          }
+        }
+      }
+    }
+  }
+  // row sums: over the 4 lanes of a quad, then over the warps (fixed order)
+  if (EPI != ROWS_EPI_THETA)
+  {
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+    {
+      cd s = rsum[m];
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, 1); s.y += __shfl_xor_sync(0xffffffffu, s.y, 1);
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, 2); s.y += __shfl_xor_sync(0xffffffffu, s.y, 2);
+      if (t == 0) red[w*RT+8*m+g] = s;
+    }
   }
   __syncthreads();
-  cd zs[NQS_TH_CH];
-#pragma unroll
-  for (int c = 0; c < NQS_TH_CH; ++c) zs[c] = cmake(0.0, 0.0);
-  for (int j = t; j < M; j += NQS_TH_THREADS)
+  // visible-bias term (RBM) and the final value of chain kbase + r: 8 lanes per chain
   {
-    cd acc[NQS_TH_CH];
-    const cd h0 = vh[j];
-#pragma unroll
-    for (int c = 0; c < NQS_TH_CH; ++c) acc[c] = h0;
-    for (int i = 0; i < N; ++i)
+    const int r = tid>>3, q = tid&7;
+    const long long k = kbase+r;
+    if (r < RT)
     {
-      const cd wv = Vw[(size_t)i*M+j];
-      const double2 * srow = reinterpret_cast<const double2*>(sp+(size_t)i*NQS_TH_CH);
-#pragma unroll
-      for (int c2 = 0; c2 < NQS_TH_CH/2; ++c2)
+      cd sv = cmake(0.0, 0.0);
+      if (MODEL == MODEL_RBM && k < a.K)
       {
-        const double2 s2 = srow[c2];
-        acc[2*c2].x = fma(s2.x, wv.x, acc[2*c2].x); acc[2*c2].y = fma(s2.x, wv.y, acc[2*c2].y);
-        acc[2*c2+1].x = fma(s2.y, wv.x, acc[2*c2+1].x); acc[2*c2+1].y = fma(s2.y, wv.y, acc[2*c2+1].y);
+        for (int i = q; i < N; i += 8)
+        {
+          const double s = (EPI == ROWS_EPI_Z) ? As[r*PA+i] : (double)a.sa_spins[k*N+i];
+          const cd ai = a.avis[i];
+          sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
+        }
       }
-    }
-    const cd lw = (MODEL == MODEL_FFNN) ? vl[j] : cmake(0.0, 0.0);
 #pragma unroll
-    for (int c = 0; c < NQS_TH_CH; ++c)
-    {
-      if (c < nk)
+      for (int o = 4; o > 0; o >>= 1) { sv.x += __shfl_xor_sync(0xffffffffu, sv.x, o); sv.y += __shfl_xor_sync(0xffffffffu, sv.y, o); }
+      if (q == 0 && k < a.K)
       {
-        cd term = cmul(T[(kbase+c)*M+j], acc[c]);
-        if (MODEL == MODEL_FFNN) term = cadd(term, cmul(L[(kbase+c)*M+j], lw));
-        zs[c] = cadd(zs[c], term);
+        cd tot = sv;
+        if (EPI != ROWS_EPI_THETA)
+          for (int ww = 0; ww < NQS_DR_THREADS/32; ++ww) tot = cadd(tot, red[ww*RT+r]);
+        if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
+        else
+        {
+          if (a.sa) a.sa[k] = sv;
+          if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
+        }
       }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NQS_TH_CH; ++c)
-  {
-    const cd s = warp_sum(zs[c]);
-    if (lane == 0) red[w*NQS_TH_CH+c] = s;
-  }
-  __syncthreads();
-  for (int c = w; c < nk; c += NQS_TH_THREADS/32)
-  {
-    cd sa = cmake(0.0, 0.0);
-    if (MODEL == MODEL_RBM)
-    {
-      for (int i = lane; i < N; i += 32)
-      {
-        const double s = sp[(size_t)i*NQS_TH_CH+c];
-        const cd ai = va[i];
-        sa.x = fma(s, ai.x, sa.x);
-        sa.y = fma(s, ai.y, sa.y);
-      }
-      sa = warp_sum(sa);
-    }
-    if (lane == 0)
-    {
-      cd tot = sa;
-      for (int ww = 0; ww < NQS_TH_THREADS/32; ++ww) tot = cadd(tot, red[ww*NQS_TH_CH+c]);
-      zk[kbase+c] = tot;
     }
   }
 }
 
-// part[rb][{re,im}][p] = sum_{k in row block rb} conj(O_kp) z_k from the factors; same tiling and output convention as
-// setup_structured_kernel (grid = hidden-unit tiles of 16 x row blocks; a thread owns hidden unit j and IPT consecutive sites)
-template <int MODEL, int IPT>
-__global__ void __launch_bounds__(NQS_SS_THREADS) sv_struct_cols_kernel(const int N, const int M, const long long K,
-  const int8_t * __restrict__ spins, const cd * __restrict__ T, const cd * __restrict__ L, const cd * __restrict__ zk,
-  double * __restrict__ part, const long long rows_per_block, const int * __restrict__ done)
+// ---- cols: part[chunk][{re,im}][p] = sum_{k in chunk} conj(O_kp) z_k from the factors ---------------------------------------
+#define NQS_DC_THREADS 256
+#define NQS_DC_KC 32        // chains per stage
+
+struct ColsArgs
 {
-  if (done != nullptr && *done) return;
-  __shared__ cd Cz[NQS_SS_CH][NQS_SS_JT], Lz[NQS_SS_CH][NQS_SS_JT];     // conj(T_kj) z_k, conj(L_kj) z_k
-  __shared__ cd zsh[NQS_SS_CH];
-  extern __shared__ __align__(16) unsigned char smem_raw[];               // spins chunk [NQS_SS_CH][16*IPT] as doubles
-  constexpr int npad = 16*IPT;
-  double * sp = reinterpret_cast<double*>(smem_raw);
-  const int t = threadIdx.x, jl = t%NQS_SS_JT, ig = t/NQS_SS_JT;
-  const int j = blockIdx.x*NQS_SS_JT+jl;
-  const bool jok = (j < M);
-  const long long k0 = (long long)blockIdx.y*rows_per_block;
-  const long long k1 = (k0+rows_per_block < K) ? k0+rows_per_block : K;
-  double ax[IPT], ay[IPT];
-#pragma unroll
-  for (int m = 0; m < IPT; ++m) { ax[m] = 0; ay[m] = 0; }
-  double bx = 0, by = 0, lx = 0, ly = 0, sx = 0, sy = 0;
+  int N, M;
+  long long K, P;
+  const int8_t * spins;
+  const cd * T;
+  const cd * L;              // FFNN
+  const cd * zk;
+  double * part;
+  long long rows_per_chunk;  // multiple of NQS_DC_KC
+  const int * done;
+};
+
+// warp grid WM (sites) x 8/WM (columns); a warp owns MTW x NTW accumulator tiles.  nsc = sites covered, cw = real columns per CTA
+inline int cols_dmma_nsc(int mtw, int wm) { return 8*mtw*wm; }
+inline int cols_dmma_cw(int ntw, int wm) { return (8/wm)*ntw*8; }
+inline size_t cols_dmma_smem(int nsc, int cw)
+{
+  return (size_t)2*NQS_DC_KC*((nsc+4)+(cw+4))*sizeof(double)+(size_t)2*NQS_DC_KC*sizeof(cd);
+}
+
+template <int MODEL, int MTW, int NTW, int WM>
+__global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const ColsArgs a)
+{
+  if (a.done != nullptr && *a.done) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int KC = NQS_DC_KC;
+  constexpr int WN = 8/WM, CW = WN*NTW*8, PC = CW+4, CH = CW/2, ns = 8*MTW*WM, PS = ns+4;
+  static_assert(ns <= 256 && CW <= 256, "tile too large for the producer mapping");
+  const int N = a.N, M = a.M;
+  double * Ss = reinterpret_cast<double*>(smem_raw);             // [2][KC][PS] spins of the stage's chains
+  double * Cs = Ss+(size_t)2*KC*PS;                              // [2][KC][PC] conj(T) z
+  cd * zs = reinterpret_cast<cd*>(Cs+(size_t)2*KC*PC);           // [2][KC]
+  const int tid = threadIdx.x, lane = tid&31, w = tid>>5, g = lane>>2, t = lane&3;
+  const int wm = w%WM, wn = w/WM;
+  const int j0 = blockIdx.x*CH;                                  // first hidden unit of this column group
+  const long long k0 = (long long)blockIdx.y*a.rows_per_chunk;
+  const long long k1 = (k0+a.rows_per_chunk < a.K) ? k0+a.rows_per_chunk : a.K;
+  const int nstages = (int)((k1-k0+KC-1)/KC);
   const bool do_a = (MODEL == MODEL_RBM && blockIdx.x == 0);
-  for (long long kc = k0; kc < k1; kc += NQS_SS_CH)
-  {
-    const int nk = (int)((k1-kc < NQS_SS_CH) ? k1-kc : NQS_SS_CH);
-    __syncthreads();
-    {
-      const int kk = ig;
-      cd c = cmake(0.0, 0.0), l = c;
-      if (kk < nk && jok)
-      {
-        const cd z = zk[kc+kk], tv = T[(kc+kk)*M+j];
-        c = cmake(tv.x*z.x+tv.y*z.y, tv.x*z.y-tv.y*z.x);             // conj(T) z
-        if (MODEL == MODEL_FFNN)
-        {
-          const cd lv = L[(kc+kk)*M+j];
-          l = cmake(lv.x*z.x+lv.y*z.y, lv.x*z.y-lv.y*z.x);
-        }
-      }
-      Cz[kk][jl] = c;
-      if (MODEL == MODEL_FFNN) Lz[kk][jl] = l;
-      if (t < NQS_SS_CH) zsh[t] = (t < nk) ? zk[kc+t] : cmake(0.0, 0.0);
-    }
-    for (int idx = t; idx < NQS_SS_CH*npad; idx += NQS_SS_THREADS)
-    {
-      const int kk = idx/npad, i = idx-kk*npad;
-      sp[idx] = (kk < nk && i < N) ? (double)spins[(kc+kk)*N+i] : 0.0;
-    }
-    __syncthreads();
-    for (int kk = 0; kk < nk; ++kk)
-    {
-      const cd c = Cz[kk][jl];
-      const double * srow = sp+kk*npad+ig*IPT;
+
+  double acc[MTW][NTW][2];
 #pragma unroll
-      for (int m = 0; m < IPT; ++m)
-      {
-        const double s = srow[m];
-        ax[m] = fma(s, c.x, ax[m]); ay[m] = fma(s, c.y, ay[m]);
-      }
-      if (ig == 0) { bx += c.x; by += c.y; }
-      if (MODEL == MODEL_FFNN && ig == 1) { const cd l = Lz[kk][jl]; lx += l.x; ly += l.y; }
+  for (int m = 0; m < MTW; ++m)
+#pragma unroll
+    for (int n = 0; n < NTW; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
+  double bsum = 0.0, asx = 0.0, asy = 0.0, lsx = 0.0, lsy = 0.0;
+
+  // producer mapping: thread -> chain kk = tid / 8 of the stage, hidden units jc = tid % 8 + 8 u
+  constexpr int TU = CH/8;
+  const int pkk = tid>>3, pj = tid&7;
+  cd tv[TU];
+  cd zv;
+  constexpr int sper = (KC*ns)/NQS_DC_THREADS;                   // spins per thread and stage
+  int8_t sv[sper];
+
+  auto prefetch = [&](const int s)
+  {
+    const long long k = k0+(long long)s*KC+pkk;
+    const bool ok = (k < k1);
+    zv = ok ? a.zk[k] : cmake(0.0, 0.0);
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+    {
+      const int jc = pj+8*u;
+      tv[u] = (ok && j0+jc < M) ? a.T[k*M+j0+jc] : cmake(0.0, 0.0);
     }
-    if (do_a)
-      for (int i = t; i < N; i += NQS_SS_THREADS)
-        for (int kk = 0; kk < nk; ++kk)
-        {
-          const double s = sp[kk*npad+i];
-          const cd z = zsh[kk];
-          sx = fma(s, z.x, sx); sy = fma(s, z.y, sy);
-        }
+#pragma unroll
+    for (int u = 0; u < sper; ++u)
+    {
+      const int idx = u*NQS_DC_THREADS+tid, kk = idx/ns, i = idx-kk*ns;
+      const long long kq = k0+(long long)s*KC+kk;
+      sv[u] = (kq < k1 && i < N) ? a.spins[kq*N+i] : (int8_t)0;
+    }
+  };
+  auto commit = [&](const int buf)
+  {
+    double * cs = Cs+(size_t)buf*KC*PC+pkk*PC;
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+    {
+      const int jc = pj+8*u;
+      *reinterpret_cast<double2*>(cs+2*jc) = make_double2(tv[u].x*zv.x+tv[u].y*zv.y, tv[u].x*zv.y-tv[u].y*zv.x);   // conj(T) z
+    }
+    if (pj == 0) zs[buf*KC+pkk] = zv;
+    double * ss = Ss+(size_t)buf*KC*PS;
+#pragma unroll
+    for (int u = 0; u < sper; ++u)
+    {
+      const int idx = u*NQS_DC_THREADS+tid, kk = idx/ns, i = idx-kk*ns;
+      ss[kk*PS+i] = (double)sv[u];
+    }
+  };
+
+  if (nstages > 0) { prefetch(0); commit(0); }
+  __syncthreads();
+  for (int s = 0; s < nstages; ++s)
+  {
+    const int buf = s&1;
+    if (s+1 < nstages) prefetch(s+1);
+    const double * ss = Ss+(size_t)buf*KC*PS;
+    const double * cs = Cs+(size_t)buf*KC*PC;
+    {
+      const double * ap = ss+t*PS+wm*MTW*8+g;
+      const double * bp = cs+t*PC+wn*NTW*8+g;
+#pragma unroll 2
+      for (int ks = 0; ks < KC/4; ++ks)
+      {
+        double af[MTW], bf[NTW];
+#pragma unroll
+        for (int m = 0; m < MTW; ++m) af[m] = ap[ks*4*PS+m*8];
+#pragma unroll
+        for (int n = 0; n < NTW; ++n) bf[n] = bp[ks*4*PC+n*8];
+#pragma unroll
+        for (int m = 0; m < MTW; ++m)
+#pragma unroll
+          for (int n = 0; n < NTW; ++n) dmma884(acc[m][n][0], acc[m][n][1], af[m], bf[n]);
+      }
+    }
+    // short blocks: column sums of C (b block / FFNN b1 block), S^T z (RBM a block), conj(L) z (FFNN w1o block)
+    if (tid < CW)
+    {
+#pragma unroll 8
+      for (int kk = 0; kk < KC; ++kk) bsum += cs[kk*PC+tid];
+    }
+    if (do_a && tid < N)
+    {
+#pragma unroll 8
+      for (int kk = 0; kk < KC; ++kk)
+      {
+        const double sp = ss[kk*PS+tid];
+        const cd z = zs[buf*KC+kk];
+        asx = fma(sp, z.x, asx); asy = fma(sp, z.y, asy);
+      }
+    }
+    if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M)
+    {
+      const long long kb = k0+(long long)s*KC;
+      for (int kk = 0; kk < KC && kb+kk < k1; ++kk)
+      {
+        const cd l = a.L[(kb+kk)*M+j0+tid];
+        const cd z = zs[buf*KC+kk];
+        lsx += l.x*z.x+l.y*z.y; lsy += l.x*z.y-l.y*z.x;
+      }
+    }
+    if (s+1 < nstages) commit(buf^1);
+    __syncthreads();
   }
-  const long long P = (MODEL == MODEL_RBM) ? (long long)N*M+N+M : (long long)N*M+2*M;
-  const long long NM = (long long)N*M;
-  double * base = part+(size_t)blockIdx.y*2*P;
-  if (jok)
-  {
+
+  const long long P = a.P, NM = (long long)N*M;
+  double * base = a.part+(size_t)blockIdx.y*2*(size_t)P;
 #pragma unroll
-    for (int m = 0; m < IPT; ++m)
+  for (int m = 0; m < MTW; ++m)
+  {
+    const int i = (wm*MTW+m)*8+g;
+    if (i >= N) continue;
+#pragma unroll
+    for (int n = 0; n < NTW; ++n)
     {
-      const int i = ig*IPT+m;
-      if (i < N)
-      {
-        const long long p = (MODEL == MODEL_RBM) ? (long long)i*M+j : (long long)j*N+i;
-        base[p] = ax[m]; base[P+p] = ay[m];
-      }
+      const int j = j0+(wn*NTW+n)*4+t;
+      if (j >= M) continue;
+      const long long p = (MODEL == MODEL_RBM) ? (long long)i*M+j : (long long)j*N+i;
+      base[p] = acc[m][n][0]; base[P+p] = acc[m][n][1];
     }
-    if (ig == 0)
+  }
+  if (tid < CW)
+  {
+    const int j = j0+(tid>>1);
+    if (j < M)
     {
       const long long p = (MODEL == MODEL_RBM) ? NM+N+j : NM+j;
-      base[p] = bx; base[P+p] = by;
-    }
-    if (MODEL == MODEL_FFNN && ig == 1)
-    {
-      const long long p = NM+M+j;
-      base[p] = lx; base[P+p] = ly;
+      base[(size_t)(tid&1)*P+p] = bsum;
     }
   }
-  if (do_a)
-    for (int i = t; i < N; i += NQS_SS_THREADS)
-    {
-      const long long p = NM+i;
-      base[p] = sx; base[P+p] = sy;
-    }
+  if (do_a && tid < N) { base[NM+tid] = asx; base[P+NM+tid] = asy; }
+  if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M) { base[NM+M+j0+tid] = lsx; base[P+NM+M+j0+tid] = lsy; }
 }
 } // namespace nqs

@@ -42,7 +42,7 @@ class Engine:
                  pbc: bool = False, order: str = "checkerboard", seed: int = 0, device: int = 0,
                  n_chains_total: int = 0, chain_offset: int = 0, max_predrawn_steps: int = 0,
                  sampler_only: bool = False, accept_log: bool = False, force_generic: bool = False,
-                 two_pass_sv: bool = False):
+                 two_pass_sv: bool = False, structured_sv: bool = False, no_dmma: bool = False):
         self.lib = L.load()
         self.model = model
         self.N, self.M, self.K = int(n_inputs), int(n_hiddens), int(n_chains)
@@ -55,7 +55,8 @@ class Engine:
         cfg.order = {"checkerboard": L.ORDER_CHECKERBOARD, "sequential": L.ORDER_SEQUENTIAL}[order]
         cfg.seed, cfg.device = int(seed), int(device)
         cfg.flags = (L.FLAG_NO_SR if sampler_only else 0) | (L.FLAG_ACCEPT_LOG if accept_log else 0) | \
-                    (L.FLAG_FORCE_GENERIC if force_generic else 0) | (L.FLAG_TWO_PASS_SV if two_pass_sv else 0)
+                    (L.FLAG_FORCE_GENERIC if force_generic else 0) | (L.FLAG_TWO_PASS_SV if two_pass_sv else 0) | \
+                    (L.FLAG_STRUCTURED_SV if structured_sv else 0) | (L.FLAG_NO_DMMA if no_dmma else 0)
         cfg.max_predrawn_steps = int(max_predrawn_steps)
         self._h = C.c_void_p()
         rc = self.lib.nqs_create(C.byref(cfg), C.byref(self._h))

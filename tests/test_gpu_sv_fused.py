@@ -19,16 +19,34 @@ H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
 SHAPES = [
     ("rbm", 16, 16, 64, 8, 8, 1),       # tiny: P = 288, 36 columns per CTA
     ("rbm", 6, 1, 40, 8, 8, 1),         # P = 13 < 2*8: trailing CTAs own no column at all
-    ("rbm", 64, 128, 300, 8, 8, 2),     # cfg2 shape, K not a multiple of the cluster count
-    ("rbm", 80, 250, 37, 8, 8, 3),      # P = 20330
-    ("rbm", 100, 260, 50, 8, 8, 7),     # P = 26360
+    ("rbm", 64, 128, 300, 8, 8, 8),     # cfg2 shape, K not a multiple of the cluster count
+    ("rbm", 80, 250, 37, 8, 8, 8),      # P = 20330
+    ("rbm", 100, 260, 50, 8, 8, 8),     # P = 26360
     ("rbm", 128, 256, 150, 8, 8, 9),    # cfg3 shape (P = 33152), portable cluster size
     ("rbm", 128, 256, 150, None, 9, 8), # cfg3 shape as shipped: 9-CTA clusters cover 135 SMs
-    ("rbm", 64, 128, 300, None, 9, 1),  # cfg2 shape as shipped
-    ("rbm", 128, 256, 150, 10, 10, 7),
+    ("rbm", 64, 128, 300, None, 16, 5), # cfg2 shape as shipped
+    ("rbm", 128, 256, 150, 10, 10, 8),
     ("ffnn", 128, 512, 40, None, 16, 9),# cfg4 shape (P = 66560): 16-CTA clusters
-    ("rbm", 128, 256, 5, None, 16, 3),  # fewer rows than clusters: the widest cluster covers most SMs
+    ("rbm", 128, 256, 5, None, 16, 8),  # fewer rows than clusters: the widest cluster covers most SMs
+    ("rbm", 24, 40, 33, 8, 8, 1),       # P = 1024: 128 columns per CTA, exactly the 128-thread floor of the fat-warp rule
 ]
+
+
+def planned_cpt(P, cs):
+    """The engine's rule (engine.cu: plan_sv): few fat warps -- 8 columns per thread down to 1 while at least 128 consumer
+    threads remain, then 9 and 10 (wide slices); slices too narrow for 128 threads take the fewest columns that fit."""
+    pc = -(-P // cs)
+
+    def need(c):
+        return (-(-pc // c) + 31) // 32 * 32
+
+    for c in (8, 7, 6, 5, 4, 3, 2, 1, 9, 10):
+        if 128 <= need(c) <= (992 if c <= 3 else 480):
+            return c
+    for c in range(1, 11):
+        if need(c) <= (992 if c <= 3 else 480):
+            return c
+    return None
 
 
 def dense_sv(O, v, lam):
@@ -57,6 +75,7 @@ def test_fused_sv_matches_dense_and_two_pass(model, N, M, K, pin_cs, cs, cpt, mo
             assert variant == "two_pass"
         else:
             assert variant.startswith("fused_cs%d_cpt%d_" % (cs, cpt)), variant
+            assert planned_cpt(e.P, cs) == cpt
         O = e.get_lnpsiGradients()
         v = rng.normal(size=e.P) + 1j * rng.normal(size=e.P) if not out else out["v"]
         Sv, aO, diag = e.smatrix_dot(0.37, v)
