@@ -205,6 +205,19 @@ bool rows_dmma_ok(const nqs_handle * h)
   return !(h->cfg.flags & NQS_FLAG_NO_DMMA) && rows_dmma_smem(h->N, 4) <= h->smem_optin;
 }
 
+// sum_ij s_i J_ij s_j of every chain as the GEMM (S J) . S on the fp64 tensor cores (ref c5 Zgemm + k10, impl_hamiltonians.cuh:226-231).
+// Returns the device vector, or null (odd N, very long chains, NQS_FLAG_NO_DMMA): the local-energy kernels then form it themselves.
+const double * launch_sjs(nqs_handle * h)
+{
+  if (!rows_dmma_ok(h) || h->N%2 != 0) return nullptr;
+  if (h->sjs.p == nullptr) h->sjs.alloc((size_t)h->K);
+  RowsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.N = h->N; a.M = h->M; a.K = h->K; a.spins = h->spins.p; a.B = h->Jmat.p; a.sjs = h->sjs.p;
+  launch_rows_dmma<MODEL_RBM, ROWS_EPI_SJS>(h, a);
+  return h->sjs.p;
+}
+
 // theta = S W + b (+ sa, + lnpsi): fp64 tensor-core GEMM with the log cosh row sum fused into its epilogue (sv_struct.cuh);
 // theta_tiled_kernel (scalar FMAs) for very long chains or on request
 void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_spins_dev, cd * theta, cd * sa, cd * lnpsi)
@@ -285,6 +298,7 @@ void launch_eloc_fast(nqs_handle * h)
   a.N = h->N; a.M = h->M; a.Npad = h->npad32; a.K = h->K; a.ctabT_a = h->ctabT_a.p; a.ctabT_b = h->ctabT_b.p; a.aexp = h->aexp.p;
   a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.Jmat = h->Jmat.p;
   a.hfield = h->cfg.h; a.htilda = h->htilda.p;
+  a.sjs = launch_sjs(h);
   launch_eloc_sites_t<4>(h, a);
   check_launch(h, "rbm_eloc_sites_kernel");
 }
@@ -368,6 +382,7 @@ void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p; a.spins = h->spins.p;
   a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.Jmat = h->Jmat.p; a.hfield = h->cfg.h;
   a.htilda = h->htilda.p; a.lnpsi1 = lnpsi1; a.single_site = single_site;
+  a.sjs = (lnpsi1 == nullptr) ? launch_sjs(h) : nullptr;
   const size_t npad = (size_t)((h->N+15)/16)*16;
   const size_t per_warp = (size_t)h->M*sizeof(cd)+npad;
   const int warps = warps_for_smem(h, per_warp, 0);

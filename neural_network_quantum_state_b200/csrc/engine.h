@@ -55,7 +55,7 @@ struct nqs_handle
   // model + chain state
   nqs::DevBuf<nqs::cd> params, theta, lnpsi0, lnpsi1, sa, htilda, tmp_theta;
   nqs::DevBuf<int8_t> spins, tmp_spins;
-  nqs::DevBuf<double> Jmat, uniforms;
+  nqs::DevBuf<double> Jmat, uniforms, sjs;
   nqs::DevBuf<int> order;
   nqs::DevBuf<unsigned char> acc_log, fresh;
   // specialised RBM path: flip tables rebuilt after every parameter change (fast_kernels.cuh)

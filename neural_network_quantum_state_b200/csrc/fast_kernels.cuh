@@ -470,6 +470,7 @@ struct FastElocArgs
   const cd * sa;
   const unsigned char * fresh;
   const double * Jmat;
+  const double * sjs;        // [K] sum_ij s_i J_ij s_j from the tensor-core GEMM (sv_struct.cuh), or null: computed here
   double hfield;
   cd * htilda;
 };
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs 
 #pragma unroll
   for (int c = 0; c < C; ++c) { part_d[c] = 0.0; part_x[c] = 0.0; part_y[c] = 0.0; }
   // 1/2 sum_ij s_i J_ij s_j  (ref c5 + k10, impl_hamiltonians.cuh:226-231,871-887): threads over i
-  for (int i = threadIdx.x; i < N; i += blockDim.x)
+  for (int i = threadIdx.x; i < N && a.sjs == nullptr; i += blockDim.x)
   {
     const double * Jrow = a.Jmat+(size_t)i*N;
     double sj[C];
@@ -622,6 +623,7 @@ __global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs 
       d += r[0]; x += r[1]; y += r[2];
       lx += red[(size_t)C*8*4+((size_t)c*8+ww)*2]; ly += red[(size_t)C*8*4+((size_t)c*8+ww)*2+1];
     }
+    if (a.sjs != nullptr) d = a.sjs[kbase+c];
     cd off = cmake(x, y);
     if (stale)
     { // exp(lnpsi(theta) - lnpsi0_tracked): != 1 only right after warm_up's quirk flip or a parameter update

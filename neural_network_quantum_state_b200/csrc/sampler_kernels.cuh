@@ -161,6 +161,7 @@ struct ElocArgs
   const cd * lnpsi0;
   const cd * sa;
   const double * Jmat; // [N][N]
+  const double * sjs;  // [K] sum_ij s_i J_ij s_j from the tensor-core GEMM (sv_struct.cuh), or null: computed here
   double hfield;
   cd * htilda;         // [K]
   cd * lnpsi1;         // optional [K]: lnpsi' of flipping `single_site` (forward(int) for tests); nullptr in E_loc mode
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256) eloc_generic_kernel(const ElocArgs a)
   }
   // 1/2 sum_ij s_i J_ij s_j: lanes over i
   double diag = 0.0;
-  for (int i = lane; i < N; i += 32)
+  for (int i = lane; i < N && a.sjs == nullptr; i += 32)
   {
     const double * Jrow = a.Jmat+(size_t)i*N;
     double sj = 0.0;
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(256) eloc_generic_kernel(const ElocArgs a)
       sj = fma(Jrow[j], (double)sp[j], sj);
     diag = fma(sj, (double)sp[i], diag);
   }
-  diag = 0.5*warp_sum(diag);
+  diag = 0.5*((a.sjs != nullptr) ? a.sjs[k] : warp_sum(diag));
   cd hsum = cmake(diag, 0.0);
   for (int site = 0; site < N; ++site)
   {

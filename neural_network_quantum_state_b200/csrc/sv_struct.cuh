@@ -63,7 +63,7 @@ __global__ void transpose_wblock_kernel(const int N, const int M, const cd * __r
 }
 
 // ---- rows: C[k][c] = sum_i s_ki B[i][c] ------------------------------------------------------------------------------------
-enum { ROWS_EPI_THETA = 0, ROWS_EPI_LNPSI = 1, ROWS_EPI_Z = 2 };
+enum { ROWS_EPI_THETA = 0, ROWS_EPI_LNPSI = 1, ROWS_EPI_Z = 2, ROWS_EPI_SJS = 3 };
 #define NQS_DR_THREADS 256
 #define NQS_DR_KC 32        // sites per staged slab of B
 #define NQS_DR_NTW 4        // n-tiles (8 real columns each) per warp
@@ -88,6 +88,8 @@ struct RowsArgs
   const cd * L;              // [K][M] FFNN
   cd * zk;                   // [K] out
   const int * done;
+  // s.J.s (ROWS_EPI_SJS): B = J [N][N] real, N even; out sjs[k] = sum_ij s_ki J_ij s_kj (ref c5 Zgemm + k10, impl_hamiltonians.cuh:226-231)
+  double * sjs;
 };
 
 inline size_t rows_dmma_smem(int N, int MT)
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
   if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RT = 8*MT, NTW = NQS_DR_NTW, CW = NQS_DR_CW, KC = NQS_DR_KC, PB = CW+4;
-  const int N = a.N, M = a.M, n4 = (N+3)/4*4, PA = n4+4, M2 = 2*M;
+  const int N = a.N, M = a.M, n4 = (N+3)/4*4, PA = n4+4, M2 = (EPI == ROWS_EPI_SJS) ? N : 2*M;
   double * As = reinterpret_cast<double*>(smem_raw);            // [RT][PA] spins of the CTA's chains (0 for padding)
   double * Bs = As+(size_t)RT*PA;                               // [KC][PB] slab of B
   cd * red = reinterpret_cast<cd*>(Bs+(size_t)KC*PB);           // [warps][RT]
@@ -152,6 +154,23 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
       }
     }
     // epilogue of this column pass: lane holds (re, im) of chain kbase + 8m + g, hidden unit (c0 + (w NTW + n) 8)/2 + t
+    if (EPI == ROWS_EPI_SJS)
+    { // lane holds (S J)[k][c], c = c0 + (w NTW + n) 8 + 2t + {0, 1}: dot with the chain's own spins
+#pragma unroll
+      for (int n = 0; n < NTW; ++n)
+      {
+        const int c = c0+(w*NTW+n)*8+2*t;
+        if (c >= N) continue;
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+        {
+          const double * srow = As+(8*m+g)*PA+c;
+          rsum[m].x = fma(acc[m][n][0], srow[0], rsum[m].x);
+          rsum[m].x = fma(acc[m][n][1], srow[1], rsum[m].x);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int n = 0; n < NTW; ++n)
     {
@@ -204,7 +223,7 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
     if (r < RT)
     {
       cd sv = cmake(0.0, 0.0);
-      if (MODEL == MODEL_RBM && k < a.K)
+      if (MODEL == MODEL_RBM && EPI != ROWS_EPI_SJS && k < a.K)
       {
         for (int i = q; i < N; i += 8)
         {
@@ -221,6 +240,7 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
         if (EPI != ROWS_EPI_THETA)
           for (int ww = 0; ww < NQS_DR_THREADS/32; ++ww) tot = cadd(tot, red[ww*RT+r]);
         if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
+        else if (EPI == ROWS_EPI_SJS) a.sjs[k] = tot.x;
         else
         {
           if (a.sa) a.sa[k] = sv;
