@@ -334,6 +334,7 @@ def main():
                "api": "Engine.set_uniforms + Engine.sr_step + get_spinStates + get_lnpsi (C ABI, host buffers)"}
 
     if rank != 0:
+        e.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -407,6 +408,7 @@ def main():
         except Exception as ex:  # the checker being absent must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
     emit(line)
+    e.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -60,19 +60,25 @@ struct CgArgs
   unsigned int epoch;      // increases by one per exchange on every rank
   double * peer_x[NQS_CG_MAX_RANKS];            // peer_x[r]: receive buffer of rank r, [2][n_ranks][2P]
   unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS][NQS_CG_MAX_CTAS]
+  unsigned long long * trace;                   // NQS_CG_TRACE=1: globaltimer stamps of CTA 0, [NQS_CG_TRACE_WORDS] per launch (else null)
 };
+#define NQS_CG_TRACE_WORDS 24   // entry, stored, released, arrival of every rank's flag [16], waited, end
+__device__ __forceinline__ unsigned long long cg_now()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // all CTAs of the grid are co-resident (grid <= #SMs, nothing else runs on the stream): spin barrier on a global counter
 __device__ __forceinline__ void cg_grid_barrier(unsigned int * counter, const unsigned int target)
 {
   __syncthreads();
   if (threadIdx.x == 0)
-  {
-    __threadfence();
-    atomicAdd(counter, 1u);
+  { // release (cumulative over the CTA's writes ordered by the barrier above) / acquire at gpu scope: no full fences needed
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
     unsigned int seen;
     do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
-    __threadfence();
   }
   __syncthreads();
 }
@@ -135,7 +141,134 @@ __device__ __forceinline__ void cg_fold_parts(const double * __restrict__ part, 
   }
 }
 
-__global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a)
+// MODE_ITER with every vector element a thread owns held in REGISTERS across the two grid sums (EPT = ceil(P / threads of the
+// grid) <= 4): one round of global loads, issued before the wait for the peers, and one round of stores at the end -- the
+// phases between the barriers touch no memory but the reduction slots.  Same arithmetic in the same order as the generic
+// loop below (bit-identical results).
+template <int EPT>
+__device__ __forceinline__ void cg_iter_regs(const CgArgs & a, double * sh, unsigned int & epoch)
+{
+  const long long P = a.P;
+  const long long i0 = (long long)blockIdx.x*blockDim.x+threadIdx.x, stride = (long long)gridDim.x*blockDim.x;
+  const double pre = 1.0+a.lambda;
+  const bool tracing = (a.trace != nullptr && blockIdx.x == 0);
+  const double aovx = a.sc->aov_x, aovy = a.sc->aov_y, rho = a.sc->rho, thr = a.sc->thr;
+  const int fixed = a.sc->fixed;
+  bool ok[EPT];
+  long long pp[EPT];
+  double trx[EPT], try_[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+  {
+    ok[e] = (i0+e*stride < P);
+    pp[e] = ok[e] ? i0+e*stride : 0;
+    trx[e] = 0.0; try_[e] = 0.0;
+    if (ok[e])
+    {
+      if (a.nparts > 0) cg_fold_parts(a.part, a.nparts, P, pp[e], trx[e], try_[e]);
+      else { trx[e] = a.traw[pp[e]]; try_[e] = a.traw[P+pp[e]]; }
+    }
+  }
+  const bool p2p = (a.n_ranks > 1 && a.nparts > 0);
+  const int par = (int)(a.epoch&1u);
+  if (p2p)
+  {
+    const size_t slot = ((size_t)par*a.n_ranks+a.rank)*2*(size_t)P;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+      if (ok[e])
+        for (int r = 0; r < a.n_ranks; ++r) { a.peer_x[r][slot+pp[e]] = trx[e]; a.peer_x[r][slot+P+pp[e]] = try_[e]; }
+  }
+  // the vectors do not depend on the exchange: their loads travel while the peers' partials do
+  cd ao[EPT], pv[EPT], xv[EPT], rv[EPT];
+  double dg[EPT];
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+  {
+    ao[e] = cmake(0.0, 0.0); pv[e] = ao[e]; xv[e] = ao[e]; rv[e] = ao[e]; dg[e] = 1.0;
+    if (ok[e]) { ao[e] = a.aO[pp[e]]; pv[e] = a.v[pp[e]]; xv[e] = a.x[pp[e]]; rv[e] = a.r[pp[e]]; dg[e] = a.diag[pp[e]]; }
+  }
+  if (p2p)
+  {
+    __syncthreads();
+    if (tracing && threadIdx.x == 0) a.trace[1] = cg_now();
+    if (threadIdx.x < a.n_ranks)
+      asm volatile("st.release.sys.global.u32 [%0], %1;"
+        :: "l"(a.peer_flag[threadIdx.x]+((size_t)par*NQS_CG_MAX_RANKS+a.rank)*NQS_CG_MAX_CTAS+blockIdx.x), "r"(a.epoch) : "memory");
+    if (tracing && threadIdx.x == 0) a.trace[2] = cg_now();
+    if (threadIdx.x < a.n_ranks)
+    {
+      const unsigned int * f = a.peer_flag[a.rank]+((size_t)par*NQS_CG_MAX_RANKS+threadIdx.x)*NQS_CG_MAX_CTAS+blockIdx.x;
+      unsigned int seen;
+      const unsigned long long t0 = cg_now();
+      for (;;)
+      {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+        if ((int)(seen-a.epoch) >= 0) break;
+        if (cg_now()-t0 > 20000000000ull) { a.sc->peer_timeout = 1; break; }
+      }
+      if (tracing) a.trace[3+threadIdx.x] = cg_now();
+    }
+    __syncthreads();
+    if (tracing && threadIdx.x == 0) a.trace[19] = cg_now();
+    const double * xin = a.peer_x[a.rank]+(size_t)par*a.n_ranks*2*(size_t)P;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e)
+    {
+      trx[e] = 0.0; try_[e] = 0.0;
+      if (ok[e])
+        for (int r = 0; r < a.n_ranks; ++r) { trx[e] += __ldcv(xin+(size_t)r*2*P+pp[e]); try_[e] += __ldcv(xin+(size_t)r*2*P+P+pp[e]); }
+    }
+  }
+  // ---- t = S p and Re<t, p>
+  cd tv[EPT];
+  double s1[1] = {0.0};
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+  {
+    const double cx = ao[e].x*aovx+ao[e].y*aovy, cy = ao[e].x*aovy-ao[e].y*aovx;
+    tv[e] = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
+    tv[e].x += a.lambda*dg[e]*pv[e].x; tv[e].y += a.lambda*dg[e]*pv[e].y;
+    if (ok[e]) s1[0] += tv[e].x*pv[e].x+tv[e].y*pv[e].y;
+  }
+  cg_grid_sum<1>(s1, a, sh, epoch);
+  const double alpha = rho/s1[0];
+  cd zv[EPT];
+  double s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+  {
+    xv[e].x += alpha*pv[e].x; xv[e].y += alpha*pv[e].y;
+    rv[e].x -= alpha*tv[e].x; rv[e].y -= alpha*tv[e].y;
+    const double den = pre*dg[e];
+    zv[e] = cmake(rv[e].x/den, rv[e].y/den);
+    if (ok[e])
+    {
+      s2[0] += cnorm(rv[e]);
+      s2[1] += zv[e].x*rv[e].x+zv[e].y*rv[e].y;
+      s2[2] += ao[e].x*zv[e].x-ao[e].y*zv[e].y; s2[3] += ao[e].x*zv[e].y+ao[e].y*zv[e].x;
+    }
+  }
+  cg_grid_sum<4>(s2, a, sh, epoch);
+  const double beta = s2[1]/rho;
+  const bool done = (!fixed && s2[0] < thr);
+#pragma unroll
+  for (int e = 0; e < EPT; ++e)
+  {
+    if (!ok[e]) continue;
+    a.x[pp[e]] = xv[e]; a.r[pp[e]] = rv[e];
+    if (!done) a.v[pp[e]] = cmake(zv[e].x+beta*pv[e].x, zv[e].y+beta*pv[e].y);        // conjugate_gradient.cuh:71
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    CgScalars * sc = a.sc;
+    sc->tp = s1[0]; sc->alpha = alpha; sc->res2 = s2[0]; sc->iters += 1; sc->rho_old = rho; sc->rho = s2[1]; sc->beta = beta;
+    sc->aov_x = s2[2]+beta*aovx; sc->aov_y = s2[3]+beta*aovy;   // <O>.(z + beta p) by linearity
+    if (done) sc->done = 1;
+  }
+}
+
+__global__ void __launch_bounds__(NQS_CG_THREADS, 1) cg_fused_kernel(const CgArgs a)
 {
   if (a.mode == CG_MODE_ITER && a.sc->done) return;     // uniform over the grid: converged earlier
   __shared__ double sh[(NQS_CG_THREADS/32)*NQS_CG_NVALS];
@@ -143,7 +276,17 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
   const long long i0 = (long long)blockIdx.x*blockDim.x+threadIdx.x, stride = (long long)gridDim.x*blockDim.x;
   unsigned int epoch = 0;
   const double pre = 1.0+a.lambda;
-
+  const bool tracing = (a.trace != nullptr && blockIdx.x == 0);
+  if (tracing && threadIdx.x == 0) a.trace[0] = cg_now();
+  const long long ept = (P+stride-1)/stride;
+  if (a.mode == CG_MODE_ITER && ept <= 4)
+  {
+    if (ept <= 1) cg_iter_regs<1>(a, sh, epoch);
+    else if (ept <= 2) cg_iter_regs<2>(a, sh, epoch);
+    else cg_iter_regs<4>(a, sh, epoch);
+  }
+  else
+  {
   // <O>.v: carried by recurrence during the iteration, computed explicitly for x0 / an arbitrary v
   double aovx, aovy;
   if (a.mode == CG_MODE_ITER) { aovx = a.sc->aov_x; aovy = a.sc->aov_y; }
@@ -176,9 +319,11 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
     // CTA only delays its own counterparts.  The release store at system scope publishes every store the CTA made before
     // the barrier (cumulativity); flags are [parity][source rank][CTA].
     __syncthreads();
+    if (tracing && threadIdx.x == 0) a.trace[1] = cg_now();
     if (threadIdx.x < a.n_ranks)
       asm volatile("st.release.sys.global.u32 [%0], %1;"
         :: "l"(a.peer_flag[threadIdx.x]+((size_t)par*NQS_CG_MAX_RANKS+a.rank)*NQS_CG_MAX_CTAS+blockIdx.x), "r"(a.epoch) : "memory");
+    if (tracing && threadIdx.x == 0) a.trace[2] = cg_now();
     if (threadIdx.x < a.n_ranks)
     {
       const unsigned int * f = a.peer_flag[a.rank]+((size_t)par*NQS_CG_MAX_RANKS+threadIdx.x)*NQS_CG_MAX_CTAS+blockIdx.x;
@@ -192,8 +337,10 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (now-t0 > 20000000000ull) { a.sc->peer_timeout = 1; break; }   // a peer died: never hang the GPU (host raises NQS_ERR_NCCL)
       }
+      if (tracing) a.trace[3+threadIdx.x] = cg_now();
     }
     __syncthreads();
+    if (tracing && threadIdx.x == 0) a.trace[19] = cg_now();
     xin = a.peer_x[a.rank]+(size_t)par*a.n_ranks*2*(size_t)P;
   }
 
@@ -287,11 +434,12 @@ __global__ void __launch_bounds__(NQS_CG_THREADS) cg_fused_kernel(const CgArgs a
       if (done) sc->done = 1;
     }
   }
+  }
+  if (tracing && threadIdx.x == 0) a.trace[20] = cg_now();
   // leave the barrier counter at zero for the next launch: the last CTA to get here resets it
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    __threadfence();
     const unsigned int n = atomicAdd(a.barrier, 1u);
     if (n == (epoch+1)*gridDim.x-1) *a.barrier = 0u;
   }

@@ -716,6 +716,24 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
   return 0;
 }
 
+#define NQS_CG_TRACE_MAX 8192
+// NQS_CG_TRACE=1: dump the time stamps of the last launches to stderr (microseconds relative to the launch's entry stamp)
+void dump_cg_trace(nqs_handle * h)
+{
+  if (h->cg_trace.p == nullptr || h->cg_trace_n == 0) return;
+  std::vector<unsigned long long> t((size_t)h->cg_trace_n*NQS_CG_TRACE_WORDS);
+  if (cudaMemcpy(t.data(), h->cg_trace.p, t.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  const long long first = std::max<long long>(0, h->cg_trace_n-60);
+  for (long long q = first; q < h->cg_trace_n; ++q)
+  {
+    const unsigned long long * r = t.data()+(size_t)q*NQS_CG_TRACE_WORDS;
+    std::fprintf(stderr, "cgtrace rank %d launch %lld gap_prev_end %.1f stored %.1f released %.1f arrivals", h->rank, q,
+      q > 0 ? ((double)r[0]-(double)t[(size_t)(q-1)*NQS_CG_TRACE_WORDS+20])*1e-3 : 0.0, ((double)r[1]-(double)r[0])*1e-3, ((double)r[2]-(double)r[0])*1e-3);
+    for (int k = 0; k < h->n_ranks; ++k) std::fprintf(stderr, " %.1f", r[3+k] ? ((double)r[3+k]-(double)r[0])*1e-3 : -1.0);
+    std::fprintf(stderr, " waited %.1f end %.1f\n", r[19] ? ((double)r[19]-(double)r[0])*1e-3 : -1.0, ((double)r[20]-(double)r[0])*1e-3);
+  }
+}
+
 int cg_ctas(const nqs_handle * h)
 {
   return std::max(1, std::min<int>(std::min(NQS_CG_MAX_CTAS, h->sm_count), (int)((h->P+NQS_CG_THREADS-1)/NQS_CG_THREADS)));
@@ -737,6 +755,15 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
       a.peer_x[r] = reinterpret_cast<double*>(h->peer_base[r]);
       a.peer_flag[r] = reinterpret_cast<unsigned int*>((char*)h->peer_base[r]+h->xbuf_data_bytes);
     }
+  }
+  a.trace = nullptr;
+  if (h->cg_trace.p != nullptr && h->cg_trace_n < NQS_CG_TRACE_MAX)
+    a.trace = h->cg_trace.p+(size_t)(h->cg_trace_n++)*NQS_CG_TRACE_WORDS;
+  static bool carveout_set = false;
+  if (!carveout_set)
+  { // same shared-memory carve-out as the S*v kernels on either side: no SM reconfiguration between the launches of an iteration
+    cudaFuncSetAttribute(cg_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    carveout_set = true;
   }
   cg_fused_kernel<<<cg_ctas(h), NQS_CG_THREADS, 0, h->stream>>>(a);
   check_launch(h, "cg_fused_kernel");
@@ -906,6 +933,12 @@ void alloc_sr(nqs_handle * h)
   NQS_CUDA(cudaMemset(h->cgbar.p, 0, sizeof(unsigned int)));
   h->scal.alloc(1);
   NQS_CUDA(cudaMemset(h->scal.p, 0, sizeof(CgScalars)));
+  { const char * tr = std::getenv("NQS_CG_TRACE");
+    if (tr && std::atoi(tr) != 0)
+    {
+      h->cg_trace.alloc((size_t)NQS_CG_TRACE_MAX*NQS_CG_TRACE_WORDS);
+      NQS_CUDA(cudaMemset(h->cg_trace.p, 0, (size_t)NQS_CG_TRACE_MAX*NQS_CG_TRACE_WORDS*sizeof(unsigned long long)));
+    } }
   NQS_CUDA(cudaMemset(h->dx.p, 0, sizeof(cd)*h->P)); // CG warm start is zero only at construction (ref impl_optimizer.cuh:55)
 }
 
@@ -1012,6 +1045,8 @@ void nqs_destroy(nqs_handle * h)
 {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  dump_cg_trace(h);
   for (int r = 0; r < 16; ++r)
     if (h->peer_base[r] && r != h->rank) cudaIpcCloseMemHandle(h->peer_base[r]);
   if (h->xbuf) cudaFree(h->xbuf);

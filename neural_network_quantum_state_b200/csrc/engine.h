@@ -105,6 +105,8 @@ struct nqs_handle
   void * peer_base[16] = {nullptr};
   bool p2p_ok = false;
   unsigned int p2p_epoch = 0;
+  nqs::DevBuf<unsigned long long> cg_trace;   // NQS_CG_TRACE=1: per-launch time stamps of cg_fused_kernel (diagnostics)
+  long long cg_trace_n = 0;
 
   // bookkeeping
   std::string err;

@@ -1,0 +1,16 @@
+mkdir -p gpurun_out
+set -x
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+run() { # name, env, args
+  env $2 timeout 600 python bench.py $3 --no-cpu-baseline --no-e2e --steps 5 > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/bench_$1.json") if l.startswith("{")][0]); print("$1", d["ms_per_step"], d["value"], d["roofline"]["kernel"], d["roofline"]["avg_launch_ms"], d["roofline"]["frac"], d["roofline"].get("other_pass"), d["phase_ms_per_step"], d["cg_iters_per_step"], d["cg_ms_per_iter"], d["energy_per_site"][:2])
+except Exception as ex: print("$1 failed", ex); print(open("gpurun_out/bench_$1.err").read()[-1500:])
+PY
+}
+run cfg3_def A=1 "--config cfg3"
+run cfg3_struct A=1 "--config cfg3 --structured-sv"
+run cfg2_def A=1 "--config cfg2"
+run cfg4_def A=1 "--config cfg4"
