@@ -178,31 +178,36 @@ void set_smem(Kern kern, size_t bytes)
 }
 
 // ---- launches ------------------------------------------------------------------------------------------------------
-// chains per CTA of the rows GEMM: 32, or 16 when that leaves SMs idle (two CTAs per SM are resident)
-int rows_dmma_mt(const nqs_handle * h) { return ((h->K+31)/32 >= 2LL*h->sm_count) ? 4 : 2; }
+// chains per CTA of the rows GEMM (8 MT): every CTA re-streams B from L2, so tall tiles when the rank has chains to spare,
+// short ones when it must still fill the SMs, and never more than fits next to the two slabs of B in shared memory
+int rows_dmma_mt(const nqs_handle * h)
+{
+  int mt = (h->K >= 64LL*h->sm_count) ? 8 : (h->K >= 32LL*h->sm_count) ? 4 : 2;
+  while (mt > 2 && rows_dmma_smem(h->N, mt) > h->smem_optin) mt >>= 1;
+  return mt;
+}
+
+template <int MODEL, int EPI, int MT>
+void launch_rows_dmma_t(nqs_handle * h, const RowsArgs & a)
+{
+  const size_t smem = rows_dmma_smem(h->N, MT);
+  set_smem(spin_rows_dmma_kernel<MODEL, EPI, MT>, smem);
+  spin_rows_dmma_kernel<MODEL, EPI, MT><<<(unsigned)((h->K+8*MT-1)/(8*MT)), NQS_DR_THREADS, smem, h->stream>>>(a);
+}
 
 template <int MODEL, int EPI>
 void launch_rows_dmma(nqs_handle * h, const RowsArgs & a)
 {
   const int mt = rows_dmma_mt(h);
-  const size_t smem = rows_dmma_smem(h->N, mt);
-  const unsigned grid = (unsigned)((h->K+8*mt-1)/(8*mt));
-  if (mt == 4)
-  {
-    set_smem(spin_rows_dmma_kernel<MODEL, EPI, 4>, smem);
-    spin_rows_dmma_kernel<MODEL, EPI, 4><<<grid, NQS_DR_THREADS, smem, h->stream>>>(a);
-  }
-  else
-  {
-    set_smem(spin_rows_dmma_kernel<MODEL, EPI, 2>, smem);
-    spin_rows_dmma_kernel<MODEL, EPI, 2><<<grid, NQS_DR_THREADS, smem, h->stream>>>(a);
-  }
+  if (mt == 8) launch_rows_dmma_t<MODEL, EPI, 8>(h, a);
+  else if (mt == 4) launch_rows_dmma_t<MODEL, EPI, 4>(h, a);
+  else launch_rows_dmma_t<MODEL, EPI, 2>(h, a);
   check_launch(h, "spin_rows_dmma_kernel");
 }
 
 bool rows_dmma_ok(const nqs_handle * h)
-{ // the spin tile of 32 chains and one slab of B must fit the shared memory of one CTA (N up to ~600)
-  return !(h->cfg.flags & NQS_FLAG_NO_DMMA) && rows_dmma_smem(h->N, 4) <= h->smem_optin;
+{ // the spin tile of 16 chains and two slabs of B must fit the shared memory of one CTA (N up to ~700)
+  return !(h->cfg.flags & NQS_FLAG_NO_DMMA) && rows_dmma_smem(h->N, 2) <= h->smem_optin;
 }
 
 // sum_ij s_i J_ij s_j of every chain as the GEMM (S J) . S on the fp64 tensor cores (ref c5 Zgemm + k10, impl_hamiltonians.cuh:226-231).
@@ -555,6 +560,72 @@ void launch_setup_structured(nqs_handle * h, dim3 grid, size_t smem, int ipt)
   else launch_setup_structured_m<MODEL_FFNN>(h, grid, smem, ipt);
 }
 
+// ---- structured S*v (sv_struct.cuh) ---------------------------------------------------------------------------------------
+void launch_hidden_values(nqs_handle * h)
+{
+  const int grid = grid_for((long long)h->K*h->M, 256, 148*8);
+  if (h->model == MODEL_RBM)
+    hidden_values_kernel<MODEL_RBM><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, nullptr);
+  else
+    hidden_values_kernel<MODEL_FFNN><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, h->Lm.p);
+  check_launch(h, "hidden_values_kernel");
+  h->hidden_valid = true;
+  h->theta_matches_O = true;   // the factors (spins, theta, params) are what S is built from: structured setup sums allowed
+}
+
+// warp grids / tile shapes of spin_cols_dmma_kernel by chain length: {MTW, NTW, WM}
+static const int kColsVariants[5][3] = {{1, 8, 2}, {1, 16, 4}, {1, 16, 8}, {2, 16, 8}, {4, 8, 8}};
+int cols_variant_for(int N) { return N <= 16 ? 0 : N <= 32 ? 1 : N <= 64 ? 2 : N <= 128 ? 3 : 4; }
+
+// geometry of spin_cols_dmma_kernel (structured S*v and the SR setup GEMM): column groups x chain chunks ~ one CTA per SM
+void plan_cols(nqs_handle * h)
+{
+  h->cols_ok = false;
+  if (h->N > 256 || (h->cfg.flags & NQS_FLAG_NO_DMMA)) return;
+  const int var = cols_variant_for(h->N);
+  const int cw = cols_dmma_cw(kColsVariants[var][1], kColsVariants[var][2]);
+  const int colgroups = (2*h->M+cw-1)/cw;
+  long long nchunks = std::max(1, h->sm_count/colgroups);
+  nchunks = std::min<long long>(nchunks, (h->K+NQS_DC_KC-1)/NQS_DC_KC);
+  long long rpc = (h->K+nchunks-1)/nchunks;
+  rpc = (rpc+NQS_DC_KC-1)/NQS_DC_KC*NQS_DC_KC;
+  h->sc_variant = var; h->sc_colgroups = colgroups; h->sc_rows_per_chunk = rpc; h->sc_nchunks = (int)((h->K+rpc-1)/rpc);
+  h->cols_ok = true;
+}
+
+void plan_struct(nqs_handle * h)
+{
+  NQS_REQUIRE(h->N <= 256, NQS_ERR_UNSUPPORTED, "NQS_FLAG_STRUCTURED_SV supports n_inputs <= 256");
+  NQS_REQUIRE(!(h->cfg.flags & (NQS_FLAG_SETUP_FROM_O | NQS_FLAG_TWO_PASS_SV | NQS_FLAG_NO_DMMA)), NQS_ERR_INVALID,
+    "NQS_FLAG_STRUCTURED_SV excludes NQS_FLAG_SETUP_FROM_O / NQS_FLAG_TWO_PASS_SV / NQS_FLAG_NO_DMMA");
+  const int var = h->sc_variant;
+  h->struct_sv = true;
+  h->variant_sv = "structured_dmma_mtw"+std::to_string(kColsVariants[var][0])+"_ntw"+std::to_string(kColsVariants[var][1])+
+    "_wm"+std::to_string(kColsVariants[var][2])+"_colgroups"+std::to_string(h->sc_colgroups)+"_chunks"+std::to_string(h->sc_nchunks);
+}
+
+template <int MODEL, int MTW, int NTW, int WM>
+void launch_cols_dmma_t(nqs_handle * h, const ColsArgs & a)
+{
+  const size_t smem = cols_dmma_smem(cols_dmma_nsc(MTW, WM), cols_dmma_cw(NTW, WM));
+  set_smem(spin_cols_dmma_kernel<MODEL, MTW, NTW, WM>, smem);
+  dim3 grid((unsigned)h->sc_colgroups, (unsigned)h->sc_nchunks, a.zmode == 1 ? 2u : 1u);
+  spin_cols_dmma_kernel<MODEL, MTW, NTW, WM><<<grid, NQS_DC_THREADS, smem, h->stream>>>(a);
+}
+template <int MODEL>
+void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
+{
+  switch (h->sc_variant)
+  {
+    case 0: launch_cols_dmma_t<MODEL, 1, 8, 2>(h, a); break;
+    case 1: launch_cols_dmma_t<MODEL, 1, 16, 4>(h, a); break;
+    case 2: launch_cols_dmma_t<MODEL, 1, 16, 8>(h, a); break;
+    case 3: launch_cols_dmma_t<MODEL, 2, 16, 8>(h, a); break;
+    default: launch_cols_dmma_t<MODEL, 4, 8, 8>(h, a); break;
+  }
+  check_launch(h, "spin_cols_dmma_kernel");
+}
+
 // <O>, F, diag from ONE pass over O (+ one all-reduce of 5P+3 doubles across ranks)
 void sr_setup(nqs_handle * h, bool want_F)
 {
@@ -562,6 +633,26 @@ void sr_setup(nqs_handle * h, bool want_F)
   htilda_sums_kernel<<<1, 1024, 0, h->stream>>>(K, h->htilda.p, h->sums.p+5*P);
   check_launch(h, "htilda_sums_kernel");
   const int ipt = (h->N+15)/16;
+  if (h->cols_ok && h->theta_matches_O && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
+  { // sums from the factors of O as ONE launch of the tensor-core column GEMM: S^T conj(T) and S^T (conj(T) h)
+    if (!h->hidden_valid) launch_hidden_values(h);
+    ColsArgs c;
+    c.N = h->N; c.M = h->M; c.K = K; c.P = P; c.spins = h->spins.p; c.T = h->Tm.p; c.L = h->Lm.p; c.zk = h->htilda.p;
+    c.part = h->part.p; c.rows_per_chunk = h->sc_rows_per_chunk; c.done = nullptr;
+    c.zmode = 1; c.part_stride = (long long)h->sc_nchunks*2*P; c.abs2 = h->abs2.p;
+    if (h->model == MODEL_RBM) launch_cols_dmma<MODEL_RBM>(h, c); else launch_cols_dmma<MODEL_FFNN>(h, c);
+    const int g = grid_for(P, 256, 148*4);
+    if (h->model == MODEL_RBM)
+      setup_fold_struct_kernel<MODEL_RBM><<<g, 256, 0, h->stream>>>(h->N, h->M, P, K, h->sc_nchunks, h->part.p, c.part_stride, h->abs2.p, h->sums.p);
+    else
+      setup_fold_struct_kernel<MODEL_FFNN><<<g, 256, 0, h->stream>>>(h->N, h->M, P, K, h->sc_nchunks, h->part.p, c.part_stride, h->abs2.p, h->sums.p);
+    check_launch(h, "setup_fold_struct_kernel");
+    allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
+    setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
+      want_F ? h->F.p : nullptr, h->diag.p);
+    check_launch(h, "setup_finalize_kernel");
+    return;
+  }
   if (ipt <= 16 && h->theta_matches_O && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
   { // sums from the factors of O (spins, tanh theta): no pass over O
     dim3 grid((unsigned)((h->M+NQS_SS_JT-1)/NQS_SS_JT), (unsigned)h->nrb);
@@ -583,63 +674,6 @@ void sr_setup(nqs_handle * h, bool want_F)
   setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
     want_F ? h->F.p : nullptr, h->diag.p);
   check_launch(h, "setup_finalize_kernel");
-}
-
-// ---- structured S*v (sv_struct.cuh) ---------------------------------------------------------------------------------------
-void launch_hidden_values(nqs_handle * h)
-{
-  const int grid = grid_for((long long)h->K*h->M, 256, 148*8);
-  if (h->model == MODEL_RBM)
-    hidden_values_kernel<MODEL_RBM><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, nullptr);
-  else
-    hidden_values_kernel<MODEL_FFNN><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, h->Lm.p);
-  check_launch(h, "hidden_values_kernel");
-  h->hidden_valid = true;
-  h->theta_matches_O = true;   // the factors (spins, theta, params) are what S is built from: structured setup sums allowed
-}
-
-// warp grids / tile shapes of spin_cols_dmma_kernel by chain length: {MTW, NTW, WM}
-static const int kColsVariants[5][3] = {{1, 8, 2}, {1, 16, 4}, {1, 16, 8}, {2, 16, 8}, {4, 8, 8}};
-int cols_variant_for(int N) { return N <= 16 ? 0 : N <= 32 ? 1 : N <= 64 ? 2 : N <= 128 ? 3 : 4; }
-
-void plan_struct(nqs_handle * h)
-{
-  NQS_REQUIRE(h->N <= 256, NQS_ERR_UNSUPPORTED, "NQS_FLAG_STRUCTURED_SV supports n_inputs <= 256");
-  NQS_REQUIRE(!(h->cfg.flags & (NQS_FLAG_SETUP_FROM_O | NQS_FLAG_TWO_PASS_SV)), NQS_ERR_INVALID,
-    "NQS_FLAG_STRUCTURED_SV excludes NQS_FLAG_SETUP_FROM_O / NQS_FLAG_TWO_PASS_SV");
-  const int var = cols_variant_for(h->N);
-  const int cw = cols_dmma_cw(kColsVariants[var][1], kColsVariants[var][2]);
-  const int colgroups = (2*h->M+cw-1)/cw;
-  long long nchunks = std::max(1, h->sm_count/colgroups);
-  nchunks = std::min<long long>(nchunks, (h->K+NQS_DC_KC-1)/NQS_DC_KC);
-  long long rpc = (h->K+nchunks-1)/nchunks;
-  rpc = (rpc+NQS_DC_KC-1)/NQS_DC_KC*NQS_DC_KC;
-  h->sc_variant = var; h->sc_colgroups = colgroups; h->sc_rows_per_chunk = rpc; h->sc_nchunks = (int)((h->K+rpc-1)/rpc);
-  h->struct_sv = true;
-  h->variant_sv = "structured_dmma_mtw"+std::to_string(kColsVariants[var][0])+"_ntw"+std::to_string(kColsVariants[var][1])+
-    "_wm"+std::to_string(kColsVariants[var][2])+"_colgroups"+std::to_string(colgroups)+"_chunks"+std::to_string(h->sc_nchunks);
-}
-
-template <int MODEL, int MTW, int NTW, int WM>
-void launch_cols_dmma_t(nqs_handle * h, const ColsArgs & a)
-{
-  const size_t smem = cols_dmma_smem(cols_dmma_nsc(MTW, WM), cols_dmma_cw(NTW, WM));
-  set_smem(spin_cols_dmma_kernel<MODEL, MTW, NTW, WM>, smem);
-  dim3 grid((unsigned)h->sc_colgroups, (unsigned)h->sc_nchunks);
-  spin_cols_dmma_kernel<MODEL, MTW, NTW, WM><<<grid, NQS_DC_THREADS, smem, h->stream>>>(a);
-}
-template <int MODEL>
-void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
-{
-  switch (h->sc_variant)
-  {
-    case 0: launch_cols_dmma_t<MODEL, 1, 8, 2>(h, a); break;
-    case 1: launch_cols_dmma_t<MODEL, 1, 16, 4>(h, a); break;
-    case 2: launch_cols_dmma_t<MODEL, 1, 16, 8>(h, a); break;
-    case 3: launch_cols_dmma_t<MODEL, 2, 16, 8>(h, a); break;
-    default: launch_cols_dmma_t<MODEL, 4, 8, 8>(h, a); break;
-  }
-  check_launch(h, "spin_cols_dmma_kernel");
 }
 
 // z = O v and the chunk partials of O^H z from the factors: two tensor-core GEMMs, no pass over O
@@ -667,7 +701,7 @@ int matvec_structured(nqs_handle * h, const cd * v, const int * done)
   }
   ColsArgs c;
   c.N = h->N; c.M = h->M; c.K = h->K; c.P = h->P; c.spins = h->spins.p; c.T = h->Tm.p; c.L = h->Lm.p; c.zk = h->zk.p;
-  c.part = h->part.p; c.rows_per_chunk = h->sc_rows_per_chunk; c.done = done;
+  c.part = h->part.p; c.rows_per_chunk = h->sc_rows_per_chunk; c.done = done; c.zmode = 0; c.part_stride = 0; c.abs2 = nullptr;
   {
     Span sp(h, TAG_COLS);
     if (h->model == MODEL_RBM) launch_cols_dmma<MODEL_RBM>(h, c); else launch_cols_dmma<MODEL_FFNN>(h, c);
@@ -909,12 +943,15 @@ std::vector<std::complex<double> > download_params(nqs_handle * h)
 void alloc_sr(nqs_handle * h)
 {
   if (h->aO.p != nullptr) return;
-  if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV)
-  { // S*v from the factors: T [K][M] (+ L, FFNN) instead of O [K][P]; O is allocated only if nqs_log_derivs asks for it
-    plan_struct(h);
+  plan_cols(h);
+  if (h->cols_ok)
+  { // hidden-unit factors T [K][M] (+ L, FFNN) for the tensor-core GEMMs (SR setup; structured S*v)
     h->Tm.alloc((size_t)h->K*h->M);
     if (h->model == MODEL_FFNN) { h->Lm.alloc((size_t)h->K*h->M); h->vnat.alloc((size_t)h->N*h->M); }
+    h->abs2.alloc((size_t)h->sc_nchunks*3*h->M);
   }
+  // structured S*v: no O [K][P]; it is allocated only if nqs_log_derivs asks for it
+  if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV) plan_struct(h);
   else h->O.alloc((size_t)h->K*(size_t)h->P);
   h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
   h->zk.alloc(h->K); h->diag.alloc(h->P);
@@ -925,7 +962,7 @@ void alloc_sr(nqs_handle * h)
   h->rows_per_block = (h->K+nrb-1)/nrb;
   h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
   if (!h->struct_sv) plan_sv(h);
-  h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*2*h->P));
+  h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->traw.alloc((size_t)2*h->P);
   h->slots.alloc((size_t)2*NQS_CG_MAX_CTAS*NQS_CG_NVALS);

@@ -95,21 +95,48 @@ struct RowsArgs
 inline size_t rows_dmma_smem(int N, int MT)
 {
   const int n4 = (N+3)/4*4;
-  return ((size_t)8*MT*(n4+4)+(size_t)NQS_DR_KC*(NQS_DR_CW+4))*sizeof(double)+(size_t)(NQS_DR_THREADS/32)*8*MT*sizeof(cd);
+  return ((size_t)8*MT*(n4+4)+(size_t)2*NQS_DR_KC*(NQS_DR_CW+4))*sizeof(double)+(size_t)(NQS_DR_THREADS/32)*8*MT*sizeof(cd);
 }
 
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills (out-of-range rows / columns of the slab)
+__device__ __forceinline__ void cp_async16(void * smem_dst, const void * gsrc, const int src_bytes)
+{
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
+
+// One CTA per SM: 8 MT chains x all columns; the slabs of B ([32 sites][256 columns], 66 KB) are double-buffered with cp.async so
+// the L2 stream of B overlaps the DMMAs.  B is re-streamed by every CTA, so fewer, taller CTAs (MT = 8: 64 chains) halve the
+// L2 traffic of MT = 4; MT = 2 / 4 keep every SM busy when a rank holds few chains.
 template <int MODEL, int EPI, int MT>
-__global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const RowsArgs a)
+__global__ void __launch_bounds__(NQS_DR_THREADS, 1) spin_rows_dmma_kernel(const RowsArgs a)
 {
   if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int RT = 8*MT, NTW = NQS_DR_NTW, CW = NQS_DR_CW, KC = NQS_DR_KC, PB = CW+4;
   const int N = a.N, M = a.M, n4 = (N+3)/4*4, PA = n4+4, M2 = (EPI == ROWS_EPI_SJS) ? N : 2*M;
   double * As = reinterpret_cast<double*>(smem_raw);            // [RT][PA] spins of the CTA's chains (0 for padding)
-  double * Bs = As+(size_t)RT*PA;                               // [KC][PB] slab of B
-  cd * red = reinterpret_cast<cd*>(Bs+(size_t)KC*PB);           // [warps][RT]
+  double * Bs = As+(size_t)RT*PA;                               // [2][KC][PB] slabs of B
+  cd * red = reinterpret_cast<cd*>(Bs+(size_t)2*KC*PB);         // [warps][RT]
   const int tid = threadIdx.x, lane = tid&31, w = tid>>5, g = lane>>2, t = lane&3;
   const long long kbase = (long long)blockIdx.x*RT;
+  const int nslab = (n4+KC-1)/KC, npass = (M2+CW-1)/CW, nstage = nslab*npass;
+  // slab q = (column pass q / nslab, site slab q % nslab) -> buffer q & 1
+  auto issue = [&](const int q)
+  {
+    const int c0 = (q/nslab)*CW, i0 = (q%nslab)*KC;
+    double * dst = Bs+(size_t)(q&1)*KC*PB;
+    for (int idx = tid; idx < KC*(CW/2); idx += NQS_DR_THREADS)
+    {
+      const int r = idx/(CW/2), c = 2*(idx-r*(CW/2));
+      const bool okb = (i0+r < N && c0+c < M2);
+      cp_async16(dst+r*PB+c, okb ? a.B+(size_t)(i0+r)*M2+c0+c : a.B, okb ? 16 : 0);
+    }
+    cp_async_commit();
+  };
+  issue(0);
   for (int idx = tid; idx < RT*n4; idx += NQS_DR_THREADS)
   {
     const int r = idx/n4, i = idx-r*n4;
@@ -119,27 +146,22 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
 #pragma unroll
   for (int m = 0; m < MT; ++m) rsum[m] = cmake(0.0, 0.0);
 
-  for (int c0 = 0; c0 < M2; c0 += CW)
+  for (int pass = 0; pass < npass; ++pass)
   {
+    const int c0 = pass*CW;
     double acc[MT][NTW][2];
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int n = 0; n < NTW; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
-    for (int i0 = 0; i0 < n4; i0 += KC)
+    for (int sl = 0; sl < nslab; ++sl)
     {
-      __syncthreads();
-      for (int idx = tid; idx < KC*(CW/2); idx += NQS_DR_THREADS)
-      {
-        const int r = idx/(CW/2), c = 2*(idx-r*(CW/2));
-        double2 v = make_double2(0.0, 0.0);
-        if (i0+r < N && c0+c < M2) v = *reinterpret_cast<const double2*>(a.B+(size_t)(i0+r)*M2+c0+c);
-        *reinterpret_cast<double2*>(Bs+r*PB+c) = v;
-      }
+      const int q = pass*nslab+sl, i0 = sl*KC;
+      if (q+1 < nstage) { issue(q+1); cp_async_wait<1>(); } else cp_async_wait<0>();
       __syncthreads();
       const int ksteps = ((n4-i0 < KC) ? n4-i0 : KC)/4;
       const double * ap = As+g*PA+i0+t;
-      const double * bp = Bs+t*PB+w*NTW*8+g;
+      const double * bp = Bs+(size_t)(q&1)*KC*PB+t*PB+w*NTW*8+g;
       for (int ks = 0; ks < ksteps; ++ks)
       {
         double af[MT], bf[NTW];
@@ -152,6 +174,7 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
 #pragma unroll
           for (int n = 0; n < NTW; ++n) dmma884(acc[m][n][0], acc[m][n][1], af[m], bf[n]);
       }
+      __syncthreads();     // buffer q & 1 is refilled by the issue of the next iteration
     }
     // epilogue of this column pass: lane holds (re, im) of chain kbase + 8m + g, hidden unit (c0 + (w NTW + n) 8)/2 + t
     if (EPI == ROWS_EPI_SJS)
@@ -217,35 +240,33 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 2) spin_rows_dmma_kernel(const
   }
   __syncthreads();
   // visible-bias term (RBM) and the final value of chain kbase + r: 8 lanes per chain
+  for (int r = tid>>3; r < RT; r += NQS_DR_THREADS/8)
   {
-    const int r = tid>>3, q = tid&7;
+    const int q = tid&7;
     const long long k = kbase+r;
-    if (r < RT)
+    cd sv = cmake(0.0, 0.0);
+    if (MODEL == MODEL_RBM && EPI != ROWS_EPI_SJS && k < a.K)
     {
-      cd sv = cmake(0.0, 0.0);
-      if (MODEL == MODEL_RBM && EPI != ROWS_EPI_SJS && k < a.K)
+      for (int i = q; i < N; i += 8)
       {
-        for (int i = q; i < N; i += 8)
-        {
-          const double s = (EPI == ROWS_EPI_Z) ? As[r*PA+i] : (double)a.sa_spins[k*N+i];
-          const cd ai = a.avis[i];
-          sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
-        }
+        const double s = (EPI == ROWS_EPI_Z) ? As[r*PA+i] : (double)a.sa_spins[k*N+i];
+        const cd ai = a.avis[i];
+        sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
       }
+    }
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) { sv.x += __shfl_xor_sync(0xffffffffu, sv.x, o); sv.y += __shfl_xor_sync(0xffffffffu, sv.y, o); }
-      if (q == 0 && k < a.K)
+    for (int o = 4; o > 0; o >>= 1) { sv.x += __shfl_xor_sync(0xffffffffu, sv.x, o); sv.y += __shfl_xor_sync(0xffffffffu, sv.y, o); }
+    if (q == 0 && k < a.K)
+    {
+      cd tot = sv;
+      if (EPI != ROWS_EPI_THETA)
+        for (int ww = 0; ww < NQS_DR_THREADS/32; ++ww) tot = cadd(tot, red[ww*RT+r]);
+      if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
+      else if (EPI == ROWS_EPI_SJS) a.sjs[k] = tot.x;
+      else
       {
-        cd tot = sv;
-        if (EPI != ROWS_EPI_THETA)
-          for (int ww = 0; ww < NQS_DR_THREADS/32; ++ww) tot = cadd(tot, red[ww*RT+r]);
-        if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
-        else if (EPI == ROWS_EPI_SJS) a.sjs[k] = tot.x;
-        else
-        {
-          if (a.sa) a.sa[k] = sv;
-          if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
-        }
+        if (a.sa) a.sa[k] = sv;
+        if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
       }
     }
   }
@@ -266,6 +287,11 @@ struct ColsArgs
   double * part;
   long long rows_per_chunk;  // multiple of NQS_DC_KC
   const int * done;
+  // SR setup (zmode = 1, gridDim.z = 2): slice z = 0 takes z_k = 1 (-> conj(sum_k O_kp)) and also sums |T|^2 (|L|^2) per hidden
+  // unit into abs2[chunk][3M]; slice z = 1 takes zk (= htilda -> conj(sum_k O_kp conj(h_k))).  Slice z writes part + z*part_stride.
+  int zmode;
+  long long part_stride;
+  double * abs2;
 };
 
 // warp grid WM (sites) x 8/WM (columns); a warp owns MTW x NTW accumulator tiles.  nsc = sites covered, cw = real columns per CTA
@@ -295,13 +321,14 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   const long long k1 = (k0+a.rows_per_chunk < a.K) ? k0+a.rows_per_chunk : a.K;
   const int nstages = (int)((k1-k0+KC-1)/KC);
   const bool do_a = (MODEL == MODEL_RBM && blockIdx.x == 0);
+  const bool ones = (a.zmode == 1 && blockIdx.z == 0);
 
   double acc[MTW][NTW][2];
 #pragma unroll
   for (int m = 0; m < MTW; ++m)
 #pragma unroll
     for (int n = 0; n < NTW; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
-  double bsum = 0.0, asx = 0.0, asy = 0.0, lsx = 0.0, lsy = 0.0;
+  double bsum = 0.0, asx = 0.0, asy = 0.0, lsx = 0.0, lsy = 0.0, b2sum = 0.0, l2sum = 0.0;
 
   // producer mapping: thread -> chain kk = tid / 8 of the stage, hidden units jc = tid % 8 + 8 u
   constexpr int TU = CH/8;
@@ -315,7 +342,7 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   {
     const long long k = k0+(long long)s*KC+pkk;
     const bool ok = (k < k1);
-    zv = ok ? a.zk[k] : cmake(0.0, 0.0);
+    zv = ok ? (ones ? cmake(1.0, 0.0) : a.zk[k]) : cmake(0.0, 0.0);
 #pragma unroll
     for (int u = 0; u < TU; ++u)
     {
@@ -378,7 +405,7 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
     if (tid < CW)
     {
 #pragma unroll 8
-      for (int kk = 0; kk < KC; ++kk) bsum += cs[kk*PC+tid];
+      for (int kk = 0; kk < KC; ++kk) { const double v = cs[kk*PC+tid]; bsum += v; b2sum = fma(v, v, b2sum); }
     }
     if (do_a && tid < N)
     {
@@ -398,6 +425,7 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
         const cd l = a.L[(kb+kk)*M+j0+tid];
         const cd z = zs[buf*KC+kk];
         lsx += l.x*z.x+l.y*z.y; lsy += l.x*z.y-l.y*z.x;
+        l2sum += cnorm(l);
       }
     }
     if (s+1 < nstages) commit(buf^1);
@@ -405,7 +433,13 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   }
 
   const long long P = a.P, NM = (long long)N*M;
-  double * base = a.part+(size_t)blockIdx.y*2*(size_t)P;
+  double * base = a.part+(size_t)blockIdx.z*(size_t)a.part_stride+(size_t)blockIdx.y*2*(size_t)P;
+  if (ones)
+  {
+    double * q = a.abs2+(size_t)blockIdx.y*3*M;
+    if (tid < CW && j0+(tid>>1) < M) q[2*j0+tid] = b2sum;
+    if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M) q[2*M+j0+tid] = l2sum;
+  }
 #pragma unroll
   for (int m = 0; m < MTW; ++m)
   {
@@ -431,5 +465,50 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   }
   if (do_a && tid < N) { base[NM+tid] = asx; base[P+NM+tid] = asy; }
   if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M) { base[NM+M+j0+tid] = lsx; base[P+NM+M+j0+tid] = lsy; }
+}
+
+// SR setup sums from the two slices of spin_cols_dmma_kernel (zmode = 1), chunks folded in fixed order:
+//   sums = [sum O (re P | im P) | sum O conj(h) (re P | im P) | sum |O|^2 (P)]   (layout of setup_finalize_kernel)
+// |O_kp|^2 of the W block does not depend on the site (s^2 = 1); the RBM a block is K_loc.
+template <int MODEL>
+__global__ void setup_fold_struct_kernel(const int N, const int M, const long long P, const long long K, const int nchunks,
+  const double * __restrict__ part, const long long part_stride, const double * __restrict__ abs2, double * __restrict__ sums)
+{
+  const long long NM = (long long)N*M;
+  for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
+  {
+    double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+    for (int c = 0; c < nchunks; ++c)
+    {
+      const double * b0 = part+(size_t)c*2*P+p;
+      ax += __ldcg(b0); ay += __ldcg(b0+P);
+      bx += __ldcg(b0+part_stride); by += __ldcg(b0+part_stride+P);
+    }
+    sums[p] = ax; sums[P+p] = -ay;
+    sums[2*P+p] = bx; sums[3*P+p] = -by;
+    int col;            // index into abs2's [2M | M] row: pair (2j, 2j+1) of T, or 2M + j of L
+    bool pair = true, visible = false;
+    if (MODEL == MODEL_RBM)
+    {
+      if (p < NM) col = (int)(p%M);
+      else if (p < NM+N) { col = 0; visible = true; }
+      else col = (int)(p-NM-N);
+    }
+    else
+    {
+      if (p < NM) col = (int)(p/N);
+      else if (p < NM+M) col = (int)(p-NM);
+      else { col = (int)(p-NM-M); pair = false; }
+    }
+    double d = 0.0;
+    if (visible) d = (double)K;
+    else
+      for (int c = 0; c < nchunks; ++c)
+      {
+        const double * q = abs2+(size_t)c*3*M;
+        d += pair ? (__ldcg(q+2*col)+__ldcg(q+2*col+1)) : __ldcg(q+2*M+col);
+      }
+    sums[4*P+p] = d;
+  }
 }
 } // namespace nqs
