@@ -178,13 +178,20 @@ void set_smem(Kern kern, size_t bytes)
 }
 
 // ---- launches ------------------------------------------------------------------------------------------------------
-// chains per CTA of the rows GEMM (8 MT): every CTA re-streams B from L2, so tall tiles when the rank has chains to spare,
-// short ones when it must still fill the SMs, and never more than fits next to the two slabs of B in shared memory
+// chains per CTA of the rows GEMM (8 MT): one CTA per SM, so the tile height decides how full the last wave is
 int rows_dmma_mt(const nqs_handle * h)
-{
-  int mt = (h->K >= 64LL*h->sm_count) ? 8 : (h->K >= 32LL*h->sm_count) ? 4 : 2;
-  while (mt > 2 && rows_dmma_smem(h->N, mt) > h->smem_optin) mt >>= 1;
-  return mt;
+{ // fewest waves x tile height over the tile heights that fit (ties: the taller tile, less L2 traffic)
+  static const int cand[] = {8, 7, 6, 4, 2};
+  int best = 2;
+  long long best_cost = -1;
+  for (const int mt : cand)
+  {
+    if (mt > 2 && rows_dmma_smem(h->N, mt) > h->smem_optin) continue;
+    const long long ctas = (h->K+8*mt-1)/(8*mt), waves = (ctas+h->sm_count-1)/h->sm_count;
+    const long long cost = waves*mt;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = mt; }
+  }
+  return best;
 }
 
 template <int MODEL, int EPI, int MT>
@@ -200,6 +207,8 @@ void launch_rows_dmma(nqs_handle * h, const RowsArgs & a)
 {
   const int mt = rows_dmma_mt(h);
   if (mt == 8) launch_rows_dmma_t<MODEL, EPI, 8>(h, a);
+  else if (mt == 7) launch_rows_dmma_t<MODEL, EPI, 7>(h, a);
+  else if (mt == 6) launch_rows_dmma_t<MODEL, EPI, 6>(h, a);
   else if (mt == 4) launch_rows_dmma_t<MODEL, EPI, 4>(h, a);
   else launch_rows_dmma_t<MODEL, EPI, 2>(h, a);
   check_launch(h, "spin_rows_dmma_kernel");
@@ -624,6 +633,12 @@ void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
     default: launch_cols_dmma_t<MODEL, 4, 8, 8>(h, a); break;
   }
   check_launch(h, "spin_cols_dmma_kernel");
+  if (MODEL == MODEL_FFNN)
+  {
+    dim3 grid((unsigned)((h->M+NQS_LB_THREADS-1)/NQS_LB_THREADS), (unsigned)h->sc_nchunks, a.zmode == 1 ? 2u : 1u);
+    ffnn_lblock_kernel<<<grid, NQS_LB_THREADS, 0, h->stream>>>(a);
+    check_launch(h, "ffnn_lblock_kernel");
+  }
 }
 
 // <O>, F, diag from ONE pass over O (+ one all-reduce of 5P+3 doubles across ranks)

@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   for (int m = 0; m < MTW; ++m)
 #pragma unroll
     for (int n = 0; n < NTW; ++n) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
-  double bsum = 0.0, asx = 0.0, asy = 0.0, lsx = 0.0, lsy = 0.0, b2sum = 0.0, l2sum = 0.0;
+  double bsum = 0.0, asx = 0.0, asy = 0.0, b2sum = 0.0;
 
   // producer mapping: thread -> chain kk = tid / 8 of the stage, hidden units jc = tid % 8 + 8 u
   constexpr int TU = CH/8;
@@ -417,17 +417,6 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
         asx = fma(sp, z.x, asx); asy = fma(sp, z.y, asy);
       }
     }
-    if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M)
-    {
-      const long long kb = k0+(long long)s*KC;
-      for (int kk = 0; kk < KC && kb+kk < k1; ++kk)
-      {
-        const cd l = a.L[(kb+kk)*M+j0+tid];
-        const cd z = zs[buf*KC+kk];
-        lsx += l.x*z.x+l.y*z.y; lsy += l.x*z.y-l.y*z.x;
-        l2sum += cnorm(l);
-      }
-    }
     if (s+1 < nstages) commit(buf^1);
     __syncthreads();
   }
@@ -438,7 +427,6 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
   {
     double * q = a.abs2+(size_t)blockIdx.y*3*M;
     if (tid < CW && j0+(tid>>1) < M) q[2*j0+tid] = b2sum;
-    if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M) q[2*M+j0+tid] = l2sum;
   }
 #pragma unroll
   for (int m = 0; m < MTW; ++m)
@@ -464,7 +452,38 @@ __global__ void __launch_bounds__(NQS_DC_THREADS, 1) spin_cols_dmma_kernel(const
     }
   }
   if (do_a && tid < N) { base[NM+tid] = asx; base[P+NM+tid] = asy; }
-  if (MODEL == MODEL_FFNN && tid < CH && j0+tid < M) { base[NM+M+j0+tid] = lsx; base[P+NM+M+j0+tid] = lsy; }
+}
+
+// FFNN w1o block of the same product: part[chunk][.][NM+M+j] = sum_k conj(L_kj) z_k (a [K][M] GEMV, too thin for the tensor
+// cores), and sum_k |L_kj|^2 for the setup slice.  Same chunks / slices / output planes as spin_cols_dmma_kernel.
+#define NQS_LB_THREADS 128
+__global__ void __launch_bounds__(NQS_LB_THREADS) ffnn_lblock_kernel(const ColsArgs a)
+{
+  if (a.done != nullptr && *a.done) return;
+  const int M = a.M, j = blockIdx.x*NQS_LB_THREADS+threadIdx.x;
+  const bool ones = (a.zmode == 1 && blockIdx.z == 0);
+  const long long k0 = (long long)blockIdx.y*a.rows_per_chunk;
+  const long long k1 = (k0+a.rows_per_chunk < a.K) ? k0+a.rows_per_chunk : a.K;
+  if (j >= M) return;
+  double lx = 0.0, ly = 0.0, l2 = 0.0;
+  long long k = k0;
+  for (; k+8 <= k1; k += 8)
+  {
+    cd l[8], z[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { l[u] = a.L[(k+u)*M+j]; z[u] = ones ? cmake(1.0, 0.0) : a.zk[k+u]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { lx += l[u].x*z[u].x+l[u].y*z[u].y; ly += l[u].x*z[u].y-l[u].y*z[u].x; l2 += cnorm(l[u]); }
+  }
+  for (; k < k1; ++k)
+  {
+    const cd l = a.L[k*M+j], z = ones ? cmake(1.0, 0.0) : a.zk[k];
+    lx += l.x*z.x+l.y*z.y; ly += l.x*z.y-l.y*z.x; l2 += cnorm(l);
+  }
+  const long long P = a.P, NM = (long long)a.N*M;
+  double * base = a.part+(size_t)blockIdx.z*(size_t)a.part_stride+(size_t)blockIdx.y*2*(size_t)P;
+  base[NM+M+j] = lx; base[P+NM+M+j] = ly;
+  if (ones) a.abs2[(size_t)blockIdx.y*3*M+2*M+j] = l2;
 }
 
 // SR setup sums from the two slices of spin_cols_dmma_kernel (zmode = 1), chunks folded in fixed order:
