@@ -71,6 +71,38 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 __device__ __forceinline__ cd warp_sum(cd v) { return cmake(warp_sum(v.x), warp_sum(v.y)); }
 
+// ---- mbarrier / TMA bulk-copy primitives (sm_90+ PTX) shared by the pipelined kernels (sv_fused.cuh, fast_kernels.cuh) ----
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t * bar, const uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, const uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, const uint32_t parity)
+{ // try_wait suspends the thread in hardware (up to the time hint) and wakes it when the phase completes: no busy polling
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// 1-D TMA bulk copy global -> this CTA's shared memory, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void * dst, const void * src, const uint32_t bytes, uint64_t * bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+    :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- Philox4x32-10 counter RNG (Salmon et al. SC'11); restated in oracle/nqs_oracle.py:philox4x32_10 ----------------
 __host__ __device__ __forceinline__ void philox_round(uint32_t c[4], uint32_t k0, uint32_t k1)
 {

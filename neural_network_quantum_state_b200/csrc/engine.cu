@@ -291,7 +291,7 @@ template <int JPL, int C>
 void launch_sweep_fast_t(nqs_handle * h, const FastSweepArgs & a)
 {
   const int warps = 4;
-  const size_t smem = fast_sweep_smem_bytes(h->N, C, warps);
+  const size_t smem = fast_sweep_smem_bytes(h->N, C, warps, h->mpad);
   set_smem(rbm_sweep_fast_kernel<JPL, C>, smem);
   const long long per_cta = (long long)warps*C;
   rbm_sweep_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);

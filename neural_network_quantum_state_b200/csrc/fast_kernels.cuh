@@ -23,7 +23,7 @@ namespace nqs
 {
 // Tables are split into 16-byte halves so that a warp's access is one fully coalesced LDG.128 per half (a 32-byte struct
 // read with 8-byte loads costs 4x the L1 wavefronts -- measured, profiles/r1b_fast_kernels.md).
-//   ftab_a = (cosh 2 Re W, sinh 2 Re W)   ftab_b = (cos 2 Im W, sin 2 Im W)
+//   ftab_a = (cosh 4 Re W, sinh 4 Re W)   ftab_b = (cos 4 Im W, sin 4 Im W)
 //   ctab_a = cosh(2W)                      ctab_b = sinh(2W)
 typedef double2 FlipTab;
 typedef double2 CoshTab;
@@ -47,7 +47,11 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     double s, co;
     sincos(2.0*w.y, &s, &co);
     const double ch = 0.5*(ex+emx), sh = sinh(2.0*w.x);
-    ftab_a[idx] = make_double2(ch, sh); ftab_b[idx] = make_double2(co, s);
+    { // the sweep carries the DOUBLE angles (cosh 2x, sinh 2x, cos 2y, sin 2y): its flip tables are those of 4W
+      double s4, c4;
+      sincos(4.0*w.y, &s4, &c4);
+      ftab_a[idx] = make_double2(cosh(4.0*w.x), sinh(4.0*w.x)); ftab_b[idx] = make_double2(c4, s4);
+    }
     ctab_a[idx] = make_double2(ch*co, sh*s); ctab_b[idx] = make_double2(sh*co, ch*s);
     w2[idx] = cmake(2.0*w.x, 2.0*w.y);
     if (j < M)
@@ -133,10 +137,16 @@ struct FastSweepArgs
   unsigned char * acc_log;
 };
 
-inline size_t fast_sweep_smem_bytes(int N, int C, int warps)
+// The flip-table rows of the next proposals are staged in shared memory by TMA bulk copies (one 2 x Mpad x 16 B row pair per
+// proposal, shared by the warps of the CTA) through a ring of NQS_SW_STAGES slots with full / empty mbarriers: the sweep walks
+// a fixed site order, so the loads are issued NQS_SW_STAGES - 1 proposals ahead and the table reads in the loop are LDS.128
+// instead of L1-missing LDG (29 % long-scoreboard stalls before, profiles/r1e_sampler_full_summary.md).
+#define NQS_SW_STAGES 4
+inline size_t fast_sweep_smem_bytes(int N, int C, int warps, int Mpad)
 {
   const size_t npad = (size_t)((N+15)/16)*16;
-  return (size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int);
+  const size_t head = ((size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int)+15)/16*16;
+  return head+(size_t)NQS_SW_STAGES*2*Mpad*sizeof(FlipTab)+(size_t)2*NQS_SW_STAGES*sizeof(uint64_t);
 }
 
 // (mantissa, exponent) products of C chains reduced over the 32 lanes with a TRANSPOSING butterfly: after the first
@@ -196,11 +206,16 @@ __device__ __forceinline__ void reduce_me_transposed(double (&m)[C], int (&e)[C]
   }
 }
 
-// State per (chain, hidden unit), in registers: (sinh x, cosh x, cos y, sin y) of theta = x + i y.  Table per (site, hidden
-// unit): ftab_a = (cosh 2ReW, sinh 2ReW), ftab_b = (cos 2ImW, sin 2ImW).  A flip of a spin sigma maps theta -> theta - 2 sigma W:
-//   sinh x' = sinh x cosh 2ReW - sigma cosh x sinh 2ReW        cos y' = cos y cos 2ImW + sigma sin y sin 2ImW
-//   |cosh theta'|^2 = sinh^2 x' + cos^2 y'
-// sigma enters as ONE sign-bit XOR per product (no selects): 7 fp64 instructions + 2 integer XORs per (proposal, chain, unit).
+// State per (chain, hidden unit), in registers: the DOUBLE angles (cosh 2x, sinh 2x, cos 2y, sin 2y) of theta = x + i y, because
+//   2 |cosh theta|^2 = cosh 2x + cos 2y .
+// Table per (site, hidden unit): ftab_a = (cosh 4ReW, sinh 4ReW), ftab_b = (cos 4ImW, sin 4ImW).  A flip of a spin sigma maps
+// theta -> theta - 2 sigma W, i.e. 2x -> 2x - 4 sigma ReW, 2y -> 2y - 4 sigma ImW:
+//   2 |cosh theta'|^2 = [cosh 2x cosh 4ReW + cos 2y cos 4ImW] + sigma [sin 2y sin 4ImW - sinh 2x sinh 4ReW] = A + sigma B
+// sigma enters as ONE fp64 register per chain in the last FMA: 6 fp64 instructions and no integer work per (proposal, chain,
+// unit).  (The earlier (sinh x, cosh x, cos y, sin y) form needed 7 + two sign-bit XORs that each cost a LOP3 and a MOV to
+// rebuild the register pair: as many integer as fp64 instructions in the loop -- SASS histogram, profiles/r1h_sweep_sass.md.)
+// Every factor carries the constant 2, so the product of a chain carries 2^Mpad: the tracked reference product R0 starts with
+// the same factor and inherits it at every accept, and the ratio never sees it.
 template <int JPL, int C>
 __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs a)
 {
@@ -212,7 +227,20 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
   int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*C*npad;                         // [C][npad]
   int8_t * rec = reinterpret_cast<int8_t*>(smem_raw)+(size_t)warps*C*npad+(size_t)w*C*N;      // [N][C]: 0 rejected, +-1 = accepted flip of a spin that was +-1
   int * ord = reinterpret_cast<int*>(smem_raw+(size_t)warps*C*npad+(size_t)warps*C*N);
+  const size_t head = ((size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int)+15)/16*16;
+  FlipTab * stage0 = reinterpret_cast<FlipTab*>(smem_raw+head);                      // [NQS_SW_STAGES][2][Mpad]
+  uint64_t * full = reinterpret_cast<uint64_t*>(stage0+(size_t)NQS_SW_STAGES*2*Mpad); // [NQS_SW_STAGES] TMA arrival
+  uint64_t * empty = full+NQS_SW_STAGES;                                              // [NQS_SW_STAGES] every active warp is done
   for (int i = threadIdx.x; i < N; i += blockDim.x) ord[i] = a.order[i];
+  const long long kblock = (long long)blockIdx.x*warps*C;
+  if (threadIdx.x == 0)
+  {
+    long long nact = (a.K-kblock+C-1)/C;                  // warps of this CTA that own at least one chain
+    if (nact > warps) nact = warps;
+    if (nact < 1) nact = 1;
+    for (int q = 0; q < NQS_SW_STAGES; ++q) { mbar_init(full+q, 1); mbar_init(empty+q, (uint32_t)nact); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   const long long kbase = ((long long)blockIdx.x*warps+w)*C;
   if (kbase >= a.K) return;
@@ -239,18 +267,31 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
     const double v = 2.0*(l0.x-s0.x)*1.4426950408889634;
     const double fl = floor(v);
     r0m = exp2(v-fl);
-    r0e = (int)fmax(fmin(fl, 100000.0), -100000.0);
+    r0e = (int)fmax(fmin(fl, 100000.0), -100000.0)+Mpad;   // every factor of the products below carries a 2
   }
   __syncwarp();
   int pos = a.pos0;
   long long t_glob = 0;
   const long long t_end = (long long)a.nsweeps*N;
+  const uint32_t row_bytes = (uint32_t)(Mpad*sizeof(FlipTab));
+  // producer (lane 0 of warp 0): table rows of proposal q -> slot q % NQS_SW_STAGES
+  auto issue_rows = [&](const long long q)
+  {
+    const int sq = ord[(int)(((long long)a.pos0+q)%N)];
+    const int slot = (int)(q%NQS_SW_STAGES);
+    FlipTab * dst = stage0+(size_t)slot*2*Mpad;
+    mbar_expect_tx(full+slot, 2*row_bytes);
+    tma_load_1d(dst, a.ftab_a+(size_t)sq*Mpad, row_bytes, full+slot);
+    tma_load_1d(dst+Mpad, a.ftab_b+(size_t)sq*Mpad, row_bytes, full+slot);
+  };
+  if (w == 0 && lane == 0)
+    for (long long q = 0; q < NQS_SW_STAGES-1 && q < t_end; ++q) issue_rows(q);
   double ubuf = 0.0;                           // uniform of proposal (t_glob rounded down to G) + lane%G of chain myc
 
   for (int sweep = 0; sweep < a.nsweeps; ++sweep)
   {
     // ---- (1) rebuild the multiplicative state from the exact theta
-    double S[C][JPL], Ch[C][JPL], cy[C][JPL], sy[C][JPL];
+    double S[C][JPL], Ch[C][JPL], cy[C][JPL], sy[C][JPL];     // sinh 2x, cosh 2x, cos 2y, sin 2y
 #pragma unroll
     for (int c = 0; c < C; ++c)
     {
@@ -261,9 +302,9 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         const int j = lane+32*jj;
         cd th = cmake(0.0, 0.0);
         if (j < M) th = a.theta[k*M+j];
-        const double ex = exp(th.x), emx = 1.0/ex;
+        const double ex = exp(2.0*th.x), emx = 1.0/ex;
         S[c][jj] = 0.5*(ex-emx); Ch[c][jj] = 0.5*(ex+emx);
-        sincos(th.y, &sy[c][jj], &cy[c][jj]);
+        sincos(2.0*th.y, &sy[c][jj], &cy[c][jj]);
       }
     }
     const int pos_sweep0 = pos;
@@ -279,22 +320,39 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
       }
       const int site = ord[pos];
       pos = (pos+1 == N) ? 0 : pos+1;
-      const FlipTab * trow_a = a.ftab_a+(size_t)site*Mpad+lane;
-      const FlipTab * trow_b = a.ftab_b+(size_t)site*Mpad+lane;
+      const int slot = (int)(t_glob&(NQS_SW_STAGES-1));
+      if (w == 0 && lane == 0)
+      { // keep NQS_SW_STAGES - 1 proposals in flight: the slot of proposal t_glob - 1 is refilled once every warp released it
+        const long long q = t_glob+NQS_SW_STAGES-1;
+        if (q < t_end)
+        {
+          if (t_glob > 0) mbar_wait(empty+(int)(q&(NQS_SW_STAGES-1)), (uint32_t)(((t_glob-1)/NQS_SW_STAGES)&1));
+          issue_rows(q);
+        }
+      }
+      mbar_wait(full+slot, (uint32_t)((t_glob/NQS_SW_STAGES)&1));
+      const FlipTab * trow_a = stage0+(size_t)slot*2*Mpad+lane;
+      const FlipTab * trow_b = trow_a+Mpad;
       int smask[C];                              // sign bit of sigma
+      double sg[C];                              // sigma
       double prod[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) { smask[c] = (sp[c*npad+site] < 0) ? (int)0x80000000 : 0; prod[c] = 1.0; }
+      for (int c = 0; c < C; ++c)
+      {
+        smask[c] = (sp[c*npad+site] < 0) ? (int)0x80000000 : 0;
+        sg[c] = smask[c] ? -1.0 : 1.0;
+        prod[c] = 1.0;
+      }
 #pragma unroll
       for (int jj = 0; jj < JPL; ++jj)
       {
-        const double2 Ta = ld_tab(trow_a+32*jj), Tb = ld_tab(trow_b+32*jj);
+        const double2 Ta = trow_a[32*jj], Tb = trow_b[32*jj];
 #pragma unroll
         for (int c = 0; c < C; ++c)
         {
-          const double shp = fma(-flip_sign(Ch[c][jj], smask[c]), Ta.y, S[c][jj]*Ta.x);
-          const double cyp = fma(flip_sign(sy[c][jj], smask[c]), Tb.y, cy[c][jj]*Tb.x);
-          prod[c] *= fma(shp, shp, cyp*cyp);
+          const double A = fma(cy[c][jj], Tb.x, Ch[c][jj]*Ta.x);
+          const double B = fma(sy[c][jj], Tb.y, -(S[c][jj]*Ta.y));
+          prod[c] *= fma(sg[c], B, A);
         }
       }
       double pm[C]; int pe[C];
@@ -334,24 +392,24 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         for (int c = 0; c < C; ++c)
           if (acc[c])
           {
-            const double sg = smask[c] ? -2.0 : 2.0;
-            sa[c] = cmake(sa[c].x-sg*ai.x, sa[c].y-sg*ai.y);
+            const double two_s = smask[c] ? -2.0 : 2.0;
+            sa[c] = cmake(sa[c].x-two_s*ai.x, sa[c].y-two_s*ai.y);
             any_acc[c] = true;
           }
 #pragma unroll
         for (int jj = 0; jj < JPL; ++jj)
         {
-          const double2 Ta = ld_tab(trow_a+32*jj), Tb = ld_tab(trow_b+32*jj);
+          const double2 Ta = trow_a[32*jj], Tb = trow_b[32*jj];
 #pragma unroll
           for (int c = 0; c < C; ++c)
           {
             if (acc[c])
             {
               const double s0 = S[c][jj], c0 = Ch[c][jj], y0 = cy[c][jj], y1 = sy[c][jj];
-              S[c][jj] = fma(-flip_sign(c0, smask[c]), Ta.y, s0*Ta.x);
-              Ch[c][jj] = fma(-flip_sign(s0, smask[c]), Ta.y, c0*Ta.x);
-              cy[c][jj] = fma(flip_sign(y1, smask[c]), Tb.y, y0*Tb.x);
-              sy[c][jj] = fma(-flip_sign(y0, smask[c]), Tb.y, y1*Tb.x);
+              S[c][jj] = fma(-sg[c], c0*Ta.y, s0*Ta.x);
+              Ch[c][jj] = fma(-sg[c], s0*Ta.y, c0*Ta.x);
+              cy[c][jj] = fma(sg[c], y1*Tb.y, y0*Tb.x);
+              sy[c][jj] = fma(-sg[c], y0*Tb.y, y1*Tb.x);
             }
           }
         }
@@ -364,6 +422,7 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         }
       }
       __syncwarp();
+      if (lane == 0) mbar_arrive(empty+slot);      // this warp is done with the table rows of the proposal
     }
     // ---- (3) replay the accepted flips of this sweep on the exact theta, in order (bit-identical to the generic kernel)
     {
@@ -543,6 +602,9 @@ __global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs 
     int smask[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) smask[c] = (ok && sp[c*npad+i] < 0) ? (int)0x80000000 : 0;
+    double sg[C];                                // sigma of this lane's site: one fp64 register instead of sign-bit XORs
+#pragma unroll
+    for (int c = 0; c < C; ++c) sg[c] = smask[c] ? -1.0 : 1.0;
     double p0x[C], p0y[C], p1x[C], p1y[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { p0x[c] = 1.0; p0y[c] = 0.0; p1x[c] = 1.0; p1y[c] = 0.0; }
@@ -557,17 +619,15 @@ __global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs 
       for (int c = 0; c < C; ++c)
       {
         const cd t0 = Tsh[c*M+j], t1 = Tsh[c*M+j+1];
-        { // f = cosh2W - (s tanh) sinh2W ; p0 *= f
-          const double tr = flip_sign(t0.x, smask[c]), ti = flip_sign(t0.y, smask[c]);
-          const double fr = fma(ti, s0.y, fma(-tr, s0.x, c0.x));
-          const double fi = fma(-ti, s0.x, fma(-tr, s0.y, c0.y));
+        { // f = cosh2W - sigma (tanh sinh2W) ; p0 *= f
+          const double gr = fma(-t0.y, s0.y, t0.x*s0.x), gi = fma(t0.y, s0.x, t0.x*s0.y);
+          const double fr = fma(-sg[c], gr, c0.x), fi = fma(-sg[c], gi, c0.y);
           const double nr = fma(p0x[c], fr, -p0y[c]*fi), ni = fma(p0x[c], fi, p0y[c]*fr);
           p0x[c] = nr; p0y[c] = ni;
         }
         {
-          const double tr = flip_sign(t1.x, smask[c]), ti = flip_sign(t1.y, smask[c]);
-          const double fr = fma(ti, s1.y, fma(-tr, s1.x, c1.x));
-          const double fi = fma(-ti, s1.x, fma(-tr, s1.y, c1.y));
+          const double gr = fma(-t1.y, s1.y, t1.x*s1.x), gi = fma(t1.y, s1.x, t1.x*s1.y);
+          const double fr = fma(-sg[c], gr, c1.x), fi = fma(-sg[c], gi, c1.y);
           const double nr = fma(p1x[c], fr, -p1y[c]*fi), ni = fma(p1x[c], fi, p1y[c]*fr);
           p1x[c] = nr; p1y[c] = ni;
         }
@@ -580,9 +640,8 @@ __global__ void __launch_bounds__(256) rbm_eloc_sites_kernel(const FastElocArgs 
       for (int c = 0; c < C; ++c)
       {
         const cd t0 = Tsh[c*M+j];
-        const double tr = flip_sign(t0.x, smask[c]), ti = flip_sign(t0.y, smask[c]);
-        const double fr = fma(ti, s0.y, fma(-tr, s0.x, c0.x));
-        const double fi = fma(-ti, s0.x, fma(-tr, s0.y, c0.y));
+        const double gr = fma(-t0.y, s0.y, t0.x*s0.x), gi = fma(t0.y, s0.x, t0.x*s0.y);
+        const double fr = fma(-sg[c], gr, c0.x), fi = fma(-sg[c], gi, c0.y);
         const double nr = fma(p0x[c], fr, -p0y[c]*fi), ni = fma(p0x[c], fi, p0y[c]*fr);
         p0x[c] = nr; p0y[c] = ni;
       }

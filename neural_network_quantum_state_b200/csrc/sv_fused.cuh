@@ -30,30 +30,6 @@ namespace nqs
 {
 namespace cg = cooperative_groups;
 
-__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t * bar, const uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, const uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t * bar, const uint32_t parity)
-{ // try_wait suspends the thread in hardware (up to the time hint) and wakes it when the phase completes: no busy polling
-  const uint32_t addr = smem_u32(bar);
-  uint32_t ok;
-  do
-  {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t * bar)
-{
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ uint32_t map_to_rank(const void * local, const uint32_t rank)
 {
   uint32_t r;
@@ -69,13 +45,6 @@ __device__ __forceinline__ void st_async_remote_cd(const uint32_t remote_addr, c
   asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];"
     :: "r"(remote_addr), "d"(v.x), "d"(v.y), "r"(remote_bar) : "memory");
 }
-// 1-D TMA bulk copy global -> this CTA's shared memory, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load_1d(void * dst, const void * src, const uint32_t bytes, uint64_t * bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-    :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
 struct SvArgs
 {
   long long K, P;

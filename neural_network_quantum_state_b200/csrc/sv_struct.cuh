@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(NQS_DR_THREADS, 1) spin_rows_dmma_kernel(const
           rsum[m].x = fma(acc[m][n][1], srow[1], rsum[m].x);
         }
       }
-      continue;
     }
+    else
 #pragma unroll
     for (int n = 0; n < NTW; ++n)
     {
