@@ -189,6 +189,8 @@ def main():
     ap.add_argument("--cg-fixed-iters", type=int, default=0, help="diagnostics: run exactly this many CG iterations per step")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: ncclAllReduce per CG iteration instead of the in-kernel exchange")
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
+    ap.add_argument("--no-structured-extra", action="store_true",
+                    help="skip the second, separately reported measurement of the same step with NQS_FLAG_STRUCTURED_SV (1 GPU only)")
     ap.add_argument("--structured-sv", action="store_true",
                     help="S*v from the factors of O as two fp64 tensor-core GEMMs (no O matrix); roofline is then the fp64 tensor pipe")
     args = ap.parse_args()
@@ -399,6 +401,50 @@ def main():
             "cg_iters_per_step": cg_iters,
             "cg_ms_per_iter": (phase["cg_ms"] / max(sum(cg_iters) + len(cg_iters), 1)),
             "energy_per_site": energies}
+    if world == 1 and not args.structured_sv and not args.no_structured_extra:
+        # the same step with S*v formed from the factors of O on the fp64 tensor cores (no O matrix): reported NEXT TO the
+        # headline, which stays on the explicit-O formulation the reference and the north star are stated on
+        try:
+            e2 = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
+                        n_chains_total=K_total, chain_offset=0, structured_sv=True)
+            e2.set_params(synthetic_params(model, N, M, cfg_id))
+            e2.warm_up(args.nwarm)
+            for _ in range(args.warmup):
+                e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
+            e2.set_timing(True)
+            e2.sync()
+            ph2 = {k: 0.0 for k in phase}
+            cnt2 = {"rows_count": 0, "cols_count": 0}
+            it2, en2 = [], []
+            e2.event_record(0)
+            for _ in range(args.steps):
+                st = e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
+                it2.append(st.cg_iters)
+                en2.append(st.e_mean.real)
+                t = e2.get_timing()
+                for k in ph2:
+                    ph2[k] += t[k]
+                for k in cnt2:
+                    cnt2[k] += t[k]
+            e2.event_record(1)
+            e2.sync()
+            ms2 = e2.event_elapsed_ms(0, 1) / args.steps
+            flops = 2.0 * K_loc * N * 2 * M
+            r_ms = ph2["rows_ms"] / max(cnt2["rows_count"], 1)
+            c_ms = ph2["cols_ms"] / max(cnt2["cols_count"], 1)
+            line["structured_sv"] = {
+                "value": K_total / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "variant": e2.kernel_variant("sv"),
+                "phase_ms_per_step": {k: v / args.steps for k, v in ph2.items()}, "cg_iters_per_step": it2,
+                "energy_per_site": en2,
+                "gemm": {"flops_per_launch": flops, "rows_ms": r_ms, "cols_ms": c_ms,
+                         "rows_tflops": flops / (r_ms * 1e-3) / 1e12 if r_ms > 0 else None,
+                         "cols_tflops": flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else None,
+                         "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS},
+                "note": "opt-in NQS_FLAG_STRUCTURED_SV: O^H(O v) as two real-by-complex GEMMs on the factors of O (mma.sync m8n8k4 f64); "
+                        "O is never written; same energies as the headline run to rounding"}
+            e2.close()
+        except Exception as ex:
+            line["structured_sv"] = {"value": None, "error": str(ex)}
     if not args.no_cpu_baseline and world == 1:
         try:
             res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=5)

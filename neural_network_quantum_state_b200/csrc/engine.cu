@@ -290,7 +290,7 @@ bool fast_path_ok(nqs_handle * h)
 template <int JPL, int C>
 void launch_sweep_fast_t(nqs_handle * h, const FastSweepArgs & a)
 {
-  const int warps = 4;
+  const int warps = SweepShape<JPL, C>::warps;
   const size_t smem = fast_sweep_smem_bytes(h->N, C, warps, h->mpad);
   set_smem(rbm_sweep_fast_kernel<JPL, C>, smem);
   const long long per_cta = (long long)warps*C;
@@ -313,7 +313,7 @@ void launch_eloc_fast(nqs_handle * h)
   a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.Jmat = h->Jmat.p;
   a.hfield = h->cfg.h; a.htilda = h->htilda.p;
   a.sjs = launch_sjs(h);
-  launch_eloc_sites_t<4>(h, a);
+  launch_eloc_sites_t<4>(h, a);     // chains per CTA: 2 -> 0.77 ms, 4 -> 0.59 ms, 8 -> 0.62 ms at cfg3
   check_launch(h, "rbm_eloc_sites_kernel");
 }
 

@@ -216,8 +216,11 @@ __device__ __forceinline__ void reduce_me_transposed(double (&m)[C], int (&e)[C]
 // rebuild the register pair: as many integer as fp64 instructions in the loop -- SASS histogram, profiles/r1h_sweep_sass.md.)
 // Every factor carries the constant 2, so the product of a chain carries 2^Mpad: the tracked reference product R0 starts with
 // the same factor and inherits it at every accept, and the ratio never sees it.
+// CTA shapes: one chain per warp with at most 8 hidden-unit slots per lane fits 128 registers and runs 8 warps per CTA (16 per SM);
+// everything else runs 4 warps per CTA, 2 CTAs per SM, at up to 255 registers.
+template <int JPL, int C> struct SweepShape { static constexpr int warps = (C == 1 && JPL <= 8) ? 8 : 4; };
 template <int JPL, int C>
-__global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs a)
+__global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fast_kernel(const FastSweepArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int G = 32/C;                      // lanes per chain group (owner lanes of a chain's accept decision)
@@ -386,7 +389,7 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
         }
       }
       if (bal != 0u)
-      { // (a warp-uniform branch per accepted chain instead of predication was measured slower: 2.71 vs 2.60 ms)
+      { // (with the table rows in shared memory a warp-uniform branch per accepted chain beats predication: no select / move per state register)
         const cd ai = avis[site];
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -396,20 +399,22 @@ __global__ void __launch_bounds__(128) rbm_sweep_fast_kernel(const FastSweepArgs
             sa[c] = cmake(sa[c].x-two_s*ai.x, sa[c].y-two_s*ai.y);
             any_acc[c] = true;
           }
+        // warp-uniform branch per accepted chain: in-place state update without predicated moves (tables re-read from smem)
 #pragma unroll
-        for (int jj = 0; jj < JPL; ++jj)
+        for (int c = 0; c < C; ++c)
         {
-          const double2 Ta = trow_a[32*jj], Tb = trow_b[32*jj];
-#pragma unroll
-          for (int c = 0; c < C; ++c)
+          if (acc[c])
           {
-            if (acc[c])
+#pragma unroll
+            for (int jj = 0; jj < JPL; ++jj)
             {
+              const double2 Ta = trow_a[32*jj], Tb = trow_b[32*jj];
               const double s0 = S[c][jj], c0 = Ch[c][jj], y0 = cy[c][jj], y1 = sy[c][jj];
-              S[c][jj] = fma(-sg[c], c0*Ta.y, s0*Ta.x);
-              Ch[c][jj] = fma(-sg[c], s0*Ta.y, c0*Ta.x);
-              cy[c][jj] = fma(sg[c], y1*Tb.y, y0*Tb.x);
-              sy[c][jj] = fma(-sg[c], y0*Tb.y, y1*Tb.x);
+              const double tys = sg[c]*Ta.y, tbs = sg[c]*Tb.y;       // sigma folded into the table entry: 10 fp64 per unit
+              S[c][jj] = fma(-c0, tys, s0*Ta.x);
+              Ch[c][jj] = fma(-s0, tys, c0*Ta.x);
+              cy[c][jj] = fma(y1, tbs, y0*Tb.x);
+              sy[c][jj] = fma(-y0, tbs, y1*Tb.x);
             }
           }
         }
