@@ -273,32 +273,33 @@ def main():
     def step():
         return e.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
 
+    def restart():
+        """Same optimisation iterations in every measured loop (lambda decays from step to step and the CG iteration count grows
+        with it): parameters, lambda schedule and CG warm start reset, chains re-warmed, W untimed steps."""
+        e.set_params(synthetic_params(model, N, M, cfg_id))
+        e.sr_reset()
+        e.warm_up(args.nwarm)
+        for _ in range(args.warmup):
+            step()
+
+    # ---- (1) the timed region: K steps, no per-kernel instrumentation, CUDA events on the engine's stream around the loop
     for _ in range(args.warmup):
         step()
-    e.set_timing(True)
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
     launches0 = e.get_timing()["kernel_launches"]
-    phase = {k: 0.0 for k in ("sweep_ms", "eloc_ms", "oderiv_ms", "setup_ms", "cg_ms", "update_ms", "rows_ms", "cols_ms")}
-    counts = {"rows_count": 0, "cols_count": 0}
     cg_iters, energies = [], []
     e.event_record(0)
     for _ in range(args.steps):
         st = step()
         cg_iters.append(st.cg_iters)
         energies.append(st.e_mean.real)
-        t = e.get_timing()
-        for k in phase:
-            phase[k] += t[k]
-        for k in counts:
-            counts[k] += t[k]
     e.event_record(1)
     barrier()
     ms_total = e.event_elapsed_ms(0, 1)
     clock_info = clocks.stop()
     launches = e.get_timing()["kernel_launches"] - launches0
-    e.set_timing(False)
     if world > 1:
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -306,6 +307,28 @@ def main():
     ms_per_step = ms_total / args.steps
     value = K_total / (ms_per_step * 1e-3)
     config["cg_exchange"] = "none (1 GPU)" if world == 1 else ("in-kernel all-reduce over NVLink peer memory" if p2p else "ncclAllReduce")
+
+    # ---- (2) the same K steps again with a CUDA-event pair around every phase and every S*v launch (phase times, roofline).
+    # The ~40 extra event records per step cost ~0.15 ms (they break back-to-back launches), which is why they stay out of (1).
+    restart()
+    e.set_timing(True)
+    barrier()
+    phase = {k: 0.0 for k in ("sweep_ms", "eloc_ms", "oderiv_ms", "setup_ms", "cg_ms", "update_ms", "rows_ms", "cols_ms")}
+    counts = {"rows_count": 0, "cols_count": 0}
+    cg_iters_inst = []
+    e.event_record(2)
+    for _ in range(args.steps):
+        st = step()
+        cg_iters_inst.append(st.cg_iters)
+        t = e.get_timing()
+        for k in phase:
+            phase[k] += t[k]
+        for k in counts:
+            counts[k] += t[k]
+    e.event_record(3)
+    barrier()
+    ms_per_step_inst = e.event_elapsed_ms(2, 3) / args.steps
+    e.set_timing(False)
 
     # ---- end-to-end through the public API with HOST buffers: pinned uniforms H2D every step, spins + lnpsi + stats D2H
     e2e = None
@@ -317,11 +340,14 @@ def main():
         u_bufs = [torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True) for _ in range(n_e2e)]
         for ub in u_bufs:
             ub.numpy()[...] = rng.random((N, K_loc))
+        restart()
+        e2e_iters = []
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
             e.set_uniforms(u_bufs[i].numpy())   # H2D inside the timed region
             st = step()
+            e2e_iters.append(st.cg_iters)
             spins = e.get_spinStates()          # D2H: what a pynqs user reads back
             lnpsi = e.get_lnpsi()
         barrier()
@@ -333,6 +359,7 @@ def main():
         e.set_uniforms(None)
         e2e = {"value": K_total / dt, "unit": UNIT, "h2d_bytes_per_step": int(u_bufs[0].numpy().nbytes) * world,
                "d2h_bytes_per_step": int(spins.nbytes + lnpsi.nbytes + 56) * world, "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "cg_iters_per_step": e2e_iters,
                "api": "Engine.set_uniforms + Engine.sr_step + get_spinStates + get_lnpsi (C ABI, host buffers)"}
 
     if rank != 0:
@@ -399,7 +426,11 @@ def main():
                       "kernel": e.kernel_variant("sweep")},
             "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "cg_iters_per_step": cg_iters,
-            "cg_ms_per_iter": (phase["cg_ms"] / max(sum(cg_iters) + len(cg_iters), 1)),
+            "cg_ms_per_iter": (phase["cg_ms"] / max(sum(cg_iters_inst) + len(cg_iters_inst), 1)),
+            "instrumented_pass": {"ms_per_step": ms_per_step_inst, "cg_iters_per_step": cg_iters_inst,
+                                  "note": "phase_ms_per_step, sweep and roofline durations come from a second pass over the same K steps "
+                                          "with CUDA events around every phase and S*v launch; value / ms_per_step from the first, "
+                                          "uninstrumented pass"},
             "energy_per_site": energies}
     if world == 1 and not args.structured_sv and not args.no_structured_extra:
         # the same step with S*v formed from the factors of O on the fp64 tensor cores (no O matrix): reported NEXT TO the
@@ -407,28 +438,35 @@ def main():
         try:
             e2 = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
                         n_chains_total=K_total, chain_offset=0, structured_sv=True)
-            e2.set_params(synthetic_params(model, N, M, cfg_id))
-            e2.warm_up(args.nwarm)
-            for _ in range(args.warmup):
-                e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
-            e2.set_timing(True)
-            e2.sync()
             ph2 = {k: 0.0 for k in phase}
             cnt2 = {"rows_count": 0, "cols_count": 0}
             it2, en2 = [], []
-            e2.event_record(0)
-            for _ in range(args.steps):
-                st = e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
-                it2.append(st.cg_iters)
-                en2.append(st.e_mean.real)
-                t = e2.get_timing()
-                for k in ph2:
-                    ph2[k] += t[k]
-                for k in cnt2:
-                    cnt2[k] += t[k]
-            e2.event_record(1)
-            e2.sync()
-            ms2 = e2.event_elapsed_ms(0, 1) / args.steps
+            ms2 = None
+            for instrumented in (False, True):      # as above: headline pass without per-kernel events, then the instrumented one
+                e2.set_params(synthetic_params(model, N, M, cfg_id))
+                e2.sr_reset()
+                e2.warm_up(args.nwarm)
+                for _ in range(args.warmup):
+                    e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
+                e2.set_timing(instrumented)
+                e2.sync()
+                e2.event_record(0)
+                for _ in range(args.steps):
+                    st = e2.sr_step(n_mc_steps=1, lr=args.lr, fixed_iters=args.cg_fixed_iters)
+                    if instrumented:
+                        t = e2.get_timing()
+                        for k in ph2:
+                            ph2[k] += t[k]
+                        for k in cnt2:
+                            cnt2[k] += t[k]
+                    else:
+                        it2.append(st.cg_iters)
+                        en2.append(st.e_mean.real)
+                e2.event_record(1)
+                e2.sync()
+                if not instrumented:
+                    ms2 = e2.event_elapsed_ms(0, 1) / args.steps
+            e2.set_timing(False)
             flops = 2.0 * K_loc * N * 2 * M
             r_ms = ph2["rows_ms"] / max(cnt2["rows_count"], 1)
             c_ms = ph2["cols_ms"] / max(cnt2["cols_count"], 1)

@@ -196,6 +196,10 @@ class Engine:
         self._chk(self.lib.nqs_sr_step(self._h, C.byref(opt), C.byref(st)))
         return SRResult(complex(st.e_re, st.e_im), st.rsd, st.lam, int(st.cg_iters), bool(st.finite), st.cg_res2, st.cg_rhs2)
 
+    def sr_reset(self):
+        """New optimisation run: lambda schedule back to its start, CG warm start zeroed (ref: a fresh StochasticReconfigurationCG)."""
+        self._chk(self.lib.nqs_sr_reset(self._h))
+
     def get_sr_vectors(self):
         F = np.empty(self.P, dtype=np.complex128)
         dx = np.empty(self.P, dtype=np.complex128)
