@@ -36,6 +36,7 @@ CONFIGS = {
     "cfg2": ("rbm", 64, 128, 4096),
     "cfg3": ("rbm", 128, 256, 16384),
     "cfg4": ("ffnn", 128, 512, 8192),
+    "cfg5": ("rbm", 256, 1024, 65536),     # 276 GB of O: explicit-O mode needs >= 2 GPUs (138 GB per rank), 8 GPUs -> 34.5 GB per rank
 }
 THETA_H = math.pi / 4
 H_FIELD, J_COUP, ALPHA_LR = -math.cos(THETA_H), math.sin(THETA_H), 2.0
@@ -180,6 +181,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--k-total", type=int, default=0, help="diagnostics: override the number of chains of the configuration")
     ap.add_argument("--nwarm", type=int, default=100, help="warm-up sweeps before the benchmark (reference default -nwarm)")
     ap.add_argument("--lr", type=float, default=1e-2)
     ap.add_argument("--cpu-sample-chains", type=int, default=256)
@@ -209,6 +211,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     model, N, M, K_total = CONFIGS[args.config]
+    if args.k_total > 0:
+        K_total = args.k_total
     cfg_id = int(args.config[3:])
     P = N * M + N + M if model == "rbm" else N * M + 2 * M
     config = {"workload": "%s: complex %s M=%d, long-range TFI chain N=%d (alpha=2, theta=pi/4, OBC), %d chains total, "
@@ -252,6 +256,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert K_total % world == 0
     K_loc = K_total // world
+    if not args.structured_sv:
+        need = K_loc * P * 16 + 4e9
+        assert need < torch.cuda.mem_get_info()[0], \
+            "%s needs %.0f GB of HBM per rank for O: use more GPUs or --structured-sv" % (args.config, need / 1e9)
     e = Engine(model, N, M, K_loc, H_FIELD, J_COUP, ALPHA_LR, pbc=False, seed=20261018, device=local_rank,
                n_chains_total=K_total, chain_offset=rank * K_loc, max_predrawn_steps=N, force_generic=args.force_generic,
                two_pass_sv=args.two_pass_sv, structured_sv=args.structured_sv)

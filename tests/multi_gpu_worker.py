@@ -18,6 +18,7 @@ def main():
     from neural_network_quantum_state_b200.dist import ShardPlan, bootstrap_comm, enable_p2p
     from neural_network_quantum_state_b200.init import reference_init
     use_p2p = "--no-p2p" not in sys.argv
+    structured = "--structured" in sys.argv
     out_path = sys.argv[1]
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -26,7 +27,7 @@ def main():
     h, J = -math.cos(math.pi / 4), math.sin(math.pi / 4)
     params = reference_init(model, N, M, np.random.default_rng(5))
     plan = ShardPlan(K, world, rank)
-    e = Engine(model, N, M, h=h, J=J, alpha=2.0, seed=11, device=local, **plan.engine_kwargs())
+    e = Engine(model, N, M, h=h, J=J, alpha=2.0, seed=11, device=local, structured_sv=structured, **plan.engine_kwargs())
     e.set_params(params)
     bootstrap_comm(e, world, rank, p2p=False)
     p2p = enable_p2p(e, world) if use_p2p else False
@@ -40,7 +41,8 @@ def main():
     dist.all_gather_object(gathered, final.view(np.float64).tolist())
     if rank == 0:
         same = all(g == gathered[0] for g in gathered)   # replicated state must be BIT-identical on all ranks
-        json.dump({"world": world, "p2p": bool(p2p), "steps": res, "params_re_im": gathered[0], "ranks_identical": same},
+        json.dump({"world": world, "p2p": bool(p2p), "steps": res, "params_re_im": gathered[0], "ranks_identical": same,
+                   "sv": e.kernel_variant("sv")},
                   open(out_path, "w"))
     e.close()
     dist.destroy_process_group()
