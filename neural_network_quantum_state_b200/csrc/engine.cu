@@ -320,7 +320,7 @@ void launch_eloc_fast(nqs_handle * h)
 void launch_sweep(nqs_handle * h, long long nsteps)
 {
   if (nsteps <= 0) return;
-  h->theta_matches_O = false; h->hidden_valid = false;
+  h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   SweepArgs a;
   a.N = h->N; a.M = h->M; a.model = h->model; a.K = h->K; a.params = h->params.p;
   a.spins = h->spins.p; a.theta = h->theta.p; a.lnpsi0 = h->lnpsi0.p; a.sa = h->sa.p; a.fresh = h->fresh.p; a.order = h->order.p;
@@ -431,14 +431,15 @@ void launch_oderiv(nqs_handle * h, cudaStream_t stream = nullptr)
     oderiv_kernel<MODEL_FFNN><<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
   }
   check_launch(h, "oderiv_kernel");
+  h->o_pending = false;
   h->theta_matches_O = true;   // O was built from the current (spins, theta, params): the setup sums may use the factors
 }
 
 // ---- one-pass S*v (sv_fused.cuh): cluster launch + plan -------------------------------------------------------------------
-template <int CPT, int DEFER>
+template <int CPT, int DEFER, int GEN = 0>
 cudaError_t sv_launch_t(const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, int * query_max_clusters)
 {
-  auto kern = sv_fused_kernel<CPT, DEFER>;
+  auto kern = sv_fused_kernel<CPT, DEFER, GEN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (cs > 8)
@@ -474,6 +475,25 @@ cudaError_t sv_launch(int cpt, int defer, const SvArgs & a, int cs, int ncluster
     case 8: return defer ? sv_launch_t<8, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<8, 0>(a, cs, nclusters, nt, smem, stream, q);
     case 9: return defer ? sv_launch_t<9, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<9, 0>(a, cs, nclusters, nt, smem, stream, q);
     case 10: return defer ? sv_launch_t<10, 1>(a, cs, nclusters, nt, smem, stream, q) : sv_launch_t<10, 0>(a, cs, nclusters, nt, smem, stream, q);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// GEN variant (the rows of O are formed from their factors inside the kernel and written out): software-pipelined form only
+cudaError_t sv_launch_gen(int cpt, const SvArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream)
+{
+  switch (cpt)
+  {
+    case 1: return sv_launch_t<1, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 2: return sv_launch_t<2, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 3: return sv_launch_t<3, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 4: return sv_launch_t<4, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 5: return sv_launch_t<5, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 6: return sv_launch_t<6, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 7: return sv_launch_t<7, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 8: return sv_launch_t<8, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 9: return sv_launch_t<9, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
+    case 10: return sv_launch_t<10, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -578,6 +598,11 @@ void launch_hidden_values(nqs_handle * h)
   else
     hidden_values_kernel<MODEL_FFNN><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, h->Lm.p);
   check_launch(h, "hidden_values_kernel");
+  if (h->Sd.p != nullptr)
+  {
+    spins_to_double_kernel<<<grid_for((long long)h->K*h->N, 256, 148*8), 256, 0, h->stream>>>((long long)h->K*h->N, h->spins.p, h->Sd.p);
+    check_launch(h, "spins_to_double_kernel");
+  }
   h->hidden_valid = true;
   h->theta_matches_O = true;   // the factors (spins, theta, params) are what S is built from: structured setup sums allowed
 }
@@ -737,8 +762,19 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
     a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
+    a.T = h->Tm.p; a.Sd = h->Sd.p; a.Ow = h->O.p; a.N = h->N; a.M = h->M;
     Span sp(h, TAG_ROWS);
-    NQS_CUDA(sv_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
+    if (h->o_pending)
+    { // first product after the sampling phase: this launch also WRITES O (no separate O writer ran)
+      NQS_REQUIRE(done == nullptr, NQS_ERR_STATE, "the O-generating S*v cannot be skipped");
+      a.nslot = NQS_SV_MAX_SLOTS; a.slot_bytes = (unsigned int)sv_gen_slot_bytes(h->N, h->M);
+      a.depth = std::min(NQS_SV_MAX_DEPTH, (a.nslot-1)/2);
+      const size_t smem = (size_t)a.nslot*a.slot_bytes+NQS_SV_TAIL_BYTES;
+      NQS_CUDA(sv_launch_gen(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, smem, h->stream));
+      h->o_pending = false;
+    }
+    else
+      NQS_CUDA(sv_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
     check_launch(h, "sv_fused_kernel");
     nparts = h->sv_nclusters;
   }
@@ -869,7 +905,7 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
 
 void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
 {
-  h->theta_matches_O = false; h->hidden_valid = false;
+  h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
   check_launch(h, "update_params_kernel");
   h->tables_valid = false;
@@ -894,7 +930,7 @@ void do_sweeps(nqs_handle * h, int n_sweeps)
 
 void do_initialize(nqs_handle * h, const int8_t * spins_host)
 {
-  h->theta_matches_O = false; h->hidden_valid = false;
+  h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   std::vector<int8_t> s((size_t)h->K*h->N, 1);
   if (spins_host) std::memcpy(s.data(), spins_host, s.size());
   else if (h->cfg.J > 0) // Neel, ref impl_hamiltonians.cuh:196-201
@@ -942,7 +978,7 @@ void build_J(nqs_handle * h)
 void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
   h->tables_valid = false;
-  h->theta_matches_O = false; h->hidden_valid = false;
+  h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
 }
@@ -977,6 +1013,16 @@ void alloc_sr(nqs_handle * h)
   h->rows_per_block = (h->K+nrb-1)/nrb;
   h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
   if (!h->struct_sv) plan_sv(h);
+  // O generated inside the first S*v of the CG (sv_fused_kernel, GEN): RBM, one-pass kernel with the software pipeline, even N
+  // (16-byte TMA rows of the double spins), factors available.  OPT-IN (NQS_SV_GEN=1): measured at cfg3 the generating launch
+  // takes 3.5 ms -- forming 2 x 8 elements per thread and row from their factors makes the kernel issue-bound (~265 instead of
+  // ~100 warp instructions per row) -- against 1.34 ms (writer) + 1.40 ms (read pass) for the two separate kernels, so the
+  // step time does not change (15.09 vs 15.06 ms); the separate O writer stays the default.
+  { const char * ng = std::getenv("NQS_SV_GEN");
+    h->gen_ok = h->sv_ok && h->sv_defer && h->cols_ok && h->model == MODEL_RBM && h->N%2 == 0 && h->M < 65535 && h->N < 32766 &&
+      (ng && std::atoi(ng) != 0) &&
+      (size_t)NQS_SV_MAX_SLOTS*sv_gen_slot_bytes(h->N, h->M)+NQS_SV_TAIL_BYTES <= h->smem_optin;
+    if (h->gen_ok) h->Sd.alloc((size_t)h->K*h->N); }
   h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->traw.alloc((size_t)2*h->P);
@@ -1134,7 +1180,7 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
     NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
     h->tables_valid = false;
-    h->theta_matches_O = false; h->hidden_valid = false;
+    h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   });
 }
 
@@ -1433,7 +1479,10 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     // (Running the HBM-write-bound O writer on a side stream next to the fp64-bound local energy was tried: the writer's K CTAs
     // occupy every SM slot, the two kernels serialise anyway and the step time does not change.)
     { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
-    { Span t(h, TAG_ODERIV); if (h->struct_sv) launch_hidden_values(h); else launch_oderiv(h); }
+    { Span t(h, TAG_ODERIV);
+      if (h->struct_sv) launch_hidden_values(h);
+      else if (h->gen_ok) { launch_hidden_values(h); h->o_pending = true; }   // O is written by the first S*v of the CG
+      else launch_oderiv(h); }
     double hs[3];
     {
       { Span t(h, TAG_SETUP); sr_setup(h, true); }

@@ -92,6 +92,8 @@ struct nqs_handle
   // structured S*v (sv_struct.cuh, NQS_FLAG_STRUCTURED_SV): hidden-unit factors T (and L, FFNN), chain chunks of the column GEMM
   bool struct_sv = false, hidden_valid = false;
   nqs::DevBuf<nqs::cd> Tm, Lm, vnat;
+  nqs::DevBuf<double> Sd;                 // [K][N] spins as doubles: factor rows of the O-generating S*v (sv_fused.cuh, GEN)
+  bool gen_ok = false, o_pending = false; // O is written by the first S*v of the CG instead of a separate writer / it still has to be
   nqs::DevBuf<double> abs2;               // [chunks][3M] sums of |T|^2, |L|^2 of the SR setup GEMM
   bool cols_ok = false;                   // spin_cols_dmma_kernel planned (N <= 256): structured S*v and the SR setup GEMM
   int sc_variant = 0, sc_nchunks = 0, sc_colgroups = 0;

@@ -57,7 +57,17 @@ struct SvArgs
   int nslot;               // shared-memory row slots (TMA pipeline depth)
   unsigned int slot_bytes; // bytes per slot: >= CPT * consumer threads * 16 (the tail past the slice stays zero)
   int depth;               // DEFER = 1: pass (3) of row k runs after pass (2) of row k+depth (1..NQS_SV_MAX_DEPTH, <= nslot-2)
+  // GEN = 1 (RBM): the rows of O do not exist yet.  The producer stages the FACTORS of row k -- T_k = tanh(theta_k) [M] and the
+  // spins as doubles [N] -- and every consumer thread forms its elements O_kp = s_ki T_kj itself, uses them for the product
+  // and WRITES them to O (coalesced 16-byte stores): the O writer (ref RBM::backward, k13 :1426-1449) and the first S*v of the
+  // CG (S x0) cost one HBM write pass instead of a write pass plus a read pass.
+  const cd * T;            // [K][M]
+  const double * Sd;       // [K][N]
+  cd * Ow;                 // [K][P] out
+  int N, M;
 };
+// GEN slot layout: T row [M] | (1,0) | spins [N] | +1.0 | 0.0   (the three constants serve the a / b blocks and the padding)
+inline size_t sv_gen_slot_bytes(int N, int M) { return (size_t)(M+1)*16+(((size_t)(N+2)*8+15)/16)*16; }
 
 #define NQS_SV_MAX_CLUSTER 16
 #define NQS_SV_MAX_SLOTS 8
@@ -74,7 +84,7 @@ struct SvArgs
 template <int CPT> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
 
 // blockDim.x = 32*(NW+1): warps 0..NW-1 consume (NT = 32*NW threads own the columns), warp NW is the TMA producer.
-template <int CPT, int DEFER>
+template <int CPT, int DEFER, int GEN>
 __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs a)
 {
   if (a.done != nullptr && *a.done) return;   // uniform over the grid
@@ -109,6 +119,16 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
     const int nz16 = (int)(((size_t)a.nslot*a.slot_bytes)/sizeof(double2));
     for (int i = tid; i < nz16; i += blockDim.x) z[i] = make_double2(0.0, 0.0);
   }
+  if (GEN)
+  {
+    __syncthreads();
+    for (int s = tid; s < a.nslot; s += blockDim.x)
+    {
+      cd * Ts = reinterpret_cast<cd*>(smem_raw+(size_t)s*a.slot_bytes);
+      Ts[a.M] = cmake(1.0, 0.0);
+      reinterpret_cast<double*>(Ts+a.M+1)[a.N] = 1.0;
+    }
+  }
   if (tid == 0)
   {
     for (int s = 0; s < a.nslot; ++s) { mbar_init(full+s, 1); mbar_init(empty+s, (uint32_t)NW); }
@@ -129,8 +149,18 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       for (int it = 0; it < nrows; ++it)
       {
         if (it >= a.nslot) mbar_wait(empty+slot, par^1u);   // consumers released the row that used this slot before
-        mbar_expect_tx(full+slot, row_bytes);
-        tma_load_1d(smem_raw+(size_t)slot*a.slot_bytes, Oslice+(k0+it)*a.P, row_bytes, full+slot);
+        if (GEN)
+        {
+          unsigned char * dst = smem_raw+(size_t)slot*a.slot_bytes;
+          mbar_expect_tx(full+slot, (uint32_t)a.M*16u+(uint32_t)a.N*8u);
+          tma_load_1d(dst, a.T+(k0+it)*a.M, (uint32_t)a.M*16u, full+slot);
+          tma_load_1d(dst+(size_t)(a.M+1)*16, a.Sd+(k0+it)*a.N, (uint32_t)a.N*8u, full+slot);
+        }
+        else
+        {
+          mbar_expect_tx(full+slot, row_bytes);
+          tma_load_1d(smem_raw+(size_t)slot*a.slot_bytes, Oslice+(k0+it)*a.P, row_bytes, full+slot);
+        }
         if (++slot == a.nslot) { slot = 0; par ^= 1u; }
       }
     }
@@ -147,6 +177,33 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
     }
     const cd * const sbase = reinterpret_cast<const cd*>(smem_raw)+tid;
     const size_t slot_elems = a.slot_bytes/sizeof(cd);
+    // GEN: where the two factors of column c sit in a slot, packed (T index | spin index << 16)
+    int fac[GEN ? CPT : 1];
+    if (GEN)
+    {
+      const long long NM = (long long)a.N*a.M;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+      {
+        const int idx = c*NT+tid;
+        const long long p = c0+idx;
+        int tj, si;
+        if (idx >= n_r) { tj = a.M; si = a.N+1; }                              // padding: (1,0) * 0
+        else if (p < NM) { tj = (int)(p%a.M); si = (int)(p/a.M); }             // s_ki T_kj
+        else if (p < NM+a.N) { tj = a.M; si = (int)(p-NM); }                   // s_ki
+        else { tj = (int)(p-NM-a.N); si = a.N; }                               // T_kj
+        fac[GEN ? c : 0] = tj|(si<<16);
+      }
+    }
+    auto gen_o = [&](const int c, const int gslot) -> cd
+    {
+      const cd * Ts = reinterpret_cast<const cd*>(smem_raw+(size_t)gslot*a.slot_bytes);
+      const double * Sd = reinterpret_cast<const double*>(Ts+a.M+1);
+      const int f = fac[GEN ? c : 0];
+      const cd t = Ts[f&0xffff];
+      const double sp = Sd[f>>16];
+      return cmake(t.x*sp, t.y*sp);
+    };
 
     // (3) for row jt: z_k = sum of the CS partials in rank order, then acc += conj(O_kp) z_k
     auto wait_z = [&](const int jt, double & zx, double & zy)
@@ -171,7 +228,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
       {
-        const cd q = prow[c*NT];
+        const cd q = GEN ? gen_o(c, jslot) : prow[c*NT];
         acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
         acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
       }
@@ -188,8 +245,21 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       cd o[CPT];
       const cd * srow = sbase+(size_t)slot*slot_elems;
       if (n_r > 0) mbar_wait(full+slot, full_par);
+      if (GEN)
+      {
+        cd * orow = a.Ow+(k0+it)*a.P+c0+tid;
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) o[c] = srow[c*NT];
+        for (int c = 0; c < CPT; ++c)
+        {
+          o[c] = gen_o(c, slot);
+          if (c*NT+tid < n_r) orow[c*NT] = o[c];
+        }
+      }
+      else
+      {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) o[c] = srow[c*NT];
+      }
       if (DEFER == 0)
       {
         __syncwarp();

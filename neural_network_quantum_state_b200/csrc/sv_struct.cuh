@@ -50,6 +50,11 @@ __global__ void hidden_values_kernel(const int N, const int M, const long long K
   }
 }
 
+__global__ void spins_to_double_kernel(const long long n, const int8_t * __restrict__ spins, double * __restrict__ out)
+{
+  for (long long i = (long long)blockIdx.x*blockDim.x+threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) out[i] = (double)spins[i];
+}
+
 // FFNN keeps the W block of O / v transposed (j*N+i): bring it to the natural i*M+j layout once per product
 __global__ void transpose_wblock_kernel(const int N, const int M, const cd * __restrict__ v, cd * __restrict__ out, const int * __restrict__ done)
 {

@@ -12,5 +12,5 @@ PY
 }
 run cfg3_def A=1 "--config cfg3"
 run cfg3_struct A=1 "--config cfg3 --structured-sv"
-run cfg4_struct A=1 "--config cfg4 --structured-sv"
+run cfg2_def A=1 "--config cfg2"
 run cfg4_def A=1 "--config cfg4"

@@ -105,3 +105,29 @@ def test_fused_sv_inside_cg_matches_two_pass_trajectory():
         e.close()
     assert res[0][0] == res[1][0]
     assert_close(res[0][1], res[1][1], rtol=1e-9, what="params after 4 SR steps")
+
+
+@pytest.mark.parametrize("N,M,K", [(16, 16, 64), (64, 128, 300), (128, 256, 150), (24, 40, 33)])
+def test_o_generated_inside_first_sv_matches_separate_writer(N, M, K, monkeypatch):
+    """nqs_sr_step writes O from inside the first S*v of the CG (sv_fused_kernel GEN: factors staged by TMA, elements formed
+    in registers, used and stored; opt-in with NQS_SV_GEN=1, see engine.cu: alloc_sr).  By default the separate writer
+    (oderiv_kernel) runs first.  Both must give the same CG trajectory bit for bit: every later S*v of the step reads the O
+    that the GEN launch wrote."""
+    from neural_network_quantum_state_b200 import Engine
+    res = []
+    for gen in ("1", "0"):
+        monkeypatch.setenv("NQS_SV_GEN", gen)
+        e = Engine("rbm", N, M, K, H, J, ALPHA, seed=5)
+        e.init_params_random(9)
+        e.warm_up(30)
+        steps = []
+        for it in range(3):
+            st = e.sr_step(n_mc_steps=1, lr=0.05, fixed_iters=5, lam=0.3)
+            F, dx = e.get_sr_vectors()
+            steps.append((st.e_mean, dx.copy()))
+        res.append((steps, e.get_params()))
+        e.close()
+    for (e0, dx0), (e1, dx1) in zip(res[0][0], res[1][0]):
+        assert e0 == e1
+        assert np.array_equal(dx0, dx1), "dx differs between the O-generating S*v and the separate O writer"
+    assert np.array_equal(res[0][1], res[1][1])
