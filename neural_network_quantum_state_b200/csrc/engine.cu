@@ -1476,8 +1476,9 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     nqs_sr_stats s;
     std::memset(&s, 0, sizeof(s));
     { Span t(h, TAG_SWEEP); do_sweeps(h, opt->n_mc_steps); }
-    // (Running the HBM-write-bound O writer on a side stream next to the fp64-bound local energy was tried: the writer's K CTAs
-    // occupy every SM slot, the two kernels serialise anyway and the step time does not change.)
+    // (Running the HBM-write-bound O writer on a side stream next to the fp64-bound local energy was tried twice -- one CTA per
+    // chain, and a grid-stride writer of 2 CTAs per SM that leaves room for the local-energy CTAs: the local energy is L1/LSU
+    // heavy and slows from 0.59 to 1.85 ms next to the writer, 14.10 vs 14.17 ms per step.  Not kept.)
     { Span t(h, TAG_ELOC); launch_eloc(h, nullptr, 0); h->flip_index = h->N-1; }
     { Span t(h, TAG_ODERIV);
       if (h->struct_sv) launch_hidden_values(h);
