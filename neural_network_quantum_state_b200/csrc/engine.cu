@@ -287,14 +287,14 @@ bool fast_path_ok(nqs_handle * h)
   return std::isfinite(h->theta_bound) && h->theta_bound < 300.0/h->jpl;
 }
 
-template <int JPL, int C>
+template <int JPL, int C, int WPC = 1>
 void launch_sweep_fast_t(nqs_handle * h, const FastSweepArgs & a)
 {
-  const int warps = SweepShape<JPL, C>::warps;
+  const int warps = SweepShape<JPL, C, WPC>::warps;
   const size_t smem = fast_sweep_smem_bytes(h->N, C, warps, h->mpad);
-  set_smem(rbm_sweep_fast_kernel<JPL, C>, smem);
-  const long long per_cta = (long long)warps*C;
-  rbm_sweep_fast_kernel<JPL, C><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
+  set_smem(rbm_sweep_fast_kernel<JPL, C, WPC>, smem);
+  const long long per_cta = (long long)(warps/WPC)*C;
+  rbm_sweep_fast_kernel<JPL, C, WPC><<<(unsigned)((h->K+per_cta-1)/per_cta), warps*32, smem, h->stream>>>(a);
 }
 
 template <int C>
@@ -339,7 +339,8 @@ void launch_sweep(nqs_handle * h, long long nsteps)
     a.acc_log = h->acc_log.p;
     h->acc_log_steps = nsteps;
   }
-  if (fast_path_ok(h) && nsteps%h->N == 0)
+  if (fast_path_ok(h) && h->jpl <= 32 && nsteps%h->N == 0 &&
+      fast_sweep_smem_bytes(h->N, 1, 8, h->mpad) <= h->smem_optin)
   {
     FastSweepArgs f;
     f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ftab_a = h->ftab_a.p; f.ftab_b = h->ftab_b.p; f.w2 = h->w2.p; f.afac = h->afac.p;
@@ -352,7 +353,8 @@ void launch_sweep(nqs_handle * h, long long nsteps)
       case 2: launch_sweep_fast_t<2, 4>(h, f); break;
       case 4: launch_sweep_fast_t<4, 4>(h, f); break;
       case 8: launch_sweep_fast_t<8, 2>(h, f); break;
-      default: launch_sweep_fast_t<16, 1>(h, f); break;
+      case 16: launch_sweep_fast_t<16, 1>(h, f); break;
+      default: launch_sweep_fast_t<16, 1, 2>(h, f); break;     // jpl = 32 (M <= 1024): two warps per chain
     }
     check_launch(h, "rbm_sweep_fast_kernel");
     h->variant_sweep = "rbm_regs_j"+std::to_string(h->jpl);
@@ -1112,7 +1114,9 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     h->Jmat.alloc((size_t)h->N*h->N); h->order.alloc(h->N);
     h->fresh.alloc(h->K);
     NQS_CUDA(cudaMemset(h->fresh.p, 0, (size_t)h->K));
-    if (h->model == MODEL_RBM && !(cfg->flags & NQS_FLAG_FORCE_GENERIC) && h->M <= 512)
+    // product-form tables: the sweep keeps its state in registers (M <= 512: 16 hidden-unit slots per lane; M <= 1024: two warps
+    // per chain); the local-energy kernel keeps tanh(theta) in shared memory and works up to M = 2048
+    if (h->model == MODEL_RBM && !(cfg->flags & NQS_FLAG_FORCE_GENERIC) && h->M <= 2048)
     {
       int jpl = 1;
       while (32*jpl < h->M) jpl <<= 1;

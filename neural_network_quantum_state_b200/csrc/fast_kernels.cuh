@@ -142,11 +142,12 @@ struct FastSweepArgs
 // a fixed site order, so the loads are issued NQS_SW_STAGES - 1 proposals ahead and the table reads in the loop are LDS.128
 // instead of L1-missing LDG (29 % long-scoreboard stalls before, profiles/r1e_sampler_full_summary.md).
 #define NQS_SW_STAGES 4
+#define NQS_SW_XCHG_BYTES 512   // WPC = 2: per-proposal (mantissa, exponent) exchange [2 parities][4 pairs][2] + final log cosh sums
 inline size_t fast_sweep_smem_bytes(int N, int C, int warps, int Mpad)
 {
   const size_t npad = (size_t)((N+15)/16)*16;
   const size_t head = ((size_t)warps*C*npad+(size_t)warps*C*N+(size_t)N*sizeof(int)+15)/16*16;
-  return head+(size_t)NQS_SW_STAGES*2*Mpad*sizeof(FlipTab)+(size_t)2*NQS_SW_STAGES*sizeof(uint64_t);
+  return head+(size_t)NQS_SW_STAGES*2*Mpad*sizeof(FlipTab)+(size_t)2*NQS_SW_STAGES*sizeof(uint64_t)+NQS_SW_XCHG_BYTES;
 }
 
 // (mantissa, exponent) products of C chains reduced over the 32 lanes with a TRANSPOSING butterfly: after the first
@@ -218,13 +219,23 @@ __device__ __forceinline__ void reduce_me_transposed(double (&m)[C], int (&e)[C]
 // the same factor and inherits it at every accept, and the ratio never sees it.
 // CTA shapes: one chain per warp with at most 8 hidden-unit slots per lane fits 128 registers and runs 8 warps per CTA (16 per SM);
 // everything else runs 4 warps per CTA, 2 CTAs per SM, at up to 255 registers.
-template <int JPL, int C> struct SweepShape { static constexpr int warps = (C == 1 && JPL <= 8) ? 8 : 4; };
-template <int JPL, int C>
-__global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fast_kernel(const FastSweepArgs a)
+// WPC = 2 (M up to 1024): TWO warps share one chain, each holding 16 hidden-unit slots per lane (512 units); per proposal
+// they exchange their (mantissa, exponent) partial products through shared memory behind a 64-thread named barrier, take the
+// same accept decision from the same numbers, and update their own half of the state.  8 warps = 4 chains per CTA, 1 CTA per SM.
+template <int JPL, int C, int WPC> struct SweepShape
+{
+  static constexpr int warps = (WPC > 1 || (C == 1 && JPL <= 8)) ? 8 : 4;
+  static constexpr int min_ctas = (WPC > 1) ? 1 : 2;
+};
+template <int JPL, int C, int WPC = 1>
+__global__ void __launch_bounds__(32*SweepShape<JPL, C, WPC>::warps, SweepShape<JPL, C, WPC>::min_ctas) rbm_sweep_fast_kernel(const FastSweepArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert(WPC == 1 || C == 1, "warp pairs hold one chain");
   constexpr int G = 32/C;                      // lanes per chain group (owner lanes of a chain's accept decision)
   const int warps = blockDim.x>>5, w = threadIdx.x>>5, lane = threadIdx.x&31;
+  const int wsub = (WPC > 1) ? (w%WPC) : 0, wgrp = w/WPC;     // which part of the hidden layer / which chain group of the CTA
+  const int joff = 32*JPL*wsub;                // first hidden unit of this warp's part
   const int N = a.N, M = a.M, Mpad = a.Mpad;
   const int npad = ((N+15)/16)*16;
   int8_t * sp = reinterpret_cast<int8_t*>(smem_raw)+(size_t)w*C*npad;                         // [C][npad]
@@ -234,18 +245,21 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
   FlipTab * stage0 = reinterpret_cast<FlipTab*>(smem_raw+head);                      // [NQS_SW_STAGES][2][Mpad]
   uint64_t * full = reinterpret_cast<uint64_t*>(stage0+(size_t)NQS_SW_STAGES*2*Mpad); // [NQS_SW_STAGES] TMA arrival
   uint64_t * empty = full+NQS_SW_STAGES;                                              // [NQS_SW_STAGES] every active warp is done
+  double * xm = reinterpret_cast<double*>(empty+NQS_SW_STAGES);                       // [2][4][2] partial mantissas (WPC = 2)
+  int * xe = reinterpret_cast<int*>(xm+16);                                           // [2][4][2] partial exponents
+  cd * xl = reinterpret_cast<cd*>(xe+16);                                             // [4][2] partial log cosh sums
   for (int i = threadIdx.x; i < N; i += blockDim.x) ord[i] = a.order[i];
-  const long long kblock = (long long)blockIdx.x*warps*C;
+  const long long kblock = (long long)blockIdx.x*(warps/WPC)*C;
   if (threadIdx.x == 0)
   {
-    long long nact = (a.K-kblock+C-1)/C;                  // warps of this CTA that own at least one chain
+    long long nact = ((a.K-kblock+C-1)/C)*WPC;            // warps of this CTA that own at least one chain
     if (nact > warps) nact = warps;
     if (nact < 1) nact = 1;
     for (int q = 0; q < NQS_SW_STAGES; ++q) { mbar_init(full+q, 1); mbar_init(empty+q, (uint32_t)nact); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const long long kbase = ((long long)blockIdx.x*warps+w)*C;
+  const long long kbase = ((long long)blockIdx.x*(warps/WPC)+wgrp)*C;
   if (kbase >= a.K) return;
   const cd * avis = a.params+(size_t)N*M;
   const int myc = lane/G;                      // the chain this lane decides for
@@ -302,7 +316,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
 #pragma unroll
       for (int jj = 0; jj < JPL; ++jj)
       {
-        const int j = lane+32*jj;
+        const int j = joff+lane+32*jj;
         cd th = cmake(0.0, 0.0);
         if (j < M) th = a.theta[k*M+j];
         const double ex = exp(2.0*th.x), emx = 1.0/ex;
@@ -334,7 +348,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
         }
       }
       mbar_wait(full+slot, (uint32_t)((t_glob/NQS_SW_STAGES)&1));
-      const FlipTab * trow_a = stage0+(size_t)slot*2*Mpad+lane;
+      const FlipTab * trow_a = stage0+(size_t)slot*2*Mpad+joff+lane;
       const FlipTab * trow_b = trow_a+Mpad;
       int smask[C];                              // sign bit of sigma
       double sg[C];                              // sigma
@@ -363,6 +377,14 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
       for (int c = 0; c < C; ++c) split_me(fmax(prod[c], 1e-300), pm[c], pe[c]);
       double m; int e;
       reduce_me_transposed<C>(pm, pe, lane, m, e);
+      if (WPC > 1)
+      { // the two halves of the hidden layer: both warps read both partials and combine them in the same order
+        const int xq = ((int)(t_glob&1)*4+wgrp)*2;
+        if (lane == 0) { xm[xq+wsub] = m; xe[xq+wsub] = e; }
+        asm volatile("bar.sync %0, %1;" :: "r"(1+wgrp), "r"(32*WPC) : "memory");
+        m = xm[xq]*xm[xq+1];
+        e = xe[xq]+xe[xq+1];
+      }
       // accept  <=>  u < P' A / R0   (== u < exp(2 (Re lnpsi' - Re lnpsi0)), ref impl_mcmc_sampler.cuh:75-99), decided by the owner lanes
       const double u = __shfl_sync(0xffffffffu, ubuf, (lane&~(G-1))|(int)(t_glob&(G-1)));
       const bool my_up = sp[myc*npad+site] > 0;
@@ -384,7 +406,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
         acc[c] = ((bal>>(c*G))&1u) != 0;
         if (lane == 0)
         {
-          if (a.acc_log && valid[c]) a.acc_log[t_glob*a.K+kbase+c] = acc[c] ? 1 : 0;
+          if (a.acc_log && valid[c] && wsub == 0) a.acc_log[t_glob*a.K+kbase+c] = acc[c] ? 1 : 0;
           rec[t*C+c] = acc[c] ? (int8_t)(smask[c] ? -1 : 1) : (int8_t)0;
         }
       }
@@ -439,7 +461,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
 #pragma unroll
         for (int jj = 0; jj < JPL; ++jj)
         {
-          const int j = lane+32*jj;
+          const int j = joff+lane+32*jj;
           th[c][jj] = (j < M) ? a.theta[k*M+j] : cmake(0.0, 0.0);
         }
       }
@@ -457,7 +479,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
 #pragma unroll
         for (int jj = 0; jj < JPL; ++jj)
         {
-          const cd wv = ld_tab(wrow+lane+32*jj);
+          const cd wv = ld_tab(wrow+joff+lane+32*jj);
 #pragma unroll
           for (int c = 0; c < C; ++c)
           {
@@ -479,7 +501,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
 #pragma unroll
         for (int jj = 0; jj < JPL; ++jj)
         {
-          const int j = lane+32*jj;
+          const int j = joff+lane+32*jj;
           if (j < M)
           {
             a.theta[k*M+j] = th[c][jj];
@@ -489,6 +511,12 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
         if (last && any_acc[c])
         {
           lsum = warp_sum(lsum);
+          if (WPC > 1)
+          { // any_acc is the same in both warps of the pair (same decisions): both reach the barrier
+            if (lane == 0) xl[wgrp*2+wsub] = lsum;
+            asm volatile("bar.sync %0, %1;" :: "r"(1+wgrp), "r"(32*WPC) : "memory");
+            lsum = cadd(xl[wgrp*2], xl[wgrp*2+1]);
+          }
           ln0[c] = cadd(lsum, sa[c]);
         }
       }
@@ -498,7 +526,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C>::warps, 2) rbm_sweep_fas
 #pragma unroll
   for (int c = 0; c < C; ++c)
   {
-    if (!valid[c]) continue;
+    if (!valid[c] || wsub != 0) continue;
     const long long k = kbase+c;
     for (int i = lane; i < N; i += 32) a.spins[k*N+i] = sp[c*npad+i];
     if (lane == 0)

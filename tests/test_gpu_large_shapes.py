@@ -4,7 +4,7 @@ GPU K_loc*P = 8192 * 263424 = 2.158e9 elements of O -- more than 2^31-1, where t
 size (34.5 GB of O) and checked through an oracle-independent identity: with O_k = [s_ki T_kj | s_ki | T_kj], T = tanh(theta),
    (O v)_k = sum_j T_kj (s_k V)_j + s_k . v_a + T_k . v_b,     O^H z = [S^T (conj(T) z) | S^T z | conj(T)^T z],
 so S v follows from the [K][N] spins and [K][M] hidden-unit values in numpy without ever forming O on the host.  M = 1024
-takes the generic sweep / local-energy kernels and P = 263424 the two-pass S*v fallback."""
+takes the two-warps-per-chain sweep and P = 263424 the two-pass S*v fallback."""
 import math
 
 import numpy as np
@@ -43,7 +43,7 @@ def test_cfg5_shard_full_size_64bit_indexing():
     assert e.kernel_variant("sv") == "two_pass"          # P/16 columns do not fit the cluster kernel's register budget
     e.init_params_random(3)
     e.warm_up(1)
-    assert e.kernel_variant("sweep") == "generic"
+    assert e.kernel_variant("sweep") == "rbm_regs_j32"   # M = 1024: two warps per chain
     e.get_lnpsiGradients(copy=False)                      # fills the 34.5 GB O on the device
     rng = np.random.default_rng(0)
     v = rng.normal(size=P) + 1j * rng.normal(size=P)

@@ -117,6 +117,9 @@ CASES = [
     ("rbm", 20, 256, 64, False),     # M = 256 (cfg3 hidden width)
     ("ffnn", 16, 48, 200, False),
     ("ffnn", 21, 70, 77, False),
+    ("rbm", 10, 600, 40, False),     # 512 < M <= 1024: two warps per chain in the sweep (cfg5 width class)
+    ("rbm", 12, 1024, 21, False),    # cfg5 hidden width, odd number of chains (a CTA with idle warp pairs)
+    ("rbm", 6, 1100, 10, False),     # M > 1024: generic sweep, product-form local energy
 ]
 
 
@@ -137,7 +140,10 @@ def test_sweep_matches_oracle_step_by_step(model, N, M, K, pbc, force_generic):
     e.set_uniforms(U)
     s.warm_up(n_warm)
     e.warm_up(n_warm)
-    expect = "generic" if (force_generic or model != "rbm") else "rbm_regs"
+    expect = "generic" if (force_generic or model != "rbm" or M > 1024) else "rbm_regs"
+    if model == "rbm" and M > 1024 and not force_generic:
+        e.get_htilda()
+        assert e.kernel_variant("eloc").startswith("rbm_sites"), e.kernel_variant("eloc")
     assert e.kernel_variant("sweep").startswith(expect), e.kernel_variant("sweep")
     acc_ref = np.array(s.accept_log)
     acc = e.get_accept_log()
