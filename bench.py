@@ -291,11 +291,13 @@ def main():
             step()
 
     # ---- (1) the timed region: K steps, no per-kernel instrumentation, CUDA events on the engine's stream around the loop
+    # nvidia-smi is started BEFORE the warm-up steps: its NVML initialisation (enumerates every GPU of the box) can stall CUDA
+    # calls of the running processes for tens of ms, which must not land inside the timed region; it then samples every 100 ms
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step()
-    clocks = ClockSampler(local_rank)
     barrier()
-    clocks.start()
     launches0 = e.get_timing()["kernel_launches"]
     cg_iters, energies = [], []
     e.event_record(0)

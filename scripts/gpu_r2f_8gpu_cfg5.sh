@@ -2,7 +2,7 @@ mkdir -p gpurun_out
 set -x
 run() { # name n args
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $2 --master-addr 127.0.0.1 --master-port 2952$2"
-timeout 400 $TR bench.py --gpus $2 --config cfg5 --steps 3 --warmup 3 --nwarm 100 --no-cpu-baseline --no-e2e $3 > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
+timeout 400 $TR bench.py --gpus $2 --config cfg5 --steps 3 --warmup 2 --nwarm 100 --no-cpu-baseline --no-e2e $3 > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
 echo "rc=$?"
 }
 run cfg5_8gpu 8 ""
