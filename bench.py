@@ -68,6 +68,9 @@ class ClockSampler:
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0:     # first sample = NVML is initialised: nothing of it is timed
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
