@@ -50,7 +50,10 @@ def launches(src, dst, cmd):
 
 
 def full(src, dst):
-    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):      # `ncu -i X.ncu-rep --page raw --csv` already run on the GPU box (the report itself was too big to bring back)
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(dst, "w") as f:
