@@ -1092,6 +1092,12 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     NQS_CUDA(cudaSetDevice(cfg->device));
     h = new nqs_handle();
     h->cfg = *cfg;
+    { // callers that cannot pass flags (the reference-compatible CLI, pynqs) opt into the structured S*v through the environment
+      const char * es = std::getenv("NQS_STRUCTURED_SV");
+      if (es && std::atoi(es) != 0 && cfg->n_inputs <= 256 &&
+          !(cfg->flags & (NQS_FLAG_SETUP_FROM_O | NQS_FLAG_TWO_PASS_SV | NQS_FLAG_NO_DMMA)))
+        h->cfg.flags |= NQS_FLAG_STRUCTURED_SV;
+    }
     h->N = cfg->n_inputs; h->M = cfg->n_hiddens; h->model = cfg->model;
     h->K = cfg->n_chains; h->Ktot = cfg->n_chains_total > 0 ? cfg->n_chains_total : cfg->n_chains; h->koff = cfg->chain_offset;
     NQS_REQUIRE(h->Ktot >= h->K, NQS_ERR_INVALID, "n_chains_total < n_chains");

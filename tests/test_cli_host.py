@@ -64,9 +64,12 @@ def test_without_gpu_the_driver_fails_loudly_after_echoing_the_arguments():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("structured_env", [False, True])
 @pytest.mark.parametrize("prog,model,sufs", [("LICH-train_rbm-gpu", "rbm", ("Dw.dat", "Da.dat", "Db.dat")),
                                               ("LICH-train_ffnn-gpu", "ffnn", ("Dw1.dat", "Dw2.dat", "Db1.dat"))])
-def test_training_run_matches_python_host_and_writes_reference_files(tmp_path, prog, model, sufs):
+def test_training_run_matches_python_host_and_writes_reference_files(tmp_path, prog, model, sufs, structured_env):
+    """structured_env: the reference-compatible CLI cannot pass engine flags; NQS_STRUCTURED_SV=1 in its environment switches the
+    S*v to the tensor-core GEMMs on the factors of O.  Same table, same files (the Python run stays on the explicit-O path)."""
     from neural_network_quantum_state_b200 import Engine
     from neural_network_quantum_state_b200.init import reference_init
     L, nh, ns, niter, alpha, theta, seed = 12, 24, 256, 6, 2.0, 0.785398, 7
@@ -80,7 +83,8 @@ def test_training_run_matches_python_host_and_writes_reference_files(tmp_path, p
     e.warm_up(20)
     want = [e.sr_step(n_mc_steps=2, lr=0.05) for _ in range(niter)]
     r = run([exe(prog), "-L=%d" % L, "-nh=%d" % nh, "-ns=%d" % ns, "-niter=%d" % niter, "-alpha=2", "-theta=%s" % theta, "-ver=3",
-             "-dev=0", "-rsd=1e-9", "-nwarm=20", "-nms=2", "-lr=0.05", "-seed=%d" % seed, "-path=%s" % tmp_path])
+             "-dev=0", "-rsd=1e-9", "-nwarm=20", "-nms=2", "-lr=0.05", "-seed=%d" % seed, "-path=%s" % tmp_path],
+            env=dict(os.environ, NQS_STRUCTURED_SV="1" if structured_env else "0"))
     assert r.returncode == 0, r.stderr
     lines = r.stdout.splitlines()
     assert "# of loop\t<H>" in lines
