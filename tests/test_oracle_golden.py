@@ -80,3 +80,41 @@ def test_exact_diagonalisation_known_answers():
     J, h = math.sin(math.pi / 4), -math.cos(math.pi / 4)
     assert o.exact_ground_energy_per_site(8, J, h, 2.0) == pytest.approx(-0.837475552251, abs=1e-10)
     assert o.exact_ground_energy_per_site(12, J, h, 2.0) == pytest.approx(-0.842986271888, abs=1e-10)
+
+
+def test_structured_factorisation_of_S_dot_v(golden):
+    """The algebra the tensor-core kernels of csrc/sv_struct.cuh rely on, checked on the CPU against the reference's golden S v:
+    every row of O is an outer product plus two short blocks, so O v and O^H z (and <O>, diag S) follow from the [K][N] spins
+    and the [K][M] hidden-unit factors without O.  RBM: O_k = [s_ki T_kj (i*M+j) | s_ki | T_kj], T = tanh(theta);
+    FFNN (GPU layout): O_k = [s_ki T'_kj (j*N+i) | T'_kj | L_kj], T' = tanh(theta) w1o, L = logcosh(theta)."""
+    g = golden
+    m, s = build(g)
+    s.warm_up(g["n_warm"], g["init_spins"].astype(np.float64) if "init_spins" in g else None)
+    N, M, K = g["N"], g["M"], g["K"]
+    S, th = m.spins, m.y
+    v = to_gpu(g, g["sm_v"])
+    lam = g["sm_lambda"]
+    if g["model"] == "rbm":
+        T = np.tanh(th)
+        V, va, vb = v[:N * M].reshape(N, M), v[N * M:N * M + N], v[N * M + N:]
+        z = np.einsum("kj,kj->k", T, S @ V + vb[None, :]) + S @ va
+        C = T.conj() * z[:, None]
+        OHz = np.concatenate([(S.T @ C).ravel(), S.T @ z, C.sum(axis=0)])
+        aO = np.concatenate([(S.T @ T).ravel(), S.sum(axis=0).astype(np.complex128), T.sum(axis=0)]) / K
+        t2 = (np.abs(T) ** 2).sum(axis=0) / K
+        m2 = np.concatenate([np.tile(t2, N), np.ones(N), t2])
+    else:
+        T = np.tanh(th) * m.w1o[None, :]
+        L = o.logcosh(th)
+        V, vb, vl = v[:N * M].reshape(M, N).T, v[N * M:N * M + M], v[N * M + M:]      # W block stored j*N+i
+        z = np.einsum("kj,kj->k", T, S @ V + vb[None, :]) + L @ vl
+        C = T.conj() * z[:, None]
+        OHz = np.concatenate([(S.T @ C).T.ravel(), C.sum(axis=0), (L.conj() * z[:, None]).sum(axis=0)])
+        aO = np.concatenate([(S.T @ T).T.ravel(), T.sum(axis=0), L.sum(axis=0)]) / K
+        t2, l2 = (np.abs(T) ** 2).sum(axis=0) / K, (np.abs(L) ** 2).sum(axis=0) / K
+        m2 = np.concatenate([np.repeat(t2, N), t2, l2])
+    diag = m2 - np.abs(aO) ** 2
+    Sv = OHz / K - aO.conj() * (aO @ v) + lam * diag * v
+    assert_close(aO, to_gpu(g, g["sm_aO"]), what="<O> from the factors")
+    assert_close(diag, to_gpu(g, g["sm_diag"]), atol=1e-11, what="diag S from the factors")
+    assert_close(Sv, to_gpu(g, g["sm_Sv"]), what="S v from the factors")
