@@ -151,12 +151,14 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
         r.warm_up(n_warm_sweeps)
         return r
 
-    # the reference's OpenMP loops do not always scale: probe 1 thread vs all threads on one sweep
+    # the reference's OpenMP loops do not always scale: probe 1 OpenMP thread vs all of them on one whole
+    # SR step (sweep + E_loc + O + CG); the BLAS calls inside (Zgemm / Zgemv, OpenBLAS) use OPENBLAS_NUM_THREADS = all cores either way
+    blas_threads = int(os.environ.get("OPENBLAS_NUM_THREADS", "1"))
     best_threads, best_t = 1, None
     for th in sorted({1, cores}):
         r = make(th)
         t0 = time.perf_counter()
-        r.do_mcmc_steps(1)
+        r.sr_step(1, 1e-2)
         dt = time.perf_counter() - t0
         r.close()
         if best_t is None or dt < best_t:
@@ -170,8 +172,8 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
         cg.append(r.sr_step(1, 1e-2)["cg_iters"])
     dt = (time.perf_counter() - t0) / max(steps, 1)
     r.close()
-    return {"value": k_sample / dt, "ms_per_step": dt * 1e3, "cores": best_threads, "host_cores": cores,
-            "cg_iters": cg, "sweep_s_probe": best_t,
+    return {"value": k_sample / dt, "ms_per_step": dt * 1e3, "cores": max(best_threads, blas_threads), "host_cores": cores,
+            "omp_threads": best_threads, "blas_threads": blas_threads, "cg_iters": cg, "step_s_probe": best_t,
             "sample": "%d of %d chains (random initial spins), same N=%d M=%d, %d warm-up sweeps, %d warm-up + %d timed SR steps; reference CPU "
                       "headers + OpenBLAS 0.3.15 (MKL/TRNG4 unavailable offline), long-range Hamiltonian shim" %
                       (k_sample, CONFIGS[cfg_name][3], N, M, n_warm_sweeps, warmup, steps)}
@@ -242,7 +244,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                                 "sample": res["sample"], "host_cores": res["host_cores"]},
+                                 "sample": res["sample"], "host_cores": res["host_cores"], "omp_threads": res["omp_threads"],
+                                 "blas_threads": res["blas_threads"]},
                 "cg_iters_per_step": res["cg_iters"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -500,7 +503,8 @@ def main():
         try:
             res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=5)
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
-                                    "sample": res["sample"], "host_cores": res["host_cores"], "ms_per_step": res["ms_per_step"],
+                                    "sample": res["sample"], "host_cores": res["host_cores"], "omp_threads": res["omp_threads"],
+                                    "blas_threads": res["blas_threads"], "ms_per_step": res["ms_per_step"],
                                     "cg_iters_per_step": res["cg_iters"]}
         except Exception as ex:  # the checker being absent must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
