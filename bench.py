@@ -115,15 +115,94 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(kernel: str):
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), else None."""
+def committed_traffic(kernel: str, cfg_name: str, world: int):
+    """dram bytes (read + write) per pass over O of the dominant kernel from the committed ncu --set full capture of exactly this
+    (config, number of GPUs) -- profiles/roofline_traffic.json, keyed "<cfg>/<world>gpu" -- else None: a capture of another
+    shard size says nothing about this run."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel)
+            return json.load(open(p)).get("%s/%dgpu" % (cfg_name, world), {}).get(kernel)
         except Exception:
             return None
     return None
+
+
+def multi_gpu_parity(world: int, rank: int, local_rank: int) -> dict:
+    """N > 1 only, untimed: the chain-sharded engine (NCCL SR sums + in-kernel NVLink exchange) must reproduce the single-GPU
+    trajectory of the same chains (the RNG is keyed by the global chain id) and leave bit-identical parameters on every rank.
+    The same check as tests/test_gpu_multi.py, run here because the driver's GPU test box has one GPU and the scaling run has N."""
+    import torch.distributed as dist
+    from neural_network_quantum_state_b200 import Engine
+    from neural_network_quantum_state_b200.dist import ShardPlan, bootstrap_comm, enable_p2p
+    from neural_network_quantum_state_b200.init import reference_init
+    model, N, M, K = "rbm", 24, 48, 1000          # 1000 chains: uneven shards for world = 3, 7, ...
+    params = reference_init(model, N, M, np.random.default_rng(5))
+    plan = ShardPlan(K, world, rank)
+    e = Engine(model, N, M, h=H_FIELD, J=J_COUP, alpha=ALPHA_LR, seed=11, device=local_rank, **plan.engine_kwargs())
+    e.set_params(params)
+    bootstrap_comm(e, world, rank, p2p=False)
+    p2p = enable_p2p(e, world)
+    e.warm_up(30)
+    traj = []
+    for _ in range(5):
+        st = e.sr_step(n_mc_steps=1, lr=0.05)
+        traj.append((st.e_mean.real, st.rsd, st.cg_iters))
+    final = e.get_params()
+    variant = e.kernel_variant("sv")
+    e.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, final.tobytes())
+    out = None
+    if rank == 0:
+        identical = all(g == gathered[0] for g in gathered)
+        e1 = Engine(model, N, M, K, H_FIELD, J_COUP, ALPHA_LR, seed=11, device=local_rank)
+        e1.set_params(params)
+        e1.warm_up(30)
+        e_err, it_ok = 0.0, True
+        for k in range(5):
+            st = e1.sr_step(n_mc_steps=1, lr=0.05)
+            e_err = max(e_err, abs(st.e_mean.real - traj[k][0]) / max(abs(st.e_mean.real), 1e-300))
+            it_ok = it_ok and (st.cg_iters == traj[k][2])
+        want = e1.get_params()
+        e1.close()
+        p_err = float(np.abs(final - want).max() / np.abs(want).max())
+        out = {"ok": bool(identical and it_ok and e_err < 1e-10 and p_err < 1e-7), "ranks_bit_identical": bool(identical),
+               "energy_max_rel_err_vs_1gpu": e_err, "params_max_rel_err_vs_1gpu": p_err, "cg_iters_equal": bool(it_ok),
+               "in_kernel_exchange": bool(p2p), "sv_variant": variant,
+               "case": "rbm N=24 M=48, 1000 chains sharded over %d ranks, 30 warm-up sweeps + 5 SR steps" % world}
+    flag = [out]
+    dist.broadcast_object_list(flag, src=0)
+    if not flag[0]["ok"]:
+        raise RuntimeError("multi-GPU parity check failed: %s" % json.dumps(flag[0]))
+    return flag[0]
+
+
+def sweep_roofline(model, N, M, K_loc, sweep_ms, hbm_peak_gbs, variant):
+    """SURVEY 8d asks for BOTH bounds of the state-resident sweep and for a statement of which one binds.
+    HBM: B_sw = theta in + out (2*K*M*16) + spins in + out (2*K*N) + lnpsi0/sa in + out (4*K*16) + the flip tables once (L2-resident
+    afterwards).  fp64: K*N*M flip factors per sweep at 6 fp64 instructions each in the product-form kernel against
+    the measured scalar-DFMA issue rate (half of FP64_DMMA_PEAK_TFLOPS flop/s = thread-instructions/s)."""
+    if sweep_ms <= 0:
+        return None
+    mpad = 32 * max(1, 1 << max(0, (M - 1).bit_length() - 5))
+    b_sw = 2.0 * K_loc * M * 16 + 2.0 * K_loc * N + 4.0 * K_loc * 16 + 3.0 * N * mpad * 16
+    factors = float(K_loc) * N * M
+    fast = variant.startswith("rbm_regs") or variant.startswith("ffnn_")
+    ipf = 6.0 if variant.startswith("rbm_regs") else None
+    hbm = b_sw / (sweep_ms * 1e-3) / 1e9
+    out = {"hbm": {"algorithmic_bytes": b_sw, "achieved_gbs": hbm, "peak_gbs": hbm_peak_gbs, "frac": hbm / hbm_peak_gbs},
+           "factor_evals_per_s": factors / (sweep_ms * 1e-3)}
+    peak_inst = FP64_DMMA_PEAK_TFLOPS * 1e12 / 2.0
+    if ipf is not None:
+        ach = factors * ipf / (sweep_ms * 1e-3)
+        out["fp64"] = {"fp64_instr_per_factor": ipf, "achieved_tinstr_s": ach / 1e12, "peak_tinstr_s": peak_inst / 1e12,
+                       "frac": ach / peak_inst,
+                       "peak_source": "scalar DFMA issue rate = measured fp64 peak / 2 (scripts/micro/dmma_bench.cu)"}
+    out["binds"] = ("fp64 issue: the chain state is resident on chip, so HBM sees only B_sw per sweep (fraction above, small by "
+                    "construction) and the time goes to dependent fp64 instructions at %s; ncu: profiles/r2_sweep_*" %
+                    ("8 warps per SM (255 registers per thread)" if fast else "one warp per chain with log cosh / exp / sincos per factor"))
+    return out
 
 
 # =====================================================================================================================
@@ -151,18 +230,35 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
         r.warm_up(n_warm_sweeps)
         return r
 
-    # the reference's OpenMP loops do not always scale: probe 1 OpenMP thread vs all of them on one whole
-    # SR step (sweep + E_loc + O + CG); the BLAS calls inside (Zgemm / Zgemv, OpenBLAS) use OPENBLAS_NUM_THREADS = all cores either way
-    blas_threads = int(os.environ.get("OPENBLAS_NUM_THREADS", "1"))
-    best_threads, best_t = 1, None
-    for th in sorted({1, cores}):
-        r = make(th)
+    # the reference's OpenMP loops do not always scale: probe one whole SR step (sweep + E_loc + O + CG)
+    # over OpenMP threads {1, 2, 4, ..., cores} (BLAS on all cores), then over BLAS threads with the best OpenMP count
+    grid = sorted({min(cores, 1 << q) for q in range(0, 12)} | {cores})
+    blas_ctl = ref_cpu.set_blas_threads(cores)
+    probes = []
+
+    def probe(omp, blas):
+        if blas_ctl:
+            ref_cpu.set_blas_threads(blas)
+        r = make(omp)
         t0 = time.perf_counter()
         r.sr_step(1, 1e-2)
         dt = time.perf_counter() - t0
         r.close()
+        probes.append({"omp": omp, "blas": blas if blas_ctl else int(os.environ.get("OPENBLAS_NUM_THREADS", "1")), "step_s": dt})
+        return dt
+
+    best_threads, best_t = 1, None
+    for th in grid:
+        dt = probe(th, cores)
         if best_t is None or dt < best_t:
             best_threads, best_t = th, dt
+    blas_threads = cores if blas_ctl else int(os.environ.get("OPENBLAS_NUM_THREADS", "1"))
+    if blas_ctl:
+        for bt in grid[:-1]:
+            dt = probe(best_threads, bt)
+            if dt < best_t:
+                blas_threads, best_t = bt, dt
+        ref_cpu.set_blas_threads(blas_threads)
     r = make(best_threads)
     cg = []
     for _ in range(warmup):
@@ -174,6 +270,7 @@ def run_reference_cpu(cfg_name: str, steps: int, warmup: int, k_sample: int, n_w
     r.close()
     return {"value": k_sample / dt, "ms_per_step": dt * 1e3, "cores": max(best_threads, blas_threads), "host_cores": cores,
             "omp_threads": best_threads, "blas_threads": blas_threads, "cg_iters": cg, "step_s_probe": best_t,
+            "thread_scan": probes, "k_sample": k_sample,
             "sample": "%d of %d chains (random initial spins), same N=%d M=%d, %d warm-up sweeps, %d warm-up + %d timed SR steps; reference CPU "
                       "headers + OpenBLAS 0.3.15 (MKL/TRNG4 unavailable offline), long-range Hamiltonian shim" %
                       (k_sample, CONFIGS[cfg_name][3], N, M, n_warm_sweeps, warmup, steps)}
@@ -198,6 +295,11 @@ def main():
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     ap.add_argument("--no-structured-extra", action="store_true",
                     help="skip the second, separately reported measurement of the same step with NQS_FLAG_STRUCTURED_SV (1 GPU only)")
+    ap.add_argument("--no-parity-check", action="store_true", help="multi-GPU: skip the (untimed) sharded-vs-single-GPU parity check")
+    ap.add_argument("--production-iters", type=int, default=100,
+                    help="extra block: steps at the lambda floor 1e-2 with this many CG iterations (the regime of a converged run, "
+                         "SURVEY 9.2); 0 = skip")
+    ap.add_argument("--production-steps", type=int, default=3)
     ap.add_argument("--structured-sv", action="store_true",
                     help="S*v from the factors of O as two fp64 tensor-core GEMMs (no O matrix); roofline is then the fp64 tensor pipe")
     args = ap.parse_args()
@@ -240,12 +342,20 @@ def main():
             emit({"impl": "reference", "unavailable": "oracle/_ref/libnqs_ref.so missing (run make -C oracle)"})
             return 0
         res = run_reference_cpu(args.config, args.steps, args.warmup, args.cpu_sample_chains, n_warm_sweeps=5)
+        # this arm runs a bounded SAMPLE of the workload: say so in its own config (chains actually run, start, warm-up)
+        config = dict(config)
+        config.update({"K_total": res["k_sample"], "K_total_workload": K_total, "sharding": "host cores (rank 0 only)",
+                       "cg_exchange": "none (CPU)", "nwarm_sweeps": 5, "initial_spins": "random (not Neel)",
+                       "rng": "pre-drawn numpy uniforms (TRNG4 shim)",
+                       "l2": "n/a (CPU)",
+                       "workload": config["workload"].replace("%d chains total" % K_total,
+                                                              "%d-chain sample of the %d-chain workload" % (res["k_sample"], K_total))})
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
                                  "sample": res["sample"], "host_cores": res["host_cores"], "omp_threads": res["omp_threads"],
-                                 "blas_threads": res["blas_threads"]},
+                                 "blas_threads": res["blas_threads"], "thread_scan": res["thread_scan"]},
                 "cg_iters_per_step": res["cg_iters"],
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
@@ -276,6 +386,7 @@ def main():
         bootstrap_comm(e, world, rank, p2p=False)          # NCCL communicator (SR-setup all-reduce)
         if not args.no_p2p:
             p2p = enable_p2p(e, world)                      # per-CG-iteration exchange inside the CG kernel over NVLink
+    parity = multi_gpu_parity(world, rank, local_rank) if (world > 1 and not args.no_parity_check) else None
     e.warm_up(args.nwarm)
 
     def barrier():
@@ -346,11 +457,38 @@ def main():
     ms_per_step_inst = e.event_elapsed_ms(2, 3) / args.steps
     e.set_timing(False)
 
+    # ---- production regime: lambda has decayed to its floor 1e-2 (schedule step >= 88) and the solve needs ~100 products per
+    # step -- the headline above measures schedule steps W+1 .. W+K, where lambda is still 53 -> 7 and 6-11 suffice
+    production = None
+    if args.production_iters > 0:
+        restart()
+        barrier()
+        fin = []
+        e.event_record(4)
+        for _ in range(args.production_steps):
+            st = e.sr_step(n_mc_steps=1, lr=args.lr, lam=1e-2, fixed_iters=args.production_iters)
+            fin.append(bool(st.finite))
+        e.event_record(5)
+        barrier()
+        pms = e.event_elapsed_ms(4, 5) / args.production_steps
+        if world > 1:
+            tt = torch.tensor([pms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            pms = float(tt.item())
+        nprod = args.production_iters + 1
+        production = {"value": K_total / (pms * 1e-3), "unit": UNIT, "ms_per_step": pms, "steps": args.production_steps,
+                      "lambda": 1e-2, "cg_iterations": args.production_iters, "finite": fin,
+                      "o_passes_per_step": nprod,
+                      "hbm_gbs_whole_step": nprod * K_loc * P * 16.0 / (pms * 1e-3) / 1e9,
+                      "note": "same workload, lambda fixed at the schedule's floor and the solve run for a fixed %d iterations; "
+                              "hbm_gbs_whole_step charges the WHOLE step (sweep, E_loc, O writer, setup, update included) to the "
+                              "algorithmic bytes of the passes over O" % args.production_iters}
+
     # ---- end-to-end through the public API with HOST buffers: pinned uniforms H2D every step, spins + lnpsi + stats D2H
     e2e = None
     if not args.no_e2e:
         rng = np.random.default_rng(1234 + rank)
-        n_e2e = max(3, min(args.steps, 10))
+        n_e2e = args.steps                  # the SAME optimisation iterations as the device-timed loop (same lambda / CG counts)
         # this step's inputs wait in PINNED host memory (one buffer per step, filled before the clock starts, as a producer
         # thread would); results are read back into host numpy arrays
         u_bufs = [torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True) for _ in range(n_e2e)]
@@ -391,8 +529,12 @@ def main():
     if sv_variant.startswith("structured"):
         dom = other = None
     elif sv_variant.startswith("fused"):
-        # one-pass cluster kernel: O is read from HBM once per S*v (the reference and the two-pass kernels read it twice)
-        dom, dom_ms, n_timed = "sv_fused_kernel", phase["rows_ms"] / max(counts["rows_count"], 1), counts["rows_count"]
+        # one-pass cluster kernel: O is read from HBM once per S*v (the reference and the two-pass kernels read it twice).
+        # Persistent CG: ONE launch per solve runs all products (passes over O) of the solve AND the vector updates between them,
+        # so the launch duration is charged with the whole solve; rows_count then counts products, not launches.
+        persistent = sv_variant.endswith("_persistentcg")
+        dom = "cg_persist_kernel" if persistent else "sv_fused_kernel"
+        dom_ms, n_timed = phase["rows_ms"] / max(counts["rows_count"], 1), counts["rows_count"]
         other = None
     else:
         dom = "matvec_cols_partial_kernel" if phase["cols_ms"] >= phase["rows_ms"] else "matvec_rows_kernel"
@@ -414,7 +556,7 @@ def main():
                     "unit": "TFLOP/s", "frac": ach / FP64_DMMA_PEAK_TFLOPS,
                     "peak_source": "fp64 DMMA peak measured on this pool's B200 with scripts/micro/dmma_bench.cu (MEASURED_PEAKS.json "
                                    "holds only the bf16 figure)",
-                    "traffic": committed_traffic(dom), "algorithmic_flops_per_launch": flops, "avg_launch_ms": dom_ms,
+                    "traffic": committed_traffic(dom, args.config, world), "algorithmic_flops_per_launch": flops, "avg_launch_ms": dom_ms,
                     "launches_timed": n_timed,
                     "other_pass": {"kernel": "spin_rows_dmma_kernel" if dom.startswith("spin_cols") else "spin_cols_dmma_kernel",
                                    "avg_launch_ms": r_ms if dom.startswith("spin_cols") else c_ms},
@@ -425,21 +567,31 @@ def main():
         achieved = bytes_per_launch / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     if achieved is not None:
         roofline = {"bound": "hbm", "kernel": dom, "variant": sv_variant, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                  "frac": achieved / peak, "peak_source": peak_src, "traffic": committed_traffic(dom),
+                  "frac": achieved / peak, "peak_source": peak_src, "traffic": committed_traffic(dom, args.config, world),
                   "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": dom_ms, "launches_timed": n_timed,
                   "note": "achieved = K_loc*P*16 B (O read once) / CUDA-event duration of the launch; SURVEY 8d's two-pass figure "
                           "B_cg = 2*K_loc*P*16 per S*v is met with %s pass(es) over O" % ("1" if other is None else "2")}
+        if dom == "cg_persist_kernel":
+            prods = counts["rows_count"] / float(args.steps)
+            roofline.update({
+                "algorithmic_bytes_per_launch": bytes_per_launch * prods, "avg_launch_ms": phase["rows_ms"] / args.steps,
+                "launches_timed": args.steps, "products_per_launch": prods, "ms_per_product": dom_ms,
+                "traffic": (lambda t: None if t is None else t * prods)(committed_traffic(dom, args.config, world)),
+                "note": "one launch = one whole CG solve: (iterations + 1) passes over O of K_loc*P*16 B each (O read once per pass) "
+                        "plus the vector updates, grid barriers and (multi-GPU) NVLink exchanges between them; achieved = bytes of "
+                        "all passes / CUDA-event duration of the launch, i.e. the non-streaming phases are charged to the kernel"})
     if other is not None:
         roofline["other_pass"] = other
     sweep_ms = phase["sweep_ms"] / args.steps
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config, "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline,
+            "roofline": roofline, "production_regime": production, "multi_gpu_parity": parity,
             "sr_step_ms": ms_per_step - sweep_ms,
             "sweep": {"ms": sweep_ms, "samples_per_s": K_total / (sweep_ms * 1e-3) if sweep_ms > 0 else None,
                       "proposals_per_s": K_total * N / (sweep_ms * 1e-3) if sweep_ms > 0 else None,
-                      "kernel": e.kernel_variant("sweep")},
+                      "kernel": e.kernel_variant("sweep"),
+                      "roofline": sweep_roofline(model, N, M, K_loc, sweep_ms, peak, e.kernel_variant("sweep"))},
             "phase_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "cg_iters_per_step": cg_iters,
             "cg_ms_per_iter": (phase["cg_ms"] / max(sum(cg_iters_inst) + len(cg_iters_inst), 1)),
@@ -505,7 +657,7 @@ def main():
             line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "reference",
                                     "sample": res["sample"], "host_cores": res["host_cores"], "omp_threads": res["omp_threads"],
                                     "blas_threads": res["blas_threads"], "ms_per_step": res["ms_per_step"],
-                                    "cg_iters_per_step": res["cg_iters"]}
+                                    "cg_iters_per_step": res["cg_iters"], "thread_scan": res["thread_scan"]}
         except Exception as ex:  # the checker being absent must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % ex}
     emit(line)

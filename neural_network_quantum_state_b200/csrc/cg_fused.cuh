@@ -70,15 +70,31 @@ __device__ __forceinline__ unsigned long long cg_now()
   return t;
 }
 
-// all CTAs of the grid are co-resident (grid <= #SMs, nothing else runs on the stream): spin barrier on a global counter
-__device__ __forceinline__ void cg_grid_barrier(unsigned int * counter, const unsigned int target)
+// All CTAs of the grid are co-resident (grid <= #SMs; the launch is cooperative, so the driver guarantees it): spin barrier on
+// a global counter.  Where a cooperative launch is not available the wait is bounded: after NQS_CG_BARRIER_TIMEOUT_NS the CTA
+// raises *timeout_flag and moves on (the results of the launch are garbage then, and the host reports the error instead of hanging).
+#define NQS_CG_BARRIER_TIMEOUT_NS 20000000000ull
+__device__ __forceinline__ void cg_grid_barrier(unsigned int * counter, const unsigned int target, int * timeout_flag)
 {
   __syncthreads();
   if (threadIdx.x == 0)
   { // release (cumulative over the CTA's writes ordered by the barrier above) / acquire at gpu scope: no full fences needed
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
     unsigned int seen;
-    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    for (;;)
+    {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen >= target) break;
+      if ((++spins&1023u) == 0u)
+      { // look at the clock only now and then: the common wait is a few hundred polls
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now-t0 > NQS_CG_BARRIER_TIMEOUT_NS) { *timeout_flag = 1; break; }
+      }
+    }
   }
   __syncthreads();
 }
@@ -105,7 +121,7 @@ __device__ __forceinline__ void cg_grid_sum(double (&vals)[NV], const CgArgs & a
     slots[(size_t)blockIdx.x*NQS_CG_NVALS+threadIdx.x] = s;
   }
   ++epoch;
-  cg_grid_barrier(a.barrier, epoch*gridDim.x);
+  cg_grid_barrier(a.barrier, epoch*gridDim.x, &a.sc->barrier_timeout);
   // every warp of every CTA folds the per-CTA partials in the same order: lane-strided, then a fixed butterfly
   double s[NV];
 #pragma unroll
@@ -119,25 +135,25 @@ __device__ __forceinline__ void cg_grid_sum(double (&vals)[NV], const CgArgs & a
   for (int i = 0; i < NV; ++i) vals[i] = warp_sum(s[i]);
 }
 
-// sum_q part[q][{re,im}][p] in a fixed order; the loads of up to 8 partials are issued before the first add (a serial chain
+// sum_q part[q][{re,im}][p] in a fixed order; the loads of up to 16 partials are issued before the first add (a serial chain
 // would expose one L2 round trip per partial: ~9 us for 15 cluster partials)
 __device__ __forceinline__ void cg_fold_parts(const double * __restrict__ part, const int nparts, const long long P, const long long p,
   double & rx, double & ry)
 {
   const double * base = part+p;
   rx = 0.0; ry = 0.0;
-  for (int q0 = 0; q0 < nparts; q0 += 8)
+  for (int q0 = 0; q0 < nparts; q0 += 16)
   {
-    double vx[8], vy[8];
+    double vx[16], vy[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 16; ++u)
     {
       const bool ok = (q0+u < nparts);
       vx[u] = ok ? __ldcg(base+(size_t)(q0+u)*2*P) : 0.0;
       vy[u] = ok ? __ldcg(base+(size_t)(q0+u)*2*P+P) : 0.0;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { rx += vx[u]; ry += vy[u]; }
+    for (int u = 0; u < 16; ++u) { rx += vx[u]; ry += vy[u]; }
   }
 }
 

@@ -18,6 +18,7 @@
 #include "sv_fused.cuh"
 #include "sv_struct.cuh"
 #include "cg_fused.cuh"
+#include "cg_persist.cuh"
 
 using namespace nqs;
 
@@ -266,18 +267,41 @@ void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_sp
 
 
 // ---- specialised RBM path (fast_kernels.cuh) -------------------------------------------------------------------------
-void ensure_tables(nqs_handle * h)
+// pinned staging area (4096 B): [0,64) scalar read-backs | [512,520) theta bound | [1024,..) CG scalars read back | [2048,..) CG scalars upload
+enum { PIN_HS = 0, PIN_BOUND = 512, PIN_CG_SNAP = 1024, PIN_CG_INIT = 2048 };
+
+// Tables of the product-form kernels for the CURRENT parameters, plus the bound that decides whether those kernels may be used.
+// The bound travels to pinned memory asynchronously and is picked up at the caller's next synchronisation (finish_tables), so
+// a parameter update inside nqs_sr_step costs no host round trip of its own.
+void build_tables_async(nqs_handle * h)
 {
-  if (h->tables_valid || h->jpl == 0) return;
+  if (h->jpl == 0 || h->tables_valid || h->bound_inflight) return;
   build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
     h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p);
   check_launch(h, "build_fast_tables_kernel");
   theta_bound_kernel<<<1, 256, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
   check_launch(h, "theta_bound_kernel");
-  NQS_CUDA(cudaMemcpyAsync(h->pinned, h->bound.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  NQS_CUDA(cudaStreamSynchronize(h->stream));
-  std::memcpy(&h->theta_bound, h->pinned, sizeof(double));
+  NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_BOUND, h->bound.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->bound_inflight = true;
+}
+void finish_tables(nqs_handle * h)
+{ // call after a synchronisation of the stream
+  if (!h->bound_inflight) return;
+  std::memcpy(&h->theta_bound, (char*)h->pinned+PIN_BOUND, sizeof(double));
+  h->bound_inflight = false;
   h->tables_valid = true;
+}
+void invalidate_tables(nqs_handle * h)
+{ // the parameters are about to change
+  if (h->bound_inflight) { NQS_CUDA(cudaStreamSynchronize(h->stream)); h->bound_inflight = false; }
+  h->tables_valid = false;
+}
+void ensure_tables(nqs_handle * h)
+{
+  if (h->tables_valid || h->jpl == 0) return;
+  build_tables_async(h);
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  finish_tables(h);
 }
 
 bool fast_path_ok(nqs_handle * h)
@@ -285,6 +309,21 @@ bool fast_path_ok(nqs_handle * h)
   if (h->jpl == 0) return false;
   ensure_tables(h);
   return std::isfinite(h->theta_bound) && h->theta_bound < 300.0/h->jpl;
+}
+
+// shared memory of the sweep variant launch_sweep picks for this hidden width (the chains-per-warp / warps-per-CTA of each case
+// below): long chains with a narrow hidden layer can exceed the opt-in limit, and then the generic kernel takes over
+bool fast_sweep_fits(const nqs_handle * h)
+{
+  int C = 1, warps = 8;
+  switch (h->jpl)
+  {
+    case 1: case 2: case 4: C = 4; warps = SweepShape<4, 4, 1>::warps; break;
+    case 8: C = 2; warps = SweepShape<8, 2, 1>::warps; break;
+    case 16: C = 1; warps = SweepShape<16, 1, 1>::warps; break;
+    default: C = 1; warps = SweepShape<16, 1, 2>::warps; break;
+  }
+  return fast_sweep_smem_bytes(h->N, C, warps, h->mpad) <= h->smem_optin;
 }
 
 template <int JPL, int C, int WPC = 1>
@@ -339,8 +378,7 @@ void launch_sweep(nqs_handle * h, long long nsteps)
     a.acc_log = h->acc_log.p;
     h->acc_log_steps = nsteps;
   }
-  if (fast_path_ok(h) && h->jpl <= 32 && nsteps%h->N == 0 &&
-      fast_sweep_smem_bytes(h->N, 1, 8, h->mpad) <= h->smem_optin)
+  if (fast_path_ok(h) && h->jpl <= 32 && nsteps%h->N == 0 && fast_sweep_fits(h))
   {
     FastSweepArgs f;
     f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ftab_a = h->ftab_a.p; f.ftab_b = h->ftab_b.p; f.w2 = h->w2.p; f.afac = h->afac.p;
@@ -498,6 +536,68 @@ cudaError_t sv_launch_gen(int cpt, const SvArgs & a, int cs, int nclusters, int 
     case 10: return sv_launch_t<10, 1, 1>(a, cs, nclusters, nt, smem, stream, nullptr);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// ---- persistent CG (cg_persist.cuh): same cluster geometry as sv_fused_kernel, cooperative so that every CTA is resident
+template <int CPT, int DEFER>
+cudaError_t cgp_launch_t(const CgpArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, bool coop, int * query_max_clusters)
+{
+  auto kern = cg_persist_kernel<CPT, DEFER>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (cs > 8)
+  {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(cs*nclusters), 1, 1);
+  cfg.blockDim = dim3((unsigned)nt+32, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeCooperative; attr[1].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = coop ? 2 : 1;
+  if (query_max_clusters) { cfg.numAttrs = 1; return cudaOccupancyMaxActiveClusters(query_max_clusters, kern, &cfg); }
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
+
+cudaError_t cgp_launch(int cpt, int defer, const CgpArgs & a, int cs, int nclusters, int nt, size_t smem, cudaStream_t stream, bool coop, int * q)
+{
+  switch (cpt)
+  {
+#define NQS_CGP_CASE(C) case C: return defer ? cgp_launch_t<C, 1>(a, cs, nclusters, nt, smem, stream, coop, q) : cgp_launch_t<C, 0>(a, cs, nclusters, nt, smem, stream, coop, q)
+    NQS_CGP_CASE(1); NQS_CGP_CASE(2); NQS_CGP_CASE(3); NQS_CGP_CASE(4); NQS_CGP_CASE(5);
+    NQS_CGP_CASE(6); NQS_CGP_CASE(7); NQS_CGP_CASE(8); NQS_CGP_CASE(9); NQS_CGP_CASE(10);
+#undef NQS_CGP_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// The persistent solve is used when the one-pass plan exists, its grid fits the per-CTA reduction slots / exchange flags, every
+// consumer thread owns at most EPT vector elements and all clusters are resident at once.  NQS_CG_PERSIST=0 keeps the
+// launch-per-iteration path (A/B runs, tests).
+void plan_cgp(nqs_handle * h)
+{
+  h->cgp_ok = false;
+  if (!h->sv_ok || h->gen_ok || h->struct_sv) return;
+  { const char * e = std::getenv("NQS_CG_PERSIST"); if (e && std::atoi(e) == 0) return; }
+  const long long ctas = (long long)h->sv_nclusters*h->sv_cs;
+  if (ctas > NQS_CGP_MAX_CTAS) return;
+  const long long threads = ctas*h->sv_nt;
+  const int ept = (h->sv_cpt <= 3) ? 1 : 2;
+  if ((h->P+threads-1)/threads > ept) return;
+  CgpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  int maxc = 0;
+  const cudaError_t e = cgp_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, 1, h->sv_nt, h->sv_smem, h->stream, false, &maxc);
+  if (e != cudaSuccess || maxc < h->sv_nclusters) { cudaGetLastError(); return; }
+  h->cgp_ok = true;
+  // NQS_CG_COOP=0: plain cluster launch (profilers cannot replay a cooperative cluster launch); the barrier time-out then guards residency
+  { const char * c = std::getenv("NQS_CG_COOP"); if (c && std::atoi(c) == 0) h->cgp_coop = 0; }
 }
 
 // Pick cluster size / columns per thread / pipeline depth for this (K, P); leaves sv_ok false when the column slice of a
@@ -807,6 +907,20 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
 // NQS_CG_TRACE=1: dump the time stamps of the last launches to stderr (microseconds relative to the launch's entry stamp)
 void dump_cg_trace(nqs_handle * h)
 {
+  if (h->cg_trace.p != nullptr && h->cgp_ok)
+  { // persistent solve: stamps of CTA 0 per product of the LAST solve (us relative to the product's start)
+    std::vector<unsigned long long> t((size_t)64*NQS_CGP_TRACE_WORDS);
+    if (cudaMemcpy(t.data(), h->cg_trace.p, t.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    for (int q = 0; q < 64; ++q)
+    {
+      const unsigned long long * r = t.data()+(size_t)q*NQS_CGP_TRACE_WORDS;
+      if (r[0] == 0 || r[1] == 0) break;
+      auto us = [&](int i) { return r[i] ? ((double)r[i]-(double)r[0])*1e-3 : -1.0; };
+      std::fprintf(stderr, "cgptrace rank %d product %d: since_prev_end %.1f rows_done %.1f barrierA %.1f flags_raised %.1f peers_seen %.1f sum1 %.1f sum2 %.1f end %.1f\n",
+        h->rank, q, q > 0 ? ((double)r[0]-(double)t[(size_t)(q-1)*NQS_CGP_TRACE_WORDS+7])*1e-3 : 0.0, us(1), us(2), us(3), us(4), us(5), us(6), us(7));
+    }
+    return;
+  }
   if (h->cg_trace.p == nullptr || h->cg_trace_n == 0) return;
   std::vector<unsigned long long> t((size_t)h->cg_trace_n*NQS_CG_TRACE_WORDS);
   if (cudaMemcpy(t.data(), h->cg_trace.p, t.size()*sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
@@ -846,11 +960,29 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
   a.trace = nullptr;
   if (h->cg_trace.p != nullptr && h->cg_trace_n < NQS_CG_TRACE_MAX)
     a.trace = h->cg_trace.p+(size_t)(h->cg_trace_n++)*NQS_CG_TRACE_WORDS;
-  static bool carveout_set = false;
-  if (!carveout_set)
+  if (!h->cg_attr_set)
   { // same shared-memory carve-out as the S*v kernels on either side: no SM reconfiguration between the launches of an iteration
+    // (function attributes are per device: kept per handle, not per process)
     cudaFuncSetAttribute(cg_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
-    carveout_set = true;
+    h->cg_attr_set = true;
+  }
+  // The kernel spins on a software grid barrier, so every CTA must be resident: a COOPERATIVE launch makes the driver guarantee
+  // that (or refuse the launch) whatever else runs on the device.  If cooperative launches are not available the plain launch
+  // is kept; the barrier then gives up after NQS_CG_BARRIER_TIMEOUT_NS and the host reports NQS_ERR_CUDA instead of hanging.
+  if (h->cg_coop != 0)
+  {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)cg_ctas(h), 1, 1); cfg.blockDim = dim3(NQS_CG_THREADS, 1, 1); cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, cg_fused_kernel, a);
+    if (e == cudaSuccess) { h->cg_coop = 1; check_launch(h, "cg_fused_kernel"); return; }
+    cudaGetLastError();
+    if (h->cg_coop == 1)
+      throw Error(NQS_ERR_CUDA, std::string("cooperative launch of cg_fused_kernel failed: ")+cudaGetErrorString(e));
+    h->cg_coop = 0;
   }
   cg_fused_kernel<<<cg_ctas(h), NQS_CG_THREADS, 0, h->stream>>>(a);
   check_launch(h, "cg_fused_kernel");
@@ -865,14 +997,13 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
   std::memset(&init, 0, sizeof(init));
   init.tol2 = tol*tol;
   init.fixed = fixed_iters > 0 ? 1 : 0;
-  NQS_CUDA(cudaStreamSynchronize(h->stream)); // pinned area is shared with earlier read-backs
-  std::memcpy(h->pinned, &init, sizeof(init));
-  NQS_CUDA(cudaMemcpyAsync(h->scal.p, h->pinned, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+  std::memcpy((char*)h->pinned+PIN_CG_INIT, &init, sizeof(init));   // own region of the pinned area: no synchronisation needed
+  NQS_CUDA(cudaMemcpyAsync(h->scal.p, (char*)h->pinned+PIN_CG_INIT, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
   int * done = &h->scal.p->done;
   int nparts = matvec_passes(h, h->dx.p, nullptr);
   launch_cg_fused(h, CG_MODE_INIT, nparts, lambda, h->dx.p);
   const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
-  CgScalars * snap = reinterpret_cast<CgScalars*>((char*)h->pinned+1024);
+  CgScalars * snap = reinterpret_cast<CgScalars*>((char*)h->pinned+PIN_CG_SNAP);
   // Iterations are enqueued without looking at the result: first as many as the previous solve needed (consecutive SR steps
   // need almost the same number), then two at a time, each batch followed by one read-back of the scalars.  Iterations past
   // convergence are skipped on the device (`done`), so the count is exact and a misprediction costs one queue bubble.
@@ -897,6 +1028,11 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
   if (fixed_iters <= 0) h->cg_prev_iters = std::max(1, s.iters);
   if (s.peer_timeout)
     throw Error(NQS_ERR_NCCL, "in-kernel NVLink exchange timed out after 20 s: a peer rank did not reach the same CG iteration");
+  if (s.barrier_timeout)
+  {
+    cudaMemsetAsync(h->cgbar.p, 0, sizeof(unsigned int), h->stream);
+    throw Error(NQS_ERR_CUDA, "grid barrier of cg_fused_kernel timed out after 20 s: its CTAs were not co-resident");
+  }
   if (st)
   {
     st->cg_iters = s.iters;
@@ -905,12 +1041,92 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
   }
 }
 
-void do_evolve(nqs_handle * h, const cd * dx_dev, double lr)
+bool cgp_usable(const nqs_handle * h)
+{ // multi-GPU: the exchange inside the kernel pairs CTA b of every rank, so all ranks must run the same grid over mapped peers
+  return h->cgp_ok && (h->comm == nullptr || (h->p2p_ok && h->cgp_peers_agree));
+}
+
+// ref: ConjugateGradient::solve -- the whole solve as ONE launch (cg_persist.cuh).  Nothing is synchronised here: the scalars
+// travel to pinned memory behind the kernel and collect_cg() reads them after the caller's next synchronisation.
+void cg_solve_persistent(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters)
+{
+  CgScalars init;
+  std::memset(&init, 0, sizeof(init));
+  init.tol2 = tol*tol;
+  init.fixed = fixed_iters > 0 ? 1 : 0;
+  std::memcpy((char*)h->pinned+PIN_CG_INIT, &init, sizeof(init));
+  NQS_CUDA(cudaMemcpyAsync(h->scal.p, (char*)h->pinned+PIN_CG_INIT, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
+  CgpArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.K = h->K; a.P = h->P; a.O = h->O.p; a.part = h->part.p; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
+  a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
+  a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.tol2 = tol*tol; a.fixed_iters = fixed_iters; a.max_iter = max_iter;
+  a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.sc = h->scal.p;
+  a.slots = h->slots.p; a.barrier = h->cgbar.p; a.hsums = h->sums.p+5*h->P;
+  a.n_ranks = 1; a.rank = 0; a.epoch0 = h->p2p_epoch;
+  if (h->comm != nullptr)
+  {
+    a.n_ranks = h->n_ranks; a.rank = h->rank;
+    for (int r = 0; r < h->n_ranks; ++r)
+    {
+      a.peer_x[r] = reinterpret_cast<double*>(h->peer_base[r]);
+      a.peer_flag[r] = reinterpret_cast<unsigned int*>((char*)h->peer_base[r]+h->xbuf_data_bytes);
+    }
+  }
+  a.trace = h->cg_trace.p;
+  a.trace_max = (int)(NQS_CG_TRACE_MAX*NQS_CG_TRACE_WORDS/NQS_CGP_TRACE_WORDS);
+  {
+    Span sp(h, TAG_ROWS);
+    cudaError_t e = cudaErrorUnknown;
+    if (h->cgp_coop != 0)
+    { // cooperative + cluster launch: the driver guarantees (or refuses) co-residency of all clusters
+      e = cgp_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, true, nullptr);
+      if (e == cudaSuccess) h->cgp_coop = 1;
+      else
+      {
+        cudaGetLastError();
+        if (h->cgp_coop == 1) throw Error(NQS_ERR_CUDA, std::string("cooperative launch of cg_persist_kernel failed: ")+cudaGetErrorString(e));
+        h->cgp_coop = 0;
+      }
+    }
+    if (h->cgp_coop == 0)
+      NQS_CUDA(cgp_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, false, nullptr));
+    check_launch(h, "cg_persist_kernel");
+  }
+  NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_CG_SNAP, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  h->cg_inflight = true;
+}
+
+// after a synchronisation: scalars of the persistent solve -> stats, exchange epoch, errors
+void collect_cg(nqs_handle * h, nqs_sr_stats * st, bool * nonfinite)
+{
+  if (!h->cg_inflight) return;
+  h->cg_inflight = false;
+  CgScalars s;
+  std::memcpy(&s, (char*)h->pinned+PIN_CG_SNAP, sizeof(s));
+  if (nonfinite) *nonfinite = s.nonfinite != 0;
+  if (s.barrier_timeout || s.peer_timeout)
+  {
+    cudaMemsetAsync(h->cgbar.p, 0, sizeof(unsigned int), h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (s.peer_timeout) throw Error(NQS_ERR_NCCL, "in-kernel NVLink exchange timed out after 20 s: a peer rank did not reach the same CG iteration");
+    throw Error(NQS_ERR_CUDA, "grid barrier of cg_persist_kernel timed out after 20 s: its CTAs were not co-resident (another kernel held SMs "
+      "and cooperative launches are unavailable)");
+  }
+  const int products = s.nonfinite ? 0 : s.iters+1;
+  h->p2p_epoch += (unsigned int)products;
+  h->timing.rows_count = products;
+  if (!s.nonfinite && !s.fixed) h->cg_prev_iters = std::max(1, s.iters);
+  if (st) { st->cg_iters = s.iters; st->cg_res2 = s.res2; st->cg_rhs2 = s.rhs2; }
+}
+
+void do_evolve(nqs_handle * h, const cd * dx_dev, double lr, const int * skip = nullptr)
 {
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
-  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p);
+  invalidate_tables(h);
+  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p, skip);
   check_launch(h, "update_params_kernel");
-  h->tables_valid = false;
+  build_tables_async(h);   // the next sweep needs them anyway; their bound rides on the caller's final read-back
   NQS_CUDA(cudaMemsetAsync(h->fresh.p, 0, (size_t)h->K, h->stream)); // lnpsi0 is now the pre-update value (ref keeps it)
   // ref update_variables tail (:161-169): theta and sa re-derived for the current spins; lnpsi0 is NOT refreshed
   launch_theta(h, h->spins.p, h->spins.p, h->theta.p, h->sa.p, nullptr);
@@ -922,12 +1138,8 @@ void do_sweeps(nqs_handle * h, int n_sweeps)
   NQS_REQUIRE(n_sweeps >= 0, NQS_ERR_INVALID, "n_sweeps < 0");
   const long long nsteps = (long long)n_sweeps*h->N;
   if (nsteps == 0) return;
-  std::vector<int> ord(h->N);
   launch_sweep(h, nsteps);
-  // the machine's index_ is the last visited site
-  NQS_CUDA(cudaMemcpyAsync(ord.data(), h->order.p, sizeof(int)*h->N, cudaMemcpyDeviceToHost, h->stream));
-  NQS_CUDA(cudaStreamSynchronize(h->stream));
-  h->flip_index = ord[(h->pos+h->N-1)%h->N];
+  h->flip_index = h->order_host[(h->pos+h->N-1)%h->N];   // the machine's index_ is the last visited site
 }
 
 void do_initialize(nqs_handle * h, const int8_t * spins_host)
@@ -960,6 +1172,7 @@ void build_order(nqs_handle * h)
   std::vector<int> ord(N);
   for (int t = 0; t < N; ++t) ord[t] = ring[(t+1)%N];
   NQS_CUDA(cudaMemcpy(h->order.p, ord.data(), sizeof(int)*N, cudaMemcpyHostToDevice));
+  h->order_host = ord;
 }
 
 void build_J(nqs_handle * h)
@@ -979,7 +1192,7 @@ void build_J(nqs_handle * h)
 
 void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
-  h->tables_valid = false;
+  invalidate_tables(h);
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
@@ -1025,10 +1238,12 @@ void alloc_sr(nqs_handle * h)
       (ng && std::atoi(ng) != 0) &&
       (size_t)NQS_SV_MAX_SLOTS*sv_gen_slot_bytes(h->N, h->M)+NQS_SV_TAIL_BYTES <= h->smem_optin;
     if (h->gen_ok) h->Sd.alloc((size_t)h->K*h->N); }
+  plan_cgp(h);
+  if (h->cgp_ok) h->variant_sv += "_persistentcg";
   h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->traw.alloc((size_t)2*h->P);
-  h->slots.alloc((size_t)2*NQS_CG_MAX_CTAS*NQS_CG_NVALS);
+  h->slots.alloc((size_t)2*NQS_CGP_MAX_CTAS*NQS_CG_NVALS);   // sized for the persistent kernel's grid (cg_fused_kernel uses the first 148 of each half)
   h->cgbar.alloc(1);
   NQS_CUDA(cudaMemset(h->cgbar.p, 0, sizeof(unsigned int)));
   h->scal.alloc(1);
@@ -1187,9 +1402,9 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
   {
     NQS_REQUIRE(params && P == h->P, NQS_ERR_INVALID, "nqs_set_params: P mismatch");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
+    invalidate_tables(h);
     NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
-    h->tables_valid = false;
     h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   });
 }
@@ -1494,22 +1709,8 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       if (h->struct_sv) launch_hidden_values(h);
       else if (h->gen_ok) { launch_hidden_values(h); h->o_pending = true; }   // O is written by the first S*v of the CG
       else launch_oderiv(h); }
-    double hs[3];
-    {
-      { Span t(h, TAG_SETUP); sr_setup(h, true); }
-      NQS_CUDA(cudaMemcpyAsync(h->pinned, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
-      NQS_CUDA(cudaStreamSynchronize(h->stream));
-      std::memcpy(hs, h->pinned, sizeof(hs));
-    }
-    const double invk = 1.0/(double)h->Ktot;
-    s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
-    s.finite = std::isfinite(s.e_re) ? 1 : 0;
-    if (!s.finite)
-    { // ref optimizer.cuh:134-138: print and stop; here: report and leave the state untouched
-      if (st) *st = s;
-      resolve_spans(h);
-      return;
-    }
+    { Span t(h, TAG_SETUP); sr_setup(h, true); }
+    const double bp_before = h->bp;
     if (opt->lambda < 0)
     { // ref schedular_, impl_optimizer.cuh:72-78
       h->bp *= 0.9;
@@ -1517,11 +1718,47 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       s.lambda = (lam > 1e-2) ? lam : 1e-2;
     }
     else s.lambda = opt->lambda;
-    { Span t(h, TAG_CG); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
-    if (opt->apply_update)
-    { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr); }
-    NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
-    resolve_spans(h);
+    double hs[3];
+    const double invk = 1.0/(double)h->Ktot;
+    const bool persistent = cgp_usable(h);
+    if (persistent)
+    { // nothing below waits for the device: the energy check (ref optimizer.cuh:134-138) is made by the CG kernel itself, which
+      // skips the solve -- and, through its flag, the update -- when <h> is not finite; one synchronisation ends the step
+      { Span t(h, TAG_CG); cg_solve_persistent(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters); }
+      if (opt->apply_update)
+      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr, &h->scal.p->nonfinite); }
+      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
+      finish_tables(h);
+      std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
+      resolve_spans(h);
+      bool nonfinite = false;
+      collect_cg(h, &s, &nonfinite);
+      s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
+      s.finite = nonfinite ? 0 : 1;
+      if (nonfinite) { h->bp = bp_before; if (st) *st = s; return; }
+    }
+    else
+    {
+      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaStreamSynchronize(h->stream));
+      std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
+      s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
+      s.finite = std::isfinite(s.e_re) ? 1 : 0;
+      if (!s.finite)
+      { // ref optimizer.cuh:134-138: print and stop; here: report and leave the state untouched
+        h->bp = bp_before;
+        if (st) *st = s;
+        resolve_spans(h);
+        return;
+      }
+      { Span t(h, TAG_CG); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
+      if (opt->apply_update)
+      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr); }
+      NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
+      finish_tables(h);
+      resolve_spans(h);
+    }
     const double n2 = s.e_re*s.e_re+s.e_im*s.e_im;
     s.rsd = std::sqrt((hs[2]*invk-n2)/n2);
     if (st) *st = s;
@@ -1553,6 +1790,7 @@ nqs_status nqs_evolve(nqs_handle * h, const nqs_cdouble * dx, double lr)
     NQS_CUDA(cudaMemcpyAsync(buf, dx, sizeof(cd)*h->P, cudaMemcpyHostToDevice, h->stream));
     do_evolve(h, buf, lr);
     NQS_CUDA(cudaStreamSynchronize(h->stream));
+    finish_tables(h);
   });
 }
 
@@ -1640,10 +1878,14 @@ nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BY
     if (h->xbuf == nullptr)
     {
       h->xbuf_data_bytes = (size_t)2*h->n_ranks*2*(size_t)h->P*sizeof(double);
-      const size_t total = h->xbuf_data_bytes+(size_t)2*NQS_CG_MAX_RANKS*NQS_CG_MAX_CTAS*sizeof(unsigned int);
+      const size_t flag_bytes = (size_t)2*NQS_CG_MAX_RANKS*NQS_CGP_MAX_CTAS*sizeof(unsigned int);
+      const size_t total = h->xbuf_data_bytes+flag_bytes+64;
       cudaError_t e = cudaMalloc(&h->xbuf, total);
       if (e != cudaSuccess) throw Error(NQS_ERR_NOMEM, std::string("cudaMalloc of the peer exchange buffer failed: ")+cudaGetErrorString(e));
       NQS_CUDA(cudaMemset(h->xbuf, 0, total));
+      // header behind the flags: the grid this rank would run the persistent CG kernel on; the importers compare them
+      const int hdr[4] = {0x4e515331, h->cgp_ok ? 1 : 0, h->sv_nclusters*h->sv_cs, h->sv_nt};
+      NQS_CUDA(cudaMemcpy((char*)h->xbuf+h->xbuf_data_bytes+flag_bytes, hdr, sizeof(hdr), cudaMemcpyHostToDevice));
       NQS_CUDA(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t ipc;
@@ -1673,6 +1915,15 @@ nqs_status nqs_comm_p2p_import(nqs_handle * h, const char * handles)
           " -- the engine keeps using ncclAllReduce");
       }
       h->peer_base[r] = ptr;
+    }
+    // the persistent CG kernel pairs CTA b of this rank with CTA b of every peer: all ranks must have planned the same grid
+    const size_t flag_bytes = (size_t)2*NQS_CG_MAX_RANKS*NQS_CGP_MAX_CTAS*sizeof(unsigned int);
+    h->cgp_peers_agree = true;
+    for (int r = 0; r < h->n_ranks; ++r)
+    {
+      int hdr[4] = {0, 0, 0, 0};
+      NQS_CUDA(cudaMemcpy(hdr, (char*)h->peer_base[r]+h->xbuf_data_bytes+flag_bytes, sizeof(hdr), cudaMemcpyDeviceToHost));
+      if (hdr[0] != 0x4e515331 || hdr[1] != 1 || !h->cgp_ok || hdr[2] != h->sv_nclusters*h->sv_cs || hdr[3] != h->sv_nt) h->cgp_peers_agree = false;
     }
     h->p2p_ok = true;
     h->p2p_epoch = 0;

@@ -57,6 +57,7 @@ struct nqs_handle
   nqs::DevBuf<int8_t> spins, tmp_spins;
   nqs::DevBuf<double> Jmat, uniforms, sjs;
   nqs::DevBuf<int> order;
+  std::vector<int> order_host;            // host copy of the site ring (the machine's index_ after a sweep is read from it)
   nqs::DevBuf<unsigned char> acc_log, fresh;
   // specialised RBM path: flip tables rebuilt after every parameter change (fast_kernels.cuh)
   nqs::DevBuf<nqs::FlipTab> ftab_a, ftab_b;
@@ -84,11 +85,19 @@ struct nqs_handle
   int nrb = 1;                            // row blocks of the column passes
   long long rows_per_block = 0;
   void * pinned = nullptr;                // small pinned staging area for scalar read-backs
+  bool cg_attr_set = false;               // cg_fused_kernel's carve-out preference was set on this handle's device
+  int cg_coop = -1;                       // -1 unknown, 1 = cooperative launches work on this device, 0 = plain launches + barrier time-out
   // one-pass S*v (sv_fused.cuh): cluster size, columns per thread, threads, TMA slots, clusters, rows per cluster
   bool sv_ok = false;
   int sv_cs = 0, sv_cpt = 0, sv_nt = 0, sv_nslot = 0, sv_nclusters = 0, sv_defer = 0, sv_depth = 0;
   size_t sv_smem = 0, sv_slot_bytes = 0;
   long long sv_pc = 0, sv_rpc = 0;
+  // persistent CG (cg_persist.cuh): the whole solve as one launch of the sv_fused clusters
+  bool cgp_ok = false;                    // planned for this handle (single GPU, or every rank planned the same grid)
+  bool cgp_peers_agree = true;            // multi-GPU: all ranks export the same persistent grid (checked at p2p import)
+  int cgp_coop = -1;                      // cooperative + cluster launch: -1 untried, 1 works, 0 refused (plain cluster launch, barrier time-out)
+  bool cg_inflight = false;               // a persistent solve was launched and its scalars are not read back yet
+  bool bound_inflight = false;            // theta_bound of freshly built tables is on its way to pinned memory
   // structured S*v (sv_struct.cuh, NQS_FLAG_STRUCTURED_SV): hidden-unit factors T (and L, FFNN), chain chunks of the column GEMM
   bool struct_sv = false, hidden_valid = false;
   nqs::DevBuf<nqs::cd> Tm, Lm, vnat;

@@ -436,12 +436,17 @@ struct CgScalars
   double tol2;
   int done, iters, zero_rhs, fixed;
   int peer_timeout;        // multi-GPU: a peer's flag did not arrive within 20 s
+  int barrier_timeout;     // the software grid barrier gave up (CTAs not co-resident on a non-cooperative launch)
+  int nonfinite;           // <h> was not finite: the solve and the update were skipped (ref optimizer.cuh:134-138)
+  int pad_;
 };
 
 // ref: update_parameters (impl_neural_quantum_state.cuh:1300-1312) / FFNN__UpdateParameters__ (:1665-1690, un-transposes the W block)
+// `skip` (may be null): device flag raised by the CG kernel when <h> was not finite -- the reference stops before the update then
 __global__ void update_params_kernel(const int N, const int M, const int model, const long long P, const cd * __restrict__ dx,
-  const double lr, cd * __restrict__ params)
+  const double lr, cd * __restrict__ params, const int * __restrict__ skip)
 {
+  if (skip != nullptr && *skip) return;
   const long long NM = (long long)N*M;
   for (long long q = (long long)blockIdx.x*blockDim.x+threadIdx.x; q < P; q += (long long)gridDim.x*blockDim.x)
   {

@@ -56,6 +56,25 @@ def lib():
     return _lib
 
 
+def set_blas_threads(n: int) -> bool:
+    """Thread count of the OpenBLAS the reference harness is linked against (openblas_set_num_threads on the copy that is
+    already mapped into this process).  Returns False if that symbol cannot be found (the OPENBLAS_NUM_THREADS value stays)."""
+    lib()
+    try:
+        with open("/proc/self/maps") as f:
+            paths = {ln.split()[-1] for ln in f if "libopenblas" in ln}
+        for path in paths:
+            fn = getattr(C.CDLL(path), "openblas_set_num_threads", None)
+            if fn is not None:
+                fn.argtypes = [C.c_int]
+                fn.restype = None
+                fn(int(n))
+                return True
+    except Exception:
+        pass
+    return False
+
+
 def _p(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
