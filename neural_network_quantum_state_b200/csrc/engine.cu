@@ -311,18 +311,31 @@ bool fast_path_ok(nqs_handle * h)
   return std::isfinite(h->theta_bound) && h->theta_bound < 300.0/h->jpl;
 }
 
-// shared memory of the sweep variant launch_sweep picks for this hidden width (the chains-per-warp / warps-per-CTA of each case
-// below): long chains with a narrow hidden layer can exceed the opt-in limit, and then the generic kernel takes over
+// Chains per warp of the register-resident sweep.  More chains per warp reuse every table row fetched from shared memory and
+// amortise the per-proposal bookkeeping (the throughput choice: 4 for <= 4 hidden-unit slots per lane, 2 for 8, 1 above), but a
+// warp then walks its chains' proposals one after the other.  When the whole shard fits the SMs at once with FEWER chains per
+// warp (a strong-scaled shard: 2048 chains per GPU at 8 GPUs), the extra warps run in parallel instead and the sweep gets
+// shorter (0.32 -> ~0.2 ms there): take the smallest C whose grid is a single wave, else the throughput choice.
+int sweep_chains_per_warp(const nqs_handle * h)
+{
+  const int cmax = (h->jpl <= 4) ? 4 : (h->jpl == 8 ? 2 : 1);
+  { const char * e = std::getenv("NQS_SWEEP_C"); if (e) { const int c = std::atoi(e); if (c == 1 || (c == 2 && cmax >= 2) || (c == 4 && cmax == 4)) return c; } }
+  if (h->jpl > 8) return 1;
+  for (int c = 1; c < cmax; c <<= 1)
+  {
+    const int warps = (c == 1) ? 8 : 4;                      // SweepShape: one chain per warp runs 8 warps per CTA, else 4; 2 CTAs per SM
+    const long long ctas = (h->K+(long long)warps*c-1)/((long long)warps*c);
+    if (ctas <= 2LL*h->sm_count) return c;
+  }
+  return cmax;
+}
+
+// shared memory of the sweep variant launch_sweep picks (long chains with a narrow hidden layer can exceed the opt-in limit, and
+// then the generic kernel takes over)
 bool fast_sweep_fits(const nqs_handle * h)
 {
-  int C = 1, warps = 8;
-  switch (h->jpl)
-  {
-    case 1: case 2: case 4: C = 4; warps = SweepShape<4, 4, 1>::warps; break;
-    case 8: C = 2; warps = SweepShape<8, 2, 1>::warps; break;
-    case 16: C = 1; warps = SweepShape<16, 1, 1>::warps; break;
-    default: C = 1; warps = SweepShape<16, 1, 2>::warps; break;
-  }
+  const int C = sweep_chains_per_warp(h);
+  const int warps = (h->jpl > 16) ? SweepShape<16, 1, 2>::warps : ((C == 1 && h->jpl <= 8) ? 8 : 4);
   return fast_sweep_smem_bytes(h->N, C, warps, h->mpad) <= h->smem_optin;
 }
 
@@ -385,17 +398,18 @@ void launch_sweep(nqs_handle * h, long long nsteps)
     f.spins = h->spins.p; f.theta = h->theta.p; f.lnpsi0 = h->lnpsi0.p; f.sa = h->sa.p; f.fresh = h->fresh.p; f.order = h->order.p;
     f.pos0 = h->pos; f.nsweeps = (int)(nsteps/h->N); f.uniforms = a.uniforms; f.seed = a.seed; f.step0 = a.step0;
     f.chain_offset = a.chain_offset; f.acc_log = a.acc_log;
+    const int C = sweep_chains_per_warp(h);
+#define NQS_SWEEP_CASE(J) case J: if (C == 4) launch_sweep_fast_t<J, 4>(h, f); else if (C == 2) launch_sweep_fast_t<J, 2>(h, f); else launch_sweep_fast_t<J, 1>(h, f); break
     switch (h->jpl)
     {
-      case 1: launch_sweep_fast_t<1, 4>(h, f); break;
-      case 2: launch_sweep_fast_t<2, 4>(h, f); break;
-      case 4: launch_sweep_fast_t<4, 4>(h, f); break;
-      case 8: launch_sweep_fast_t<8, 2>(h, f); break;
+      NQS_SWEEP_CASE(1); NQS_SWEEP_CASE(2); NQS_SWEEP_CASE(4);
+      case 8: if (C == 2) launch_sweep_fast_t<8, 2>(h, f); else launch_sweep_fast_t<8, 1>(h, f); break;
       case 16: launch_sweep_fast_t<16, 1>(h, f); break;
       default: launch_sweep_fast_t<16, 1, 2>(h, f); break;     // jpl = 32 (M <= 1024): two warps per chain
     }
+#undef NQS_SWEEP_CASE
     check_launch(h, "rbm_sweep_fast_kernel");
-    h->variant_sweep = "rbm_regs_j"+std::to_string(h->jpl);
+    h->variant_sweep = "rbm_regs_j"+std::to_string(h->jpl)+"_c"+std::to_string(C);
     h->pos = (int)((h->pos+nsteps)%h->N);
     if (h->u_steps > 0) h->u_used += nsteps;
     h->step_counter += (unsigned long long)nsteps;
@@ -664,6 +678,8 @@ void plan_sv(nqs_handle * h)
   }
 }
 
+int cg_ctas(const nqs_handle * h);
+
 void allreduce_sum(nqs_handle * h, double * buf, size_t count)
 {
   if (h->comm == nullptr) return;
@@ -768,6 +784,32 @@ void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
   }
 }
 
+// local sums -> all ranks' sums -> <O>, F, diag S.  Multi-GPU with mapped peers: one kernel that exchanges over NVLink and
+// finalises (setup_exchange_finalize_kernel); otherwise ncclAllReduce (if sharded) + setup_finalize_kernel.
+void finish_setup(nqs_handle * h, bool want_F)
+{
+  const long long P = h->P;
+  if (h->comm != nullptr && h->p2p_ok && h->xbuf_setup_off != 0)
+  {
+    SetupXArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.P = P; a.inv_ktot = 1.0/(double)h->Ktot; a.sums = h->sums.p; a.hsall = h->hsall.p; a.aO = h->aO.p; a.F = want_F ? h->F.p : nullptr;
+    a.diag = h->diag.p; a.n_ranks = h->n_ranks; a.rank = h->rank; a.epoch = ++h->setup_epoch; a.timeout_flag = &h->scal.p->peer_timeout;
+    for (int r = 0; r < h->n_ranks; ++r)
+    {
+      a.peer_x[r] = reinterpret_cast<double*>((char*)h->peer_base[r]+h->xbuf_setup_off);
+      a.peer_flag[r] = reinterpret_cast<unsigned int*>((char*)h->peer_base[r]+h->xbuf_setup_flag_off);
+    }
+    setup_exchange_finalize_kernel<<<cg_ctas(h), 256, 0, h->stream>>>(a);
+    check_launch(h, "setup_exchange_finalize_kernel");
+    return;
+  }
+  allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
+  setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
+    want_F ? h->F.p : nullptr, h->diag.p, h->hsall.p);
+  check_launch(h, "setup_finalize_kernel");
+}
+
 // <O>, F, diag from ONE pass over O (+ one all-reduce of 5P+3 doubles across ranks)
 void sr_setup(nqs_handle * h, bool want_F)
 {
@@ -789,10 +831,7 @@ void sr_setup(nqs_handle * h, bool want_F)
     else
       setup_fold_struct_kernel<MODEL_FFNN><<<g, 256, 0, h->stream>>>(h->N, h->M, P, K, h->sc_nchunks, h->part.p, c.part_stride, h->abs2.p, h->sums.p);
     check_launch(h, "setup_fold_struct_kernel");
-    allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
-    setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
-      want_F ? h->F.p : nullptr, h->diag.p);
-    check_launch(h, "setup_finalize_kernel");
+    finish_setup(h, want_F);
     return;
   }
   if (ipt <= 16 && h->theta_matches_O && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
@@ -812,10 +851,7 @@ void sr_setup(nqs_handle * h, bool want_F)
   }
   colsum_reduce_kernel<<<grid_for(5*P, 256, 148*8), 256, 0, h->stream>>>(P, 5, h->nrb, h->part.p, h->sums.p, nullptr);
   check_launch(h, "colsum_reduce_kernel");
-  allreduce_sum(h, h->sums.p, (size_t)(5*P+3));
-  setup_finalize_kernel<<<grid_for(P, 256, 148*4), 256, 0, h->stream>>>(P, 1.0/(double)h->Ktot, h->sums.p, h->aO.p,
-    want_F ? h->F.p : nullptr, h->diag.p);
-  check_launch(h, "setup_finalize_kernel");
+  finish_setup(h, want_F);
 }
 
 // z = O v and the chunk partials of O^H z from the factors: two tensor-core GEMMs, no pass over O
@@ -1062,7 +1098,7 @@ void cg_solve_persistent(nqs_handle * h, double lambda, double tol, int max_iter
   a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
   a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.tol2 = tol*tol; a.fixed_iters = fixed_iters; a.max_iter = max_iter;
   a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.sc = h->scal.p;
-  a.slots = h->slots.p; a.barrier = h->cgbar.p; a.hsums = h->sums.p+5*h->P;
+  a.slots = h->slots.p; a.barrier = h->cgbar.p; a.hsums = h->hsall.p;
   a.n_ranks = 1; a.rank = 0; a.epoch0 = h->p2p_epoch;
   if (h->comm != nullptr)
   {
@@ -1242,6 +1278,7 @@ void alloc_sr(nqs_handle * h)
   if (h->cgp_ok) h->variant_sv += "_persistentcg";
   h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P));
   h->sums.alloc((size_t)5*h->P+3);
+  h->hsall.alloc(4);
   h->traw.alloc((size_t)2*h->P);
   h->slots.alloc((size_t)2*NQS_CGP_MAX_CTAS*NQS_CG_NVALS);   // sized for the persistent kernel's grid (cg_fused_kernel uses the first 148 of each half)
   h->cgbar.alloc(1);
@@ -1727,7 +1764,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       { Span t(h, TAG_CG); cg_solve_persistent(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters); }
       if (opt->apply_update)
       { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr, &h->scal.p->nonfinite); }
-      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->hsall.p, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
       NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
       finish_tables(h);
       std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
@@ -1740,7 +1777,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
     }
     else
     {
-      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->sums.p+5*h->P, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
+      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->hsall.p, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
       NQS_CUDA(cudaStreamSynchronize(h->stream));
       std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
       s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
@@ -1879,7 +1916,10 @@ nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BY
     {
       h->xbuf_data_bytes = (size_t)2*h->n_ranks*2*(size_t)h->P*sizeof(double);
       const size_t flag_bytes = (size_t)2*NQS_CG_MAX_RANKS*NQS_CGP_MAX_CTAS*sizeof(unsigned int);
-      const size_t total = h->xbuf_data_bytes+flag_bytes+64;
+      // behind the CG region: the SR-setup exchange (setup_exchange_finalize_kernel): data [2][n_ranks][5P+4] doubles + flags
+      h->xbuf_setup_off = (h->xbuf_data_bytes+flag_bytes+64+255)/256*256;
+      h->xbuf_setup_flag_off = h->xbuf_setup_off+(size_t)2*h->n_ranks*(5*(size_t)h->P+4)*sizeof(double);
+      const size_t total = h->xbuf_setup_flag_off+(size_t)2*NQS_CG_MAX_RANKS*NQS_CG_MAX_CTAS*sizeof(unsigned int);
       cudaError_t e = cudaMalloc(&h->xbuf, total);
       if (e != cudaSuccess) throw Error(NQS_ERR_NOMEM, std::string("cudaMalloc of the peer exchange buffer failed: ")+cudaGetErrorString(e));
       NQS_CUDA(cudaMemset(h->xbuf, 0, total));

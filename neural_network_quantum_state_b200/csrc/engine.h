@@ -77,7 +77,7 @@ struct nqs_handle
 
   // SR
   nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
-  nqs::DevBuf<double> diag, part, sums, traw, slots;
+  nqs::DevBuf<double> diag, part, sums, traw, slots, hsall;
   nqs::DevBuf<nqs::CgScalars> scal;
   nqs::DevBuf<unsigned int> cgbar;         // grid-barrier counter of cg_fused_kernel (zero between launches)
   double bp = 1.0;                        // lambda schedule state (ref bp_, optimizer.cuh:176)
@@ -118,6 +118,8 @@ struct nqs_handle
   void * peer_base[16] = {nullptr};
   bool p2p_ok = false;
   unsigned int p2p_epoch = 0;
+  size_t xbuf_setup_off = 0, xbuf_setup_flag_off = 0;   // SR-setup exchange region of xbuf (data [2][n_ranks][5P+4], flags)
+  unsigned int setup_epoch = 0;
   nqs::DevBuf<unsigned long long> cg_trace;   // NQS_CG_TRACE=1: per-launch time stamps of cg_fused_kernel (diagnostics)
   long long cg_trace_n = 0;
 

@@ -330,10 +330,11 @@ __global__ void __launch_bounds__(1024) htilda_sums_kernel(const long long K, co
 // sums = [sum O (re P | im P) | sum O conj(h) (re P | im P) | sum |O|^2 (P) | sum h (2) | sum |h|^2 (1)]  (all-reduced over ranks before)
 //   aO = sumO/K ; F = conj( sumOh/K - conj(<h>) aO )  (ref SR__FStep2__, impl_optimizer.cuh:82-96) ; diag = sumO2/K - |aO|^2 (ref k19)
 __global__ void setup_finalize_kernel(const long long P, const double inv_ktot, const double * __restrict__ sums,
-  cd * __restrict__ aO, cd * __restrict__ F, double * __restrict__ diag)
+  cd * __restrict__ aO, cd * __restrict__ F, double * __restrict__ diag, double * __restrict__ hsall)
 {
   const double * hs = sums+5*P;
   const cd conj_havg = cmake(hs[0]*inv_ktot, -hs[1]*inv_ktot);
+  if (blockIdx.x == 0 && threadIdx.x < 3) hsall[threadIdx.x] = hs[threadIdx.x];   // where the CG kernel and the host read <h>, <|h|^2>
   for (long long p = (long long)blockIdx.x*blockDim.x+threadIdx.x; p < P; p += (long long)gridDim.x*blockDim.x)
   {
     const cd ao = cmake(sums[p]*inv_ktot, sums[P+p]*inv_ktot);

@@ -43,7 +43,7 @@ def test_cfg5_shard_full_size_64bit_indexing():
     assert e.kernel_variant("sv") == "two_pass"          # P/16 columns do not fit the cluster kernel's register budget
     e.init_params_random(3)
     e.warm_up(1)
-    assert e.kernel_variant("sweep") == "rbm_regs_j32"   # M = 1024: two warps per chain
+    assert e.kernel_variant("sweep").startswith("rbm_regs_j32")   # M = 1024: two warps per chain
     e.get_lnpsiGradients(copy=False)                      # fills the 34.5 GB O on the device
     rng = np.random.default_rng(0)
     v = rng.normal(size=P) + 1j * rng.normal(size=P)

@@ -180,6 +180,18 @@ def test_sweep_matches_oracle_step_by_step(model, N, M, K, pbc, force_generic):
     e.close()
 
 
+# chains per warp of the register-resident sweep: small shards take one chain per warp (a single wave), big ones the throughput
+# choice; NQS_SWEEP_C pins it so that every instantiation meets the oracle whatever the shard size of the test
+@pytest.mark.parametrize("N,M,K,C", [(16, 16, 70, 4), (16, 16, 70, 2), (16, 16, 70, 1), (24, 40, 50, 4), (24, 40, 50, 2), (24, 40, 50, 1),
+                                     (20, 128, 45, 4), (20, 128, 45, 2), (20, 128, 45, 1), (20, 256, 33, 2), (20, 256, 33, 1),
+                                     (128, 256, 40, 2), (128, 256, 40, 1)])
+def test_sweep_chains_per_warp_variants(monkeypatch, N, M, K, C):
+    monkeypatch.setenv("NQS_SWEEP_C", str(C))
+    e, _, _ = _sweep_vs_oracle("rbm", N, M, K, False, False, 3, 1, check_O=False)
+    assert e.kernel_variant("sweep").endswith("_c%d" % C), e.kernel_variant("sweep")
+    e.close()
+
+
 @pytest.mark.parametrize("model,N,M,K,n_warm,n_more", BASELINE_SHAPES)
 def test_baseline_shapes_match_oracle(model, N, M, K, n_warm, n_more):
     """Sampler, local energy, O, SR sums and S*v at the (N, M) of BASELINE.json's configurations, against the numpy oracle."""

@@ -115,6 +115,7 @@ def test_o_generated_inside_first_sv_matches_separate_writer(N, M, K, monkeypatc
     that the GEN launch wrote."""
     from neural_network_quantum_state_b200 import Engine
     res = []
+    monkeypatch.setenv("NQS_CG_PERSIST", "0")   # the O-generating first product belongs to the launch-per-iteration path: like with like
     for gen in ("1", "0"):
         monkeypatch.setenv("NQS_SV_GEN", gen)
         e = Engine("rbm", N, M, K, H, J, ALPHA, seed=5)
