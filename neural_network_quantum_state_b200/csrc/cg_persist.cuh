@@ -22,6 +22,8 @@
 //           cg_fused.cuh with x, r, p, z held in registers across its two grid sums.  Same arithmetic per element as
 //           cg_fused_kernel; the grid sums fold the elements in a different (equally fixed) order, so the iterates agree
 //           with the launch-per-iteration path to rounding and are run-to-run deterministic (tests).
+//   (single_red, opt-in NQS_CG_SINGLE=1) the two grid sums of an iteration merge into one, see the ITER branch -- measured no
+//           faster: one 11-value sum takes ~15 us against 7.5 + 5 us for the two small ones, so the reference recurrence stays.
 //   (no barrier B) the next direction d = z + beta d is NOT waited for: z is stored before the second grid sum, beta is known to
 //           every thread after it, and the previous direction was stored one product earlier -- so every CTA forms its slice
 //           of the new direction itself at the top of the next row pass (same fma as the owner: same bits).
@@ -54,7 +56,9 @@ struct CgpArgs
   cd * x;                   // in: warm start, out: solution
   cd * r;
   cd * pb[2];               // direction d_k of product k lives in pb[k & 1] (written by its owner thread during product k-1)
-  cd * zv;                  // z_k = M^-1 r_k, written before the second grid sum of product k
+  cd * zv;                  // z = M^-1 r, written before the last grid sum of product k
+  cd * wv;                  // single_red: w_k = M^-1 t_k
+  int single_red;           // one grid sum per iteration instead of two (see the ITER branch); 0 = the reference's two-sum recurrence
   CgScalars * sc;
   double * slots;           // [2][NQS_CGP_MAX_CTAS][NQS_CG_NVALS]
   unsigned int * barrier;   // zero between launches
@@ -62,15 +66,23 @@ struct CgpArgs
   // ---- in-kernel all-reduce over peer memory (n_ranks > 1)
   int n_ranks, rank;
   unsigned int epoch0;      // exchange epochs used by this launch: epoch0 + 1, epoch0 + 2, ... (one per product)
-  double * peer_x[NQS_CG_MAX_RANKS];
-  unsigned int * peer_flag[NQS_CG_MAX_RANKS];
+  // Reduce-scatter + all-gather in "LL" packets (NCCL's low-latency protocol): every double travels as a 16-byte packet
+  // {lo32, epoch, hi32, epoch}, so the data carries its own arrival flag -- 8-byte stores are atomic, the receiver polls the
+  // packet itself, and no release fence / flag round trip follows the stores.
+  //   phase 1: rank r sends the elements of slice q (P/n_ranks of them) of its folded partial to rank q        -> ll1[q][r][slice]
+  //   phase 2: rank q adds the n_ranks copies of its slice in RANK ORDER and sends the sums to every rank     -> ll2[*][P]
+  // (the earlier all-to-all push of whole vectors moved n_ranks times the bytes: 3.7 MB per rank and product at 8 GPUs, ~12 us
+  // with its system-scope release, trace of round 2)
+  uint4 * peer_ll1[NQS_CG_MAX_RANKS];     // [n_ranks][S][2] packets, S = ceil(P / n_ranks)
+  uint4 * peer_ll2[NQS_CG_MAX_RANKS];     // [P][2] packets
   unsigned long long * trace;   // NQS_CG_TRACE=1: [NQS_CGP_TRACE_WORDS] globaltimer stamps of CTA 0 per product (else null)
   int trace_max;
 };
+#define NQS_CGP_NVALS 12         // values per grid sum (single-reduction iteration: 11)
 #define NQS_CGP_MAX_CTAS 2048    // small problems run several narrow CTAs per SM; slots / exchange flags are sized for this many
 #define NQS_CGP_TRACE_WORDS 8   // product start, rows done, barrier A passed, pushed + flags raised, peers seen, sum 1, sum 2, end
 // shared memory after sv_fused's core tail (part of NQS_SV_TAIL_BYTES): reduction scratch [NQS_SV_MAX_WARPS][NQS_CG_NVALS] doubles | control words
-static_assert(NQS_CG_NVALS == 6, "NQS_SV_TAIL_BYTES reserves 6 doubles per warp");
+static_assert(NQS_SV_TAIL_BYTES-NQS_SV_TAIL_CORE >= NQS_SV_MAX_WARPS*NQS_CGP_NVALS*8+64+64, "NQS_SV_TAIL_BYTES reserves the scratch");
 template <int CPT> struct CgpEpt { static const int value = (CPT <= 3) ? 1 : 2; };
 
 // mbarrier primitives on precomputed shared-memory addresses
@@ -90,6 +102,32 @@ __device__ __forceinline__ void mbar_arrive_a(const uint32_t addr)
 __device__ __forceinline__ void mbar_expect_tx_a(const uint32_t addr, const uint32_t bytes)
 {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(addr), "r"(bytes) : "memory");
+}
+
+// ---- LL packets
+__device__ __forceinline__ void ll_store(uint4 * dst, const double v, const unsigned int flag)
+{
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+    :: "l"(dst), "r"((unsigned int)__double2loint(v)), "r"(flag), "r"((unsigned int)__double2hiint(v)), "r"(flag) : "memory");
+}
+// waits until both halves of the packet carry `flag`; false after NQS_CG_BARRIER_TIMEOUT_NS (a peer died)
+__device__ __forceinline__ bool ll_wait(const uint4 * src, const unsigned int flag, double & v)
+{
+  unsigned int lo, f1, hi, f2, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;)
+  {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(src) : "memory");
+    if (f1 == flag && f2 == flag) break;
+    if ((++spins&4095u) == 0u)
+    {
+      const unsigned long long now = cg_now();
+      if (t0 == 0) t0 = now;
+      else if (now-t0 > NQS_CG_BARRIER_TIMEOUT_NS) { v = 0.0; return false; }
+    }
+  }
+  v = __hiloint2double((int)hi, (int)lo);
+  return true;
 }
 
 // CTA-level barrier of the consumer warps only (the producer warp never joins): named barrier 1
@@ -133,7 +171,7 @@ __device__ __forceinline__ bool cgp_grid_sum(double (&vals)[NV], const CgpArgs &
   const int NT, volatile int * ctl)
 {
   const int lane = threadIdx.x&31, w = threadIdx.x>>5, NW = NT>>5;
-  double * slots = a.slots+(size_t)(nsum&1u)*NQS_CGP_MAX_CTAS*NQS_CG_NVALS;
+  double * slots = a.slots+(size_t)(nsum&1u)*NQS_CGP_MAX_CTAS*NQS_CGP_NVALS;
 #pragma unroll
   for (int i = 0; i < NV; ++i) vals[i] = warp_sum(vals[i]);
   if (lane == 0)
@@ -146,7 +184,7 @@ __device__ __forceinline__ bool cgp_grid_sum(double (&vals)[NV], const CgpArgs &
   {
     double s = 0.0;
     for (int ww = 0; ww < NW; ++ww) s += sh[ww*NV+threadIdx.x];
-    slots[(size_t)blockIdx.x*NQS_CG_NVALS+threadIdx.x] = s;
+    slots[(size_t)blockIdx.x*NQS_CGP_NVALS+threadIdx.x] = s;
   }
   ++epoch; ++nsum;
   const bool ok = cgp_grid_barrier(a, epoch*gridDim.x, NT, ctl);
@@ -166,7 +204,7 @@ __device__ __forceinline__ bool cgp_grid_sum(double (&vals)[NV], const CgpArgs &
       {
         const int b = b0+32*q+lane;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) v[q][i] = (b < (int)gridDim.x) ? __ldcg(slots+(size_t)b*NQS_CG_NVALS+i) : 0.0;
+        for (int i = 0; i < NV; ++i) v[q][i] = (b < (int)gridDim.x) ? __ldcg(slots+(size_t)b*NQS_CGP_NVALS+i) : 0.0;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -205,8 +243,8 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
   uint64_t * empty = full+NQS_SV_MAX_SLOTS;
   uint64_t * wfull = empty+NQS_SV_MAX_SLOTS;
   uint64_t * zfull = wfull+NQS_SV_RBUFS;
-  double * sh = reinterpret_cast<double*>(tail+NQS_SV_TAIL_CORE);                    // [NW][NQS_CG_NVALS] reduction scratch
-  volatile int * ctl = reinterpret_cast<volatile int*>(sh+NQS_SV_MAX_WARPS*NQS_CG_NVALS); // [0] stop, [1] rows consumed, [2] barrier gave up, [3] iterations done
+  double * sh = reinterpret_cast<double*>(tail+NQS_SV_TAIL_CORE);                    // [NW][NQS_CGP_NVALS] reduction scratch
+  volatile int * ctl = reinterpret_cast<volatile int*>(sh+NQS_SV_MAX_WARPS*NQS_CGP_NVALS+8); // [0] stop, [1] rows consumed, [2] barrier gave up, [3] iterations done
 
   const long long P = a.P;
   const long long c0 = (long long)crank*a.pc;
@@ -286,7 +324,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
     const bool p2p = (a.n_ranks > 1);
     // scalars of the recurrence live in shared memory between products (identical in every thread; thread 0 stores them), so the
     // row loop -- which is at the register limit -- carries nothing of the vector phase
-    double * fsc = sh+(NQS_SV_MAX_WARPS-1)*NQS_CG_NVALS;       // [0] rho [1] thr [2] aov_x [3] aov_y [4] beta (the last warp row is never used)
+    double * fsc = sh+NQS_SV_MAX_WARPS*NQS_CGP_NVALS;           // [0] rho [1] thr [2] aov_x [3] aov_y [4] beta [5] alpha
     const cd * const sbase = reinterpret_cast<const cd*>(smem_raw)+tid;
     const size_t slot_elems = a.slot_bytes/sizeof(cd);
     const int depth = a.depth;
@@ -324,11 +362,17 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
           }
           if (prod >= 2)
           {
+            const double nalpha_prev = -fsc[5];
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
             {
               const int idx = c*NT+tid;
-              const cd zz = (idx < n_r) ? __ldcg(a.zv+c0+idx) : cmake(0.0, 0.0);
+              cd zz = (idx < n_r) ? __ldcg(a.zv+c0+idx) : cmake(0.0, 0.0);
+              if (a.single_red)
+              { // z_{k} = z_{k-1} - alpha w: the same fma as the owner's
+                const cd ww = (idx < n_r) ? __ldcg(a.wv+c0+idx) : cmake(0.0, 0.0);
+                zz = cmake(fma(nalpha_prev, ww.x, zz.x), fma(nalpha_prev, ww.y, zz.y));
+              }
               vr[c] = cmake(fma(beta_prev, vr[c].x, zz.x), fma(beta_prev, vr[c].y, zz.y));
             }
           }
@@ -440,15 +484,19 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
         trx[e] = 0.0; try_[e] = 0.0;
         if (ok[e]) cg_fold_parts(a.part, ncl, P, pp[e], trx[e], try_[e]);
       }
-      const unsigned int xepoch = a.epoch0+1u+(unsigned int)prod;
-      const int par = (int)(xepoch&1u);
+      const unsigned int xepoch = a.epoch0+1u+(unsigned int)prod;      // LL flag of this product: never 0, never repeated
+      bool peer_ok = true;
+      const long long S = (P+a.n_ranks-1)/a.n_ranks;          // elements per slice
       if (p2p)
-      {
-        const size_t xslot = ((size_t)par*a.n_ranks+a.rank)*2*(size_t)P;
+      { // phase 1: each element of the folded partial goes to the rank that owns its slice
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
           if (ok[e])
-            for (int r = 0; r < a.n_ranks; ++r) { a.peer_x[r][xslot+pp[e]] = trx[e]; a.peer_x[r][xslot+P+pp[e]] = try_[e]; }
+          {
+            const int q = (int)(pp[e]/S);
+            uint4 * dst = a.peer_ll1[q]+(((size_t)a.rank*S+(size_t)(pp[e]-q*S))<<1);
+            ll_store(dst, trx[e], xepoch); ll_store(dst+1, try_[e], xepoch);
+          }
       }
       // the vectors do not depend on the exchange: their loads travel while the peers' partials do
       cd ao[EPT], pv[EPT], xv[EPT], rv[EPT];
@@ -465,35 +513,40 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
         }
       }
       if (p2p)
-      { // CTA b of every rank owns the same elements (equal grids, checked by the host): the hand-shake is per CTA
-        cgp_cta_sync(NT);
-        if (tid < a.n_ranks)
-          asm volatile("st.release.sys.global.u32 [%0], %1;"
-            :: "l"(a.peer_flag[tid]+((size_t)par*NQS_CG_MAX_RANKS+a.rank)*NQS_CGP_MAX_CTAS+blockIdx.x), "r"(xepoch) : "memory");
+      {
         if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+3] = cg_now();
-        if (tid < a.n_ranks)
+        // phase 1 receive / phase 2 send: the elements of THIS rank's slice, spread over all CTAs (thread t of CTA b takes slice
+        // element t*gridDim + b, so every SM injects its share into NVLink)
+        long long s_mine = P-(long long)a.rank*S;
+        if (s_mine > S) s_mine = S;
+        for (long long i = (long long)tid*gridDim.x+blockIdx.x; i < s_mine; i += (long long)NT*gridDim.x)
         {
-          const unsigned int * f = a.peer_flag[a.rank]+((size_t)par*NQS_CG_MAX_RANKS+tid)*NQS_CGP_MAX_CTAS+blockIdx.x;
-          unsigned int seen;
-          const unsigned long long t0 = cg_now();
-          for (;;)
-          {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
-            if ((int)(seen-xepoch) >= 0) break;
-            if (cg_now()-t0 > NQS_CG_BARRIER_TIMEOUT_NS) { a.sc->peer_timeout = 1; a.sc->barrier_timeout = 1; ctl[2] = 1; break; }
+          double fx = 0.0, fy = 0.0;
+          for (int r = 0; r < a.n_ranks; ++r)
+          { // rank order: the same bits on every rank
+            const uint4 * src = a.peer_ll1[a.rank]+(((size_t)r*S+(size_t)i)<<1);
+            double vx, vy;
+            peer_ok = ll_wait(src, xepoch, vx) && peer_ok;
+            peer_ok = ll_wait(src+1, xepoch, vy) && peer_ok;
+            fx += vx; fy += vy;
           }
+          const size_t pe = ((size_t)a.rank*S+(size_t)i)<<1;
+          for (int r = 0; r < a.n_ranks; ++r) { ll_store(a.peer_ll2[r]+pe, fx, xepoch); ll_store(a.peer_ll2[r]+pe+1, fy, xepoch); }
         }
-        cgp_cta_sync(NT);
-        if (ctl[2]) break;
-        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+4] = cg_now();
-        const double * xin = a.peer_x[a.rank]+(size_t)par*a.n_ranks*2*(size_t)P;
+        // phase 2 receive: this thread's own elements, summed over all ranks
 #pragma unroll
         for (int e = 0; e < EPT; ++e)
         {
           trx[e] = 0.0; try_[e] = 0.0;
           if (ok[e])
-            for (int r = 0; r < a.n_ranks; ++r) { trx[e] += __ldcv(xin+(size_t)r*2*P+pp[e]); try_[e] += __ldcv(xin+(size_t)r*2*P+P+pp[e]); }
+          {
+            const uint4 * src = a.peer_ll2[a.rank]+((size_t)pp[e]<<1);
+            peer_ok = ll_wait(src, xepoch, trx[e]) && peer_ok;
+            peer_ok = ll_wait(src+1, xepoch, try_[e]) && peer_ok;
+          }
         }
+        if (!peer_ok) { a.sc->peer_timeout = 1; a.sc->barrier_timeout = 1; ctl[2] = 1; }
+        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+4] = cg_now();
       }
 
       if (prod == 0)
@@ -541,6 +594,75 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
           sc->rhs2 = rhs2; sc->res2 = res2; sc->rho = rho; sc->aov_x = aovx; sc->aov_y = aovy;
           sc->zero_rhs = zero_rhs ? 1 : 0; sc->thr = thr; sc->iters = 0; sc->done = done ? 1 : 0;
         }
+        if (done) alive = false;
+      }
+      else if (a.single_red)
+      { // ---- one iteration with ONE grid sum.  With z = M^-1 r and w = M^-1 t (M real diagonal) everything the step needs is a
+        // scalar product of vectors known BEFORE alpha:  alpha = <z,r>/<t,p>,  r' = r - alpha t,  z' = z - alpha w,
+        //   rho' = <z',r'> = <z,r> - 2 alpha Re<w,r> + alpha^2 <w,t>,   |r'|^2 = |r|^2 - 2 alpha Re<r,t> + alpha^2 |t|^2,
+        //   <O>.z' = <O>.z - alpha <O>.w.
+        // <z,r> and |r|^2 are formed DIRECTLY from this iteration's vectors every time (nothing is carried by recurrence), so the
+        // one-step predictions of rho' and |r'|^2 carry a relative error of ~1e-16 |r|^2/|r'|^2 (~1e-13) and none accumulates:
+        // beta and the stopping test see that much of a difference to the two-sum recurrence of conjugate_gradient.cuh:50-72.
+        const double thr = fsc[1], aovx = fsc[2], aovy = fsc[3];
+        const int iters = ctl[3]+1;
+        cd tv[EPT], zv[EPT], wv[EPT];
+        double sm[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) sm[i] = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          const double cx = ao[e].x*aovx+ao[e].y*aovy, cy = ao[e].x*aovy-ao[e].y*aovx;
+          tv[e] = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
+          tv[e].x += a.lambda*dg[e]*pv[e].x; tv[e].y += a.lambda*dg[e]*pv[e].y;
+          const double den = pre*dg[e];
+          zv[e] = cmake(rv[e].x/den, rv[e].y/den);
+          wv[e] = cmake(tv[e].x/den, tv[e].y/den);
+          if (ok[e])
+          {
+            a.zv[pp[e]] = zv[e]; a.wv[pp[e]] = wv[e];      // visible to every CTA behind the barrier of the grid sum below
+            sm[0] += tv[e].x*pv[e].x+tv[e].y*pv[e].y;          // Re<t,p>
+            sm[1] += zv[e].x*rv[e].x+zv[e].y*rv[e].y;          // rho = Re<z,r>
+            sm[2] += wv[e].x*rv[e].x+wv[e].y*rv[e].y;          // Re<w,r>
+            sm[3] += wv[e].x*tv[e].x+wv[e].y*tv[e].y;          // <w,t>
+            sm[4] += cnorm(rv[e]);
+            sm[5] += rv[e].x*tv[e].x+rv[e].y*tv[e].y;          // Re<r,t>
+            sm[6] += cnorm(tv[e]);
+            sm[7] += ao[e].x*zv[e].x-ao[e].y*zv[e].y; sm[8] += ao[e].x*zv[e].y+ao[e].y*zv[e].x;     // <O>.z
+            sm[9] += ao[e].x*wv[e].x-ao[e].y*wv[e].y; sm[10] += ao[e].x*wv[e].y+ao[e].y*wv[e].x;    // <O>.w
+          }
+        }
+        if (!cgp_grid_sum<11>(sm, a, sh, epoch, nsum, NT, ctl)) break;
+        if (tracing && prod < a.trace_max) { a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+5] = cg_now(); a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+6] = cg_now(); }
+        const double rho = sm[1];
+        const double alpha = rho/sm[0];
+        const double rho_n = fma(alpha, fma(alpha, sm[3], -2.0*sm[2]), rho);
+        const double res_n = fma(alpha, fma(alpha, sm[6], -2.0*sm[5]), sm[4]);
+        const double beta = rho_n/rho;
+        const bool conv = (a.fixed_iters <= 0 && res_n < thr);
+        const bool done = conv || (a.fixed_iters > 0 ? iters >= a.fixed_iters : iters >= a.max_iter);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          if (!ok[e]) continue;
+          a.x[pp[e]] = cmake(xv[e].x+alpha*pv[e].x, xv[e].y+alpha*pv[e].y);
+          a.r[pp[e]] = cmake(rv[e].x-alpha*tv[e].x, rv[e].y-alpha*tv[e].y);
+          if (!conv)
+          { // d_{k+1} = (z - alpha w) + beta d_k: the row passes of the next product form the same expression from zv, wv, pb
+            const cd zn = cmake(fma(-alpha, wv[e].x, zv[e].x), fma(-alpha, wv[e].y, zv[e].y));
+            a.pb[(prod+1)&1][pp[e]] = cmake(fma(beta, pv[e].x, zn.x), fma(beta, pv[e].y, zn.y));
+          }
+        }
+        const double naovx = (sm[7]-alpha*sm[9])+beta*aovx, naovy = (sm[8]-alpha*sm[10])+beta*aovy;   // <O>.(z' + beta p)
+        if (blockIdx.x == 0 && tid == 0)
+        {
+          CgScalars * sc = a.sc;
+          sc->tp = sm[0]; sc->alpha = alpha; sc->res2 = res_n; sc->iters = iters; sc->rho_old = rho; sc->rho = rho_n; sc->beta = beta;
+          sc->aov_x = naovx; sc->aov_y = naovy;
+          if (conv) sc->done = 1;
+        }
+        if (tid == 0) { fsc[0] = rho_n; fsc[2] = naovx; fsc[3] = naovy; fsc[4] = beta; fsc[5] = alpha; ctl[3] = iters; }
         if (done) alive = false;
       }
       else

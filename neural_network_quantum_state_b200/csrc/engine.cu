@@ -277,9 +277,9 @@ void build_tables_async(nqs_handle * h)
 {
   if (h->jpl == 0 || h->tables_valid || h->bound_inflight) return;
   build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
-    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p);
+    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p, h->bound.p);
   check_launch(h, "build_fast_tables_kernel");
-  theta_bound_kernel<<<1, 256, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
+  theta_bound_kernel<<<(h->M+31)/32, NQS_TB_THREADS, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
   check_launch(h, "theta_bound_kernel");
   NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_BOUND, h->bound.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->bound_inflight = true;
@@ -1078,7 +1078,7 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
 }
 
 bool cgp_usable(const nqs_handle * h)
-{ // multi-GPU: the exchange inside the kernel pairs CTA b of every rank, so all ranks must run the same grid over mapped peers
+{ // multi-GPU: the packet exchange inside the kernel needs mapped peers and every rank on the persistent path
   return h->cgp_ok && (h->comm == nullptr || (h->p2p_ok && h->cgp_peers_agree));
 }
 
@@ -1097,7 +1097,8 @@ void cg_solve_persistent(nqs_handle * h, double lambda, double tol, int max_iter
   a.K = h->K; a.P = h->P; a.O = h->O.p; a.part = h->part.p; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
   a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
   a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.tol2 = tol*tol; a.fixed_iters = fixed_iters; a.max_iter = max_iter;
-  a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.sc = h->scal.p;
+  a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.wv = h->wvec.p; a.sc = h->scal.p;
+  { const char * e = std::getenv("NQS_CG_SINGLE"); a.single_red = (e && std::atoi(e) != 0) ? 1 : 0; }   // opt-in: measured no faster (one 11-value sum ~15 us vs 7.5 + 5 us)
   a.slots = h->slots.p; a.barrier = h->cgbar.p; a.hsums = h->hsall.p;
   a.n_ranks = 1; a.rank = 0; a.epoch0 = h->p2p_epoch;
   if (h->comm != nullptr)
@@ -1105,8 +1106,8 @@ void cg_solve_persistent(nqs_handle * h, double lambda, double tol, int max_iter
     a.n_ranks = h->n_ranks; a.rank = h->rank;
     for (int r = 0; r < h->n_ranks; ++r)
     {
-      a.peer_x[r] = reinterpret_cast<double*>(h->peer_base[r]);
-      a.peer_flag[r] = reinterpret_cast<unsigned int*>((char*)h->peer_base[r]+h->xbuf_data_bytes);
+      a.peer_ll1[r] = reinterpret_cast<uint4*>((char*)h->peer_base[r]+h->xbuf_ll1_off);
+      a.peer_ll2[r] = reinterpret_cast<uint4*>((char*)h->peer_base[r]+h->xbuf_ll2_off);
     }
   }
   a.trace = h->cg_trace.p;
@@ -1255,7 +1256,7 @@ void alloc_sr(nqs_handle * h)
   // structured S*v: no O [K][P]; it is allocated only if nqs_log_derivs asks for it
   if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV) plan_struct(h);
   else h->O.alloc((size_t)h->K*(size_t)h->P);
-  h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
+  h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P); h->wvec.alloc(h->P);
   h->zk.alloc(h->K); h->diag.alloc(h->P);
   const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
   long long nrb = (2LL*16*h->sm_count+ctiles-1)/ctiles;
@@ -1280,7 +1281,7 @@ void alloc_sr(nqs_handle * h)
   h->sums.alloc((size_t)5*h->P+3);
   h->hsall.alloc(4);
   h->traw.alloc((size_t)2*h->P);
-  h->slots.alloc((size_t)2*NQS_CGP_MAX_CTAS*NQS_CG_NVALS);   // sized for the persistent kernel's grid (cg_fused_kernel uses the first 148 of each half)
+  h->slots.alloc((size_t)2*NQS_CGP_MAX_CTAS*NQS_CGP_NVALS);   // sized for the persistent kernel's grid (cg_fused_kernel uses the first 148 of each half)
   h->cgbar.alloc(1);
   NQS_CUDA(cudaMemset(h->cgbar.p, 0, sizeof(unsigned int)));
   h->scal.alloc(1);
@@ -1919,7 +1920,11 @@ nqs_status nqs_comm_p2p_export(nqs_handle * h, char handle_out[NQS_IPC_HANDLE_BY
       // behind the CG region: the SR-setup exchange (setup_exchange_finalize_kernel): data [2][n_ranks][5P+4] doubles + flags
       h->xbuf_setup_off = (h->xbuf_data_bytes+flag_bytes+64+255)/256*256;
       h->xbuf_setup_flag_off = h->xbuf_setup_off+(size_t)2*h->n_ranks*(5*(size_t)h->P+4)*sizeof(double);
-      const size_t total = h->xbuf_setup_flag_off+(size_t)2*NQS_CG_MAX_RANKS*NQS_CG_MAX_CTAS*sizeof(unsigned int);
+      // behind that: the LL packet regions of cg_persist_kernel (16-byte packets; zero = no packet yet)
+      const size_t slice = ((size_t)h->P+h->n_ranks-1)/h->n_ranks;
+      h->xbuf_ll1_off = (h->xbuf_setup_flag_off+(size_t)2*NQS_CG_MAX_RANKS*NQS_CG_MAX_CTAS*sizeof(unsigned int)+255)/256*256;
+      h->xbuf_ll2_off = h->xbuf_ll1_off+(size_t)h->n_ranks*slice*2*16;
+      const size_t total = h->xbuf_ll2_off+(size_t)h->P*2*16;
       cudaError_t e = cudaMalloc(&h->xbuf, total);
       if (e != cudaSuccess) throw Error(NQS_ERR_NOMEM, std::string("cudaMalloc of the peer exchange buffer failed: ")+cudaGetErrorString(e));
       NQS_CUDA(cudaMemset(h->xbuf, 0, total));
@@ -1956,14 +1961,14 @@ nqs_status nqs_comm_p2p_import(nqs_handle * h, const char * handles)
       }
       h->peer_base[r] = ptr;
     }
-    // the persistent CG kernel pairs CTA b of this rank with CTA b of every peer: all ranks must have planned the same grid
+    // every rank must run the persistent CG kernel (its packet exchange is a protocol of its own) or none
     const size_t flag_bytes = (size_t)2*NQS_CG_MAX_RANKS*NQS_CGP_MAX_CTAS*sizeof(unsigned int);
     h->cgp_peers_agree = true;
     for (int r = 0; r < h->n_ranks; ++r)
     {
       int hdr[4] = {0, 0, 0, 0};
       NQS_CUDA(cudaMemcpy(hdr, (char*)h->peer_base[r]+h->xbuf_data_bytes+flag_bytes, sizeof(hdr), cudaMemcpyDeviceToHost));
-      if (hdr[0] != 0x4e515331 || hdr[1] != 1 || !h->cgp_ok || hdr[2] != h->sv_nclusters*h->sv_cs || hdr[3] != h->sv_nt) h->cgp_peers_agree = false;
+      if (hdr[0] != 0x4e515331 || hdr[1] != 1 || !h->cgp_ok) h->cgp_peers_agree = false;   // (the LL exchange pairs no CTAs: grids may differ)
     }
     h->p2p_ok = true;
     h->p2p_epoch = 0;

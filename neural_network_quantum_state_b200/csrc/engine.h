@@ -76,7 +76,7 @@ struct nqs_handle
   bool theta_matches_O = false;           // O was written from the current spins / theta / params (structured SR setup allowed)
 
   // SR
-  nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
+  nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk, wvec;
   nqs::DevBuf<double> diag, part, sums, traw, slots, hsall;
   nqs::DevBuf<nqs::CgScalars> scal;
   nqs::DevBuf<unsigned int> cgbar;         // grid-barrier counter of cg_fused_kernel (zero between launches)
@@ -118,6 +118,7 @@ struct nqs_handle
   void * peer_base[16] = {nullptr};
   bool p2p_ok = false;
   unsigned int p2p_epoch = 0;
+  size_t xbuf_ll1_off = 0, xbuf_ll2_off = 0;             // LL packet regions of the persistent CG kernel's reduce-scatter / all-gather
   size_t xbuf_setup_off = 0, xbuf_setup_flag_off = 0;   // SR-setup exchange region of xbuf (data [2][n_ranks][5P+4], flags)
   unsigned int setup_epoch = 0;
   nqs::DevBuf<unsigned long long> cg_trace;   // NQS_CG_TRACE=1: per-launch time stamps of cg_fused_kernel (diagnostics)

@@ -33,7 +33,7 @@ __device__ __forceinline__ double2 ld_tab(const double2 * p) { return __ldg(p); 
 __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpad, const cd * __restrict__ params,
   FlipTab * __restrict__ ftab_a, FlipTab * __restrict__ ftab_b, CoshTab * __restrict__ ctab_a, CoshTab * __restrict__ ctab_b,
   CoshTab * __restrict__ ctabT_a, CoshTab * __restrict__ ctabT_b, const int Npad,
-  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp)
+  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp, double * __restrict__ bound)
 {
   const cd * W = params;
   const cd * a = params+(size_t)N*M;
@@ -67,6 +67,7 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     ctabT_a[(size_t)j*Npad+i] = make_double2(1.0, 0.0);
     ctabT_b[(size_t)j*Npad+i] = make_double2(0.0, 0.0);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bound != nullptr) *bound = 0.0;   // theta_bound_kernel (launched next) accumulates a maximum
   for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < N; i += gridDim.x*blockDim.x)
   {
     const cd ai = a[i];
@@ -77,27 +78,32 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
   }
 }
 
-// bound[0] = max_j (|Re b_j| + sum_i |Re W_ij|) >= max |Re theta|: decides whether the product form cannot overflow
-__global__ void theta_bound_kernel(const int N, const int M, const cd * __restrict__ params, double * __restrict__ bound)
+// bound[0] = max_j (|Re b_j| + sum_i |Re W_ij|) >= max |Re theta|: decides whether the product form cannot overflow.
+// Grid of column tiles (32 hidden units x 8 row groups per CTA): the single-CTA version walked the N rows of W serially, one L2
+// round trip each (22 us at N = 128, on the critical path of every parameter update).  bound[0] must be zero at launch
+// (build_fast_tables_kernel, which always runs just before, clears it); non-negative doubles order like their bit patterns,
+// so the maximum is an integer atomicMax.
+#define NQS_TB_THREADS 256
+__global__ void __launch_bounds__(NQS_TB_THREADS) theta_bound_kernel(const int N, const int M, const cd * __restrict__ params, double * __restrict__ bound)
 {
-  __shared__ double sh[32];
+  __shared__ double sh[8][32];
   const cd * W = params;
   const cd * b = params+(size_t)N*M+N;
-  double mx = 0.0;
-  for (int j = threadIdx.x; j < M; j += blockDim.x)
-  {
-    double s = fabs(b[j].x);
-    for (int i = 0; i < N; ++i) s += fabs(W[(size_t)i*M+j].x);
-    mx = fmax(mx, s);
-  }
-  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((threadIdx.x&31) == 0) sh[threadIdx.x>>5] = mx;
+  const int jl = threadIdx.x&31, ig = threadIdx.x>>5;
+  const int j = blockIdx.x*32+jl;
+  double s = 0.0;
+  if (j < M)
+    for (int i = ig; i < N; i += 8) s += fabs(W[(size_t)i*M+j].x);
+  sh[ig][jl] = s;
   __syncthreads();
-  if (threadIdx.x == 0)
+  if (ig == 0)
   {
-    double m2 = 0.0;
-    for (int w = 0; w < (int)(blockDim.x>>5); ++w) m2 = fmax(m2, sh[w]);
-    bound[0] = m2;
+    double t = (j < M) ? fabs(b[j].x) : 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][jl];
+    if (!(t == t)) t = __longlong_as_double(0x7ff0000000000000ll);     // NaN parameters: report +inf (the product form is refused)
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (jl == 0) atomicMax(reinterpret_cast<unsigned long long*>(bound), (unsigned long long)__double_as_longlong(t));
   }
 }
 
