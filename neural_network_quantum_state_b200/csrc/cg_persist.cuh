@@ -22,8 +22,8 @@
 //           cg_fused.cuh with x, r, p, z held in registers across its two grid sums.  Same arithmetic per element as
 //           cg_fused_kernel; the grid sums fold the elements in a different (equally fixed) order, so the iterates agree
 //           with the launch-per-iteration path to rounding and are run-to-run deterministic (tests).
-//   (single_red, opt-in NQS_CG_SINGLE=1) the two grid sums of an iteration merge into one, see the ITER branch -- measured no
-//           faster: one 11-value sum takes ~15 us against 7.5 + 5 us for the two small ones, so the reference recurrence stays.
+//   (Merging the two grid sums of an iteration into one 11-value sum -- alpha, the predicted rho' and |r'|^2 from scalar products
+//           known before alpha -- was measured: ~15 us against 7.5 + 5 us for the two small sums.  Not kept.)
 //   (no barrier B) the next direction d = z + beta d is NOT waited for: z is stored before the second grid sum, beta is known to
 //           every thread after it, and the previous direction was stored one product earlier -- so every CTA forms its slice
 //           of the new direction itself at the top of the next row pass (same fma as the owner: same bits).
@@ -56,9 +56,7 @@ struct CgpArgs
   cd * x;                   // in: warm start, out: solution
   cd * r;
   cd * pb[2];               // direction d_k of product k lives in pb[k & 1] (written by its owner thread during product k-1)
-  cd * zv;                  // z = M^-1 r, written before the last grid sum of product k
-  cd * wv;                  // single_red: w_k = M^-1 t_k
-  int single_red;           // one grid sum per iteration instead of two (see the ITER branch); 0 = the reference's two-sum recurrence
+  cd * zv;                  // z_k = M^-1 r_k, written before the second grid sum of product k
   CgScalars * sc;
   double * slots;           // [2][NQS_CGP_MAX_CTAS][NQS_CG_NVALS]
   unsigned int * barrier;   // zero between launches
@@ -78,7 +76,7 @@ struct CgpArgs
   unsigned long long * trace;   // NQS_CG_TRACE=1: [NQS_CGP_TRACE_WORDS] globaltimer stamps of CTA 0 per product (else null)
   int trace_max;
 };
-#define NQS_CGP_NVALS 12         // values per grid sum (single-reduction iteration: 11)
+#define NQS_CGP_NVALS 8          // values per grid sum (at most 5 are used)
 #define NQS_CGP_MAX_CTAS 2048    // small problems run several narrow CTAs per SM; slots / exchange flags are sized for this many
 #define NQS_CGP_TRACE_WORDS 8   // product start, rows done, barrier A passed, pushed + flags raised, peers seen, sum 1, sum 2, end
 // shared memory after sv_fused's core tail (part of NQS_SV_TAIL_BYTES): reduction scratch [NQS_SV_MAX_WARPS][NQS_CG_NVALS] doubles | control words
@@ -226,6 +224,235 @@ __device__ __forceinline__ bool cgp_grid_sum(double (&vals)[NV], const CgpArgs &
   return ok;
 }
 
+// Everything of one product that is not the pass over O: barrier A, fold / exchange of the partials, the CG recurrence with its
+// two grid sums, and (product 0 only) barrier B.  Returns 1 when the solve is over (converged, iteration limit, or a barrier /
+// peer gave up), else 0.
+struct CgpCtx
+{
+  double * sh;              // reduction scratch
+  double * fsc;             // recurrence scalars
+  volatile int * ctl;       // control words
+  unsigned int epoch, nsum; // grid barriers passed / grid sums done
+  int NT, CS;
+  bool tracing;
+};
+template <int EPT>
+__device__ __noinline__ int cgp_vector_phase(const CgpArgs & a, const int prod, CgpCtx & cx)
+{
+  double * const sh = cx.sh;
+  double * const fsc = cx.fsc;
+  volatile int * const ctl = cx.ctl;
+  unsigned int & epoch = cx.epoch, & nsum = cx.nsum;
+  const int NT = cx.NT, tid = threadIdx.x;
+  const unsigned int CS = (unsigned int)cx.CS;
+  const bool tracing = cx.tracing;
+  const long long P = a.P;
+  const long long gtid = (long long)blockIdx.x*NT+tid, gstride = (long long)gridDim.x*NT;
+  const double pre = 1.0+a.lambda;
+  const bool p2p = (a.n_ranks > 1);
+  bool alive = true;
+  {
+      // ================================================================ A: every cluster's partials are visible
+      ++epoch;
+      if (!cgp_grid_barrier(a, epoch*gridDim.x, NT, ctl)) return 1;
+      if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+2] = cg_now();
+
+      // ================================================================ vector phase
+      bool ok[EPT];
+      long long pp[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) { ok[e] = (gtid+e*gstride < P); pp[e] = ok[e] ? gtid+e*gstride : 0; }
+      // traw_p = sum over clusters (fixed order) [and ranks, in rank order]
+      double trx[EPT], try_[EPT];
+      const int ncl = (int)(gridDim.x/CS);
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+      {
+        trx[e] = 0.0; try_[e] = 0.0;
+        if (ok[e]) cg_fold_parts(a.part, ncl, P, pp[e], trx[e], try_[e]);
+      }
+      const unsigned int xepoch = a.epoch0+1u+(unsigned int)prod;      // LL flag of this product: never 0, never repeated
+      bool peer_ok = true;
+      const long long S = (P+a.n_ranks-1)/a.n_ranks;          // elements per slice
+      if (p2p)
+      { // phase 1: each element of the folded partial goes to the rank that owns its slice
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+          if (ok[e])
+          {
+            const int q = (int)(pp[e]/S);
+            uint4 * dst = a.peer_ll1[q]+(((size_t)a.rank*S+(size_t)(pp[e]-q*S))<<1);
+            ll_store(dst, trx[e], xepoch); ll_store(dst+1, try_[e], xepoch);
+          }
+      }
+      // the vectors do not depend on the exchange: their loads travel while the peers' partials do
+      cd ao[EPT], pv[EPT], xv[EPT], rv[EPT];
+      double dg[EPT];
+#pragma unroll
+      for (int e = 0; e < EPT; ++e)
+      {
+        ao[e] = cmake(0.0, 0.0); pv[e] = ao[e]; xv[e] = ao[e]; rv[e] = ao[e]; dg[e] = 1.0;
+        if (ok[e])
+        {
+          ao[e] = a.aO[pp[e]]; dg[e] = a.diag[pp[e]]; xv[e] = __ldcg(a.x+pp[e]);
+          if (prod > 0) { pv[e] = __ldcg(a.pb[prod&1]+pp[e]); rv[e] = __ldcg(a.r+pp[e]); }
+          else { pv[e] = xv[e]; rv[e] = a.F[pp[e]]; }     // product 0: v = x0, and r starts from F
+        }
+      }
+      if (p2p)
+      {
+        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+3] = cg_now();
+        // phase 1 receive / phase 2 send: the elements of THIS rank's slice, spread over all CTAs (thread t of CTA b takes slice
+        // element t*gridDim + b, so every SM injects its share into NVLink)
+        long long s_mine = P-(long long)a.rank*S;
+        if (s_mine > S) s_mine = S;
+        for (long long i = (long long)tid*gridDim.x+blockIdx.x; i < s_mine; i += (long long)NT*gridDim.x)
+        {
+          double fx = 0.0, fy = 0.0;
+          for (int r = 0; r < a.n_ranks; ++r)
+          { // rank order: the same bits on every rank
+            const uint4 * src = a.peer_ll1[a.rank]+(((size_t)r*S+(size_t)i)<<1);
+            double vx, vy;
+            peer_ok = ll_wait(src, xepoch, vx) && peer_ok;
+            peer_ok = ll_wait(src+1, xepoch, vy) && peer_ok;
+            fx += vx; fy += vy;
+          }
+          const size_t pe = ((size_t)a.rank*S+(size_t)i)<<1;
+          for (int r = 0; r < a.n_ranks; ++r) { ll_store(a.peer_ll2[r]+pe, fx, xepoch); ll_store(a.peer_ll2[r]+pe+1, fy, xepoch); }
+        }
+        // phase 2 receive: this thread's own elements, summed over all ranks
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          trx[e] = 0.0; try_[e] = 0.0;
+          if (ok[e])
+          {
+            const uint4 * src = a.peer_ll2[a.rank]+((size_t)pp[e]<<1);
+            peer_ok = ll_wait(src, xepoch, trx[e]) && peer_ok;
+            peer_ok = ll_wait(src+1, xepoch, try_[e]) && peer_ok;
+          }
+        }
+        if (!peer_ok) { a.sc->peer_timeout = 1; a.sc->barrier_timeout = 1; ctl[2] = 1; }
+        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+4] = cg_now();
+      }
+
+      if (prod == 0)
+      { // ---- MODE_INIT of cg_fused.cuh: <O>.x0, t = S x0, r = F - t, p = M^-1 r
+        double s0[2] = {0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+          if (ok[e]) { s0[0] += ao[e].x*xv[e].x-ao[e].y*xv[e].y; s0[1] += ao[e].x*xv[e].y+ao[e].y*xv[e].x; }
+        if (!cgp_grid_sum<2>(s0, a, sh, epoch, nsum, NT, ctl)) return 1;
+        double s1[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          const double cx = ao[e].x*s0[0]+ao[e].y*s0[1], cy = ao[e].x*s0[1]-ao[e].y*s0[0];
+          cd tv = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
+          tv.x += a.lambda*dg[e]*xv[e].x; tv.y += a.lambda*dg[e]*xv[e].y;
+          const cd f = rv[e];
+          rv[e] = csub(f, tv);
+          const double den = pre*dg[e];
+          pv[e] = cmake(rv[e].x/den, rv[e].y/den);
+          if (ok[e])
+          {
+            s1[0] += cnorm(f); s1[1] += cnorm(rv[e]);
+            s1[2] += pv[e].x*rv[e].x+pv[e].y*rv[e].y;
+            s1[3] += ao[e].x*pv[e].x-ao[e].y*pv[e].y; s1[4] += ao[e].x*pv[e].y+ao[e].y*pv[e].x;
+          }
+        }
+        if (!cgp_grid_sum<5>(s1, a, sh, epoch, nsum, NT, ctl)) return 1;
+        const double rhs2 = s1[0], res2 = s1[1];
+        const bool zero_rhs = (rhs2 == 0.0);
+        const double thr = fmax(a.tol2*rhs2, 2.2250738585072014e-308);
+        const double rho = s1[2], aovx = s1[3], aovy = s1[4];
+        const bool done = zero_rhs || (a.fixed_iters <= 0 && res2 < thr);
+        if (tid == 0) { fsc[0] = rho; fsc[1] = thr; fsc[2] = aovx; fsc[3] = aovy; fsc[4] = 0.0; ctl[3] = 0; }
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          if (!ok[e]) continue;
+          a.r[pp[e]] = rv[e]; a.pb[1][pp[e]] = pv[e];                          // d_1
+          if (zero_rhs) a.x[pp[e]] = cmake(0.0, 0.0);                          // conjugate_gradient.cuh:39-43
+        }
+        if (blockIdx.x == 0 && tid == 0)
+        {
+          CgScalars * sc = a.sc;
+          sc->rhs2 = rhs2; sc->res2 = res2; sc->rho = rho; sc->aov_x = aovx; sc->aov_y = aovy;
+          sc->zero_rhs = zero_rhs ? 1 : 0; sc->thr = thr; sc->iters = 0; sc->done = done ? 1 : 0;
+        }
+        if (done) alive = false;
+      }
+      else
+      { // ---- MODE_ITER of cg_fused.cuh (cg_iter_regs), same arithmetic in the same order
+        const double rho = fsc[0], thr = fsc[1], aovx = fsc[2], aovy = fsc[3];
+        const int iters = ctl[3]+1;
+        cd tv[EPT];
+        double s1[1] = {0.0};
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          const double cx = ao[e].x*aovx+ao[e].y*aovy, cy = ao[e].x*aovy-ao[e].y*aovx;
+          tv[e] = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
+          tv[e].x += a.lambda*dg[e]*pv[e].x; tv[e].y += a.lambda*dg[e]*pv[e].y;
+          if (ok[e]) s1[0] += tv[e].x*pv[e].x+tv[e].y*pv[e].y;
+        }
+        if (!cgp_grid_sum<1>(s1, a, sh, epoch, nsum, NT, ctl)) return 1;
+        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+5] = cg_now();
+        const double alpha = rho/s1[0];
+        cd zv[EPT];
+        double s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          xv[e].x += alpha*pv[e].x; xv[e].y += alpha*pv[e].y;
+          rv[e].x -= alpha*tv[e].x; rv[e].y -= alpha*tv[e].y;
+          const double den = pre*dg[e];
+          zv[e] = cmake(rv[e].x/den, rv[e].y/den);
+          if (ok[e])
+          {
+            a.zv[pp[e]] = zv[e];             // visible to every CTA behind the barrier of the grid sum below
+            s2[0] += cnorm(rv[e]);
+            s2[1] += zv[e].x*rv[e].x+zv[e].y*rv[e].y;
+            s2[2] += ao[e].x*zv[e].x-ao[e].y*zv[e].y; s2[3] += ao[e].x*zv[e].y+ao[e].y*zv[e].x;
+          }
+        }
+        if (!cgp_grid_sum<4>(s2, a, sh, epoch, nsum, NT, ctl)) return 1;
+        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+6] = cg_now();
+        const double beta = s2[1]/rho;
+        const bool conv = (a.fixed_iters <= 0 && s2[0] < thr);
+        const bool done = conv || (a.fixed_iters > 0 ? iters >= a.fixed_iters : iters >= a.max_iter);
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+        {
+          if (!ok[e]) continue;
+          a.x[pp[e]] = xv[e]; a.r[pp[e]] = rv[e];
+          // d_{k+1} = z_k + beta_k d_k (conjugate_gradient.cuh:71) for this thread's own use in product k+1 and for the row passes of k+2
+          if (!conv) a.pb[(prod+1)&1][pp[e]] = cmake(fma(beta, pv[e].x, zv[e].x), fma(beta, pv[e].y, zv[e].y));
+        }
+        if (blockIdx.x == 0 && tid == 0)
+        {
+          CgScalars * sc = a.sc;
+          sc->tp = s1[0]; sc->alpha = alpha; sc->res2 = s2[0]; sc->iters = iters; sc->rho_old = rho; sc->rho = s2[1]; sc->beta = beta;
+          sc->aov_x = s2[2]+beta*aovx; sc->aov_y = s2[3]+beta*aovy;
+          if (conv) sc->done = 1;
+        }
+        // every thread has read the old scalars before the two grid sums above (CTA barriers inside), so thread 0 may overwrite them
+        if (tid == 0) { fsc[0] = s2[1]; fsc[2] = s2[2]+beta*aovx; fsc[3] = s2[3]+beta*aovy; fsc[4] = beta; ctl[3] = iters; }   // <O>.(z + beta p) by linearity
+        if (done) alive = false;
+      }
+      if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+7] = cg_now();
+      if (!alive) return 1;
+      if (prod == 0)
+      { // ============================================================== B (once per solve): d_1 is visible to every CTA
+        ++epoch;
+        if (!cgp_grid_barrier(a, epoch*gridDim.x, NT, ctl)) return 1;
+      }
+      else cgp_cta_sync(NT);   // beta of this product (shared memory, thread 0) before the next row pass reads it
+  }
+  return 0;
+}
+
 // blockDim.x = 32*(NW+1) as in sv_fused_kernel; grid = clusters x cluster size, every CTA resident (cooperative launch)
 template <int CPT, int DEFER>
 __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpArgs a)
@@ -362,17 +589,11 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
           }
           if (prod >= 2)
           {
-            const double nalpha_prev = -fsc[5];
 #pragma unroll
             for (int c = 0; c < CPT; ++c)
             {
               const int idx = c*NT+tid;
-              cd zz = (idx < n_r) ? __ldcg(a.zv+c0+idx) : cmake(0.0, 0.0);
-              if (a.single_red)
-              { // z_{k} = z_{k-1} - alpha w: the same fma as the owner's
-                const cd ww = (idx < n_r) ? __ldcg(a.wv+c0+idx) : cmake(0.0, 0.0);
-                zz = cmake(fma(nalpha_prev, ww.x, zz.x), fma(nalpha_prev, ww.y, zz.y));
-              }
+              const cd zz = (idx < n_r) ? __ldcg(a.zv+c0+idx) : cmake(0.0, 0.0);
               vr[c] = cmake(fma(beta_prev, vr[c].x, zz.x), fma(beta_prev, vr[c].y, zz.y));
             }
           }
@@ -465,272 +686,16 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
         }
       }
       if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+1] = cg_now();
-      // ================================================================ A: every cluster's partials are visible
-      ++epoch;
-      if (!cgp_grid_barrier(a, epoch*gridDim.x, NT, ctl)) break;
-      if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+2] = cg_now();
-
-      // ================================================================ vector phase
-      bool ok[EPT];
-      long long pp[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e) { ok[e] = (gtid+e*gstride < P); pp[e] = ok[e] ? gtid+e*gstride : 0; }
-      // traw_p = sum over clusters (fixed order) [and ranks, in rank order]
-      double trx[EPT], try_[EPT];
-      const int ncl = (int)(gridDim.x/CS);
-#pragma unroll
-      for (int e = 0; e < EPT; ++e)
+      // ================================================================ A, vector phase, (B): kept OUT of line on purpose -- inlined, its
+      // live ranges pushed the row loop above (which sits at the register limit) into spilling: 27 local-memory accesses per row
+      // and 15 % on the pass over O
       {
-        trx[e] = 0.0; try_[e] = 0.0;
-        if (ok[e]) cg_fold_parts(a.part, ncl, P, pp[e], trx[e], try_[e]);
+        CgpCtx cx;
+        cx.sh = sh; cx.fsc = fsc; cx.ctl = ctl; cx.epoch = epoch; cx.nsum = nsum; cx.NT = NT; cx.CS = (int)CS; cx.tracing = tracing;
+        const int stop = cgp_vector_phase<EPT>(a, prod, cx);
+        epoch = cx.epoch; nsum = cx.nsum;
+        if (stop) break;
       }
-      const unsigned int xepoch = a.epoch0+1u+(unsigned int)prod;      // LL flag of this product: never 0, never repeated
-      bool peer_ok = true;
-      const long long S = (P+a.n_ranks-1)/a.n_ranks;          // elements per slice
-      if (p2p)
-      { // phase 1: each element of the folded partial goes to the rank that owns its slice
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-          if (ok[e])
-          {
-            const int q = (int)(pp[e]/S);
-            uint4 * dst = a.peer_ll1[q]+(((size_t)a.rank*S+(size_t)(pp[e]-q*S))<<1);
-            ll_store(dst, trx[e], xepoch); ll_store(dst+1, try_[e], xepoch);
-          }
-      }
-      // the vectors do not depend on the exchange: their loads travel while the peers' partials do
-      cd ao[EPT], pv[EPT], xv[EPT], rv[EPT];
-      double dg[EPT];
-#pragma unroll
-      for (int e = 0; e < EPT; ++e)
-      {
-        ao[e] = cmake(0.0, 0.0); pv[e] = ao[e]; xv[e] = ao[e]; rv[e] = ao[e]; dg[e] = 1.0;
-        if (ok[e])
-        {
-          ao[e] = a.aO[pp[e]]; dg[e] = a.diag[pp[e]]; xv[e] = __ldcg(a.x+pp[e]);
-          if (prod > 0) { pv[e] = __ldcg(a.pb[prod&1]+pp[e]); rv[e] = __ldcg(a.r+pp[e]); }
-          else { pv[e] = xv[e]; rv[e] = a.F[pp[e]]; }     // product 0: v = x0, and r starts from F
-        }
-      }
-      if (p2p)
-      {
-        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+3] = cg_now();
-        // phase 1 receive / phase 2 send: the elements of THIS rank's slice, spread over all CTAs (thread t of CTA b takes slice
-        // element t*gridDim + b, so every SM injects its share into NVLink)
-        long long s_mine = P-(long long)a.rank*S;
-        if (s_mine > S) s_mine = S;
-        for (long long i = (long long)tid*gridDim.x+blockIdx.x; i < s_mine; i += (long long)NT*gridDim.x)
-        {
-          double fx = 0.0, fy = 0.0;
-          for (int r = 0; r < a.n_ranks; ++r)
-          { // rank order: the same bits on every rank
-            const uint4 * src = a.peer_ll1[a.rank]+(((size_t)r*S+(size_t)i)<<1);
-            double vx, vy;
-            peer_ok = ll_wait(src, xepoch, vx) && peer_ok;
-            peer_ok = ll_wait(src+1, xepoch, vy) && peer_ok;
-            fx += vx; fy += vy;
-          }
-          const size_t pe = ((size_t)a.rank*S+(size_t)i)<<1;
-          for (int r = 0; r < a.n_ranks; ++r) { ll_store(a.peer_ll2[r]+pe, fx, xepoch); ll_store(a.peer_ll2[r]+pe+1, fy, xepoch); }
-        }
-        // phase 2 receive: this thread's own elements, summed over all ranks
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          trx[e] = 0.0; try_[e] = 0.0;
-          if (ok[e])
-          {
-            const uint4 * src = a.peer_ll2[a.rank]+((size_t)pp[e]<<1);
-            peer_ok = ll_wait(src, xepoch, trx[e]) && peer_ok;
-            peer_ok = ll_wait(src+1, xepoch, try_[e]) && peer_ok;
-          }
-        }
-        if (!peer_ok) { a.sc->peer_timeout = 1; a.sc->barrier_timeout = 1; ctl[2] = 1; }
-        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+4] = cg_now();
-      }
-
-      if (prod == 0)
-      { // ---- MODE_INIT of cg_fused.cuh: <O>.x0, t = S x0, r = F - t, p = M^-1 r
-        double s0[2] = {0.0, 0.0};
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-          if (ok[e]) { s0[0] += ao[e].x*xv[e].x-ao[e].y*xv[e].y; s0[1] += ao[e].x*xv[e].y+ao[e].y*xv[e].x; }
-        if (!cgp_grid_sum<2>(s0, a, sh, epoch, nsum, NT, ctl)) break;
-        double s1[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          const double cx = ao[e].x*s0[0]+ao[e].y*s0[1], cy = ao[e].x*s0[1]-ao[e].y*s0[0];
-          cd tv = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
-          tv.x += a.lambda*dg[e]*xv[e].x; tv.y += a.lambda*dg[e]*xv[e].y;
-          const cd f = rv[e];
-          rv[e] = csub(f, tv);
-          const double den = pre*dg[e];
-          pv[e] = cmake(rv[e].x/den, rv[e].y/den);
-          if (ok[e])
-          {
-            s1[0] += cnorm(f); s1[1] += cnorm(rv[e]);
-            s1[2] += pv[e].x*rv[e].x+pv[e].y*rv[e].y;
-            s1[3] += ao[e].x*pv[e].x-ao[e].y*pv[e].y; s1[4] += ao[e].x*pv[e].y+ao[e].y*pv[e].x;
-          }
-        }
-        if (!cgp_grid_sum<5>(s1, a, sh, epoch, nsum, NT, ctl)) break;
-        const double rhs2 = s1[0], res2 = s1[1];
-        const bool zero_rhs = (rhs2 == 0.0);
-        const double thr = fmax(a.tol2*rhs2, 2.2250738585072014e-308);
-        const double rho = s1[2], aovx = s1[3], aovy = s1[4];
-        const bool done = zero_rhs || (a.fixed_iters <= 0 && res2 < thr);
-        if (tid == 0) { fsc[0] = rho; fsc[1] = thr; fsc[2] = aovx; fsc[3] = aovy; fsc[4] = 0.0; ctl[3] = 0; }
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          if (!ok[e]) continue;
-          a.r[pp[e]] = rv[e]; a.pb[1][pp[e]] = pv[e];                          // d_1
-          if (zero_rhs) a.x[pp[e]] = cmake(0.0, 0.0);                          // conjugate_gradient.cuh:39-43
-        }
-        if (blockIdx.x == 0 && tid == 0)
-        {
-          CgScalars * sc = a.sc;
-          sc->rhs2 = rhs2; sc->res2 = res2; sc->rho = rho; sc->aov_x = aovx; sc->aov_y = aovy;
-          sc->zero_rhs = zero_rhs ? 1 : 0; sc->thr = thr; sc->iters = 0; sc->done = done ? 1 : 0;
-        }
-        if (done) alive = false;
-      }
-      else if (a.single_red)
-      { // ---- one iteration with ONE grid sum.  With z = M^-1 r and w = M^-1 t (M real diagonal) everything the step needs is a
-        // scalar product of vectors known BEFORE alpha:  alpha = <z,r>/<t,p>,  r' = r - alpha t,  z' = z - alpha w,
-        //   rho' = <z',r'> = <z,r> - 2 alpha Re<w,r> + alpha^2 <w,t>,   |r'|^2 = |r|^2 - 2 alpha Re<r,t> + alpha^2 |t|^2,
-        //   <O>.z' = <O>.z - alpha <O>.w.
-        // <z,r> and |r|^2 are formed DIRECTLY from this iteration's vectors every time (nothing is carried by recurrence), so the
-        // one-step predictions of rho' and |r'|^2 carry a relative error of ~1e-16 |r|^2/|r'|^2 (~1e-13) and none accumulates:
-        // beta and the stopping test see that much of a difference to the two-sum recurrence of conjugate_gradient.cuh:50-72.
-        const double thr = fsc[1], aovx = fsc[2], aovy = fsc[3];
-        const int iters = ctl[3]+1;
-        cd tv[EPT], zv[EPT], wv[EPT];
-        double sm[11];
-#pragma unroll
-        for (int i = 0; i < 11; ++i) sm[i] = 0.0;
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          const double cx = ao[e].x*aovx+ao[e].y*aovy, cy = ao[e].x*aovy-ao[e].y*aovx;
-          tv[e] = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
-          tv[e].x += a.lambda*dg[e]*pv[e].x; tv[e].y += a.lambda*dg[e]*pv[e].y;
-          const double den = pre*dg[e];
-          zv[e] = cmake(rv[e].x/den, rv[e].y/den);
-          wv[e] = cmake(tv[e].x/den, tv[e].y/den);
-          if (ok[e])
-          {
-            a.zv[pp[e]] = zv[e]; a.wv[pp[e]] = wv[e];      // visible to every CTA behind the barrier of the grid sum below
-            sm[0] += tv[e].x*pv[e].x+tv[e].y*pv[e].y;          // Re<t,p>
-            sm[1] += zv[e].x*rv[e].x+zv[e].y*rv[e].y;          // rho = Re<z,r>
-            sm[2] += wv[e].x*rv[e].x+wv[e].y*rv[e].y;          // Re<w,r>
-            sm[3] += wv[e].x*tv[e].x+wv[e].y*tv[e].y;          // <w,t>
-            sm[4] += cnorm(rv[e]);
-            sm[5] += rv[e].x*tv[e].x+rv[e].y*tv[e].y;          // Re<r,t>
-            sm[6] += cnorm(tv[e]);
-            sm[7] += ao[e].x*zv[e].x-ao[e].y*zv[e].y; sm[8] += ao[e].x*zv[e].y+ao[e].y*zv[e].x;     // <O>.z
-            sm[9] += ao[e].x*wv[e].x-ao[e].y*wv[e].y; sm[10] += ao[e].x*wv[e].y+ao[e].y*wv[e].x;    // <O>.w
-          }
-        }
-        if (!cgp_grid_sum<11>(sm, a, sh, epoch, nsum, NT, ctl)) break;
-        if (tracing && prod < a.trace_max) { a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+5] = cg_now(); a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+6] = cg_now(); }
-        const double rho = sm[1];
-        const double alpha = rho/sm[0];
-        const double rho_n = fma(alpha, fma(alpha, sm[3], -2.0*sm[2]), rho);
-        const double res_n = fma(alpha, fma(alpha, sm[6], -2.0*sm[5]), sm[4]);
-        const double beta = rho_n/rho;
-        const bool conv = (a.fixed_iters <= 0 && res_n < thr);
-        const bool done = conv || (a.fixed_iters > 0 ? iters >= a.fixed_iters : iters >= a.max_iter);
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          if (!ok[e]) continue;
-          a.x[pp[e]] = cmake(xv[e].x+alpha*pv[e].x, xv[e].y+alpha*pv[e].y);
-          a.r[pp[e]] = cmake(rv[e].x-alpha*tv[e].x, rv[e].y-alpha*tv[e].y);
-          if (!conv)
-          { // d_{k+1} = (z - alpha w) + beta d_k: the row passes of the next product form the same expression from zv, wv, pb
-            const cd zn = cmake(fma(-alpha, wv[e].x, zv[e].x), fma(-alpha, wv[e].y, zv[e].y));
-            a.pb[(prod+1)&1][pp[e]] = cmake(fma(beta, pv[e].x, zn.x), fma(beta, pv[e].y, zn.y));
-          }
-        }
-        const double naovx = (sm[7]-alpha*sm[9])+beta*aovx, naovy = (sm[8]-alpha*sm[10])+beta*aovy;   // <O>.(z' + beta p)
-        if (blockIdx.x == 0 && tid == 0)
-        {
-          CgScalars * sc = a.sc;
-          sc->tp = sm[0]; sc->alpha = alpha; sc->res2 = res_n; sc->iters = iters; sc->rho_old = rho; sc->rho = rho_n; sc->beta = beta;
-          sc->aov_x = naovx; sc->aov_y = naovy;
-          if (conv) sc->done = 1;
-        }
-        if (tid == 0) { fsc[0] = rho_n; fsc[2] = naovx; fsc[3] = naovy; fsc[4] = beta; fsc[5] = alpha; ctl[3] = iters; }
-        if (done) alive = false;
-      }
-      else
-      { // ---- MODE_ITER of cg_fused.cuh (cg_iter_regs), same arithmetic in the same order
-        const double rho = fsc[0], thr = fsc[1], aovx = fsc[2], aovy = fsc[3];
-        const int iters = ctl[3]+1;
-        cd tv[EPT];
-        double s1[1] = {0.0};
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          const double cx = ao[e].x*aovx+ao[e].y*aovy, cy = ao[e].x*aovy-ao[e].y*aovx;
-          tv[e] = cmake(trx[e]*a.inv_ktot-cx, try_[e]*a.inv_ktot-cy);
-          tv[e].x += a.lambda*dg[e]*pv[e].x; tv[e].y += a.lambda*dg[e]*pv[e].y;
-          if (ok[e]) s1[0] += tv[e].x*pv[e].x+tv[e].y*pv[e].y;
-        }
-        if (!cgp_grid_sum<1>(s1, a, sh, epoch, nsum, NT, ctl)) break;
-        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+5] = cg_now();
-        const double alpha = rho/s1[0];
-        cd zv[EPT];
-        double s2[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          xv[e].x += alpha*pv[e].x; xv[e].y += alpha*pv[e].y;
-          rv[e].x -= alpha*tv[e].x; rv[e].y -= alpha*tv[e].y;
-          const double den = pre*dg[e];
-          zv[e] = cmake(rv[e].x/den, rv[e].y/den);
-          if (ok[e])
-          {
-            a.zv[pp[e]] = zv[e];             // visible to every CTA behind the barrier of the grid sum below
-            s2[0] += cnorm(rv[e]);
-            s2[1] += zv[e].x*rv[e].x+zv[e].y*rv[e].y;
-            s2[2] += ao[e].x*zv[e].x-ao[e].y*zv[e].y; s2[3] += ao[e].x*zv[e].y+ao[e].y*zv[e].x;
-          }
-        }
-        if (!cgp_grid_sum<4>(s2, a, sh, epoch, nsum, NT, ctl)) break;
-        if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+6] = cg_now();
-        const double beta = s2[1]/rho;
-        const bool conv = (a.fixed_iters <= 0 && s2[0] < thr);
-        const bool done = conv || (a.fixed_iters > 0 ? iters >= a.fixed_iters : iters >= a.max_iter);
-#pragma unroll
-        for (int e = 0; e < EPT; ++e)
-        {
-          if (!ok[e]) continue;
-          a.x[pp[e]] = xv[e]; a.r[pp[e]] = rv[e];
-          // d_{k+1} = z_k + beta_k d_k (conjugate_gradient.cuh:71) for this thread's own use in product k+1 and for the row passes of k+2
-          if (!conv) a.pb[(prod+1)&1][pp[e]] = cmake(fma(beta, pv[e].x, zv[e].x), fma(beta, pv[e].y, zv[e].y));
-        }
-        if (blockIdx.x == 0 && tid == 0)
-        {
-          CgScalars * sc = a.sc;
-          sc->tp = s1[0]; sc->alpha = alpha; sc->res2 = s2[0]; sc->iters = iters; sc->rho_old = rho; sc->rho = s2[1]; sc->beta = beta;
-          sc->aov_x = s2[2]+beta*aovx; sc->aov_y = s2[3]+beta*aovy;
-          if (conv) sc->done = 1;
-        }
-        // every thread has read the old scalars before the two grid sums above (CTA barriers inside), so thread 0 may overwrite them
-        if (tid == 0) { fsc[0] = s2[1]; fsc[2] = s2[2]+beta*aovx; fsc[3] = s2[3]+beta*aovy; fsc[4] = beta; ctl[3] = iters; }   // <O>.(z + beta p) by linearity
-        if (done) alive = false;
-      }
-      if (tracing && prod < a.trace_max) a.trace[(size_t)prod*NQS_CGP_TRACE_WORDS+7] = cg_now();
-      if (!alive) break;
-      if (prod == 0)
-      { // ============================================================== B (once per solve): d_1 is visible to every CTA
-        ++epoch;
-        if (!cgp_grid_barrier(a, epoch*gridDim.x, NT, ctl)) break;
-      }
-      else cgp_cta_sync(NT);   // beta of this product (shared memory, thread 0) before the next row pass reads it
     }
     if (!finite_h && blockIdx.x == 0 && tid == 0) { a.sc->nonfinite = 1; a.sc->done = 1; a.sc->iters = 0; }
     // tell the producer how far the consumers got, then leave the grid-barrier counter at zero for the next launch

@@ -1097,8 +1097,7 @@ void cg_solve_persistent(nqs_handle * h, double lambda, double tol, int max_iter
   a.K = h->K; a.P = h->P; a.O = h->O.p; a.part = h->part.p; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
   a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
   a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.tol2 = tol*tol; a.fixed_iters = fixed_iters; a.max_iter = max_iter;
-  a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.wv = h->wvec.p; a.sc = h->scal.p;
-  { const char * e = std::getenv("NQS_CG_SINGLE"); a.single_red = (e && std::atoi(e) != 0) ? 1 : 0; }   // opt-in: measured no faster (one 11-value sum ~15 us vs 7.5 + 5 us)
+  a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p; a.x = h->dx.p; a.r = h->r.p; a.pb[0] = h->t.p; a.pb[1] = h->pvec.p; a.zv = h->z.p; a.sc = h->scal.p;
   a.slots = h->slots.p; a.barrier = h->cgbar.p; a.hsums = h->hsall.p;
   a.n_ranks = 1; a.rank = 0; a.epoch0 = h->p2p_epoch;
   if (h->comm != nullptr)
@@ -1256,7 +1255,7 @@ void alloc_sr(nqs_handle * h)
   // structured S*v: no O [K][P]; it is allocated only if nqs_log_derivs asks for it
   if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV) plan_struct(h);
   else h->O.alloc((size_t)h->K*(size_t)h->P);
-  h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P); h->wvec.alloc(h->P);
+  h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
   h->zk.alloc(h->K); h->diag.alloc(h->P);
   const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
   long long nrb = (2LL*16*h->sm_count+ctiles-1)/ctiles;

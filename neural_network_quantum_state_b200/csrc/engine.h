@@ -76,7 +76,7 @@ struct nqs_handle
   bool theta_matches_O = false;           // O was written from the current spins / theta / params (structured SR setup allowed)
 
   // SR
-  nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk, wvec;
+  nqs::DevBuf<nqs::cd> O, aO, F, dx, r, pvec, z, t, zk;
   nqs::DevBuf<double> diag, part, sums, traw, slots, hsall;
   nqs::DevBuf<nqs::CgScalars> scal;
   nqs::DevBuf<unsigned int> cgbar;         // grid-barrier counter of cg_fused_kernel (zero between launches)

@@ -77,8 +77,8 @@ inline size_t sv_gen_slot_bytes(int N, int M) { return (size_t)(M+1)*16+(((size_
 #define NQS_SV_RBUFS 4     // CTA-level reduction buffers, >= depth+1: a warp may run (2) up to depth rows ahead of a reducer
 // shared memory after the slots: red[RBUFS][warps] | zbuf[ZBUFS][cluster] | full[8] | empty[8] | wfull[RBUFS] | zfull[ZBUFS]
 #define NQS_SV_TAIL_CORE (NQS_SV_RBUFS*NQS_SV_MAX_WARPS*16+NQS_SV_ZBUFS*NQS_SV_MAX_CLUSTER*16+2*NQS_SV_MAX_SLOTS*8+NQS_SV_RBUFS*8+NQS_SV_ZBUFS*8)
-// + the reduction scratch [warps][12], the recurrence scalars and the control words of the persistent CG kernel (cg_persist.cuh), so both kernels share one launch plan
-#define NQS_SV_TAIL_BYTES (NQS_SV_TAIL_CORE+NQS_SV_MAX_WARPS*12*8+64+64)
+// + the reduction scratch [warps][8], the recurrence scalars and the control words of the persistent CG kernel (cg_persist.cuh), so both kernels share one launch plan
+#define NQS_SV_TAIL_BYTES (NQS_SV_TAIL_CORE+NQS_SV_MAX_WARPS*8*8+64+64)
 
 // register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 992+32 threads (8 warps per sub-partition x 64
 // registers), larger CPT up to 480+32 threads (4 warps per sub-partition x 128 registers)
