@@ -61,6 +61,7 @@ struct CgArgs
   double * peer_x[NQS_CG_MAX_RANKS];            // peer_x[r]: receive buffer of rank r, [2][n_ranks][2P]
   unsigned int * peer_flag[NQS_CG_MAX_RANKS];   // peer_flag[r]: flags of rank r, [2][NQS_CG_MAX_RANKS][NQS_CG_MAX_CTAS]
   unsigned long long * trace;                   // NQS_CG_TRACE=1: globaltimer stamps of CTA 0, [NQS_CG_TRACE_WORDS] per launch (else null)
+  const double * hsums;    // INIT (may be null): all-reduced (sum Re h, ...) -- a non-finite energy ends the solve before it starts
 };
 #define NQS_CG_TRACE_WORDS 24   // entry, stored, released, arrival of every rank's flag [16], waited, end
 __device__ __forceinline__ unsigned long long cg_now()
@@ -287,6 +288,11 @@ __device__ __forceinline__ void cg_iter_regs(const CgArgs & a, double * sh, unsi
 __global__ void __launch_bounds__(NQS_CG_THREADS, 1) cg_fused_kernel(const CgArgs a)
 {
   if (a.mode == CG_MODE_ITER && a.sc->done) return;     // uniform over the grid: converged earlier
+  if (a.mode == CG_MODE_INIT && a.hsums != nullptr && !isfinite(a.hsums[0]))
+  { // ref optimizer.cuh:134-138: <h> not finite -> no solve, no update (uniform over the grid and over the ranks)
+    if (blockIdx.x == 0 && threadIdx.x == 0) { a.sc->nonfinite = 1; a.sc->done = 1; a.sc->iters = 0; }
+    return;
+  }
   __shared__ double sh[(NQS_CG_THREADS/32)*NQS_CG_NVALS];
   const long long P = a.P;
   const long long i0 = (long long)blockIdx.x*blockDim.x+threadIdx.x, stride = (long long)gridDim.x*blockDim.x;

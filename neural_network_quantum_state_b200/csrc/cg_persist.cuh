@@ -555,12 +555,10 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
     const cd * const sbase = reinterpret_cast<const cd*>(smem_raw)+tid;
     const size_t slot_elems = a.slot_bytes/sizeof(cd);
     const int depth = a.depth;
-    int g = 0;                                  // rows of this cluster consumed so far (all products)
-    // Rolling ring positions / mbarrier phase parities: they keep counting across products (no per-row divisions or modulos).
-    // slot/full_par: TMA slot of the row in pass (2); tail_slot: slot of the oldest row waiting for pass (3); rq/wpar: warp-partial
-    // buffer of the row in (2); zq: z buffer of the row in (2); tzq/tzpar: z buffer of the row in (3); redw: this row's reducer warp
-    int slot = 0, tail_slot = 0, rq = 0, zq = 0, tzq = 0, redw = 0;
-    uint32_t full_par = 0, wpar = 0, tzpar = 0;
+    // Ring positions / mbarrier phase parities keep counting across products: the TMA slots and the reducer warp roll, the
+    // power-of-two rings (warp partials, z buffers) are bit fields of the running row counters
+    int slot = 0, tail_slot = 0, redw = 0, gi = 0, gt = 0;   // gi / gt: rows that went through pass (2) / pass (3) so far
+    uint32_t full_par = 0;
     const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), wfull_a = smem_u32(wfull), zfull_a = smem_u32(zfull);
     // where this CTA's partial lands in CTA `lane` of the cluster (shared::cluster addresses are linear inside a CTA's window)
     const uint32_t rz_data = (lane < (int)CS) ? map_to_rank(zbuf+crank, (uint32_t)lane) : 0u;
@@ -601,7 +599,8 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
         // (3) for the oldest row still waiting for it: z_k = sum of the CS partials in rank order, acc += conj(O_kp) z_k
         auto wait_z = [&](double & zx, double & zy)
         {
-          mbar_wait_a(zfull_a+8u*(uint32_t)tzq, tzpar);
+          const int tzq = gt&(NQS_SV_ZBUFS-1);
+          mbar_wait_a(zfull_a+8u*(uint32_t)tzq, (uint32_t)((gt>>3)&1));
           const cd * zrow = zbuf+tzq*NQS_SV_MAX_CLUSTER;
           zx = 0.0; zy = 0.0;
           for (unsigned int r = 0; r < CS; ++r)
@@ -609,7 +608,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
             const cd t = zrow[r];
             zx += t.x; zy += t.y;
           }
-          if (++tzq == NQS_SV_ZBUFS) { tzq = 0; tzpar ^= 1u; }
+          ++gt;
         };
         auto pass3_from_slot = [&]()
         {
@@ -647,18 +646,18 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
             pc_ = fma(o[c].x, vr[c].y, pc_); pd = fma(o[c].y, vr[c].x, pd);
           }
           const cd wp = warp_sum(cmake(pa-pb, pc_+pd));
+          const int rq = gi&(NQS_SV_RBUFS-1), zq = gi&(NQS_SV_ZBUFS-1);
           cd * redrow = red+rq*NQS_SV_MAX_WARPS;
           if (lane == 0) { redrow[w] = wp; mbar_arrive_a(wfull_a+8u*(uint32_t)rq); }
           if (w == redw)
           { // this row's reducer warp: CTA partial = fixed-order fold of the warp partials, sent to every CTA of the cluster
-            mbar_wait_a(wfull_a+8u*(uint32_t)rq, wpar);
+            mbar_wait_a(wfull_a+8u*(uint32_t)rq, (uint32_t)((gi>>2)&1));
             const cd sred = warp_sum((lane < NW) ? redrow[lane] : cmake(0.0, 0.0));
             if (lane == 0) mbar_expect_tx_a(zfull_a+8u*(uint32_t)zq, CS*(uint32_t)sizeof(cd));
             if (lane < (int)CS)
               st_async_remote_cd(rz_data+(uint32_t)zq*(uint32_t)(NQS_SV_MAX_CLUSTER*sizeof(cd)), sred, rz_bar+8u*(uint32_t)zq);
           }
-          if (++rq == NQS_SV_RBUFS) { rq = 0; wpar ^= 1u; }
-          if (++zq == NQS_SV_ZBUFS) zq = 0;
+          ++gi;
           if (++redw == NW) redw = 0;
           if (DEFER == 0)
           {
@@ -676,7 +675,6 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
         }
         if (DEFER != 0)
           for (int jt = (nrows > depth ? nrows-depth : 0); jt < nrows; ++jt) pass3_from_slot();
-        g += nrows;
         double * base = a.part+(size_t)cid*2*(size_t)P;
 #pragma unroll
         for (int c = 0; c < CPT; ++c)
@@ -702,7 +700,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) cg_persist_kernel(const CgpAr
     cgp_cta_sync(NT);
     if (tid == 0)
     {
-      ctl[1] = g;
+      ctl[1] = gi;
       __threadfence_block();
       ctl[0] = 1;
       const unsigned int n = atomicAdd(a.barrier, 1u);

@@ -983,6 +983,7 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
   a.inv_ktot = 1.0/(double)h->Ktot; a.lambda = lambda; a.aO = h->aO.p; a.diag = h->diag.p; a.F = h->F.p;
   a.v = v; a.pvec = h->pvec.p; a.x = h->dx.p; a.r = h->r.p; a.t = h->t.p; a.sc = h->scal.p; a.slots = h->slots.p; a.barrier = h->cgbar.p;
   a.n_ranks = 1; a.rank = 0; a.epoch = 0;
+  a.hsums = (mode == CG_MODE_INIT && h->cg_check_finite) ? h->hsall.p : nullptr;
   for (int r = 0; r < NQS_CG_MAX_RANKS; ++r) { a.peer_x[r] = nullptr; a.peer_flag[r] = nullptr; }
   if (h->p2p_ok && nparts > 0)
   {
@@ -1025,43 +1026,37 @@ void launch_cg_fused(nqs_handle * h, int mode, int nparts, double lambda, cd * v
 }
 
 // ref: ConjugateGradient::solve(SMatrixFunctor_, F, dx), conjugate_gradient.cuh:29-74, warm start in dx.
-// Two launches per iteration (pass over O + cg_fused_kernel) and no host round trip inside an iteration (the reference
-// synchronises four times per iteration).
-void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters, nqs_sr_stats * st)
+// The launch-per-iteration solve WITHOUT polling: S x0 + INIT, then as many iterations as the previous solve needed plus two,
+// and the scalars on their way to pinned memory -- nothing is synchronised.  Iterations past convergence exit at entry (`done`);
+// the INIT launch also makes the finite-energy check.  Returns the number of iterations enqueued.  After the caller's next
+// synchronisation cg_finish_async() reads the scalars and, in the rare case that the solve needs more iterations than were
+// enqueued, runs them with the polling loop of cg_solve.
+int cg_solve_async_begin(nqs_handle * h, double lambda, double tol, int max_iter, int fixed_iters)
 {
   CgScalars init;
   std::memset(&init, 0, sizeof(init));
   init.tol2 = tol*tol;
   init.fixed = fixed_iters > 0 ? 1 : 0;
-  std::memcpy((char*)h->pinned+PIN_CG_INIT, &init, sizeof(init));   // own region of the pinned area: no synchronisation needed
+  std::memcpy((char*)h->pinned+PIN_CG_INIT, &init, sizeof(init));
   NQS_CUDA(cudaMemcpyAsync(h->scal.p, (char*)h->pinned+PIN_CG_INIT, sizeof(CgScalars), cudaMemcpyHostToDevice, h->stream));
   int * done = &h->scal.p->done;
   int nparts = matvec_passes(h, h->dx.p, nullptr);
+  h->cg_check_finite = true;
   launch_cg_fused(h, CG_MODE_INIT, nparts, lambda, h->dx.p);
+  h->cg_check_finite = false;
   const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
-  CgScalars * snap = reinterpret_cast<CgScalars*>((char*)h->pinned+PIN_CG_SNAP);
-  // Iterations are enqueued without looking at the result: first as many as the previous solve needed (consecutive SR steps
-  // need almost the same number), then two at a time, each batch followed by one read-back of the scalars.  Iterations past
-  // convergence are skipped on the device (`done`), so the count is exact and a misprediction costs one queue bubble.
-  int enq = 0;
-  CgScalars s;
-  std::memset(&s, 0, sizeof(s));
-  int n_here = fixed_iters > 0 ? n_max : std::max(1, std::min(n_max, h->cg_prev_iters));
-  for (;;)
+  const int n = fixed_iters > 0 ? n_max : std::max(1, std::min(n_max, h->cg_prev_iters+2));
+  for (int q = 0; q < n; ++q)
   {
-    for (int q = 0; q < n_here; ++q)
-    {
-      nparts = matvec_passes(h, h->pvec.p, done);
-      launch_cg_fused(h, CG_MODE_ITER, nparts, lambda, h->pvec.p);
-    }
-    enq += n_here;
-    NQS_CUDA(cudaMemcpyAsync(snap, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
-    NQS_CUDA(cudaStreamSynchronize(h->stream));
-    s = *snap;
-    if (s.done || enq >= n_max) break;
-    n_here = std::min(2, n_max-enq);
+    nparts = matvec_passes(h, h->pvec.p, done);
+    launch_cg_fused(h, CG_MODE_ITER, nparts, lambda, h->pvec.p);
   }
-  if (fixed_iters <= 0) h->cg_prev_iters = std::max(1, s.iters);
+  NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_CG_SNAP, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+  return n;
+}
+
+void cg_check_errors(nqs_handle * h, const CgScalars & s)
+{
   if (s.peer_timeout)
     throw Error(NQS_ERR_NCCL, "in-kernel NVLink exchange timed out after 20 s: a peer rank did not reach the same CG iteration");
   if (s.barrier_timeout)
@@ -1069,12 +1064,37 @@ void cg_solve(nqs_handle * h, double lambda, double tol, int max_iter, int fixed
     cudaMemsetAsync(h->cgbar.p, 0, sizeof(unsigned int), h->stream);
     throw Error(NQS_ERR_CUDA, "grid barrier of cg_fused_kernel timed out after 20 s: its CTAs were not co-resident");
   }
-  if (st)
+}
+
+// after a synchronisation.  Returns true when more iterations had to be run here (the caller's update, enqueued behind the first
+// batch, declined on the device and must be enqueued again).
+bool cg_finish_async(nqs_handle * h, double lambda, int max_iter, int fixed_iters, int enq, nqs_sr_stats * st, bool * nonfinite)
+{
+  CgScalars * snap = reinterpret_cast<CgScalars*>((char*)h->pinned+PIN_CG_SNAP);
+  CgScalars s = *snap;
+  cg_check_errors(h, s);
+  *nonfinite = s.nonfinite != 0;
+  bool more = false;
+  const int n_max = fixed_iters > 0 ? fixed_iters : max_iter;
+  int * done = &h->scal.p->done;
+  while (!s.nonfinite && !s.done && enq < n_max)
   {
-    st->cg_iters = s.iters;
-    st->cg_res2 = s.res2;
-    st->cg_rhs2 = s.rhs2;
+    more = true;
+    const int n_here = std::min(2, n_max-enq);
+    for (int q = 0; q < n_here; ++q)
+    {
+      const int nparts = matvec_passes(h, h->pvec.p, done);
+      launch_cg_fused(h, CG_MODE_ITER, nparts, lambda, h->pvec.p);
+    }
+    enq += n_here;
+    NQS_CUDA(cudaMemcpyAsync(snap, h->scal.p, sizeof(CgScalars), cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    s = *snap;
+    cg_check_errors(h, s);
   }
+  if (fixed_iters <= 0 && !s.nonfinite) h->cg_prev_iters = std::max(1, s.iters);
+  if (st) { st->cg_iters = s.iters; st->cg_res2 = s.res2; st->cg_rhs2 = s.rhs2; }
+  return more;
 }
 
 bool cgp_usable(const nqs_handle * h)
@@ -1156,11 +1176,11 @@ void collect_cg(nqs_handle * h, nqs_sr_stats * st, bool * nonfinite)
   if (st) { st->cg_iters = s.iters; st->cg_res2 = s.res2; st->cg_rhs2 = s.rhs2; }
 }
 
-void do_evolve(nqs_handle * h, const cd * dx_dev, double lr, const int * skip = nullptr)
+void do_evolve(nqs_handle * h, const cd * dx_dev, double lr, const CgScalars * sc = nullptr, int need_done = 0)
 {
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   invalidate_tables(h);
-  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p, skip);
+  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p, sc, need_done);
   check_launch(h, "update_params_kernel");
   build_tables_async(h);   // the next sweep needs them anyway; their bound rides on the caller's final read-back
   NQS_CUDA(cudaMemsetAsync(h->fresh.p, 0, (size_t)h->K, h->stream)); // lnpsi0 is now the pre-update value (ref keeps it)
@@ -1763,7 +1783,7 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       // skips the solve -- and, through its flag, the update -- when <h> is not finite; one synchronisation ends the step
       { Span t(h, TAG_CG); cg_solve_persistent(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters); }
       if (opt->apply_update)
-      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr, &h->scal.p->nonfinite); }
+      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr, h->scal.p, 0); }
       NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->hsall.p, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
       NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
       finish_tables(h);
@@ -1776,24 +1796,27 @@ nqs_status nqs_sr_step(nqs_handle * h, const nqs_sr_options * opt, nqs_sr_stats 
       if (nonfinite) { h->bp = bp_before; if (st) *st = s; return; }
     }
     else
-    {
-      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->hsall.p, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
-      NQS_CUDA(cudaStreamSynchronize(h->stream));
-      std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
-      s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
-      s.finite = std::isfinite(s.e_re) ? 1 : 0;
-      if (!s.finite)
-      { // ref optimizer.cuh:134-138: print and stop; here: report and leave the state untouched
-        h->bp = bp_before;
-        if (st) *st = s;
-        resolve_spans(h);
-        return;
-      }
-      { Span t(h, TAG_CG); cg_solve(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters, &s); }
+    { // launch per iteration (two-pass / structured / O-generating S*v, or NQS_CG_PERSIST=0): the same asynchronous shape -- the
+      // first batch of iterations and the update are enqueued without looking at the device; one synchronisation ends the step
+      int enq = 0;
+      { Span t(h, TAG_CG); enq = cg_solve_async_begin(h, s.lambda, opt->tol, opt->max_iter, opt->fixed_iters); }
       if (opt->apply_update)
-      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr); }
+      { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr, h->scal.p, opt->fixed_iters > 0 ? 0 : 1); }
+      NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_HS, h->hsall.p, sizeof(double)*3, cudaMemcpyDeviceToHost, h->stream));
       NQS_CUDA(cudaStreamSynchronize(h->stream)); // ref cudaDeviceSynchronize, optimizer.cuh:153
       finish_tables(h);
+      std::memcpy(hs, (char*)h->pinned+PIN_HS, sizeof(hs));
+      bool nonfinite = false;
+      const bool more = cg_finish_async(h, s.lambda, opt->max_iter, opt->fixed_iters, enq, &s, &nonfinite);
+      s.e_re = hs[0]*invk; s.e_im = hs[1]*invk;
+      s.finite = nonfinite ? 0 : 1;
+      if (nonfinite) { h->bp = bp_before; resolve_spans(h); if (st) *st = s; return; }
+      if (more && opt->apply_update)
+      { // the update enqueued behind the first batch saw an unconverged solve and declined: now it applies
+        { Span t(h, TAG_UPDATE); do_evolve(h, h->dx.p, opt->lr); }
+        NQS_CUDA(cudaStreamSynchronize(h->stream));
+        finish_tables(h);
+      }
       resolve_spans(h);
     }
     const double n2 = s.e_re*s.e_re+s.e_im*s.e_im;

@@ -96,6 +96,8 @@ struct nqs_handle
   bool cgp_ok = false;                    // planned for this handle (single GPU, or every rank planned the same grid)
   bool cgp_peers_agree = true;            // multi-GPU: all ranks export the same persistent grid (checked at p2p import)
   int cgp_coop = -1;                      // cooperative + cluster launch: -1 untried, 1 works, 0 refused (plain cluster launch, barrier time-out)
+  bool cg_check_finite = false;           // the INIT launch of the launch-per-iteration solve checks <h> itself (nqs_sr_step)
+  int cg_async_enq = 0;                   // launch-per-iteration solve enqueued without polling: iterations in the queue (0 = none pending)
   bool cg_inflight = false;               // a persistent solve was launched and its scalars are not read back yet
   bool bound_inflight = false;            // theta_bound of freshly built tables is on its way to pinned memory
   // structured S*v (sv_struct.cuh, NQS_FLAG_STRUCTURED_SV): hidden-unit factors T (and L, FFNN), chain chunks of the column GEMM

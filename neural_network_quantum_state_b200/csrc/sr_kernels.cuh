@@ -443,11 +443,14 @@ struct CgScalars
 };
 
 // ref: update_parameters (impl_neural_quantum_state.cuh:1300-1312) / FFNN__UpdateParameters__ (:1665-1690, un-transposes the W block)
-// `skip` (may be null): device flag raised by the CG kernel when <h> was not finite -- the reference stops before the update then
+// `sc` (may be null): scalars of the solve that produced dx.  The update is enqueued behind the solve without a host round trip,
+// so the kernel itself declines when <h> was not finite (the reference stops before the update then, optimizer.cuh:134-138) or
+// when `need_done` is set and the solve has not converged within the iterations enqueued so far (the host then finishes the
+// solve and enqueues the update again).
 __global__ void update_params_kernel(const int N, const int M, const int model, const long long P, const cd * __restrict__ dx,
-  const double lr, cd * __restrict__ params, const int * __restrict__ skip)
+  const double lr, cd * __restrict__ params, const CgScalars * __restrict__ sc, const int need_done)
 {
-  if (skip != nullptr && *skip) return;
+  if (sc != nullptr && (sc->nonfinite || (need_done && !sc->done))) return;
   const long long NM = (long long)N*M;
   for (long long q = (long long)blockIdx.x*blockDim.x+threadIdx.x; q < P; q += (long long)gridDim.x*blockDim.x)
   {
