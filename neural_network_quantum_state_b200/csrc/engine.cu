@@ -591,14 +591,18 @@ cudaError_t cgp_launch(int cpt, int defer, const CgpArgs & a, int cs, int nclust
   }
 }
 
-// The persistent solve is used when the one-pass plan exists, its grid fits the per-CTA reduction slots / exchange flags, every
-// consumer thread owns at most EPT vector elements and all clusters are resident at once.  NQS_CG_PERSIST=0 keeps the
-// launch-per-iteration path (A/B runs, tests).
+// The persistent solve can be used when the one-pass plan exists, its grid fits the per-CTA reduction slots, every consumer
+// thread owns at most EPT vector elements and all clusters are resident at once.
 void plan_cgp(nqs_handle * h)
 {
   h->cgp_ok = false;
   if (!h->sv_ok || h->gen_ok || h->struct_sv) return;
-  { const char * e = std::getenv("NQS_CG_PERSIST"); if (e && std::atoi(e) == 0) return; }
+  // OPT-IN (NQS_CG_PERSIST=1).  Measured in round 2 (profiles/r2_cg_persistent.md): the persistent kernel's pass over O carries
+  // ~8 % more instructions per row than sv_fused_kernel's (ring bookkeeping across products, register moves) and that loop is
+  // issue-sensitive, so it streams 3-7 % slower; its vector phase (3 grid barriers + folds, ~20 us; ~37 us with the 8-GPU
+  // exchange and rank skew) is no shorter than one cg_fused_kernel launch (~27 / ~42 us).  Net: 2 % slower on one GPU, equal on
+  // eight, once the launch-per-iteration path stopped polling (cg_solve_async_begin).  Kept for the record and for A/B runs.
+  { const char * e = std::getenv("NQS_CG_PERSIST"); if (!(e && std::atoi(e) != 0)) return; }
   const long long ctas = (long long)h->sv_nclusters*h->sv_cs;
   if (ctas > NQS_CGP_MAX_CTAS) return;
   const long long threads = ctas*h->sv_nt;

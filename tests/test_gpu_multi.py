@@ -23,7 +23,7 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("mode", ["p2p", "nccl", "p2p_struct"])
+@pytest.mark.parametrize("mode", ["p2p", "nccl", "p2p_struct", "p2p_persist"])
 def test_sharded_run_matches_single_gpu(tmp_path, mode):
     from neural_network_quantum_state_b200 import Engine
     from neural_network_quantum_state_b200.init import reference_init
@@ -32,12 +32,16 @@ def test_sharded_run_matches_single_gpu(tmp_path, mode):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_worker.py"), out] + (["--no-p2p"] if mode == "nccl" else []) + \
           (["--structured"] if mode == "p2p_struct" else [])
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    env["NQS_CG_PERSIST"] = "1" if mode == "p2p_persist" else "0"    # persistent CG kernel: packet (LL) exchange inside the kernel
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     got = json.load(open(out))
     assert got["ranks_identical"]
     if mode == "p2p_struct":
         assert got["sv"].startswith("structured_dmma"), got["sv"]
+    if mode == "p2p_persist":
+        assert got["sv"].endswith("_persistentcg"), got["sv"]
     if mode.startswith("p2p"):
         assert got["p2p"], "peer mapping unavailable: the in-kernel exchange was not exercised"
     model, N, M, K = "rbm", 24, 48, 1000
