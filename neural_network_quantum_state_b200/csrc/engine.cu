@@ -277,8 +277,15 @@ void build_tables_async(nqs_handle * h)
 {
   if (h->jpl == 0 || h->tables_valid || h->bound_inflight) return;
   build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
-    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p, h->bound.p);
+    h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p, h->bound.p,
+    h->model == MODEL_RBM ? 1 : 0);
   check_launch(h, "build_fast_tables_kernel");
+  if (h->model == MODEL_FFNN)
+  { // the FNN kernels hold tanh(theta) and log f, nothing that could overflow: no bound to wait for
+    h->theta_bound = 0.0;
+    h->tables_valid = true;
+    return;
+  }
   theta_bound_kernel<<<(h->M+31)/32, NQS_TB_THREADS, 0, h->stream>>>(h->N, h->M, h->params.p, h->bound.p);
   check_launch(h, "theta_bound_kernel");
   NQS_CUDA(cudaMemcpyAsync((char*)h->pinned+PIN_BOUND, h->bound.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -391,7 +398,33 @@ void launch_sweep(nqs_handle * h, long long nsteps)
     a.acc_log = h->acc_log.p;
     h->acc_log_steps = nsteps;
   }
-  if (fast_path_ok(h) && h->jpl <= 32 && nsteps%h->N == 0 && fast_sweep_fits(h))
+  if (h->model == MODEL_FFNN && fast_path_ok(h) && h->jpl <= 16 && nsteps%h->N == 0)
+  { // hidden-unit state resident on chip, one complex log per (proposal, hidden unit): ffnn_fast_kernels.cuh
+    // as many chains (warps) per CTA as the shared memory holds: the kernel is latency-bound (one dependent reduction per proposal)
+    int warps = NQS_FF_MAX_WARPS;
+    while (warps > 1 && ffnn_sweep_smem_bytes(h->N, warps, h->mpad) > h->smem_optin) --warps;
+    { const char * e = std::getenv("NQS_FF_WARPS"); if (e && std::atoi(e) >= 1 && std::atoi(e) <= warps) warps = std::atoi(e); }
+    if (ffnn_sweep_smem_bytes(h->N, warps, h->mpad) <= h->smem_optin)
+    {
+      FfnnSweepArgs f;
+      f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ctab_a = h->ctab_a.p; f.ctab_b = h->ctab_b.p; f.w2 = h->w2.p;
+      f.spins = h->spins.p; f.theta = h->theta.p; f.lnpsi0 = h->lnpsi0.p; f.fresh = h->fresh.p; f.order = h->order.p;
+      f.pos0 = h->pos; f.nsweeps = (int)(nsteps/h->N); f.uniforms = a.uniforms; f.seed = a.seed; f.step0 = a.step0;
+      f.chain_offset = a.chain_offset; f.acc_log = a.acc_log;
+      const size_t smem = ffnn_sweep_smem_bytes(h->N, warps, h->mpad);
+      const unsigned grid = (unsigned)((h->K+warps-1)/warps);
+#define NQS_FF_CASE(J) case J: set_smem(ffnn_sweep_fast_kernel<J>, smem); ffnn_sweep_fast_kernel<J><<<grid, warps*32, smem, h->stream>>>(f); break
+      switch (h->jpl) { NQS_FF_CASE(1); NQS_FF_CASE(2); NQS_FF_CASE(4); NQS_FF_CASE(8); default: NQS_FF_CASE(16); }
+#undef NQS_FF_CASE
+      check_launch(h, "ffnn_sweep_fast_kernel");
+      h->variant_sweep = "ffnn_resident_j"+std::to_string(h->jpl)+"_w"+std::to_string(warps);
+      h->pos = (int)((h->pos+nsteps)%h->N);
+      if (h->u_steps > 0) h->u_used += nsteps;
+      h->step_counter += (unsigned long long)nsteps;
+      return;
+    }
+  }
+  if (h->model == MODEL_RBM && fast_path_ok(h) && h->jpl <= 32 && nsteps%h->N == 0 && fast_sweep_fits(h))
   {
     FastSweepArgs f;
     f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ftab_a = h->ftab_a.p; f.ftab_b = h->ftab_b.p; f.w2 = h->w2.p; f.afac = h->afac.p;
@@ -439,10 +472,24 @@ void launch_sweep(nqs_handle * h, long long nsteps)
 
 void launch_eloc(nqs_handle * h, cd * lnpsi1, int single_site)
 {
-  if (lnpsi1 == nullptr && fast_path_ok(h))
+  if (lnpsi1 == nullptr && h->model == MODEL_RBM && fast_path_ok(h))
   {
     launch_eloc_fast(h);
     h->variant_eloc = "rbm_sites_c4";
+    return;
+  }
+  if (lnpsi1 == nullptr && h->model == MODEL_FFNN && fast_path_ok(h) && ffnn_eloc_smem_bytes(h->N, h->M, 4) <= h->smem_optin)
+  {
+    FfnnElocArgs f;
+    f.N = h->N; f.M = h->M; f.Npad = h->npad32; f.K = h->K; f.params = h->params.p; f.ctabT_a = h->ctabT_a.p; f.ctabT_b = h->ctabT_b.p;
+    f.spins = h->spins.p; f.theta = h->theta.p; f.lnpsi0 = h->lnpsi0.p; f.Jmat = h->Jmat.p; f.hfield = h->cfg.h; f.htilda = h->htilda.p;
+    f.sjs = launch_sjs(h);
+    const int nwarps = std::max(1, std::min(8, (h->N+31)/32));
+    const size_t smem = ffnn_eloc_smem_bytes(h->N, h->M, 4);
+    set_smem(ffnn_eloc_fast_kernel<4>, smem);
+    ffnn_eloc_fast_kernel<4><<<(unsigned)((h->K+3)/4), nwarps*32, smem, h->stream>>>(f);
+    check_launch(h, "ffnn_eloc_fast_kernel");
+    h->variant_eloc = "ffnn_sites_c4";
     return;
   }
   if (lnpsi1 == nullptr) h->variant_eloc = "generic";
@@ -1398,8 +1445,8 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     NQS_CUDA(cudaMemset(h->fresh.p, 0, (size_t)h->K));
     // product-form tables: the sweep keeps its state in registers (M <= 512: 16 hidden-unit slots per lane; M <= 1024: two warps
     // per chain); the local-energy kernel keeps tanh(theta) in shared memory and works up to M = 2048
-    if (h->model == MODEL_RBM && !(cfg->flags & NQS_FLAG_FORCE_GENERIC) && h->M <= 2048)
-    {
+    if (!(cfg->flags & NQS_FLAG_FORCE_GENERIC) && h->M <= 2048)
+    { // (FNN: the same cosh 2W / sinh 2W / 2W tables serve ffnn_fast_kernels.cuh)
       int jpl = 1;
       while (32*jpl < h->M) jpl <<= 1;
       h->jpl = jpl; h->mpad = 32*jpl;

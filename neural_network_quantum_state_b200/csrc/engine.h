@@ -9,6 +9,7 @@
 #include "../../include/nqs_b200.h"
 #include "device_math.cuh"
 #include "fast_kernels.cuh"
+#include "ffnn_fast_kernels.cuh"
 
 namespace nqs
 {

@@ -33,7 +33,7 @@ __device__ __forceinline__ double2 ld_tab(const double2 * p) { return __ldg(p); 
 __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpad, const cd * __restrict__ params,
   FlipTab * __restrict__ ftab_a, FlipTab * __restrict__ ftab_b, CoshTab * __restrict__ ctab_a, CoshTab * __restrict__ ctab_b,
   CoshTab * __restrict__ ctabT_a, CoshTab * __restrict__ ctabT_b, const int Npad,
-  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp, double * __restrict__ bound)
+  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp, double * __restrict__ bound, const int has_visible_bias)
 {
   const cd * W = params;
   const cd * a = params+(size_t)N*M;
@@ -68,7 +68,7 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     ctabT_b[(size_t)j*Npad+i] = make_double2(0.0, 0.0);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && bound != nullptr) *bound = 0.0;   // theta_bound_kernel (launched next) accumulates a maximum
-  for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < N; i += gridDim.x*blockDim.x)
+  for (int i = blockIdx.x*blockDim.x+threadIdx.x; i < N && has_visible_bias; i += gridDim.x*blockDim.x)
   {
     const cd ai = a[i];
     afac[2*i] = exp(-4.0*ai.x);   // sigma = +1

@@ -94,7 +94,7 @@ def test_golden_param_files(golden, tmp_path):
 # engine vs numpy oracle on seeded inputs (ragged sizes: M not a multiple of 32, odd N, K not a multiple of the CTA size)
 # ---------------------------------------------------------------------------------------------------------------------
 H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
-FFNN_SWEEP_VARIANT = "generic"     # kernel_variant("sweep") prefix the FNN sampler must report when not forced generic
+FFNN_SWEEP_VARIANT = "ffnn_resident"     # kernel_variant("sweep") prefix the FNN sampler must report when not forced generic (M <= 512)
 
 
 def synth(model, N, M, rng, scale=1.0):
