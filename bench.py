@@ -178,6 +178,43 @@ def multi_gpu_parity(world: int, rank: int, local_rank: int) -> dict:
     return flag[0]
 
 
+def gpu_reference_leg(model: str, N: int, M: int, K: int, cfg_id: int, device: int) -> dict:
+    """The reference's OWN CUDA driver (gpu/src/LICH-train_rbm.cu, unmodified, compiled for sm_100 by baseline/Makefile) on this
+    GPU, same parameter files, same uniforms (Philox TRNG shim), next to this engine: ms per SR step from two runs (3 and 8
+    iterations after 100 warm-up sweeps) and the energy trajectories side by side.  A second leg next to the CPU reference arm,
+    not a replacement for it."""
+    import tempfile
+    from baseline import ref_cuda
+    from neural_network_quantum_state_b200 import Engine
+    if model != "rbm":
+        return {"unavailable": "the reference ships no LICH-train_ffnn driver (SURVEY 0.2)"}
+    if not ref_cuda.available():
+        return {"unavailable": "baseline/_ref/LICH-train_rbm-gpu-ref missing (make -C baseline in the development container)"}
+    theta = float(ref_cuda.THETA_STR)
+    h, J = -math.cos(theta), math.sin(theta)
+    # 100 warm-up sweeps as in the main run: from the identical Neel start fewer leave zero-variance columns in O, whose 0/0 in
+    # the preconditioner turns BOTH programs' parameters into NaN at the second iteration (SURVEY 0.8; seen with 10 sweeps)
+    seed, nwarm, n_a, n_b = 20261018, 100, 3, 8
+    with tempfile.TemporaryDirectory() as tmp:
+        prefix = ref_cuda.prefix_for(tmp, N, M)
+        e = Engine(model, N, M, K, h, J, ALPHA_LR, seed=seed, device=device)
+        e.set_params(synthetic_params(model, N, M, cfg_id))
+        e.save(prefix, 17)
+        e.load(prefix)
+        ra = ref_cuda.run(N, M, K, n_a, nwarm, seed, tmp, device=device)
+        e.save(prefix, 17)                     # the driver overwrote the files with its final parameters: restore the start
+        rb = ref_cuda.run(N, M, K, n_b, nwarm, seed, tmp, device=device)
+        e.warm_up(nwarm)
+        ours = [e.sr_step(n_mc_steps=1, lr=1e-2).e_mean.real for _ in range(n_b)]
+        e.close()
+    ms = (rb["elapsed_s"] - ra["elapsed_s"]) / (n_b - n_a) * 1e3
+    diff = max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(ours, rb["energies"])) if rb["energies"] else None
+    return {"ms_per_step": ms, "value": K / (ms * 1e-3), "unit": UNIT, "steps_timed": n_b - n_a,
+            "energies_reference": rb["energies"], "energies_engine": ours, "energy_max_rel_diff": diff,
+            "how": "unmodified gpu/src/LICH-train_rbm.cu, nvcc -arch=sm_100, TRNG4 -> Philox shim (same uniforms as the engine); "
+                   "(elapsed of 8 iterations - elapsed of 3) / 5, 100 warm-up sweeps each; energies printed with 7 digits"}
+
+
 def sweep_roofline(model, N, M, K_loc, sweep_ms, hbm_peak_gbs, variant):
     """SURVEY 8d asks for BOTH bounds of the state-resident sweep and for a statement of which one binds.
     HBM: B_sw = theta in + out (2*K*M*16) + spins in + out (2*K*N) + lnpsi0/sa in + out (4*K*16) + the flip tables once (L2-resident
@@ -295,6 +332,7 @@ def main():
     ap.add_argument("--two-pass-sv", action="store_true", help="S*v as two streaming passes over O (reference structure)")
     ap.add_argument("--no-structured-extra", action="store_true",
                     help="skip the second, separately reported measurement of the same step with NQS_FLAG_STRUCTURED_SV (1 GPU only)")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the same-box run of the reference's own CUDA driver (1 GPU, RBM)")
     ap.add_argument("--no-parity-check", action="store_true", help="multi-GPU: skip the (untimed) sharded-vs-single-GPU parity check")
     ap.add_argument("--production-iters", type=int, default=100,
                     help="extra block: steps at the lambda floor 1e-2 with this many CG iterations (the regime of a converged run, "
@@ -651,6 +689,13 @@ def main():
             e2.close()
         except Exception as ex:
             line["structured_sv"] = {"value": None, "error": str(ex)}
+    if world == 1 and not args.no_gpu_reference and not args.structured_sv:
+        # the engine's O (and the reference's two copies of it) must fit together: release ours first
+        e.close()
+        try:
+            line["gpu_reference"] = gpu_reference_leg(model, N, M, K_total, cfg_id, local_rank)
+        except Exception as ex:
+            line["gpu_reference"] = {"unavailable": "failed: %s" % str(ex)[-300:]}
     if not args.no_cpu_baseline and world == 1:
         try:
             res = run_reference_cpu(args.config, steps=2, warmup=1, k_sample=args.cpu_sample_chains, n_warm_sweeps=5)

@@ -45,7 +45,12 @@ typedef enum nqs_status {
   NQS_ERR_UNSUPPORTED = 8
 } nqs_status;
 
-typedef enum nqs_model { NQS_MODEL_RBM = 0, NQS_MODEL_FFNN = 1 } nqs_model;
+/* NQS_MODEL_RBMTRSYMM: the translation-symmetric RBM (ref: RBMTrSymm<T>(nInputs, alpha, nChains), gpu/include/
+ * neural_quantum_state.cuh:62-105, impl :301-538, kernels :1487-1553; driver gpu/src/LICH-train_rbmtrsymm.cu).  Variables are
+ * [w (f*N+i, alpha filters) | a (1) | b (alpha)], P = N*alpha + 1 + alpha; the sampler works on the expanded RBM
+ * wf[i][f*N+j] = w[f][(i+j)%N], bf[f*N+j] = b[f], af[i] = a[0].  nqs_config.n_hiddens is the EXPANDED width alpha*N
+ * (a multiple of n_inputs); parameter files: ONE file `prefix` holding all P variables (ref :474-482). */
+typedef enum nqs_model { NQS_MODEL_RBM = 0, NQS_MODEL_FFNN = 1, NQS_MODEL_RBMTRSYMM = 2 } nqs_model;
 /* site visiting order of one sweep */
 typedef enum nqs_order {
   NQS_ORDER_CHECKERBOARD = 0, /* 2,4,..,1,3,..,0  ref: gpu/include/impl_hamiltonians.cuh:163-180,209-210 (LITFIChain)   */

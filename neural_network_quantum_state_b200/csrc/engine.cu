@@ -163,6 +163,16 @@ void check_launch(nqs_handle * h, const char * what)
   h->timing.kernel_launches += 1;
 }
 
+// the vector the optimiser moves: the parameters themselves, or the tied variables of the translation-symmetric RBM
+cd * var_ptr(nqs_handle * h) { return h->trsymm ? h->vars.p : h->params.p; }
+// vars -> expanded network (ref symmetrize_variables_, impl_neural_quantum_state.cuh:534-538); no-op for the plain ansaetze
+void expand_vars(nqs_handle * h)
+{
+  if (!h->trsymm) return;
+  trsymm_expand_kernel<<<grid_for(h->Pfull, 256, 148*4), 256, 0, h->stream>>>(h->N, h->alpha_f, h->vars.p, h->params.p);
+  check_launch(h, "trsymm_expand_kernel");
+}
+
 int warps_for_smem(const nqs_handle * h, size_t per_warp, size_t fixed)
 { // as many warps per CTA (<= 8) as fit the opt-in shared memory
   int w = 8;
@@ -521,7 +531,12 @@ void launch_oderiv(nqs_handle * h, cudaStream_t stream = nullptr)
   if (stream == nullptr) stream = h->stream;
   const size_t smem = (size_t)(h->model == MODEL_FFNN ? 2 : 1)*h->M*sizeof(cd)+(size_t)h->N*sizeof(double);
   NQS_REQUIRE(smem <= h->smem_optin, NQS_ERR_UNSUPPORTED, "n_hiddens too large for oderiv_kernel shared memory");
-  if (h->model == MODEL_RBM)
+  if (h->trsymm)
+  {
+    set_smem(oderiv_trsymm_kernel, smem);
+    oderiv_trsymm_kernel<<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->alpha_f, h->K, h->spins.p, h->theta.p, h->O.p);
+  }
+  else if (h->model == MODEL_RBM)
   {
     set_smem(oderiv_kernel<MODEL_RBM>, smem);
     oderiv_kernel<MODEL_RBM><<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->M, h->K, h->params.p, h->spins.p, h->theta.p, h->O.p);
@@ -784,7 +799,7 @@ int cols_variant_for(int N) { return N <= 16 ? 0 : N <= 32 ? 1 : N <= 64 ? 2 : N
 void plan_cols(nqs_handle * h)
 {
   h->cols_ok = false;
-  if (h->N > 256 || (h->cfg.flags & NQS_FLAG_NO_DMMA)) return;
+  if (h->N > 256 || (h->cfg.flags & NQS_FLAG_NO_DMMA) || h->trsymm) return;    // (tied weights: the rows of O are not outer products)
   const int var = cols_variant_for(h->N);
   const int cw = cols_dmma_cw(kColsVariants[var][1], kColsVariants[var][2]);
   const int colgroups = (2*h->M+cw-1)/cw;
@@ -799,6 +814,7 @@ void plan_cols(nqs_handle * h)
 void plan_struct(nqs_handle * h)
 {
   NQS_REQUIRE(h->N <= 256, NQS_ERR_UNSUPPORTED, "NQS_FLAG_STRUCTURED_SV supports n_inputs <= 256");
+  NQS_REQUIRE(!h->trsymm, NQS_ERR_UNSUPPORTED, "NQS_FLAG_STRUCTURED_SV is not available for the translation-symmetric RBM");
   NQS_REQUIRE(!(h->cfg.flags & (NQS_FLAG_SETUP_FROM_O | NQS_FLAG_TWO_PASS_SV | NQS_FLAG_NO_DMMA)), NQS_ERR_INVALID,
     "NQS_FLAG_STRUCTURED_SV excludes NQS_FLAG_SETUP_FROM_O / NQS_FLAG_TWO_PASS_SV / NQS_FLAG_NO_DMMA");
   const int var = h->sc_variant;
@@ -885,7 +901,7 @@ void sr_setup(nqs_handle * h, bool want_F)
     finish_setup(h, want_F);
     return;
   }
-  if (ipt <= 16 && h->theta_matches_O && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
+  if (ipt <= 16 && h->theta_matches_O && !h->trsymm && !(h->cfg.flags & NQS_FLAG_SETUP_FROM_O))
   { // sums from the factors of O (spins, tanh theta): no pass over O
     dim3 grid((unsigned)((h->M+NQS_SS_JT-1)/NQS_SS_JT), (unsigned)h->nrb);
     int ipt_t = 1;
@@ -1231,8 +1247,9 @@ void do_evolve(nqs_handle * h, const cd * dx_dev, double lr, const CgScalars * s
 {
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   invalidate_tables(h);
-  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, h->params.p, sc, need_done);
+  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, var_ptr(h), sc, need_done);
   check_launch(h, "update_params_kernel");
+  expand_vars(h);
   build_tables_async(h);   // the next sweep needs them anyway; their bound rides on the caller's final read-back
   NQS_CUDA(cudaMemsetAsync(h->fresh.p, 0, (size_t)h->K, h->stream)); // lnpsi0 is now the pre-update value (ref keeps it)
   // ref update_variables tail (:161-169): theta and sa re-derived for the current spins; lnpsi0 is NOT refreshed
@@ -1301,13 +1318,14 @@ void upload_params(nqs_handle * h, const std::vector<std::complex<double> > & v)
 {
   invalidate_tables(h);
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
-  NQS_CUDA(cudaMemcpyAsync(h->params.p, v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
+  NQS_CUDA(cudaMemcpyAsync(var_ptr(h), v.data(), sizeof(cd)*v.size(), cudaMemcpyHostToDevice, h->stream));
+  expand_vars(h);
   NQS_CUDA(cudaStreamSynchronize(h->stream));
 }
 std::vector<std::complex<double> > download_params(nqs_handle * h)
 {
   std::vector<std::complex<double> > v((size_t)h->P);
-  NQS_CUDA(cudaMemcpyAsync(v.data(), h->params.p, sizeof(cd)*v.size(), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaMemcpyAsync(v.data(), var_ptr(h), sizeof(cd)*v.size(), cudaMemcpyDeviceToHost, h->stream));
   NQS_CUDA(cudaStreamSynchronize(h->stream));
   return v;
 }
@@ -1369,6 +1387,8 @@ struct ParamFile { const char * suffix; long long off, count, row; const char * 
 std::vector<ParamFile> param_files(const nqs_handle * h)
 { // ref save/load: RBM Dw/Da/Db (:225-232,281-286); FFNN Dw1/Dw2(=w1o)/Db1 (:931-937,985-991)
   const long long NM = (long long)h->N*h->M;
+  if (h->trsymm)   // ref RBMTrSymm::save / load (:474-517): every variable in ONE file named by the prefix itself
+    return {{"", 0, h->P, h->P+1, "variables"}};
   if (h->model == MODEL_RBM)
     return {{"Dw.dat", 0, NM, h->M, "w"}, {"Da.dat", NM, h->N, h->N, "a"}, {"Db.dat", NM+h->N, h->M, h->M, "b"}};
   return {{"Dw1.dat", 0, NM, h->M, "w1"}, {"Dw2.dat", NM+h->M, h->M, h->M, "w2"}, {"Db1.dat", NM, h->M, h->M, "b1"}};
@@ -1403,7 +1423,10 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
   {
     NQS_REQUIRE(cfg && out, NQS_ERR_INVALID, "nqs_create: null argument");
     NQS_REQUIRE(cfg->abi_version == NQS_B200_ABI_VERSION, NQS_ERR_INVALID, "nqs_create: abi_version mismatch");
-    NQS_REQUIRE(cfg->model == NQS_MODEL_RBM || cfg->model == NQS_MODEL_FFNN, NQS_ERR_INVALID, "nqs_create: unknown model");
+    NQS_REQUIRE(cfg->model == NQS_MODEL_RBM || cfg->model == NQS_MODEL_FFNN || cfg->model == NQS_MODEL_RBMTRSYMM, NQS_ERR_INVALID,
+      "nqs_create: unknown model");
+    NQS_REQUIRE(cfg->model != NQS_MODEL_RBMTRSYMM || cfg->n_hiddens%cfg->n_inputs == 0, NQS_ERR_INVALID,
+      "nqs_create: translation-symmetric RBM needs n_hiddens = alpha * n_inputs (the expanded width)");
     NQS_REQUIRE(cfg->n_inputs >= 1 && cfg->n_hiddens >= 1 && cfg->n_chains >= 1, NQS_ERR_INVALID, "nqs_create: sizes must be >= 1");
     NQS_REQUIRE(!(cfg->pbc && cfg->n_inputs%2 == 1), NQS_ERR_INVALID, "kL%2 == 1 (set \"isPBC\" to \"false\".)"); // ref :141-142
     NQS_REQUIRE(cfg->order == NQS_ORDER_CHECKERBOARD || cfg->order == NQS_ORDER_SEQUENTIAL, NQS_ERR_INVALID, "nqs_create: unknown order");
@@ -1422,9 +1445,12 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
         h->cfg.flags |= NQS_FLAG_STRUCTURED_SV;
     }
     h->N = cfg->n_inputs; h->M = cfg->n_hiddens; h->model = cfg->model;
+    if (cfg->model == NQS_MODEL_RBMTRSYMM) { h->model = MODEL_RBM; h->trsymm = true; h->alpha_f = h->M/h->N; }
     h->K = cfg->n_chains; h->Ktot = cfg->n_chains_total > 0 ? cfg->n_chains_total : cfg->n_chains; h->koff = cfg->chain_offset;
     NQS_REQUIRE(h->Ktot >= h->K, NQS_ERR_INVALID, "n_chains_total < n_chains");
     h->P = (h->model == MODEL_RBM) ? (long long)h->N*h->M+h->N+h->M : (long long)h->N*h->M+2*h->M;
+    h->Pfull = h->P;
+    if (h->trsymm) h->P = (long long)h->N*h->alpha_f+1+h->alpha_f;
     std::memset(&h->timing, 0, sizeof(h->timing));
     cudaDeviceProp prop;
     NQS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1437,7 +1463,8 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
     h->ev_ok = true;
     NQS_CUDA(cudaMallocHost(&h->pinned, 4096));
     const size_t KM = (size_t)h->K*h->M, KN = (size_t)h->K*h->N;
-    h->params.alloc(h->P); h->theta.alloc(KM); h->tmp_theta.alloc(0);
+    h->params.alloc(h->Pfull); h->theta.alloc(KM); h->tmp_theta.alloc(0);
+    if (h->trsymm) { h->vars.alloc(h->P); NQS_CUDA(cudaMemset(h->vars.p, 0, sizeof(cd)*h->P)); }
     h->lnpsi0.alloc(h->K); h->lnpsi1.alloc(h->K); h->sa.alloc(h->K); h->htilda.alloc(h->K);
     h->spins.alloc(KN); h->tmp_spins.alloc(KN);
     h->Jmat.alloc((size_t)h->N*h->N); h->order.alloc(h->N);
@@ -1455,7 +1482,7 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
       h->npad32 = ((h->N+31)/32)*32;
       h->ctabT_a.alloc((size_t)h->M*h->npad32); h->ctabT_b.alloc((size_t)h->M*h->npad32); h->w2.alloc(nm); h->afac.alloc((size_t)2*h->N); h->aexp.alloc((size_t)2*h->N); h->bound.alloc(1);
     }
-    NQS_CUDA(cudaMemset(h->params.p, 0, sizeof(cd)*h->P));
+    NQS_CUDA(cudaMemset(h->params.p, 0, sizeof(cd)*h->Pfull));
     NQS_CUDA(cudaMemset(h->spins.p, 0, KN));   // like the reference's zero-initialised spinStates_dev_
     NQS_CUDA(cudaMemset(h->theta.p, 0, sizeof(cd)*KM));
     NQS_CUDA(cudaMemset(h->lnpsi0.p, 0, sizeof(cd)*h->K));
@@ -1511,7 +1538,8 @@ nqs_status nqs_set_params(nqs_handle * h, const nqs_cdouble * params, int64_t P)
     NQS_REQUIRE(params && P == h->P, NQS_ERR_INVALID, "nqs_set_params: P mismatch");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     invalidate_tables(h);
-    NQS_CUDA(cudaMemcpyAsync(h->params.p, params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
+    NQS_CUDA(cudaMemcpyAsync(var_ptr(h), params, sizeof(cd)*P, cudaMemcpyHostToDevice, h->stream));
+    expand_vars(h);
     NQS_CUDA(cudaStreamSynchronize(h->stream));
     h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   });
@@ -1524,7 +1552,7 @@ nqs_status nqs_get_params(nqs_handle * h, nqs_cdouble * params, int64_t P)
   {
     NQS_REQUIRE(params && P == h->P, NQS_ERR_INVALID, "nqs_get_params: P mismatch");
     NQS_CUDA(cudaSetDevice(h->cfg.device));
-    NQS_CUDA(cudaMemcpyAsync(params, h->params.p, sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
+    NQS_CUDA(cudaMemcpyAsync(params, var_ptr(h), sizeof(cd)*P, cudaMemcpyDeviceToHost, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
   });
 }
@@ -1539,7 +1567,15 @@ nqs_status nqs_init_params_random(nqs_handle * h, uint64_t seed)
     const int N = h->N, M = h->M;
     std::vector<std::complex<double> > v((size_t)h->P);
     const long long NM = (long long)N*M;
-    if (h->model == MODEL_RBM)
+    if (h->trsymm)
+    { // ref ctor impl_neural_quantum_state.cuh:325-345
+      const int al = h->alpha_f;
+      std::normal_distribution<double> randw(0, std::sqrt(1.0/((1+al)*N))), randb(0, std::sqrt(1.0/(N*al)));
+      for (long long i = 0; i < (long long)N*al; ++i) { const double re = 1e-1*randw(ran), im = 1e-1*randw(ran); v[i] = {re, im}; }
+      v[(size_t)N*al] = {0.0, 0.0};
+      for (int j = 0; j < al; ++j) { const double re = 1e-1*randb(ran), im = 1e-1*randb(ran); v[(size_t)N*al+1+j] = {re, im}; }
+    }
+    else if (h->model == MODEL_RBM)
     { // ref ctor impl_neural_quantum_state.cuh:30-48
       std::normal_distribution<double> randw(0, std::sqrt(1.0/(N+M))), randb(0, std::sqrt(1.0/M));
       for (long long i = 0; i < NM; ++i) { const double re = 1e-1*randw(ran), im = 1e-1*randw(ran); v[i] = {re, im}; }
@@ -1732,7 +1768,8 @@ nqs_status nqs_lnpsi_fixed_spins(nqs_handle * h, const int8_t * spins, nqs_cdoub
     NQS_CUDA(cudaSetDevice(h->cfg.device));
     NQS_CUDA(cudaMemcpyAsync(h->tmp_spins.p, spins, (size_t)h->K*h->N, cudaMemcpyHostToDevice, h->stream));
     // ref forward(spins, lnpsi, false): theta from the argument, sa from the MEMBER spins (:119-120); chain state untouched here
-    launch_theta(h, h->tmp_spins.p, h->spins.p, nullptr, nullptr, h->lnpsi1.p);
+    // (RBMTrSymm::forward(spins, ...) takes sa from its ARGUMENT, :401-403)
+    launch_theta(h, h->tmp_spins.p, h->trsymm ? h->tmp_spins.p : h->spins.p, nullptr, nullptr, h->lnpsi1.p);
     NQS_CUDA(cudaMemcpyAsync(lnpsi, h->lnpsi1.p, sizeof(cd)*h->K, cudaMemcpyDeviceToHost, h->stream));
     NQS_CUDA(cudaStreamSynchronize(h->stream));
   });

@@ -49,6 +49,12 @@ struct nqs_handle
   nqs_config cfg;
   int N = 0, M = 0, model = 0;
   long long K = 0, Ktot = 0, koff = 0, P = 0;
+  // translation-symmetric RBM (NQS_MODEL_RBMTRSYMM): `model` is MODEL_RBM for every sampler kernel, `params` holds the EXPANDED
+  // network [wf | af | bf] (Pfull entries), `vars` the P = N*alpha+1+alpha variables the optimiser moves
+  bool trsymm = false;
+  int alpha_f = 0;
+  long long Pfull = 0;
+  nqs::DevBuf<nqs::cd> vars;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   size_t smem_optin = 0;

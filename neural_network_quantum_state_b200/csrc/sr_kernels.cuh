@@ -72,6 +72,72 @@ __global__ void __launch_bounds__(256) oderiv_kernel(const int N, const int M, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Translation-symmetric RBM (ref RBMTrSymm, impl_neural_quantum_state.cuh:301-538).
+// expand: wf[i][f*N+j] = w[f][(i+j)%N], af[i] = a[0], bf[f*N+j] = b[f]  (ref RBMTrSymm__ConstructWeightAndBias__, :1523-1553) into
+// the plain-RBM parameter layout [wf (i*M+j') | af | bf], M = alpha*N, which every sampler kernel of this library reads.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void trsymm_expand_kernel(const int N, const int alpha, const cd * __restrict__ vars, cd * __restrict__ full)
+{
+  const int M = alpha*N;
+  const cd * w = vars;
+  const cd a0 = vars[(size_t)N*alpha];
+  const cd * b = vars+(size_t)N*alpha+1;
+  const long long NM = (long long)N*M;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < NM+N+M; idx += (long long)gridDim.x*blockDim.x)
+  {
+    if (idx < NM)
+    {
+      const int i = (int)(idx/M), c = (int)(idx-(long long)i*M), f = c/N, j = c-f*N;
+      full[idx] = w[(size_t)f*N+(i+j)%N];
+    }
+    else if (idx < NM+N) full[idx] = a0;
+    else full[idx] = b[(idx-NM-N)/N];
+  }
+}
+
+// O writer (ref RBMTrSymm__GetGradientsOfParameters__, :1487-1521): per chain, with T = tanh(theta) of the expanded hidden layer,
+//   d_w[f*N+i] = sum_j T[f*N+j] s[(N+i-j)%N] ,  d_a = sum_i s_i ,  d_b[f] = sum_j T[f*N+j]      (row = [d_w | d_a | d_b]).
+// One CTA per chain; tanh once per hidden unit into shared memory (the reference evaluates it N times per unit).
+__global__ void __launch_bounds__(256) oderiv_trsymm_kernel(const int N, const int alpha, const long long K,
+  const int8_t * __restrict__ spins, const cd * __restrict__ theta, cd * __restrict__ O)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = alpha*N;
+  cd * T = reinterpret_cast<cd*>(smem_raw);             // [M]
+  double * s = reinterpret_cast<double*>(T+M);         // [N]
+  const long long k = blockIdx.x;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) T[j] = c_tanh(theta[k*M+j]);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s[i] = (double)spins[k*N+i];
+  __syncthreads();
+  const long long P = (long long)N*alpha+1+alpha;
+  cd * row = O+k*P;
+  for (int q = threadIdx.x; q < M; q += blockDim.x)
+  {
+    const int f = q/N, i = q-f*N;
+    cd acc = cmake(0.0, 0.0);
+    for (int j = 0; j < N; ++j)
+    {
+      const cd t = T[f*N+j];
+      const double sv = s[(N+i-j)%N];
+      acc.x += t.x*sv; acc.y += t.y*sv;
+    }
+    st_stream(row+q, acc);
+  }
+  if (threadIdx.x == 0)
+  {
+    double sa = 0.0;
+    for (int i = 0; i < N; ++i) sa += s[i];
+    st_stream(row+M, cmake(sa, 0.0));
+  }
+  for (int f = threadIdx.x; f < alpha; f += blockDim.x)
+  {
+    cd acc = cmake(0.0, 0.0);
+    for (int j = 0; j < N; ++j) acc = cadd(acc, T[f*N+j]);
+    st_stream(row+M+1+f, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Column-direction passes over O.  Grid = (column tiles, row blocks); one thread owns ONE column p of its tile and walks the
 // rows of its row block, so a warp reads 32 consecutive complex numbers (512 B) per row: fully coalesced.  Row-block
 // partials go to part[rb][...][P] and are summed in fixed order by colsum_reduce_kernel.

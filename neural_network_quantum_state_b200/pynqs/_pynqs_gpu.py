@@ -10,8 +10,8 @@ nqs1's own spin register is never set (all zero, as the reference's zero-initial
 visible-bias term -- computed from the MEMBER spins, ref impl_neural_quantum_state.cuh:119-120 -- contributes nothing there;
 that reference quirk is kept bit for bit.
 
-In scope natively: dRBMSampler, dFFNNSampler (fp64, the arithmetic type of the engine).  The float32 and symmetric variants
-exist as names and raise NotImplementedError.
+In scope natively: dRBMSampler, dFFNNSampler, dRBMTrSymmSampler (fp64, the arithmetic type of the engine).  The float32 and the
+other symmetric variants exist as names and raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -25,6 +25,8 @@ class _PySampler:
 
     def __init__(self, kwargs: dict):
         self._N, self._M, self._K = int(kwargs["nInputs"]), int(kwargs["nHiddens"]), int(kwargs["nChains"])
+        if self._model == "rbmtrsymm":
+            self._M *= self._N     # RBMTrSymm(nInputs, alpha, nChains): "nHiddens" is the number of filters; the engine takes alpha*N
         self._seed, self._seed_distance = int(kwargs["seedNumber"]), int(kwargs["seedDistance"])
         dev = int(kwargs.get("device", 0))
         # Sampler4SpinHalf has no Hamiltonian: h = J = 0; sequential order; O / CG buffers are not allocated
@@ -68,6 +70,12 @@ class dFFNNSampler(_PySampler):
     _model = "ffnn"
 
 
+class dRBMTrSymmSampler(_PySampler):
+    """ref MAKE_PYSAMPLER_MODULE(m, "dRBMTrSymmSampler", spinhalf::RBMTrSymm, double), pywrapping_sampler.cu:125; kwargs["nHiddens"]
+    is the number of filters alpha, load(path) reads the single variables file (impl_neural_quantum_state.cuh:484-517)."""
+    _model = "rbmtrsymm"
+
+
 def _unsupported(name: str, why: str):
     class _U:
         def __init__(self, *a, **k):
@@ -77,11 +85,10 @@ def _unsupported(name: str, why: str):
 
 
 _FP32 = "libnqs_b200 computes in fp64 only (the reference's float32 instantiation is out of scope)"
-_SYMM = "symmetric ansaetze are out of scope of the B200 hot path (SURVEY 8f)"
+_SYMM = "this symmetric ansatz is out of scope of the B200 hot path (SURVEY 8f; the translation-symmetric RBM is dRBMTrSymmSampler)"
 sRBMSampler = _unsupported("sRBMSampler", _FP32)
 sFFNNSampler = _unsupported("sFFNNSampler", _FP32)
 sRBMTrSymmSampler = _unsupported("sRBMTrSymmSampler", _SYMM)
-dRBMTrSymmSampler = _unsupported("dRBMTrSymmSampler", _SYMM)
 sRBMZ2PrSymmSampler = _unsupported("sRBMZ2PrSymmSampler", _SYMM)
 dRBMZ2PrSymmSampler = _unsupported("dRBMZ2PrSymmSampler", _SYMM)
 sFFNNTrSymmSampler = _unsupported("sFFNNTrSymmSampler", _SYMM)

@@ -441,11 +441,131 @@ class FFNN:
                 print("# check '%s' size... " % name)
 
 
+class RBMTrSymm:
+    """Translation-symmetric complex RBM, GPU semantics.  gpu/include/impl_neural_quantum_state.cuh:301-538, kernels
+    :1487-1553 (the ansatz of gpu/src/LICH-train_rbmtrsymm.cu).
+
+    variables = [w (alpha*N, index f*N+i) | a (1) | b (alpha)], P = N*alpha + 1 + alpha.  symmetrize_variables_ (:534-538,
+    kernel :1523-1553) expands them to wf[i][f*N+j] = w[f][(i+j)%N], bf[f*N+j] = b[f], af[i] = a[0]; every sampler operation
+    (initialize / forward / spin_flip, :364-472) is the plain RBM's on (wf, af, bf) with M = alpha*N hidden units.
+    backward (:443-450, kernel :1487-1521):  d_w[f*N+i] = sum_j tanh(y[f*N+j]) s[(N+i-j)%N],  d_a = sum_i s_i,
+    d_b[f] = sum_j tanh(y[f*N+j]).  NOTE forward(spins, lnpsi, save) takes sa from its ARGUMENT here (:401-403), unlike RBM.
+    """
+
+    kind = "rbmtrsymm"
+
+    def __init__(self, n_inputs: int, alpha: int, n_chains: int, rng: Optional[np.random.Generator] = None):
+        self.N, self.alpha, self.K = n_inputs, alpha, n_chains
+        self.M = alpha * n_inputs
+        self.P = n_inputs * alpha + 1 + alpha
+        self.variables = np.zeros(self.P, dtype=np.complex128)
+        self.spins = np.ones((n_chains, n_inputs), dtype=np.float64)
+        self.y = np.zeros((n_chains, self.M), dtype=np.complex128)
+        self.sa = np.zeros(n_chains, dtype=np.complex128)
+        self.index_ = 0
+        if rng is not None:
+            self.random_init(rng)
+
+    def random_init(self, rng: np.random.Generator):
+        """ctor :325-345: w = 0.1 (g + i g'), g ~ N(0, 1/((1+alpha) N)); a = 0; b = 0.1 (g + i g'), g ~ N(0, 1/(N alpha))."""
+        N, al = self.N, self.alpha
+        sw, sb = math.sqrt(1.0 / ((1 + al) * N)), math.sqrt(1.0 / (N * al))
+        self.variables[: N * al] = 0.1 * (rng.normal(0, sw, N * al) + 1j * rng.normal(0, sw, N * al))
+        self.variables[N * al] = 0.0
+        self.variables[N * al + 1:] = 0.1 * (rng.normal(0, sb, al) + 1j * rng.normal(0, sb, al))
+
+    # expanded network (recomputed from the variables on every use: the variables are the state)
+    @property
+    def W(self):
+        N, al = self.N, self.alpha
+        w = self.variables[: N * al].reshape(al, N)
+        i = np.arange(N)[:, None, None]
+        f = np.arange(al)[None, :, None]
+        j = np.arange(N)[None, None, :]
+        return w[f, (i + j) % N].reshape(N, al * N)          # wf[i][f*N+j]
+
+    @property
+    def a(self):
+        return np.full(self.N, self.variables[self.N * self.alpha])
+
+    @property
+    def b(self):
+        return np.repeat(self.variables[self.N * self.alpha + 1:], self.N)
+
+    def _theta(self, spins):
+        return spins @ self.W + self.b[None, :]
+
+    def initialize(self, spins: np.ndarray) -> np.ndarray:
+        self.spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(self.spins)
+        self.sa = self.spins @ self.a
+        return logcosh(self.y).sum(axis=1) + self.sa
+
+    def forward_flip(self, idx: int) -> np.ndarray:
+        self.index_ = idx
+        s = self.spins[:, idx]
+        ly = logcosh(self.y - self.W[idx][None, :] * (2.0 * s)[:, None])
+        return (self.sa - (2.0 * s) * self.a[idx]) + ly.sum(axis=1)
+
+    def forward_spins(self, spins: np.ndarray, save: bool = True) -> np.ndarray:
+        spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(spins)
+        self.sa = spins @ self.a                                 # the ARGUMENT's spins (:401-403)
+        out = logcosh(self.y).sum(axis=1) + self.sa
+        if save:
+            self.spins = spins.copy()
+        return out
+
+    def spin_flip(self, mask: np.ndarray, idx: int = -1):
+        if idx != -1:
+            self.index_ = idx
+        i = self.index_
+        two_delta = np.where(mask, 2.0, 0.0)
+        s = self.spins[:, i]
+        self.y = self.y - self.W[i][None, :] * (two_delta * s)[:, None]
+        self.sa = self.sa - (two_delta * s) * self.a[i]
+        self.spins[:, i] = (1.0 - two_delta) * s
+
+    def backward(self) -> np.ndarray:
+        N, al = self.N, self.alpha
+        t = np.tanh(self.y).reshape(self.K, al, N)              # [k][f][j]
+        O = np.empty((self.K, self.P), dtype=np.complex128)
+        i = np.arange(N)[:, None]
+        j = np.arange(N)[None, :]
+        sh = self.spins[:, (N + i - j) % N]                      # [k][i][j] = s[(N+i-j)%N]
+        O[:, : N * al] = np.einsum("kfj,kij->kfi", t, sh).reshape(self.K, N * al)
+        O[:, N * al] = self.spins.sum(axis=1)
+        O[:, N * al + 1:] = t.sum(axis=2)
+        return O
+
+    def update_variables(self, dx: np.ndarray, lr: float):
+        """:452-465: variables -= lr*dx, symmetrize, y and sa re-derived for the current spins."""
+        self.variables = self.variables - lr * np.asarray(dx, dtype=np.complex128)
+        self.y = self._theta(self.spins)
+        self.sa = self.spins @ self.a
+
+    def save(self, path: str, prec: int = 10):
+        """:474-482: every variable, blank separated, in one file."""
+        _write_rows(path, [self.variables], prec, False)
+
+    def load(self, path: str):
+        raw = _read_complex_tokens(path)
+        if raw is None:
+            print("# --- file-path: %s is not exist..." % path)
+        elif raw.size == self.variables.size:
+            self.variables[...] = raw
+        else:
+            print(" check parameter size... ")
+
+
 def make_ansatz(kind: str, N: int, M: int, K: int, rng=None):
     if kind == "rbm":
         return RBM(N, M, K, rng)
     if kind == "ffnn":
         return FFNN(N, M, K, rng)
+    if kind == "rbmtrsymm":          # M = the expanded width alpha*N (as in nqs_config.n_hiddens)
+        assert M % N == 0
+        return RBMTrSymm(N, M // N, K, rng)
     raise ValueError(kind)
 
 
