@@ -88,6 +88,8 @@ SYMBOLS = {
     "nqs_event_record": (_i32, [_vp, _i32]),
     "nqs_event_elapsed_ms": (_i32, [_vp, _i32, _i32, C.POINTER(C.c_float)]),
     "nqs_kernel_variant": (_cp, [_vp, _cp]),
+    "nqs_checkpoint_save": (_i32, [_vp, _cp]),
+    "nqs_checkpoint_load": (_i32, [_vp, _cp]),
 }
 
 _lib = None

@@ -48,6 +48,7 @@ BIN_DIR = os.path.join(PKG_DIR, "bin")
 HOST_PROGRAMS = {
     "LICH-train_rbm-gpu": ("LICH-train_rbm.cpp", []),
     "LICH-train_ffnn-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_FFNN"]),
+    "LICH-train_rbmtrsymm-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_RBMTRSYMM"]),
 }
 
 

@@ -2123,6 +2123,115 @@ nqs_status nqs_event_elapsed_ms(nqs_handle * h, int32_t a, int32_t b, float * ms
   });
 }
 
+extern "C++"
+{
+namespace
+{
+struct CkptHeader
+{
+  char magic[8];            // "NQSCKPT1"
+  int32_t model, N, M, trsymm;
+  int64_t K, Ktot, koff, P;
+  int32_t pos, flip_index, cg_prev_iters, has_sr;
+  uint64_t step_counter, seed;
+  double bp, hfield, J, alpha;
+  int32_t pbc, order;
+};
+template <typename T>
+void ckpt_write(std::ofstream & f, nqs_handle * h, const T * dev, size_t n)
+{
+  std::vector<T> buf(n);
+  NQS_CUDA(cudaMemcpyAsync(buf.data(), dev, n*sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+  f.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)(n*sizeof(T)));
+}
+template <typename T>
+void ckpt_read(std::ifstream & f, nqs_handle * h, T * dev, size_t n)
+{
+  std::vector<T> buf(n);
+  f.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(n*sizeof(T)));
+  NQS_REQUIRE((size_t)f.gcount() == n*sizeof(T), NQS_ERR_IO, "checkpoint file truncated");
+  NQS_CUDA(cudaMemcpyAsync(dev, buf.data(), n*sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  NQS_CUDA(cudaStreamSynchronize(h->stream));
+}
+} // namespace
+} // extern "C++"
+
+nqs_status nqs_checkpoint_save(nqs_handle * h, const char * path)
+{
+  if (!h || !path) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(h->initialized, NQS_ERR_STATE, "nqs_checkpoint_save before nqs_initialize / nqs_warm_up");
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    finish_tables(h);
+    std::ofstream f(path, std::ios::binary);
+    NQS_REQUIRE(f.is_open(), NQS_ERR_IO, std::string("cannot write ")+path);
+    CkptHeader hd;
+    std::memset(&hd, 0, sizeof(hd));
+    std::memcpy(hd.magic, "NQSCKPT1", 8);
+    hd.model = h->model; hd.N = h->N; hd.M = h->M; hd.trsymm = h->trsymm ? 1 : 0;
+    hd.K = h->K; hd.Ktot = h->Ktot; hd.koff = h->koff; hd.P = h->P;
+    hd.pos = h->pos; hd.flip_index = h->flip_index; hd.cg_prev_iters = h->cg_prev_iters; hd.has_sr = h->aO.p != nullptr ? 1 : 0;
+    hd.step_counter = h->step_counter; hd.seed = h->cfg.seed; hd.bp = h->bp;
+    hd.hfield = h->cfg.h; hd.J = h->cfg.J; hd.alpha = h->cfg.alpha; hd.pbc = h->cfg.pbc; hd.order = h->cfg.order;
+    f.write(reinterpret_cast<const char*>(&hd), sizeof(hd));
+    ckpt_write(f, h, var_ptr(h), (size_t)h->P);
+    ckpt_write(f, h, h->spins.p, (size_t)h->K*h->N);
+    ckpt_write(f, h, h->theta.p, (size_t)h->K*h->M);
+    ckpt_write(f, h, h->lnpsi0.p, (size_t)h->K);
+    ckpt_write(f, h, h->sa.p, (size_t)h->K);
+    ckpt_write(f, h, h->fresh.p, (size_t)h->K);
+    if (hd.has_sr) ckpt_write(f, h, h->dx.p, (size_t)h->P);
+    f.close();
+    NQS_REQUIRE(f.good(), NQS_ERR_IO, std::string("write error on ")+path);
+  });
+}
+
+nqs_status nqs_checkpoint_load(nqs_handle * h, const char * path)
+{
+  if (!h || !path) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_CUDA(cudaSetDevice(h->cfg.device));
+    std::ifstream f(path, std::ios::binary);
+    NQS_REQUIRE(f.is_open(), NQS_ERR_IO, std::string("cannot read ")+path);
+    CkptHeader hd;
+    f.read(reinterpret_cast<char*>(&hd), sizeof(hd));
+    NQS_REQUIRE((size_t)f.gcount() == sizeof(hd) && std::memcmp(hd.magic, "NQSCKPT1", 8) == 0, NQS_ERR_IO, "not a libnqs_b200 checkpoint");
+    NQS_REQUIRE(hd.model == h->model && hd.N == h->N && hd.M == h->M && (hd.trsymm != 0) == h->trsymm && hd.K == h->K &&
+      hd.Ktot == h->Ktot && hd.koff == h->koff && hd.P == h->P, NQS_ERR_INVALID,
+      "checkpoint was written by a handle of another shape (model, sizes, chains or chain offset differ)");
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    invalidate_tables(h);
+    h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
+    ckpt_read(f, h, var_ptr(h), (size_t)h->P);
+    expand_vars(h);
+    ckpt_read(f, h, h->spins.p, (size_t)h->K*h->N);
+    ckpt_read(f, h, h->theta.p, (size_t)h->K*h->M);
+    ckpt_read(f, h, h->lnpsi0.p, (size_t)h->K);
+    ckpt_read(f, h, h->sa.p, (size_t)h->K);
+    ckpt_read(f, h, h->fresh.p, (size_t)h->K);
+    if (hd.has_sr)
+    {
+      alloc_sr(h);
+      ckpt_read(f, h, h->dx.p, (size_t)h->P);
+    }
+    h->pos = hd.pos; h->flip_index = hd.flip_index; h->cg_prev_iters = hd.cg_prev_iters;
+    h->step_counter = hd.step_counter; h->cfg.seed = hd.seed; h->bp = hd.bp;
+    if (hd.hfield != h->cfg.h || hd.J != h->cfg.J || hd.alpha != h->cfg.alpha || hd.pbc != h->cfg.pbc || hd.order != h->cfg.order)
+    { // the Hamiltonian travels with the state
+      h->cfg.h = hd.hfield; h->cfg.J = hd.J; h->cfg.alpha = hd.alpha; h->cfg.pbc = hd.pbc; h->cfg.order = hd.order;
+      build_order(h);
+      build_J(h);
+    }
+    h->u_steps = 0; h->u_used = 0;
+    h->initialized = true;
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
 const char * nqs_kernel_variant(const nqs_handle * h, const char * stage)
 {
   if (!h || !stage) return "";

@@ -211,6 +211,15 @@ class Engine:
         assert dx.size == self.P
         self._chk(self.lib.nqs_evolve(self._h, _ptr(dx), float(lr)))
 
+    # ---- full-state checkpoint (sidecar next to the reference's parameter files)
+    def save_state(self, path: str):
+        """Variables, chain state, RNG counter, lambda-schedule state and CG warm start of this handle (one rank's shard)."""
+        self._chk(self.lib.nqs_checkpoint_save(self._h, path.encode()))
+
+    def load_state(self, path: str):
+        """Continue bit-identically from save_state() of a handle with the same shape."""
+        self._chk(self.lib.nqs_checkpoint_load(self._h, path.encode()))
+
     # ---- multi-GPU
     @staticmethod
     def comm_unique_id() -> bytes:

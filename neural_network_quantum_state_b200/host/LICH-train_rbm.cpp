@@ -2,7 +2,8 @@
 // Drop-in for the reference program of the same name (ref gpu/src/LICH-train_rbm.cu:14-119): same options and defaults,
 // same parameter-file prefix  <path>/RBMLICH-L{L}NH{nh}A{alpha}T{theta}V{ver}D{w,a,b}.dat, same stdout table.
 // The hot path runs in libnqs_b200.so (hand-written sm_100a kernels) through the classes of nqs_host.hpp.
-// -DNQS_DRIVER_FFNN builds LICH-train_ffnn-gpu: the same driver for the one-hidden-layer FNN (the reference ships the
+// -DNQS_DRIVER_RBMTRSYMM builds LICH-train_rbmtrsymm-gpu (ref gpu/src/LICH-train_rbmtrsymm.cu: the translation-symmetric RBM on
+// the periodic chain, the CMake default target of the reference).  -DNQS_DRIVER_FFNN builds LICH-train_ffnn-gpu: the same driver for the one-hidden-layer FNN (the reference ships the
 // ansatz, gpu/src/CH-train_ffnn.cu:75, but no LICH driver for it; prefix FFNNLICH-..., files Dw1/Dw2/Db1).
 #include <chrono>
 #include <cmath>
@@ -26,7 +27,12 @@ static std::string remove_zeros_in_str(const FloatType val)
 
 int main(int argc, char * argv[])
 {
-#ifdef NQS_DRIVER_FFNN
+#if defined(NQS_DRIVER_RBMTRSYMM)
+  // ref gpu/src/LICH-train_rbmtrsymm.cu:14-110: -nf filters instead of -nh, periodic chain, nwarm 500 / rsd 1e-3 by default,
+  // ONE variables file <path>/RBMTrSymmLICH-L{L}NF{nf}A{alpha}T{theta}V{ver}
+  using Machine = RBMTrSymm<double>;
+  const std::string tag = "RBMTrSymmLICH-L", what = "RBMTrSymm";
+#elif defined(NQS_DRIVER_FFNN)
   using Machine = FFNN<double>;
   const std::string tag = "FFNNLICH-L", what = "FFNN";
 #else
@@ -34,15 +40,30 @@ int main(int argc, char * argv[])
   const std::string tag = "RBMLICH-L", what = "RBM";
 #endif
   const std::vector<pair_t> options = {
+#if defined(NQS_DRIVER_RBMTRSYMM)
+    {"L", "# of lattice sites"}, {"nf", "# of filters"}, {"ns", "# of spin samples for parallel Monte-Carlo"},
+#else
     {"L", "# of lattice sites"}, {"nh", "# of hidden nodes"}, {"ns", "# of spin samples for parallel Monte-Carlo"},
+#endif
     {"niter", "# of iterations to train "+what}, {"alpha", "exponent in the two-body interaction: J_{i,j} ~ 1/|i-j|^{alpha}"},
     {"theta", "J = sin(theta), h = -cos(theta)"}, {"ver", "version"}, {"nwarm", "# of MCMC steps for warming-up"},
     {"nms", "# of MCMC steps for sampling spins"}, {"dev", "device number"}, {"lr", "learning_rate"},
     {"rsd", "cutoff value of the energy deviation per energy (convergence criterion)"},
     {"path", "directory to load and save files"}, {"seed", "seed of the parallel random number generator"},
     {"ifprefix", "prefix of the file to load data"}};
+#if defined(NQS_DRIVER_RBMTRSYMM)
+  const std::vector<pair_t> defaults = {
+    {"nwarm", "500"}, {"nms", "1"}, {"lr", "1e-2"}, {"rsd", "1e-3"}, {"path", "."}, {"seed", "0"}, {"ifprefix", "None"}};
+  const char * width_opt = "nf";
+  const std::string width_tag = "NF";
+  const bool isPBC = true;
+#else
   const std::vector<pair_t> defaults = {
     {"nwarm", "100"}, {"nms", "1"}, {"lr", "1e-2"}, {"path", "."}, {"seed", "0"}, {"ifprefix", "None"}};
+  const char * width_opt = "nh";
+  const std::string width_tag = "NH";
+  const bool isPBC = false;
+#endif
   argsparse parser(argc, argv, options, defaults);
 
   const int L = parser.find<int>("L"), nChains = parser.find<int>("ns"), nWarmup = parser.find<int>("nwarm"),
@@ -50,7 +71,7 @@ int main(int argc, char * argv[])
   const double lr = parser.find<double>("lr"), RSDcutoff = parser.find<double>("rsd");
   const unsigned long long seed = parser.find<unsigned long long>("seed");
   const std::string path = parser.find<>("path")+"/", Lstr = parser.find<>("L"), ifprefix = parser.find<>("ifprefix");
-  const auto nhArr = parser.mfind<int>("nh");
+  const auto nhArr = parser.mfind<int>(width_opt);
   const auto alphaArr = parser.mfind<double>("alpha");
   const auto verArr = parser.mfind<int>("ver");
   const auto thetaArr = parser.mfind<double>("theta");
@@ -69,11 +90,11 @@ int main(int argc, char * argv[])
           {
             Machine machine(L, nh, nChains);
             const double J = std::sin(theta), h = -std::cos(theta);
-            const std::string prefix = path+tag+Lstr+"NH"+std::to_string(nh)+"A"+remove_zeros_in_str(alpha)+"T"+
+            const std::string prefix = path+tag+Lstr+width_tag+std::to_string(nh)+"A"+remove_zeros_in_str(alpha)+"T"+
               remove_zeros_in_str(theta)+"V"+std::to_string(ver);
             const std::string prefix0 = (ifprefix.compare("None")) ? path+ifprefix : prefix;
             machine.load(prefix0);
-            LITFIChain<SamplerTraits> sampler(machine, L, h, J, alpha, false, seed, nBlocks, prefix);
+            LITFIChain<SamplerTraits> sampler(machine, L, h, J, alpha, isPBC, seed, nBlocks, prefix);
             const auto start = std::chrono::system_clock::now();
             sampler.warm_up(nWarmup);
             StochasticReconfigurationCG<double> iTimePropagator(nChains, machine.get_nVariables());

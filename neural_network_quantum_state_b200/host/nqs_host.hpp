@@ -4,6 +4,7 @@
 // no arithmetic on the host and no CPU fallback.
 //
 //   spinhalf::RBM<double>, spinhalf::FFNN<double>      ref gpu/include/neural_quantum_state.cuh:17-59,151-194
+//   spinhalf::RBMTrSymm<double>                         ref gpu/include/neural_quantum_state.cuh:62-105
 //   spinhalf::LITFIChain<Traits>                        ref gpu/include/hamiltonians.cuh:43-75 + mcmc_sampler.cuh:16-37
 //   StochasticReconfigurationCG<double>                 ref gpu/include/optimizer.cuh:112-181
 //
@@ -141,6 +142,20 @@ class FFNN: public nqs_host::Ansatz
   static_assert(sizeof(FloatType) == sizeof(double), "libnqs_b200 computes in fp64 only");
 public:
   FFNN(const int nInputs, const int nHiddens, const int nChains): nqs_host::Ansatz(NQS_MODEL_FFNN, nInputs, nHiddens, nChains) {}
+};
+
+// ref: RBMTrSymm<T>(nInputs, alpha, nChains), gpu/include/neural_quantum_state.cuh:62-105: `alpha` filters of N tied weights each,
+// nVariables = N*alpha + 1 + alpha; save / load take the FILE path (one file with every variable, impl :474-517)
+template <typename FloatType>
+class RBMTrSymm: public nqs_host::Ansatz
+{
+  static_assert(sizeof(FloatType) == sizeof(double), "libnqs_b200 computes in fp64 only");
+public:
+  RBMTrSymm(const int nInputs, const int alpha, const int nChains):
+    nqs_host::Ansatz(NQS_MODEL_RBMTRSYMM, nInputs, alpha*nInputs, nChains), kAlpha(alpha) {}
+  int get_alpha() const { return kAlpha; }
+private:
+  const int kAlpha;
 };
 
 // ref: LITFIChain<TraitsClass> (gpu/include/hamiltonians.cuh:43-75) with the BaseParallelSampler interface (mcmc_sampler.cuh:21-29)

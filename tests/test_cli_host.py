@@ -38,6 +38,16 @@ def test_help_lists_reference_options_and_defaults():
     assert "-option1=value1 -option2=value2" in r.stdout
 
 
+def test_trsymm_driver_help_lists_its_own_options_and_defaults():
+    """ref gpu/src/LICH-train_rbmtrsymm.cu:17-40: -nf instead of -nh, nwarm 500 and rsd 1e-3 by default."""
+    r = run([exe("LICH-train_rbmtrsymm-gpu"), "--help"])
+    assert r.returncode == 1
+    assert re.search(r"^\s*nf : # of filters", r.stdout, re.M)
+    assert not re.search(r"^\s*nh : ", r.stdout, re.M)
+    assert "nwarm : # of MCMC steps for warming-up (default : 500)" in r.stdout
+    assert "(default : 1e-3)" in r.stdout
+
+
 def test_missing_and_malformed_options_exit_1_with_reference_messages():
     r = run([exe(), "-L=8"])
     assert r.returncode == 1

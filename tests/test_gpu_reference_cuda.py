@@ -73,3 +73,45 @@ def test_trsymm_trajectory_matches_reference_cuda_build(tmp_path, L, nf, ns, nwa
     assert want.size == have.size
     assert np.abs(have - want).max() <= 3e-9 * max(1.0, np.abs(want).max())
     e.close()
+
+
+@pytest.mark.skipif(not (ref_cuda.available("rbm") and ref_cuda.available("rbmtrsymm")), reason="reference CUDA drivers not built")
+@pytest.mark.parametrize("driver,width", [("rbm", ("nh", 32)), ("rbmtrsymm", ("nf", 2))])
+def test_cli_driver_prints_the_reference_drivers_table(tmp_path, driver, width):
+    """Drop-in at the command line: the same argument list to the reference's own program and to this repository's
+    LICH-train_*-gpu, same parameter file(s) to start from -- the iteration tables on stdout must agree to the printed digits."""
+    import re
+    import shutil
+    import subprocess
+    from neural_network_quantum_state_b200 import Engine, build
+    from neural_network_quantum_state_b200.init import reference_init
+    L, ns, niter, nwarm = 16, 512, 5, 40
+    theta = float(ref_cuda.THETA_STR)
+    dirs = [tmp_path / "ref", tmp_path / "ours"]
+    for d in dirs:
+        d.mkdir()
+    if driver == "rbm":
+        e = Engine("rbm", L, width[1], 4, 0.0, 0.0, 0.0, sampler_only=True)
+        e.set_params(reference_init("rbm", L, width[1], np.random.default_rng(8)))
+    else:
+        e = Engine("rbmtrsymm", L, width[1] * L, 4, 0.0, 0.0, 0.0, sampler_only=True)
+        e.init_params_random(8)
+    for d in dirs:
+        e.save(ref_cuda.prefix_for(str(d), L, width[1], driver=driver), 17)
+    e.close()
+    args = ["-L=%d" % L, "-%s=%d" % width, "-ns=%d" % ns, "-niter=%d" % niter, "-alpha=2", "-theta=%s" % ref_cuda.THETA_STR,
+            "-ver=0", "-nwarm=%d" % nwarm, "-dev=0", "-lr=0.02", "-rsd=1e-30", "-seed=99"]
+    ref_bin = ref_cuda.BINARY if driver == "rbm" else ref_cuda.BINARY_TRSYMM
+    our_bin = os.path.join(build.BIN_DIR, "LICH-train_rbm-gpu" if driver == "rbm" else "LICH-train_rbmtrsymm-gpu")
+    outs = []
+    for b, d in zip((ref_bin, our_bin), dirs):
+        r = subprocess.run([b] + args + ["-path=%s" % d], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        rows = [ln.split() for ln in r.stdout.splitlines() if re.match(r"^\s*\d+\s+\S+\s+\S+\s*$", ln)]
+        outs.append([(int(a), float(b_), float(c)) for a, b_, c in rows])
+        assert "# of loop\t<H>" in r.stdout and "# elapsed time:" in r.stdout
+    assert len(outs[0]) == niter and len(outs[1]) == niter
+    for (n0, e0, r0), (n1, e1, r1) in zip(*outs):
+        assert n0 == n1
+        assert e1 == pytest.approx(e0, rel=3e-6, abs=2e-7)
+        assert r1 == pytest.approx(r0, rel=3e-5, abs=2e-7)
