@@ -693,9 +693,12 @@ void plan_sv(nqs_handle * h)
   // on a B200 15 clusters of 8 cover 120 SMs, 15 clusters of 9 cover 135 (1.39 vs 1.47 ms per S*v at N=128, M=256, K=16384),
   // 11 clusters of 10 cover 110 and 7 clusters of 16 cover 112 (measured, profiles/r1d_sv_fused_experiments.md).  Sizes above 8
   // are "non-portable" and need cudaFuncAttributeNonPortableClusterSizeAllowed.  NQS_SV_CS pins the size (tests).
-  std::vector<int> cs_list = {8, 9, 10, 12, 16};
+  // Small clusters (1 .. 7) serve NARROW rows: the reduction + DSMEM exchange costs every row ~0.75 us whatever the slice width, so
+  // a slice must carry >= ~0.75 us of HBM time per row or the kernel is latency-bound (N=64, M=128: 16 CTAs x 8 KB slices ran at
+  // 0.33 of the HBM peak; 2 CTAs x 67 KB slices are bandwidth-bound again).  The plan with the smallest ESTIMATED time wins.
+  std::vector<int> cs_list = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16};
   { const char * c = std::getenv("NQS_SV_CS"); if (c && std::atoi(c) >= 1 && std::atoi(c) <= NQS_SV_MAX_CLUSTER) cs_list = {std::atoi(c)}; }
-  long long best_score = -1;
+  double best_time = -1.0;
   for (const int cs : cs_list)
   {
     const long long pc = (h->P+cs-1)/cs;
@@ -729,10 +732,14 @@ void plan_sv(nqs_handle * h)
     long long ncl = std::min<long long>(maxc, h->K);
     const long long rpc = (h->K+ncl-1)/ncl;
     ncl = (h->K+rpc-1)/rpc;
-    // score: SMs kept busy; the pipelined variant (>= 3 slots) beats the in-order one at equal coverage
-    const long long score = ncl*cs*4+(defer ? 2 : 0)+(cpt > 3 ? 1 : 0);
-    if (score <= best_score) continue;
-    best_score = score;
+    // estimated time of one S*v: the HBM stream over the SMs the clusters cover (several narrow CTAs per SM cover it once),
+    // against the per-row latency floor of the exchange (software-pipelined: ~0.75 us per row; in order: ~1.2 us)
+    const double cover = std::min(1.0, (double)(ncl*cs)/(double)h->sm_count);
+    const double t_hbm = (double)h->K*(double)h->P*16.0/(6.4e12*cover);
+    const double t_lat = (double)rpc*(defer ? 0.75e-6 : 1.2e-6)*(cs == 1 ? 0.6 : 1.0);
+    const double t_est = std::max(t_hbm, t_lat)*(1.0+0.002*cs);       // ties: the smaller cluster (fewer exchange partners)
+    if (best_time >= 0.0 && t_est >= best_time) continue;
+    best_time = t_est;
     h->sv_defer = defer;
     h->sv_depth = defer ? std::max(1, std::min(NQS_SV_MAX_DEPTH, (nslot-1)/2)) : 0;   // keep >= depth+1 slots for rows in flight
     { const char * d = std::getenv("NQS_SV_DEPTH"); if (d && defer) h->sv_depth = std::max(1, std::min(std::min(NQS_SV_MAX_DEPTH, nslot-2), std::atoi(d))); }
@@ -1343,7 +1350,24 @@ void alloc_sr(nqs_handle * h)
   }
   // structured S*v: no O [K][P]; it is allocated only if nqs_log_derivs asks for it
   if (h->cfg.flags & NQS_FLAG_STRUCTURED_SV) plan_struct(h);
-  else h->O.alloc((size_t)h->K*(size_t)h->P);
+  else
+  {
+    plan_sv(h);
+    // Rows too wide for the one-pass kernel (P/16 columns beyond the register file of a 16-CTA cluster: RBM alpha=4 at N=256,
+    // P = 263 424): the explicit formulation would stream O TWICE per product (two-pass kernels, 2 x 34.5 GB per product and
+    // rank at 8 GPUs: 106 of 138 ms per step).  The factor form of the same product, two tensor-core GEMMs on [K][N] spins and
+    // [K][M] tanh(theta), needs no O at all (35 ms per step there), so it takes over -- unless the caller asked for the two-pass
+    // kernels (NQS_FLAG_TWO_PASS_SV) or NQS_AUTO_STRUCTURED=0.  kernel_variant("sv") says which ran.
+    const char * au = std::getenv("NQS_AUTO_STRUCTURED");
+    if (!h->sv_ok && h->cols_ok && !h->trsymm && !(h->cfg.flags & (NQS_FLAG_TWO_PASS_SV | NQS_FLAG_SETUP_FROM_O | NQS_FLAG_NO_DMMA)) &&
+        !(au && std::atoi(au) == 0))
+    {
+      h->cfg.flags |= NQS_FLAG_STRUCTURED_SV;
+      plan_struct(h);
+      h->variant_sv += "_auto(P/16_columns_exceed_the_one-pass_kernel)";
+    }
+    else h->O.alloc((size_t)h->K*(size_t)h->P);
+  }
   h->aO.alloc(h->P); h->F.alloc(h->P); h->dx.alloc(h->P); h->r.alloc(h->P); h->pvec.alloc(h->P); h->z.alloc(h->P); h->t.alloc(h->P);
   h->zk.alloc(h->K); h->diag.alloc(h->P);
   const long long ctiles = (h->P+NQS_COL_THREADS-1)/NQS_COL_THREADS;
@@ -1352,7 +1376,6 @@ void alloc_sr(nqs_handle * h)
   h->nrb = (int)nrb;
   h->rows_per_block = (h->K+nrb-1)/nrb;
   h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
-  if (!h->struct_sv) plan_sv(h);
   // O generated inside the first S*v of the CG (sv_fused_kernel, GEN): RBM, one-pass kernel with the software pipeline, even N
   // (16-byte TMA rows of the double spins), factors available.  OPT-IN (NQS_SV_GEN=1): measured at cfg3 the generating launch
   // takes 3.5 ms -- forming 2 x 8 elements per thread and row from their factors makes the kernel issue-bound (~265 instead of

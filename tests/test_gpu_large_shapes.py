@@ -39,7 +39,7 @@ def test_cfg5_shard_full_size_64bit_indexing():
         pytest.skip("needs ~41 GB of free HBM")
     assert K * P > 2 ** 31 - 1
     from neural_network_quantum_state_b200 import Engine
-    e = Engine("rbm", N, M, K, H, J, ALPHA, seed=1)
+    e = Engine("rbm", N, M, K, H, J, ALPHA, seed=1, two_pass_sv=True)   # the explicit-O formulation, asked for by flag
     assert e.kernel_variant("sv") == "two_pass"          # P/16 columns do not fit the cluster kernel's register budget
     e.init_params_random(3)
     e.warm_up(1)
@@ -75,4 +75,27 @@ def test_medium_shape_fused_path_against_structure():
     assert_close(aO, aO_w, what="<O>")
     assert_close(diag, diag_w, atol=1e-11, what="diag S")
     assert_close(Sv, want, rtol=1e-9, what="S v")
+    e.close()
+
+
+def test_cfg5_width_takes_the_factor_form_by_itself():
+    """N=256, M=1024: the one-pass kernel cannot hold P/16 columns per CTA, and two passes over a 34.5 GB shard of O per product
+    would be the alternative -- the engine switches to the tensor-core factor form (no O) and says so."""
+    from neural_network_quantum_state_b200 import Engine
+    N, M, K = 256, 1024, 600
+    P = N * M + N + M
+    e = Engine("rbm", N, M, K, H, J, ALPHA, seed=1)
+    assert e.kernel_variant("sv").startswith("structured_dmma") and "auto" in e.kernel_variant("sv"), e.kernel_variant("sv")
+    e.init_params_random(3)
+    rng = np.random.default_rng(0)
+    e.warm_up(2, (2 * rng.integers(0, 2, size=(K, N)) - 1).astype(np.int8))
+    e.get_htilda()
+    v = rng.normal(size=P) + 1j * rng.normal(size=P)
+    Sv, aO, diag = e.smatrix_dot(0.25, v)
+    want, aO_w, diag_w = structured_sv(e.get_spinStates(), np.tanh(e.get_theta()), v, 0.25, N, M)
+    assert_close(aO, aO_w, what="<O>")
+    assert_close(diag, diag_w, atol=1e-11, what="diag S")
+    assert_close(Sv, want, rtol=1e-9, what="S v")
+    st = e.sr_step(n_mc_steps=1, lr=0.01)
+    assert st.finite and st.cg_iters >= 1
     e.close()

@@ -29,6 +29,10 @@ SHAPES = [
     ("ffnn", 128, 512, 40, None, 16, 9),# cfg4 shape (P = 66560): 16-CTA clusters
     ("rbm", 128, 256, 5, None, 16, 8),  # fewer rows than clusters: the widest cluster covers most SMs
     ("rbm", 24, 40, 33, 8, 8, 1),       # P = 1024: 128 columns per CTA, exactly the 128-thread floor of the fat-warp rule
+    ("rbm", 64, 128, 300, 2, 2, 9),     # narrow rows on SMALL clusters (the cfg2 plan): 2 CTAs x 4192 columns
+    ("rbm", 24, 40, 130, 1, 1, 8),      # a cluster of ONE CTA: the whole row in one slice, the DSMEM exchange targets itself
+    ("rbm", 32, 64, 90, 3, 3, 7),
+    ("ffnn", 16, 48, 77, 4, 4, 2),
 ]
 
 
@@ -73,9 +77,16 @@ def test_fused_sv_matches_dense_and_two_pass(model, N, M, K, pin_cs, cs, cpt, mo
         variant = e.kernel_variant("sv")
         if two_pass:
             assert variant == "two_pass"
-        else:
+        elif pin_cs is not None:
             assert variant.startswith("fused_cs%d_cpt%d_" % (cs, cpt)), variant
             assert planned_cpt(e.P, cs) == cpt
+        else:
+            # unpinned: the planner takes the cluster size with the smallest estimated time (small clusters for narrow rows);
+            # whatever it chose, its columns per thread follow the fat-warp rule
+            import re
+            m = re.match(r"fused_cs(\d+)_cpt(\d+)_", variant)
+            assert m, variant
+            assert planned_cpt(e.P, int(m.group(1))) == int(m.group(2)), variant
         O = e.get_lnpsiGradients()
         v = rng.normal(size=e.P) + 1j * rng.normal(size=e.P) if not out else out["v"]
         Sv, aO, diag = e.smatrix_dot(0.37, v)
