@@ -82,8 +82,14 @@ def full(src, dst):
 
 def stalls(src, dst, kernel, launch="0"):
     """Per-instruction warp-stall samples (ncu source page) of one launch: stall-reason totals + the hottest SASS lines."""
-    raw = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel, "--launch-skip", launch,
-                          "--launch-count", "1"], capture_output=True, text=True).stdout
+    if src.endswith(".csv.gz"):   # `ncu -i X.ncu-rep --page source --csv | gzip` already run on the GPU box (one kernel per file)
+        import gzip
+        raw = gzip.open(src, "rt").read()
+    elif src.endswith(".csv"):
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--kernel-name", "regex:" + kernel, "--launch-skip", launch,
+                              "--launch-count", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     kname = rows[0][1] if rows and len(rows[0]) > 1 else kernel
     hdr = rows[1]
