@@ -288,7 +288,7 @@ void build_tables_async(nqs_handle * h)
   if (h->jpl == 0 || h->tables_valid || h->bound_inflight) return;
   build_fast_tables_kernel<<<grid_for((long long)h->N*h->mpad, 256, 148*8), 256, 0, h->stream>>>(h->N, h->M, h->mpad, h->params.p,
     h->ftab_a.p, h->ftab_b.p, h->ctab_a.p, h->ctab_b.p, h->ctabT_a.p, h->ctabT_b.p, h->npad32, h->w2.p, h->afac.p, h->aexp.p, h->bound.p,
-    h->model == MODEL_RBM ? 1 : 0);
+    h->model == MODEL_RBM ? 1 : 0, h->ftab32.p);
   check_launch(h, "build_fast_tables_kernel");
   if (h->model == MODEL_FFNN)
   { // the FNN kernels hold tanh(theta) and log f, nothing that could overflow: no bound to wait for
@@ -428,6 +428,41 @@ void launch_sweep(nqs_handle * h, long long nsteps)
 #undef NQS_FF_CASE
       check_launch(h, "ffnn_sweep_fast_kernel");
       h->variant_sweep = "ffnn_resident_j"+std::to_string(h->jpl)+"_w"+std::to_string(warps);
+      h->pos = (int)((h->pos+nsteps)%h->N);
+      if (h->u_steps > 0) h->u_used += nsteps;
+      h->step_counter += (unsigned long long)nsteps;
+      return;
+    }
+  }
+  // fp32-filtered exact sweep (sweep_f32.cuh): one chain per warp, fp64 state in shared memory.  OPT-IN (NQS_SWEEP_F32=1): exact
+  // (tests/test_gpu_parity.py::test_f32_filtered_sweep_is_exact) but SLOWER than the all-fp64 register kernel -- 2.85 vs 1.94 ms
+  // per sweep at N=128, M=256, K=16384, 0.43 vs 0.29 ms at K=2048: the accept path through shared memory and the fp64 decision
+  // arithmetic cost what the fp32 product saves (~375 instructions per proposal and chain either way), so the dependency chain
+  // per proposal did not get shorter.  Kept as the record of the experiment.  The fp32 product of up to 16 factors per lane
+  // must stay far inside the fp32 range: 16 * 2 max|Re theta| * log2(e) < ~100.
+  if (h->model == MODEL_RBM && fast_path_ok(h) && h->jpl <= 16 && nsteps%h->N == 0 && h->ftab32.p != nullptr &&
+      h->theta_bound < 30.0/h->jpl && (std::getenv("NQS_SWEEP_F32") && std::atoi(std::getenv("NQS_SWEEP_F32")) != 0))
+  {
+    int warps = 8;
+    while (warps > 1 && f32_sweep_smem_bytes(h->N, warps, h->mpad) > h->smem_optin) warps >>= 1;
+    if (f32_sweep_smem_bytes(h->N, warps, h->mpad) <= h->smem_optin)
+    {
+      F32SweepArgs fa;
+      FastSweepArgs & f = fa.b;
+      f.N = h->N; f.M = h->M; f.Mpad = h->mpad; f.K = h->K; f.params = h->params.p; f.ftab_a = h->ftab_a.p; f.ftab_b = h->ftab_b.p; f.w2 = h->w2.p; f.afac = h->afac.p;
+      f.spins = h->spins.p; f.theta = h->theta.p; f.lnpsi0 = h->lnpsi0.p; f.sa = h->sa.p; f.fresh = h->fresh.p; f.order = h->order.p;
+      f.pos0 = h->pos; f.nsweeps = (int)(nsteps/h->N); f.uniforms = a.uniforms; f.seed = a.seed; f.step0 = a.step0;
+      f.chain_offset = a.chain_offset; f.acc_log = a.acc_log;
+      fa.ftab32 = h->ftab32.p; fa.stats = h->f32_stats.p;
+      fa.delta_scale = 1.0f;
+      { const char * e = std::getenv("NQS_SWEEP_F32_DELTA"); if (e) fa.delta_scale = (float)std::atof(e); }
+      const size_t smem = f32_sweep_smem_bytes(h->N, warps, h->mpad);
+      const unsigned grid = (unsigned)((h->K+warps-1)/warps);
+#define NQS_S32_CASE(J) case J: set_smem(rbm_sweep_f32_kernel<J>, smem); rbm_sweep_f32_kernel<J><<<grid, warps*32, smem, h->stream>>>(fa); break
+      switch (h->jpl) { NQS_S32_CASE(1); NQS_S32_CASE(2); NQS_S32_CASE(4); NQS_S32_CASE(8); default: NQS_S32_CASE(16); }
+#undef NQS_S32_CASE
+      check_launch(h, "rbm_sweep_f32_kernel");
+      h->variant_sweep = "rbm_f32filter_j"+std::to_string(h->jpl)+"_w"+std::to_string(warps);
       h->pos = (int)((h->pos+nsteps)%h->N);
       if (h->u_steps > 0) h->u_used += nsteps;
       h->step_counter += (unsigned long long)nsteps;
@@ -1502,6 +1537,7 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
       h->jpl = jpl; h->mpad = 32*jpl;
       const size_t nm = (size_t)h->N*h->mpad;
       h->ftab_a.alloc(nm); h->ftab_b.alloc(nm); h->ctab_a.alloc(nm); h->ctab_b.alloc(nm);
+      if (h->model == MODEL_RBM) { h->ftab32.alloc(nm); h->f32_stats.alloc(2); NQS_CUDA(cudaMemset(h->f32_stats.p, 0, 16)); }
       h->npad32 = ((h->N+31)/32)*32;
       h->ctabT_a.alloc((size_t)h->M*h->npad32); h->ctabT_b.alloc((size_t)h->M*h->npad32); h->w2.alloc(nm); h->afac.alloc((size_t)2*h->N); h->aexp.alloc((size_t)2*h->N); h->bound.alloc(1);
     }

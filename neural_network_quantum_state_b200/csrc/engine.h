@@ -10,6 +10,7 @@
 #include "device_math.cuh"
 #include "fast_kernels.cuh"
 #include "ffnn_fast_kernels.cuh"
+#include "sweep_f32.cuh"
 
 namespace nqs
 {
@@ -68,6 +69,8 @@ struct nqs_handle
   nqs::DevBuf<unsigned char> acc_log, fresh;
   // specialised RBM path: flip tables rebuilt after every parameter change (fast_kernels.cuh)
   nqs::DevBuf<nqs::FlipTab> ftab_a, ftab_b;
+  nqs::DevBuf<float4> ftab32;             // fp32 copy of the flip tables (sweep_f32.cuh)
+  nqs::DevBuf<unsigned long long> f32_stats;   // [2] proposals / proposals decided by the fp64 path
   nqs::DevBuf<nqs::CoshTab> ctab_a, ctab_b, ctabT_a, ctabT_b;
   nqs::DevBuf<nqs::cd> w2, aexp;
   nqs::DevBuf<double> afac, bound;

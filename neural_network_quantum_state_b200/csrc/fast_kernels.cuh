@@ -33,7 +33,8 @@ __device__ __forceinline__ double2 ld_tab(const double2 * p) { return __ldg(p); 
 __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpad, const cd * __restrict__ params,
   FlipTab * __restrict__ ftab_a, FlipTab * __restrict__ ftab_b, CoshTab * __restrict__ ctab_a, CoshTab * __restrict__ ctab_b,
   CoshTab * __restrict__ ctabT_a, CoshTab * __restrict__ ctabT_b, const int Npad,
-  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp, double * __restrict__ bound, const int has_visible_bias)
+  cd * __restrict__ w2, double * __restrict__ afac, cd * __restrict__ aexp, double * __restrict__ bound, const int has_visible_bias,
+  float4 * __restrict__ ftab32)
 {
   const cd * W = params;
   const cd * a = params+(size_t)N*M;
@@ -50,7 +51,9 @@ __global__ void build_fast_tables_kernel(const int N, const int M, const int Mpa
     { // the sweep carries the DOUBLE angles (cosh 2x, sinh 2x, cos 2y, sin 2y): its flip tables are those of 4W
       double s4, c4;
       sincos(4.0*w.y, &s4, &c4);
-      ftab_a[idx] = make_double2(cosh(4.0*w.x), sinh(4.0*w.x)); ftab_b[idx] = make_double2(c4, s4);
+      const double ch4 = cosh(4.0*w.x), sh4 = sinh(4.0*w.x);
+      ftab_a[idx] = make_double2(ch4, sh4); ftab_b[idx] = make_double2(c4, s4);
+      if (ftab32 != nullptr) ftab32[idx] = make_float4((float)ch4, (float)sh4, (float)c4, (float)s4);   // sweep_f32.cuh
     }
     ctab_a[idx] = make_double2(ch*co, sh*s); ctab_b[idx] = make_double2(sh*co, ch*s);
     w2[idx] = cmake(2.0*w.x, 2.0*w.y);

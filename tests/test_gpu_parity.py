@@ -94,6 +94,7 @@ def test_golden_param_files(golden, tmp_path):
 # engine vs numpy oracle on seeded inputs (ragged sizes: M not a multiple of 32, odd N, K not a multiple of the CTA size)
 # ---------------------------------------------------------------------------------------------------------------------
 H, J, ALPHA = -math.cos(math.pi / 4), math.sin(math.pi / 4), 2.0
+RBM_SWEEP_VARIANTS = ("rbm_f32filter", "rbm_regs")   # fp32-filtered exact sweep (M <= 512) / all-fp64 register-resident sweep
 FFNN_SWEEP_VARIANT = "ffnn_resident"     # kernel_variant("sweep") prefix the FNN sampler must report when not forced generic (M <= 512)
 
 
@@ -150,7 +151,7 @@ def _sweep_vs_oracle(model, N, M, K, pbc, force_generic, n_warm, n_more, check_O
     e.set_uniforms(U)
     s.warm_up(n_warm)
     e.warm_up(n_warm)
-    expect = "generic" if (force_generic or M > 1024) else ("rbm_regs" if model == "rbm" else FFNN_SWEEP_VARIANT)
+    expect = "generic" if (force_generic or M > 1024) else (RBM_SWEEP_VARIANTS if model == "rbm" else FFNN_SWEEP_VARIANT)
     if model == "rbm" and M > 1024 and not force_generic:
         e.get_htilda()
         assert e.kernel_variant("eloc").startswith("rbm_sites"), e.kernel_variant("eloc")
@@ -186,10 +187,46 @@ def test_sweep_matches_oracle_step_by_step(model, N, M, K, pbc, force_generic):
                                      (20, 128, 45, 4), (20, 128, 45, 2), (20, 128, 45, 1), (20, 256, 33, 2), (20, 256, 33, 1),
                                      (128, 256, 40, 2), (128, 256, 40, 1)])
 def test_sweep_chains_per_warp_variants(monkeypatch, N, M, K, C):
+    monkeypatch.setenv("NQS_SWEEP_F32", "0")           # the all-fp64 register-resident kernels (fast_kernels.cuh)
     monkeypatch.setenv("NQS_SWEEP_C", str(C))
     e, _, _ = _sweep_vs_oracle("rbm", N, M, K, False, False, 3, 1, check_O=False)
     assert e.kernel_variant("sweep").endswith("_c%d" % C), e.kernel_variant("sweep")
     e.close()
+
+
+@pytest.mark.parametrize("delta", ["1", "1e7"])
+@pytest.mark.parametrize("N,M,K", [(16, 16, 70), (24, 40, 50), (20, 128, 45), (20, 256, 33), (12, 384, 40), (14, 512, 33), (128, 256, 40)])
+def test_f32_filtered_sweep_is_exact(monkeypatch, N, M, K, delta):
+    """sweep_f32.cuh: the fp32 product only DECIDES when u R0 lies outside its rigorous error interval, otherwise the fp64 product
+    does -- accept masks must equal the oracle's whatever the share of each path: "1" = the real bound (almost everything fp32),
+    "1e7" = an interval wider than any ratio (every proposal takes the fp64 path)."""
+    monkeypatch.setenv("NQS_SWEEP_F32", "1")
+    monkeypatch.setenv("NQS_SWEEP_F32_DELTA", delta)
+    e, _, _ = _sweep_vs_oracle("rbm", N, M, K, False, False, 3, 1, check_O=False)
+    if N < 100:      # (with these weights the overflow bound of 128 sites exceeds the fp32 kernel's range guard: the fp64 kernel runs)
+        assert e.kernel_variant("sweep").startswith("rbm_f32filter"), e.kernel_variant("sweep")
+    e.close()
+
+
+def test_f32_filter_agrees_bitwise_with_the_fp64_sweep(monkeypatch):
+    """Same seeds through the fp32-filtered kernel and the all-fp64 register kernel: spins and theta bit-identical after many sweeps
+    (the decisions are the same; theta is replayed exactly in both)."""
+    from neural_network_quantum_state_b200 import Engine
+    model, N, M, K = "rbm", 64, 128, 700
+    params = synth(model, N, M, np.random.default_rng(9), scale=3.0)
+    outs = []
+    for f32 in ("1", "0"):
+        monkeypatch.setenv("NQS_SWEEP_F32", f32)
+        e = Engine(model, N, M, K, H, J, ALPHA, seed=99)
+        e.set_params(params)
+        e.warm_up(20)
+        e.do_mcmc_steps(5)
+        outs.append((e.get_spinStates(), e.get_theta(), e.get_lnpsi(), e.kernel_variant("sweep")))
+        e.close()
+    assert outs[0][3].startswith("rbm_f32filter") and outs[1][3].startswith("rbm_regs")
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert_close(outs[0][2], outs[1][2], what="lnpsi0")
 
 
 @pytest.mark.parametrize("model,N,M,K,n_warm,n_more", BASELINE_SHAPES)
@@ -294,7 +331,7 @@ def test_fast_and_generic_kernels_agree_bitwise_on_theta():
         e.do_mcmc_steps(3)
         outs.append((e.get_spinStates(), e.get_theta(), e.get_lnpsi(), e.get_htilda(), e.kernel_variant("sweep")))
         e.close()
-    assert outs[0][4].startswith("rbm_regs") and outs[1][4] == "generic"
+    assert outs[0][4].startswith(RBM_SWEEP_VARIANTS) and outs[1][4] == "generic"
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(outs[0][1], outs[1][1])
     assert_close(outs[0][2], outs[1][2], what="lnpsi0 fast vs generic")
