@@ -151,7 +151,11 @@ nqs_status nqs_warm_up(nqs_handle * h, int32_t n_sweeps, const int8_t * spins);
 /* ref: do_mcmc_steps(n) :28-39; one sweep = N single-site proposals per chain. */
 nqs_status nqs_do_mcmc_steps(nqs_handle * h, int32_t n_sweeps);
 /* Pre-drawn uniforms u[steps][K_loc] replacing TRNGWrapper::get_uniformDist (gpu/include/trng4cuda.cuh:62-65): proposal t
- * (counted from this call) of chain k uses u[t][k].  u == NULL -> internal Philox4x32-10 keyed by (seed, global chain, step). */
+ * (counted from this call) of chain k uses u[t][k].  u == NULL -> internal Philox4x32-10 keyed by (seed, global chain, step).
+ * u is consumed asynchronously: it must stay valid and unchanged until the sweeps that use it have completed (any later
+ * synchronising call).  Pageable memory is staged through HBM (steps <= nqs_config.max_predrawn_steps); a page-locked
+ * buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory) is read in place over PCIe by the sweep kernels, with no
+ * staging copy and no limit on steps (NQS_UNIFORMS_ZEROCOPY=0 restores the copy). */
 nqs_status nqs_set_uniforms(nqs_handle * h, const double * u, int64_t steps);
 nqs_status nqs_get_spins(nqs_handle * h, int8_t * spins);                  /* ref: get_spinStates() (real part) */
 nqs_status nqs_get_lnpsi(nqs_handle * h, nqs_cdouble * lnpsi);             /* ref: BaseParallelSampler::get_lnpsi() */

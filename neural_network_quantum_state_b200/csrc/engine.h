@@ -78,6 +78,7 @@ struct nqs_handle
   double theta_bound = 0.0;
   int jpl = 0, mpad = 0, npad32 = 0;
   long long u_steps = 0, u_used = 0;      // pre-drawn feed: proposals available / consumed
+  const double * u_zc = nullptr;          // the feed is read IN PLACE from the caller's pinned host buffer (device alias), else null
   long long acc_log_steps = 0;
   int pos = 0;                            // next position in the site ring
   int flip_index = 0;                     // the machine's index_ (ref impl_neural_quantum_state.cuh:19)

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C, WPC>::warps, SweepShape<
   };
   if (w == 0 && lane == 0)
     for (long long q = 0; q < NQS_SW_STAGES-1 && q < t_end; ++q) issue_rows(q);
-  double ubuf = 0.0;                           // uniform of proposal (t_glob rounded down to G) + lane%G of chain myc
+  double ubuf = 0.0, unext = 0.0;              // uniform of proposal (t_glob rounded down to G) + lane%G of chain myc; next group's
 
   for (int sweep = 0; sweep < a.nsweeps; ++sweep)
   {
@@ -338,11 +338,24 @@ __global__ void __launch_bounds__(32*SweepShape<JPL, C, WPC>::warps, SweepShape<
     for (int t = 0; t < N; ++t, ++t_glob)
     {
       if ((t_glob&(G-1)) == 0)
-      {
-        const long long tt = t_glob+(lane&(G-1));
-        if (tt < t_end)
-          ubuf = a.uniforms ? a.uniforms[tt*a.K+my_k]
-                            : philox_uniform(a.seed, (unsigned long long)(a.chain_offset+my_k), a.step0+(unsigned long long)tt);
+      { // the uniforms of this group of G proposals were fetched one group ahead (a pre-drawn feed may live in pinned HOST
+        // memory: its latency must not sit on the accept decision); fetch the next group's now
+        if (a.uniforms)
+        {
+          if (t_glob == 0)
+          {
+            const long long tt = (long long)(lane&(G-1));
+            unext = (tt < t_end) ? a.uniforms[tt*a.K+my_k] : 0.0;
+          }
+          ubuf = unext;
+          const long long tn = t_glob+G+(lane&(G-1));
+          unext = (tn < t_end) ? a.uniforms[tn*a.K+my_k] : 0.0;
+        }
+        else
+        {
+          const long long tt = t_glob+(lane&(G-1));
+          if (tt < t_end) ubuf = philox_uniform(a.seed, (unsigned long long)(a.chain_offset+my_k), a.step0+(unsigned long long)tt);
+        }
       }
       const int site = ord[pos];
       pos = (pos+1 == N) ? 0 : pos+1;

@@ -213,7 +213,7 @@ def test_f32_filter_agrees_bitwise_with_the_fp64_sweep(monkeypatch):
     (the decisions are the same; theta is replayed exactly in both)."""
     from neural_network_quantum_state_b200 import Engine
     model, N, M, K = "rbm", 64, 128, 700
-    params = synth(model, N, M, np.random.default_rng(9), scale=3.0)
+    params = synth(model, N, M, np.random.default_rng(9), scale=1.5)   # (larger weights trip the fp32 kernel's range guard)
     outs = []
     for f32 in ("1", "0"):
         monkeypatch.setenv("NQS_SWEEP_F32", f32)
@@ -386,3 +386,40 @@ def test_zero_chains_edge_and_single_chain():
     e.warm_up(3)
     assert e.get_spinStates().shape == (1, 5)
     e.close()
+
+
+@pytest.mark.parametrize("model,N,M,K", [("rbm", 128, 256, 130), ("rbm", 24, 40, 200), ("ffnn", 16, 48, 77), ("rbm", 12, 1024, 21),
+                                          ("rbm", 6, 1100, 10)])
+def test_pinned_uniforms_are_read_in_place_and_give_the_same_chain(model, N, M, K, monkeypatch):
+    """nqs_set_uniforms with a page-locked buffer: the sweep kernels read it over PCIe (no staging copy, a group of proposals
+    fetched ahead); pageable memory is staged through HBM.  Same uniforms -> the same accept decisions, bit for bit -- including
+    when the feed is longer than max_predrawn_steps (no device buffer is involved) and when a sweep starts in the middle of it."""
+    import torch
+    rng = np.random.default_rng(N + M)
+    n_sweeps = 5
+    U = rng.random((n_sweeps * N, K))
+    params = synth(model, N, M, np.random.default_rng(3))
+    res = []
+    for mode in ("pageable", "pinned", "pinned_copy"):
+        monkeypatch.setenv("NQS_UNIFORMS_ZEROCOPY", "0" if mode == "pinned_copy" else "1")
+        # the pinned run gets a device staging buffer far too small for the feed: it must not need it
+        e = _engine(model, N, M, K, H, J, ALPHA, max_predrawn_steps=(2 if mode == "pinned" else U.shape[0]), accept_log=True,
+                    sampler_only=True)
+        e.set_params(params)
+        if mode == "pageable":
+            buf = U.copy()
+        else:
+            t = torch.empty(U.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = U
+            buf = t.numpy()
+        e.set_uniforms(buf)
+        e.warm_up(2)
+        e.do_mcmc_steps(1)
+        e.do_mcmc_steps(2)
+        res.append((e.get_spinStates(), e.get_theta(), e.get_lnpsi()))
+        e.set_uniforms(None)
+        e.close()
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]), "accept decisions differ between the staged and the in-place uniform feed"
+        assert np.array_equal(res[0][1], r[1])
+        assert np.array_equal(res[0][2], r[2])
