@@ -225,6 +225,39 @@ void launch_rows_dmma(nqs_handle * h, const RowsArgs & a)
   check_launch(h, "spin_rows_dmma_kernel");
 }
 
+// tcgen05 int8 rows kernel (rows_umma.cuh): one CTA per 128 chains, so it only pays when a rank holds enough chains to cover
+// most of the SMs; N <= 512 keeps the int64 recombination exact.  NQS_ROWS_UMMA=0/1 overrides.
+bool rows_umma_ok(nqs_handle * h)
+{
+  if (h->rows_umma < 0)
+  {
+    const char * e = std::getenv("NQS_ROWS_UMMA");
+    bool on = (h->K >= 64ll*128);
+    if (e) on = (std::atoi(e) != 0);
+    on = on && !(h->cfg.flags & NQS_FLAG_NO_DMMA) && h->N <= 512 && rows_umma_smem(h->N) <= h->smem_optin;
+    if (on)
+    {
+      const size_t bytes = (size_t)ru_nchunks(2*h->M)*ru_chunk_bytes(h->N);
+      h->bq.alloc(bytes);
+      NQS_CUDA(cudaMemsetAsync(h->bq.p, 0, bytes, h->stream));
+      h->bscale.alloc((size_t)2*h->M);
+    }
+    h->rows_umma = on ? 1 : 0;
+  }
+  return h->rows_umma == 1;
+}
+
+template <int MODEL, int EPI>
+void launch_rows_umma(nqs_handle * h, const RowsArgs & a)
+{
+  ozaki_split_kernel<<<(unsigned)ru_nchunks(2*h->M), 256, 0, h->stream>>>(h->N, 2*h->M, a.B, h->bq.p, h->bscale.p, EPI == ROWS_EPI_Z ? a.done : nullptr);
+  check_launch(h, "ozaki_split_kernel");
+  const size_t smem = rows_umma_smem(h->N);
+  set_smem(spin_rows_umma_kernel<MODEL, EPI>, smem);
+  spin_rows_umma_kernel<MODEL, EPI><<<(unsigned)((h->K+127)/128), NQS_RU_THREADS, smem, h->stream>>>(a, h->bq.p, h->bscale.p);
+  check_launch(h, "spin_rows_umma_kernel");
+}
+
 bool rows_dmma_ok(const nqs_handle * h)
 { // the spin tile of 16 chains and two slabs of B must fit the shared memory of one CTA (N up to ~700)
   return !(h->cfg.flags & NQS_FLAG_NO_DMMA) && rows_dmma_smem(h->N, 2) <= h->smem_optin;
@@ -254,6 +287,15 @@ void launch_theta(nqs_handle * h, const int8_t * spins_dev, const int8_t * sa_sp
     std::memset(&a, 0, sizeof(a));
     a.N = h->N; a.M = h->M; a.K = h->K; a.spins = spins_dev; a.B = reinterpret_cast<const double*>(mp.W); a.bias = mp.b;
     a.theta = theta; a.sa_spins = sa_spins_dev; a.avis = mp.a; a.w1o = mp.w1o; a.sa = sa; a.lnpsi = lnpsi;
+    if (rows_umma_ok(h))
+    {
+      if (h->model == MODEL_RBM)
+      { if (lnpsi) launch_rows_umma<MODEL_RBM, ROWS_EPI_LNPSI>(h, a); else launch_rows_umma<MODEL_RBM, ROWS_EPI_THETA>(h, a); }
+      else
+      { if (lnpsi) launch_rows_umma<MODEL_FFNN, ROWS_EPI_LNPSI>(h, a); else launch_rows_umma<MODEL_FFNN, ROWS_EPI_THETA>(h, a); }
+      h->variant_theta = "umma_i8_ozaki7_rows";
+      return;
+    }
     if (h->model == MODEL_RBM)
     { if (lnpsi) launch_rows_dmma<MODEL_RBM, ROWS_EPI_LNPSI>(h, a); else launch_rows_dmma<MODEL_RBM, ROWS_EPI_THETA>(h, a); }
     else
@@ -976,14 +1018,14 @@ int matvec_structured(nqs_handle * h, const cd * v, const int * done)
     if (h->model == MODEL_RBM)
     { // v = [V (i*M+j) | a block | b block]
       r.B = reinterpret_cast<const double*>(v); r.avis = v+NM; r.bias = v+NM+h->N;
-      launch_rows_dmma<MODEL_RBM, ROWS_EPI_Z>(h, r);
+      if (rows_umma_ok(h)) launch_rows_umma<MODEL_RBM, ROWS_EPI_Z>(h, r); else launch_rows_dmma<MODEL_RBM, ROWS_EPI_Z>(h, r);
     }
     else
     { // v = [V (j*N+i) | b1 block | w1o block]
       transpose_wblock_kernel<<<grid_for(NM, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, v, h->vnat.p, done);
       check_launch(h, "transpose_wblock_kernel");
       r.B = reinterpret_cast<const double*>(h->vnat.p); r.bias = v+NM; r.w1o = v+NM+h->M;
-      launch_rows_dmma<MODEL_FFNN, ROWS_EPI_Z>(h, r);
+      if (rows_umma_ok(h)) launch_rows_umma<MODEL_FFNN, ROWS_EPI_Z>(h, r); else launch_rows_dmma<MODEL_FFNN, ROWS_EPI_Z>(h, r);
     }
   }
   ColsArgs c;

@@ -11,6 +11,7 @@
 #include "fast_kernels.cuh"
 #include "ffnn_fast_kernels.cuh"
 #include "sweep_f32.cuh"
+#include "rows_umma.cuh"
 
 namespace nqs
 {
@@ -114,6 +115,9 @@ struct nqs_handle
   // structured S*v (sv_struct.cuh, NQS_FLAG_STRUCTURED_SV): hidden-unit factors T (and L, FFNN), chain chunks of the column GEMM
   bool struct_sv = false, hidden_valid = false;
   nqs::DevBuf<nqs::cd> Tm, Lm, vnat;
+  nqs::DevBuf<int8_t> bq;                 // rows_umma.cuh: int8 digit planes of the B operand (W, or the W block of v), UMMA tile order
+  nqs::DevBuf<double> bscale;             // their per-column power-of-two scales [2M]
+  int rows_umma = -1;                     // -1 undecided, 0 fp64 DMMA rows kernel, 1 tcgen05 int8 (Ozaki) rows kernel
   nqs::DevBuf<double> Sd;                 // [K][N] spins as doubles: factor rows of the O-generating S*v (sv_fused.cuh, GEN)
   bool gen_ok = false, o_pending = false; // O is written by the first S*v of the CG instead of a separate writer / it still has to be
   nqs::DevBuf<double> abs2;               // [chunks][3M] sums of |T|^2, |L|^2 of the SR setup GEMM

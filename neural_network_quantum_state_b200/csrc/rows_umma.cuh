@@ -1,0 +1,284 @@
+// C[k][c] = sum_i s_ki B[i][c] on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) with fp64-grade
+// results: the spins are +-1 (exact in int8) and B is split ERROR-FREE into 7 signed base-256 digits per column (an Ozaki
+// split with one power-of-two scale per column), so every int32 accumulator is exact and the digits are recombined in int64:
+//
+//   B[i][c] ~ Q[i][c] 2^(e_c-53),  Q = rint(B 2^(53-e_c)),  |Q| <= 2^53,  2^(e_c-1) <= max_i |B[i][c]| < 2^e_c
+//   Q = sum_{s<7} d_s 256^s, d_s in [-128, 127]           (balanced digits: int8)
+//   sum_i s_ki B[i][c] ~ 2^(e_c-53) sum_s 256^s (sum_i s_ki d_s[i][c])   -- 7 int8 GEMMs sharing the same A: ONE GEMM whose
+//                                                                          B operand carries the 7 digit planes side by side
+//
+// The only rounding is Q's: |error| <= N 2^(e_c-54) <= N 2^-53 max_i|B[i][c]| per output, below the rounding error bound of the
+// fp64 dot product it replaces (N 2^-53 sum_i |B[i][c]|); the final int64 -> double conversion adds one more rounding.
+// N <= 512 keeps |sum| <= N 2^53 inside int64.
+//
+// Same operands, outputs and epilogues as spin_rows_dmma_kernel (sv_struct.cuh): theta = S W + b with the log cosh row sum
+// (ref: Zgemm + logcosh pass, gpu/include/impl_neural_quantum_state.cuh:78,114) and z = O v from the factors of O.
+//
+// Layout: one CTA per 128 chains (UMMA M = 128: chain r of the tile = TMEM lane r).  A = the spin tile [128][Npad] int8,
+// K-major, no swizzle: 8 x 16 B core matrices, (r/8) SBO + (i/16) 128 + (r%8) 16 + i%16.  B is consumed in chunks of 32 real
+// columns: tile [7 digit planes x 32 columns = 224 rows][Npad] in the same core-matrix order, prepared once per product by
+// ozaki_split_kernel and fetched with one 1-D TMA bulk copy per chunk (double-buffered).  One MMA of 128 x 224 x 32 per 32
+// sites; D = 224 TMEM columns, double-buffered (448 of 512), so the MMAs of chunk c+1 run under the epilogue of chunk c.
+// Epilogue: 16 warps = 4 lane quadrants x 4 column groups; a thread owns one chain and 8 real columns of the chunk:
+// 7 tcgen05.ld (32x32b.x8), Horner in int64, one I2F, scale, then the complex epilogue of the DMMA kernel.
+#pragma once
+#include <cfloat>
+#include "sv_struct.cuh"
+
+namespace nqs
+{
+
+#define NQS_RU_THREADS 512
+#define NQS_RU_NC 32                          // real columns of B per chunk
+#define NQS_RU_NS 7                           // digit planes
+#define NQS_RU_NB (NQS_RU_NC*NQS_RU_NS)       // rows of the B tile = UMMA N
+#define NQS_RU_TMEM_COLS 512
+#define NQS_RU_TBUF 256                       // TMEM column stride between the two accumulator buffers
+
+inline int ru_npad(const int N) { return (N+31)/32*32; }
+inline size_t ru_chunk_bytes(const int N) { return (size_t)NQS_RU_NB*ru_npad(N); }
+inline int ru_nchunks(const int M2) { return (M2+NQS_RU_NC-1)/NQS_RU_NC; }
+inline size_t rows_umma_smem(const int N)
+{
+  return (size_t)128*ru_npad(N)+2*ru_chunk_bytes(N)+(size_t)4*128*sizeof(cd)+64;
+}
+
+// B [N][M2] -> digit planes in the UMMA tile order (one block per chunk of 32 columns) + scale[c] = 2^(e_c-53)
+// (0 for an all-zero column, NaN for a column holding a non-finite value: the product then propagates NaN like the fp64 GEMM)
+__global__ void __launch_bounds__(256) ozaki_split_kernel(const int N, const int M2, const double * __restrict__ B,
+                                                          int8_t * __restrict__ Bq, double * __restrict__ scale, const int * __restrict__ done)
+{
+  if (done != nullptr && *done) return;
+  __shared__ double smax[8][32];
+  const int lane = threadIdx.x&31, w = threadIdx.x>>5, c = blockIdx.x*NQS_RU_NC+lane;
+  double m = 0.0;
+  if (c < M2)
+    for (int i = w; i < N; i += 8)
+    {
+      const double v = fabs(B[(size_t)i*M2+c]);
+      m = (v <= DBL_MAX) ? fmax(m, v) : INFINITY;     // NaN and Inf both land on Inf
+    }
+  smax[w][lane] = m;
+  __syncthreads();
+  double cm = smax[0][lane];
+#pragma unroll
+  for (int ww = 1; ww < 8; ++ww) cm = fmax(cm, smax[ww][lane]);
+  const bool usable = (cm > 0.0 && cm <= DBL_MAX);
+  const int e = usable ? ilogb(cm)+1 : 0;
+  if (w == 0 && c < M2) scale[c] = usable ? scalbn(1.0, e-53) : (cm == 0.0 ? 0.0 : nan(""));
+  if (c >= M2) return;
+  const int npad = (N+31)/32*32, kch = npad/16;
+  int8_t * tile = Bq+(size_t)blockIdx.x*NQS_RU_NB*npad;
+  for (int i = w; i < N; i += 8)
+  {
+    long long Q = usable ? llrint(scalbn(B[(size_t)i*M2+c], 53-e)) : 0ll;
+#pragma unroll
+    for (int s = 0; s < NQS_RU_NS; ++s)
+    {
+      const int d = (int)((Q+128)&255)-128;
+      Q = (Q-d)>>8;
+      const int n = s*NQS_RU_NC+lane;
+      tile[(size_t)(n>>3)*(kch*128)+(i>>4)*128+(n&7)*16+(i&15)] = (int8_t)d;
+    }
+  }
+}
+
+// bounded mbarrier wait: a descriptor mistake must end in a trap, not in a hung GPU
+__device__ __forceinline__ void ru_mbar_wait(uint64_t * bar, const uint32_t parity)
+{
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  const long long t0 = clock64();
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+    if (!ok && clock64()-t0 > 4000000000ll) __trap();
+  } while (!ok);
+}
+// shared-memory matrix descriptor (sm_100 version 1), no swizzle: start address, leading (K) and stride (M/N) byte offsets / 16
+__device__ __forceinline__ uint64_t ru_desc(const uint32_t saddr, const uint32_t lbo, const uint32_t sbo)
+{
+  return (uint64_t)((saddr&0x3FFFFu)>>4)|((uint64_t)(lbo>>4)<<16)|((uint64_t)(sbo>>4)<<32)|(1ull<<46);
+}
+__device__ __forceinline__ void ru_mma_i8(const uint32_t tmem_d, const uint64_t adesc, const uint64_t bdesc, const uint32_t idesc, const uint32_t accumulate)
+{
+  const uint32_t zero = 0u;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+    :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(zero) : "memory");
+}
+__device__ __forceinline__ void ru_commit(uint64_t * bar)
+{
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ru_tmem_ld8(const uint32_t taddr, uint32_t (&v)[8])
+{
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr) : "memory");
+}
+
+template <int MODEL, int EPI>
+__global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const RowsArgs a, const int8_t * __restrict__ Bq, const double * __restrict__ scale)
+{
+  if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int NC = NQS_RU_NC, NS = NQS_RU_NS, NB = NQS_RU_NB;
+  const int N = a.N, M = a.M, M2 = 2*M, npad = (N+31)/32*32, kch = npad/16, nch = (M2+NC-1)/NC;
+  const uint32_t sbo = (uint32_t)kch*128u, chunk_bytes = (uint32_t)NB*(uint32_t)npad;
+  unsigned char * As = smem_raw;                                  // [128][npad] spins, core-matrix order
+  unsigned char * Bs = As+(size_t)128*npad;                       // [2] chunk tiles
+  cd * red = reinterpret_cast<cd*>(Bs+(size_t)2*chunk_bytes);     // [4 column groups][128 chains]
+  uint64_t * bfull = reinterpret_cast<uint64_t*>(red+4*128);      // [2] chunk tile landed
+  uint64_t * mdone = bfull+2;                                     // [2] MMAs of the chunk complete
+  uint32_t * tptr = reinterpret_cast<uint32_t*>(mdone+2);
+  const int tid = threadIdx.x, lane = tid&31, w = tid>>5, q = w&3, g = w>>2, row = 32*q+lane;
+  const long long kbase = (long long)blockIdx.x*128, k = kbase+row;
+
+  if (w == 0)
+  {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tptr)), "r"((uint32_t)NQS_RU_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32)
+  {
+    mbar_init(bfull, 1); mbar_init(bfull+1, 1); mbar_init(mdone, 1); mbar_init(mdone+1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  { // spin tile: 16-byte pieces, consecutive threads along a chain's row
+    const bool vec = (N%16 == 0) && ((reinterpret_cast<size_t>(a.spins)&15) == 0);
+    for (int idx = tid; idx < 128*kch; idx += NQS_RU_THREADS)
+    {
+      const int r = idx/kch, kc = idx-r*kch;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (kbase+r < a.K)
+      {
+        const int8_t * src = a.spins+(size_t)(kbase+r)*N+kc*16;
+        if (vec) { if (kc*16 < N) val = *reinterpret_cast<const uint4*>(src); }
+        else
+        {
+          unsigned char b[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) b[t] = (kc*16+t < N) ? (unsigned char)src[t] : (unsigned char)0;
+          val.x = b[0]|(b[1]<<8)|(b[2]<<16)|((uint32_t)b[3]<<24);   val.y = b[4]|(b[5]<<8)|(b[6]<<16)|((uint32_t)b[7]<<24);
+          val.z = b[8]|(b[9]<<8)|(b[10]<<16)|((uint32_t)b[11]<<24); val.w = b[12]|(b[13]<<8)|(b[14]<<16)|((uint32_t)b[15]<<24);
+        }
+      }
+      *reinterpret_cast<uint4*>(As+(size_t)(r>>3)*sbo+kc*128+(r&7)*16) = val;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A before the tensor core reads them
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = *tptr;
+  // instruction descriptor: D = s32, A = B = s8, both K-major, N = 224, M = 128
+  constexpr uint32_t idesc = (2u<<4)|(1u<<7)|(1u<<10)|((uint32_t)(NB>>3)<<17)|((128u>>4)<<24);
+  const uint64_t adesc = ru_desc(smem_u32(As), 128u, sbo);
+
+  auto issue_tma = [&](const int c)
+  {
+    mbar_expect_tx(bfull+(c&1), chunk_bytes);
+    tma_load_1d(Bs+(size_t)(c&1)*chunk_bytes, Bq+(size_t)c*chunk_bytes, chunk_bytes, bfull+(c&1));
+  };
+  auto issue_mma = [&](const int c)
+  {
+    ru_mbar_wait(bfull+(c&1), (uint32_t)((c>>1)&1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint64_t bdesc = ru_desc(smem_u32(Bs+(size_t)(c&1)*chunk_bytes), 128u, sbo);
+    for (int kk = 0; kk < npad/32; ++kk)     // 32 sites = two 16-byte K chunks = 256 bytes further along both operands
+      ru_mma_i8(tbase+(uint32_t)(c&1)*NQS_RU_TBUF, adesc+(uint64_t)(kk*16), bdesc+(uint64_t)(kk*16), idesc, kk > 0 ? 1u : 0u);
+    ru_commit(mdone+(c&1));
+  };
+  if (tid == 0)
+  {
+    issue_tma(0);
+    if (nch > 1) issue_tma(1);
+    issue_mma(0);
+  }
+  cd rsum = cmake(0.0, 0.0);
+  for (int c = 0; c < nch; ++c)
+  {
+    // here: MMAs of chunk c issued, tile of chunk c+1 on its way; the accumulator buffer (c+1)&1 was drained before the
+    // __syncthreads that ended the previous iteration
+    if (tid == 0 && c+1 < nch) issue_mma(c+1);
+    __syncwarp();
+    ru_mbar_wait(mdone+(c&1), (uint32_t)((c>>1)&1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0 && c+2 < nch) issue_tma(c+2);     // the tile buffer c&1 is free: its MMAs completed
+    __syncwarp();
+    uint32_t v[NS][8];
+    const uint32_t taddr = tbase+((uint32_t)(32*q)<<16)+(uint32_t)(c&1)*NQS_RU_TBUF+(uint32_t)(g*8);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) ru_tmem_ld8(taddr+(uint32_t)(s*NC), v[s]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int col0 = c*NC+g*8;
+    double x[8];
+#pragma unroll
+    for (int cc = 0; cc < 8; ++cc)
+    {
+      long long tot = (long long)(int)v[NS-1][cc];
+#pragma unroll
+      for (int s = NS-2; s >= 0; --s) tot = tot*256+(long long)(int)v[s][cc];
+      x[cc] = (col0+cc < M2) ? (double)tot*scale[col0+cc] : 0.0;
+    }
+    if (k < a.K)
+    {
+#pragma unroll
+      for (int cc = 0; cc < 8; cc += 2)
+      {
+        const int j = (col0+cc)>>1;
+        if (j >= M) continue;
+        const cd bj = a.bias[j];
+        cd wj = cmake(1.0, 0.0);
+        if (MODEL == MODEL_FFNN && EPI != ROWS_EPI_THETA) wj = a.w1o[j];
+        const cd val = cmake(x[cc]+bj.x, x[cc+1]+bj.y);
+        if (EPI == ROWS_EPI_Z)
+        {
+          cd term = cmul(a.T[k*M+j], val);
+          if (MODEL == MODEL_FFNN) term = cadd(term, cmul(a.L[k*M+j], wj));
+          rsum = cadd(rsum, term);
+        }
+        else
+        {
+          if (a.theta) a.theta[k*M+j] = val;
+          if (EPI == ROWS_EPI_LNPSI)
+          {
+            const cd lc = c_logcosh(val);
+            rsum = cadd(rsum, (MODEL == MODEL_RBM) ? lc : cmul(wj, lc));
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  red[g*128+row] = rsum;
+  __syncthreads();
+  if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((uint32_t)NQS_RU_TMEM_COLS) : "memory");
+  if (tid < 128 && k < a.K)
+  { // (tid < 128 <=> g == 0, row == tid) visible-bias term (RBM) and the final value of the chain, column groups in fixed order
+    cd sv = cmake(0.0, 0.0);
+    if (MODEL == MODEL_RBM)
+    {
+      const unsigned char * arow = As+(size_t)(row>>3)*sbo+(row&7)*16;
+      for (int i = 0; i < N; ++i)
+      {
+        const double s = (EPI == ROWS_EPI_Z) ? (double)(int8_t)arow[(i>>4)*128+(i&15)] : (double)a.sa_spins[k*N+i];
+        const cd ai = a.avis[i];
+        sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
+      }
+    }
+    cd tot = sv;
+    if (EPI != ROWS_EPI_THETA)
+      for (int gg = 0; gg < 4; ++gg) tot = cadd(tot, red[gg*128+row]);
+    if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
+    else
+    {
+      if (a.sa) a.sa[k] = sv;
+      if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
+    }
+  }
+}
+
+} // namespace nqs
