@@ -234,13 +234,14 @@ bool rows_umma_ok(nqs_handle * h)
     const char * e = std::getenv("NQS_ROWS_UMMA");
     bool on = (h->K >= 64ll*128);
     if (e) on = (std::atoi(e) != 0);
-    on = on && !(h->cfg.flags & NQS_FLAG_NO_DMMA) && h->N <= 512 && rows_umma_smem(h->N) <= h->smem_optin;
+    const int m2 = std::max(2*h->M, h->N);     // widest B: W / the W block of v (2M real columns), J (N columns)
+    on = on && !(h->cfg.flags & NQS_FLAG_NO_DMMA) && h->N <= 512 && rows_umma_smem(h->N, h->M, m2, 2) <= h->smem_optin;
     if (on)
     {
-      const size_t bytes = (size_t)ru_nchunks(2*h->M)*ru_chunk_bytes(h->N);
+      const size_t bytes = (size_t)ru_nchunks(m2)*ru_chunk_bytes(h->N);
       h->bq.alloc(bytes);
       NQS_CUDA(cudaMemsetAsync(h->bq.p, 0, bytes, h->stream));
-      h->bscale.alloc((size_t)2*h->M);
+      h->bscale.alloc((size_t)m2);
     }
     h->rows_umma = on ? 1 : 0;
   }
@@ -250,11 +251,23 @@ bool rows_umma_ok(nqs_handle * h)
 template <int MODEL, int EPI>
 void launch_rows_umma(nqs_handle * h, const RowsArgs & a)
 {
-  ozaki_split_kernel<<<(unsigned)ru_nchunks(2*h->M), 256, 0, h->stream>>>(h->N, 2*h->M, a.B, h->bq.p, h->bscale.p, EPI == ROWS_EPI_Z ? a.done : nullptr);
+  const int m2 = (EPI == ROWS_EPI_SJS) ? h->N : 2*h->M;
+  ozaki_split_kernel<<<(unsigned)ru_nchunks(m2), 32*(ru_npad(h->N)/16), 0, h->stream>>>(h->N, m2, a.B, h->bq.p, h->bscale.p, EPI == ROWS_EPI_Z ? a.done : nullptr);
   check_launch(h, "ozaki_split_kernel");
-  const size_t smem = rows_umma_smem(h->N);
+  const int nbuf = rows_umma_nbuf(h->N, h->M, m2, h->smem_optin);
+  const size_t smem = rows_umma_smem(h->N, h->M, m2, nbuf);
   set_smem(spin_rows_umma_kernel<MODEL, EPI>, smem);
-  spin_rows_umma_kernel<MODEL, EPI><<<(unsigned)((h->K+127)/128), NQS_RU_THREADS, smem, h->stream>>>(a, h->bq.p, h->bscale.p);
+  // programmatic dependent launch: the CTAs start (TMEM allocation, spin tile) while the split kernel drains
+  cudaLaunchConfig_t lc;
+  std::memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)((h->K+127)/128)); lc.blockDim = dim3(NQS_RU_THREADS); lc.dynamicSmemBytes = smem; lc.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  const int8_t * bq = h->bq.p;
+  const double * bs = h->bscale.p;
+  NQS_CUDA(cudaLaunchKernelEx(&lc, spin_rows_umma_kernel<MODEL, EPI>, a, bq, bs, nbuf));
   check_launch(h, "spin_rows_umma_kernel");
 }
 
@@ -272,7 +285,7 @@ const double * launch_sjs(nqs_handle * h)
   RowsArgs a;
   std::memset(&a, 0, sizeof(a));
   a.N = h->N; a.M = h->M; a.K = h->K; a.spins = h->spins.p; a.B = h->Jmat.p; a.sjs = h->sjs.p;
-  launch_rows_dmma<MODEL_RBM, ROWS_EPI_SJS>(h, a);
+  if (rows_umma_ok(h)) launch_rows_umma<MODEL_RBM, ROWS_EPI_SJS>(h, a); else launch_rows_dmma<MODEL_RBM, ROWS_EPI_SJS>(h, a);
   return h->sjs.p;
 }
 

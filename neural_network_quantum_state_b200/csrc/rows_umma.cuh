@@ -17,10 +17,15 @@
 // Layout: one CTA per 128 chains (UMMA M = 128: chain r of the tile = TMEM lane r).  A = the spin tile [128][Npad] int8,
 // K-major, no swizzle: 8 x 16 B core matrices, (r/8) SBO + (i/16) 128 + (r%8) 16 + i%16.  B is consumed in chunks of 32 real
 // columns: tile [7 digit planes x 32 columns = 224 rows][Npad] in the same core-matrix order, prepared once per product by
-// ozaki_split_kernel and fetched with one 1-D TMA bulk copy per chunk (double-buffered).  One MMA of 128 x 224 x 32 per 32
-// sites; D = 224 TMEM columns, double-buffered (448 of 512), so the MMAs of chunk c+1 run under the epilogue of chunk c.
+// ozaki_split_kernel and fetched with one 1-D TMA bulk copy per chunk (ring of up to 6 tiles).  One MMA of 128 x 224 x 32 per
+// 32 sites; D = 224 TMEM columns, double-buffered (448 of 512), so the MMAs of chunk c+1 run under the epilogue of chunk c.
 // Epilogue: 16 warps = 4 lane quadrants x 4 column groups; a thread owns one chain and 8 real columns of the chunk:
-// 7 tcgen05.ld (32x32b.x8), Horner in int64, one I2F, scale, then the complex epilogue of the DMMA kernel.
+// 7 tcgen05.ld (32x32b.x8), Horner in int64, one I2F, scale, then the complex epilogue of the DMMA kernel.  The chunks run in
+// lockstep (one __syncthreads each), so nothing with a global-memory latency may sit inside the chunk loop: scales, biases and
+// output weights are staged in shared memory, the factors T (L) of the next chunk are fetched one chunk ahead, and the
+// visible-bias sum is taken while the first tile is still in flight (measured with in-kernel clocks: 4500 -> cycles per chunk).
+// The kernel is launched with programmatic stream serialization: TMEM allocation, barrier setup and the spin tile overlap the
+// tail of ozaki_split_kernel.
 #pragma once
 #include <cfloat>
 #include "sv_struct.cuh"
@@ -34,52 +39,83 @@ namespace nqs
 #define NQS_RU_NB (NQS_RU_NC*NQS_RU_NS)       // rows of the B tile = UMMA N
 #define NQS_RU_TMEM_COLS 512
 #define NQS_RU_TBUF 256                       // TMEM column stride between the two accumulator buffers
+#define NQS_RU_MAXBUF 6                       // tile buffers in flight
 
 inline int ru_npad(const int N) { return (N+31)/32*32; }
 inline size_t ru_chunk_bytes(const int N) { return (size_t)NQS_RU_NB*ru_npad(N); }
 inline int ru_nchunks(const int M2) { return (M2+NQS_RU_NC-1)/NQS_RU_NC; }
-inline size_t rows_umma_smem(const int N)
+// spin tile | nbuf chunk tiles | row sums + visible-bias sums [8][128] | scales [chunks*32] | bias [M] | w1o [M] | barriers
+inline size_t rows_umma_smem(const int N, const int M, const int M2, const int nbuf)
 {
-  return (size_t)128*ru_npad(N)+2*ru_chunk_bytes(N)+(size_t)4*128*sizeof(cd)+64;
+  return (size_t)128*ru_npad(N)+(size_t)nbuf*ru_chunk_bytes(N)+(size_t)8*128*sizeof(cd)+(size_t)ru_nchunks(M2)*NQS_RU_NC*sizeof(double)
+        +(size_t)2*M*sizeof(cd)+128;
+}
+// as many tile buffers as fit: the TMA of a chunk is issued several chunks ahead of its MMAs
+inline int rows_umma_nbuf(const int N, const int M, const int M2, const size_t smem_limit)
+{
+  int nb = NQS_RU_MAXBUF;
+  if (nb > ru_nchunks(M2)) nb = ru_nchunks(M2);
+  if (nb < 2) nb = 2;
+  while (nb > 2 && rows_umma_smem(N, M, M2, nb) > smem_limit) --nb;
+  return nb;
 }
 
-// B [N][M2] -> digit planes in the UMMA tile order (one block per chunk of 32 columns) + scale[c] = 2^(e_c-53)
-// (0 for an all-zero column, NaN for a column holding a non-finite value: the product then propagates NaN like the fp64 GEMM)
-__global__ void __launch_bounds__(256) ozaki_split_kernel(const int N, const int M2, const double * __restrict__ B,
-                                                          int8_t * __restrict__ Bq, double * __restrict__ scale, const int * __restrict__ done)
+// B [N][M2] -> digit planes in the UMMA tile order + scale[c] = 2^(e_c-53) (0 for an all-zero column, NaN for a column holding
+// a non-finite value: the product then propagates NaN like the fp64 GEMM).  One block per chunk of 32 columns; a thread owns one
+// column and 16 consecutive sites, i.e. exactly one 16-byte row of a core matrix in each of the 7 planes: 7 vector stores.
+__global__ void __launch_bounds__(1024) ozaki_split_kernel(const int N, const int M2, const double * __restrict__ B,
+                                                           int8_t * __restrict__ Bq, double * __restrict__ scale, const int * __restrict__ done)
 {
+  // the consumer (spin_rows_umma_kernel, launched with programmatic stream serialization) may start its prologue right away;
+  // it waits (griddepcontrol.wait) for this grid to complete before it touches Bq / scale
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (done != nullptr && *done) return;
-  __shared__ double smax[8][32];
-  const int lane = threadIdx.x&31, w = threadIdx.x>>5, c = blockIdx.x*NQS_RU_NC+lane;
+  __shared__ double smax[32][32];
+  const int lane = threadIdx.x&31, kc = threadIdx.x>>5, c = blockIdx.x*NQS_RU_NC+lane;     // blockDim = 32 x (npad/16)
+  const int npad = (N+31)/32*32, kch = npad/16;
+  double val[16];
   double m = 0.0;
-  if (c < M2)
-    for (int i = w; i < N; i += 8)
-    {
-      const double v = fabs(B[(size_t)i*M2+c]);
-      m = (v <= DBL_MAX) ? fmax(m, v) : INFINITY;     // NaN and Inf both land on Inf
-    }
-  smax[w][lane] = m;
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
+  {
+    const int i = kc*16+t;
+    val[t] = (c < M2 && i < N) ? B[(size_t)i*M2+c] : 0.0;
+    const double v = fabs(val[t]);
+    m = (v <= DBL_MAX) ? fmax(m, v) : INFINITY;     // NaN and Inf both land on Inf
+  }
+  smax[kc][lane] = m;
   __syncthreads();
   double cm = smax[0][lane];
-#pragma unroll
-  for (int ww = 1; ww < 8; ++ww) cm = fmax(cm, smax[ww][lane]);
+  for (int ww = 1; ww < kch; ++ww) cm = fmax(cm, smax[ww][lane]);
+  if (c >= M2) return;
   const bool usable = (cm > 0.0 && cm <= DBL_MAX);
   const int e = usable ? ilogb(cm)+1 : 0;
-  if (w == 0 && c < M2) scale[c] = usable ? scalbn(1.0, e-53) : (cm == 0.0 ? 0.0 : nan(""));
-  if (c >= M2) return;
-  const int npad = (N+31)/32*32, kch = npad/16;
-  int8_t * tile = Bq+(size_t)blockIdx.x*NQS_RU_NB*npad;
-  for (int i = w; i < N; i += 8)
+  if (kc == 0) scale[c] = usable ? scalbn(1.0, e-53) : (cm == 0.0 ? 0.0 : nan(""));
+  // 2^(53-e) as a bit pattern when it is a normal number (always, short of columns below 2^-960 or above 2^1020)
+  const int be = 1023+53-e;
+  const bool direct = (be >= 1 && be <= 2046);
+  const double up = direct ? __hiloint2double(be<<20, 0) : 0.0;
+  uint32_t pk[NQS_RU_NS][4];
+#pragma unroll
+  for (int s = 0; s < NQS_RU_NS; ++s) { pk[s][0] = 0u; pk[s][1] = 0u; pk[s][2] = 0u; pk[s][3] = 0u; }
+#pragma unroll
+  for (int t = 0; t < 16; ++t)
   {
-    long long Q = usable ? llrint(scalbn(B[(size_t)i*M2+c], 53-e)) : 0ll;
+    long long Q = !usable ? 0ll : (direct ? __double2ll_rn(val[t]*up) : llrint(scalbn(val[t], 53-e)));
 #pragma unroll
     for (int s = 0; s < NQS_RU_NS; ++s)
     {
       const int d = (int)((Q+128)&255)-128;
       Q = (Q-d)>>8;
-      const int n = s*NQS_RU_NC+lane;
-      tile[(size_t)(n>>3)*(kch*128)+(i>>4)*128+(n&7)*16+(i&15)] = (int8_t)d;
+      pk[s][t>>2] |= (uint32_t)(d&255)<<(8*(t&3));
     }
+  }
+  int8_t * tile = Bq+(size_t)blockIdx.x*NQS_RU_NB*npad;
+#pragma unroll
+  for (int s = 0; s < NQS_RU_NS; ++s)
+  {
+    const int n = s*NQS_RU_NC+lane;
+    *reinterpret_cast<uint4*>(tile+(size_t)(n>>3)*(kch*128)+kc*128+(n&7)*16) = make_uint4(pk[s][0], pk[s][1], pk[s][2], pk[s][3]);
   }
 }
 
@@ -119,18 +155,22 @@ __device__ __forceinline__ void ru_tmem_ld8(const uint32_t taddr, uint32_t (&v)[
 }
 
 template <int MODEL, int EPI>
-__global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const RowsArgs a, const int8_t * __restrict__ Bq, const double * __restrict__ scale)
+__global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const RowsArgs a, const int8_t * __restrict__ Bq, const double * __restrict__ scale, const int nbuf)
 {
   if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int NC = NQS_RU_NC, NS = NQS_RU_NS, NB = NQS_RU_NB;
-  const int N = a.N, M = a.M, M2 = 2*M, npad = (N+31)/32*32, kch = npad/16, nch = (M2+NC-1)/NC;
+  constexpr bool ZF = (EPI == ROWS_EPI_Z);
+  const int N = a.N, M = a.M, M2 = (EPI == ROWS_EPI_SJS) ? N : 2*M, npad = (N+31)/32*32, kch = npad/16, nch = (M2+NC-1)/NC;
   const uint32_t sbo = (uint32_t)kch*128u, chunk_bytes = (uint32_t)NB*(uint32_t)npad;
   unsigned char * As = smem_raw;                                  // [128][npad] spins, core-matrix order
-  unsigned char * Bs = As+(size_t)128*npad;                       // [2] chunk tiles
-  cd * red = reinterpret_cast<cd*>(Bs+(size_t)2*chunk_bytes);     // [4 column groups][128 chains]
-  uint64_t * bfull = reinterpret_cast<uint64_t*>(red+4*128);      // [2] chunk tile landed
-  uint64_t * mdone = bfull+2;                                     // [2] MMAs of the chunk complete
+  unsigned char * Bs = As+(size_t)128*npad;                       // [nbuf] chunk tiles
+  cd * red = reinterpret_cast<cd*>(Bs+(size_t)nbuf*chunk_bytes);  // [2][4 column groups][128 chains]: row sums, visible-bias sums
+  double * scs = reinterpret_cast<double*>(red+8*128);            // [nch*NC] column scales (0 beyond M2)
+  cd * bias_s = reinterpret_cast<cd*>(scs+(size_t)nch*NC);        // [M]
+  cd * w1o_s = bias_s+M;                                          // [M] (FFNN)
+  uint64_t * bfull = reinterpret_cast<uint64_t*>(w1o_s+M);        // [NQS_RU_MAXBUF] chunk tile landed
+  uint64_t * mdone = bfull+NQS_RU_MAXBUF;                         // [2] MMAs of the chunk complete
   uint32_t * tptr = reinterpret_cast<uint32_t*>(mdone+2);
   const int tid = threadIdx.x, lane = tid&31, w = tid>>5, q = w&3, g = w>>2, row = 32*q+lane;
   const long long kbase = (long long)blockIdx.x*128, k = kbase+row;
@@ -142,7 +182,8 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   }
   if (tid == 32)
   {
-    mbar_init(bfull, 1); mbar_init(bfull+1, 1); mbar_init(mdone, 1); mbar_init(mdone+1, 1);
+    for (int b = 0; b < NQS_RU_MAXBUF; ++b) mbar_init(bfull+b, 1);
+    mbar_init(mdone, 1); mbar_init(mdone+1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   { // spin tile: 16-byte pieces, consecutive threads along a chain's row
@@ -167,6 +208,16 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
       *reinterpret_cast<uint4*>(As+(size_t)(r>>3)*sbo+kc*128+(r&7)*16) = val;
     }
   }
+  if (EPI != ROWS_EPI_SJS)
+    for (int j = tid; j < M; j += NQS_RU_THREADS)
+    {
+      bias_s[j] = a.bias[j];
+      if (MODEL == MODEL_FFNN && EPI != ROWS_EPI_THETA) w1o_s[j] = a.w1o[j];
+    }
+  // everything above overlapped the tail of ozaki_split_kernel (programmatic dependent launch); its digit planes and scales are
+  // read from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int c = tid; c < nch*NC; c += NQS_RU_THREADS) scs[c] = (c < M2) ? scale[c] : 0.0;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A before the tensor core reads them
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -178,34 +229,69 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
 
   auto issue_tma = [&](const int c)
   {
-    mbar_expect_tx(bfull+(c&1), chunk_bytes);
-    tma_load_1d(Bs+(size_t)(c&1)*chunk_bytes, Bq+(size_t)c*chunk_bytes, chunk_bytes, bfull+(c&1));
+    const int b = c%nbuf;
+    mbar_expect_tx(bfull+b, chunk_bytes);
+    tma_load_1d(Bs+(size_t)b*chunk_bytes, Bq+(size_t)c*chunk_bytes, chunk_bytes, bfull+b);
   };
   auto issue_mma = [&](const int c)
   {
-    ru_mbar_wait(bfull+(c&1), (uint32_t)((c>>1)&1));
+    const int b = c%nbuf;
+    ru_mbar_wait(bfull+b, (uint32_t)((c/nbuf)&1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint64_t bdesc = ru_desc(smem_u32(Bs+(size_t)(c&1)*chunk_bytes), 128u, sbo);
+    const uint64_t bdesc = ru_desc(smem_u32(Bs+(size_t)b*chunk_bytes), 128u, sbo);
     for (int kk = 0; kk < npad/32; ++kk)     // 32 sites = two 16-byte K chunks = 256 bytes further along both operands
       ru_mma_i8(tbase+(uint32_t)(c&1)*NQS_RU_TBUF, adesc+(uint64_t)(kk*16), bdesc+(uint64_t)(kk*16), idesc, kk > 0 ? 1u : 0u);
     ru_commit(mdone+(c&1));
   };
   if (tid == 0)
+    for (int c = 0; c < nbuf && c < nch; ++c) issue_tma(c);
+  // while the first tiles are in flight: the factors of chunk 0 and the visible-bias term (RBM; every column group takes a
+  // quarter of the sites)
+  const unsigned char * arow = As+(size_t)(row>>3)*sbo+(row&7)*16;     // this chain's spins: site i at arow[(i/16) 128 + i%16]
+  const bool live = (k < a.K);
+  cd Tn[4], Ln[4];
+  auto fetch_factors = [&](const int c)
   {
-    issue_tma(0);
-    if (nch > 1) issue_tma(1);
-    issue_mma(0);
+    const int j0 = (c*NC+g*8)>>1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (live && j0+t < M)
+      {
+        Tn[t] = a.T[k*M+j0+t];
+        if (MODEL == MODEL_FFNN) Ln[t] = a.L[k*M+j0+t];
+      }
+  };
+  if (ZF) fetch_factors(0);
+  cd sv = cmake(0.0, 0.0);
+  if (MODEL == MODEL_RBM && EPI != ROWS_EPI_SJS && live)
+  {
+    const int per = (N+3)/4, i1 = (g+1)*per < N ? (g+1)*per : N;
+    for (int i = g*per; i < i1; ++i)
+    {
+      const double s = ZF ? (double)(int8_t)arow[(i>>4)*128+(i&15)] : (double)a.sa_spins[k*N+i];
+      const cd ai = a.avis[i];
+      sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
+    }
   }
+  if (tid == 0) issue_mma(0);
+  __syncwarp();
   cd rsum = cmake(0.0, 0.0);
   for (int c = 0; c < nch; ++c)
   {
-    // here: MMAs of chunk c issued, tile of chunk c+1 on its way; the accumulator buffer (c+1)&1 was drained before the
+    // here: MMAs of chunk c issued, later tiles on their way; the accumulator buffer (c+1)&1 was drained before the
     // __syncthreads that ended the previous iteration
     if (tid == 0 && c+1 < nch) issue_mma(c+1);
     __syncwarp();
+    cd Tv[4], Lv[4];
+    if (ZF)
+    {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { Tv[t] = Tn[t]; if (MODEL == MODEL_FFNN) Lv[t] = Ln[t]; }
+      if (c+1 < nch) fetch_factors(c+1);       // one chunk ahead: consumed after the next __syncthreads
+    }
     ru_mbar_wait(mdone+(c&1), (uint32_t)((c>>1)&1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (tid == 0 && c+2 < nch) issue_tma(c+2);     // the tile buffer c&1 is free: its MMAs completed
+    if (tid == 0 && c+nbuf < nch) issue_tma(c+nbuf);     // the tile buffer of chunk c is free: its MMAs completed
     __syncwarp();
     uint32_t v[NS][8];
     const uint32_t taddr = tbase+((uint32_t)(32*q)<<16)+(uint32_t)(c&1)*NQS_RU_TBUF+(uint32_t)(g*8);
@@ -220,23 +306,32 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
       long long tot = (long long)(int)v[NS-1][cc];
 #pragma unroll
       for (int s = NS-2; s >= 0; --s) tot = tot*256+(long long)(int)v[s][cc];
-      x[cc] = (col0+cc < M2) ? (double)tot*scale[col0+cc] : 0.0;
+      x[cc] = (double)tot*scs[col0+cc];
     }
-    if (k < a.K)
+    if (EPI == ROWS_EPI_SJS)
+    { // x = (S J)[k][col]: dot with the chain's own spins (0 in the padding)
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc)
+      {
+        const int col = col0+cc;
+        if (col < N) rsum.x = fma(x[cc], (double)(int8_t)arow[(col>>4)*128+(col&15)], rsum.x);
+      }
+    }
+    else if (live)
     {
 #pragma unroll
       for (int cc = 0; cc < 8; cc += 2)
       {
         const int j = (col0+cc)>>1;
         if (j >= M) continue;
-        const cd bj = a.bias[j];
+        const cd bj = bias_s[j];
         cd wj = cmake(1.0, 0.0);
-        if (MODEL == MODEL_FFNN && EPI != ROWS_EPI_THETA) wj = a.w1o[j];
+        if (MODEL == MODEL_FFNN && EPI != ROWS_EPI_THETA) wj = w1o_s[j];
         const cd val = cmake(x[cc]+bj.x, x[cc+1]+bj.y);
-        if (EPI == ROWS_EPI_Z)
+        if (ZF)
         {
-          cd term = cmul(a.T[k*M+j], val);
-          if (MODEL == MODEL_FFNN) term = cadd(term, cmul(a.L[k*M+j], wj));
+          cd term = cmul(Tv[cc>>1], val);
+          if (MODEL == MODEL_FFNN) term = cadd(term, cmul(Lv[cc>>1], wj));
           rsum = cadd(rsum, term);
         }
         else
@@ -254,28 +349,19 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
     __syncthreads();
   }
   red[g*128+row] = rsum;
+  red[(4+g)*128+row] = sv;
   __syncthreads();
   if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"((uint32_t)NQS_RU_TMEM_COLS) : "memory");
-  if (tid < 128 && k < a.K)
-  { // (tid < 128 <=> g == 0, row == tid) visible-bias term (RBM) and the final value of the chain, column groups in fixed order
-    cd sv = cmake(0.0, 0.0);
-    if (MODEL == MODEL_RBM)
-    {
-      const unsigned char * arow = As+(size_t)(row>>3)*sbo+(row&7)*16;
-      for (int i = 0; i < N; ++i)
-      {
-        const double s = (EPI == ROWS_EPI_Z) ? (double)(int8_t)arow[(i>>4)*128+(i&15)] : (double)a.sa_spins[k*N+i];
-        const cd ai = a.avis[i];
-        sv.x = fma(s, ai.x, sv.x); sv.y = fma(s, ai.y, sv.y);
-      }
-    }
-    cd tot = sv;
-    if (EPI != ROWS_EPI_THETA)
-      for (int gg = 0; gg < 4; ++gg) tot = cadd(tot, red[gg*128+row]);
-    if (EPI == ROWS_EPI_Z) a.zk[k] = tot;
+  if (tid < 128 && live)
+  { // (tid < 128 <=> g == 0, row == tid) the final value of the chain, column groups in fixed order
+    cd svt = cmake(0.0, 0.0), tot = cmake(0.0, 0.0);
+    for (int gg = 0; gg < 4; ++gg) { svt = cadd(svt, red[(4+gg)*128+row]); tot = cadd(tot, red[gg*128+row]); }
+    tot = cadd(tot, svt);
+    if (ZF) a.zk[k] = tot;
+    else if (EPI == ROWS_EPI_SJS) a.sjs[k] = tot.x;
     else
     {
-      if (a.sa) a.sa[k] = sv;
+      if (a.sa) a.sa[k] = svt;
       if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
     }
   }

@@ -43,10 +43,11 @@ def test_umma_theta_and_lnpsi_match_dmma_and_oracle(model, N, M, K, monkeypatch)
         e.set_params(params)
         e.initialize(spins)
         assert e.kernel_variant("theta") == ("umma_i8_ozaki7_rows" if umma else "dmma_rows"), e.kernel_variant("theta")
-        out.append((e.get_theta(), e.get_lnpsi()))
+        out.append((e.get_theta(), e.get_lnpsi(), e.get_htilda()))     # htilda: s.J.s through the same kernel (B = J)
         e.close()
     assert_close(out[0][0], out[1][0], rtol=1e-13, atol=0.0, what="theta: tcgen05 int8 vs DMMA")
     assert_close(out[0][1], out[1][1], rtol=1e-12, atol=0.0, what="lnpsi: tcgen05 int8 vs DMMA")
+    assert_close(out[0][2], out[1][2], rtol=1e-12, atol=0.0, what="local energy: tcgen05 int8 vs DMMA")
     net = o.make_ansatz(model, N, M, K)
     net.variables = params.copy()
     lnpsi = net.initialize(spins.astype(np.float64))
