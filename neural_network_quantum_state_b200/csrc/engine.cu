@@ -235,7 +235,7 @@ bool rows_umma_ok(nqs_handle * h)
     bool on = (h->K >= 64ll*128);
     if (e) on = (std::atoi(e) != 0);
     const int m2 = std::max(2*h->M, h->N);     // widest B: W / the W block of v (2M real columns), J (N columns)
-    on = on && !(h->cfg.flags & NQS_FLAG_NO_DMMA) && h->N <= 512 && rows_umma_smem(h->N, h->M, m2, 2) <= h->smem_optin;
+    on = on && !(h->cfg.flags & NQS_FLAG_NO_DMMA) && h->N <= 512 && rows_umma_smem(h->N, h->M, m2, 2, 2) <= h->smem_optin;
     if (on)
     {
       const size_t bytes = (size_t)ru_nchunks(m2)*ru_chunk_bytes(h->N);
@@ -254,8 +254,9 @@ void launch_rows_umma(nqs_handle * h, const RowsArgs & a)
   const int m2 = (EPI == ROWS_EPI_SJS) ? h->N : 2*h->M;
   ozaki_split_kernel<<<(unsigned)ru_nchunks(m2), 32*(ru_npad(h->N)/16), 0, h->stream>>>(h->N, m2, a.B, h->bq.p, h->bscale.p, EPI == ROWS_EPI_Z ? a.done : nullptr);
   check_launch(h, "ozaki_split_kernel");
-  const int nbuf = rows_umma_nbuf(h->N, h->M, m2, h->smem_optin);
-  const size_t smem = rows_umma_smem(h->N, h->M, m2, nbuf);
+  int nbuf, nt;
+  rows_umma_plan(h->N, h->M, m2, EPI == ROWS_EPI_Z, h->smem_optin, nbuf, nt);
+  const size_t smem = rows_umma_smem(h->N, h->M, m2, nbuf, nt);
   set_smem(spin_rows_umma_kernel<MODEL, EPI>, smem);
   // programmatic dependent launch: the CTAs start (TMEM allocation, spin tile) while the split kernel drains
   cudaLaunchConfig_t lc;
@@ -267,7 +268,12 @@ void launch_rows_umma(nqs_handle * h, const RowsArgs & a)
   lc.attrs = at; lc.numAttrs = 1;
   const int8_t * bq = h->bq.p;
   const double * bs = h->bscale.p;
-  NQS_CUDA(cudaLaunchKernelEx(&lc, spin_rows_umma_kernel<MODEL, EPI>, a, bq, bs, nbuf));
+  static const int trace_cta = std::getenv("NQS_RU_TRACE") ? std::atoi(std::getenv("NQS_RU_TRACE")) : -1;
+  if (const char * e = std::getenv("NQS_RU_NBUF")) { nbuf = std::max(2, std::min(std::atoi(e), NQS_RU_MAXBUF)); }
+  if (const char * e = std::getenv("NQS_RU_NT")) { if (EPI == ROWS_EPI_Z) nt = std::max(2, std::min(std::atoi(e), 4)); }
+  const size_t smem2 = rows_umma_smem(h->N, h->M, m2, nbuf, nt);
+  if (smem2 != smem) { set_smem(spin_rows_umma_kernel<MODEL, EPI>, smem2); lc.dynamicSmemBytes = smem2; }
+  NQS_CUDA(cudaLaunchKernelEx(&lc, spin_rows_umma_kernel<MODEL, EPI>, a, bq, bs, nbuf, nt, trace_cta));
   check_launch(h, "spin_rows_umma_kernel");
 }
 

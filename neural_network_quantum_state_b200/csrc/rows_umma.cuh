@@ -1,6 +1,6 @@
 // C[k][c] = sum_i s_ki B[i][c] on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) with fp64-grade
 // results: the spins are +-1 (exact in int8) and B is split ERROR-FREE into 7 signed base-256 digits per column (an Ozaki
-// split with one power-of-two scale per column), so every int32 accumulator is exact and the digits are recombined in int64:
+// split with one power-of-two scale per column), so every int32 accumulator is exact and so is their recombination up to one final rounding:
 //
 //   B[i][c] ~ Q[i][c] 2^(e_c-53),  Q = rint(B 2^(53-e_c)),  |Q| <= 2^53,  2^(e_c-1) <= max_i |B[i][c]| < 2^e_c
 //   Q = sum_{s<7} d_s 256^s, d_s in [-128, 127]           (balanced digits: int8)
@@ -8,8 +8,8 @@
 //                                                                          B operand carries the 7 digit planes side by side
 //
 // The only rounding is Q's: |error| <= N 2^(e_c-54) <= N 2^-53 max_i|B[i][c]| per output, below the rounding error bound of the
-// fp64 dot product it replaces (N 2^-53 sum_i |B[i][c]|); the final int64 -> double conversion adds one more rounding.
-// N <= 512 keeps |sum| <= N 2^53 inside int64.
+// fp64 dot product it replaces (N 2^-53 sum_i |B[i][c]|); the recombination of the planes adds one more rounding.
+// N <= 512 keeps every partial recombination exact (|acc_s| <= 128 N = 2^16).
 //
 // Same operands, outputs and epilogues as spin_rows_dmma_kernel (sv_struct.cuh): theta = S W + b with the log cosh row sum
 // (ref: Zgemm + logcosh pass, gpu/include/impl_neural_quantum_state.cuh:78,114) and z = O v from the factors of O.
@@ -20,10 +20,13 @@
 // ozaki_split_kernel and fetched with one 1-D TMA bulk copy per chunk (ring of up to 6 tiles).  One MMA of 128 x 224 x 32 per
 // 32 sites; D = 224 TMEM columns, double-buffered (448 of 512), so the MMAs of chunk c+1 run under the epilogue of chunk c.
 // Epilogue: 16 warps = 4 lane quadrants x 4 column groups; a thread owns one chain and 8 real columns of the chunk:
-// 7 tcgen05.ld (32x32b.x8), Horner in int64, one I2F, scale, then the complex epilogue of the DMMA kernel.  The chunks run in
+// 7 tcgen05.ld (32x32b.x8), the planes recombined (pairs in int32, pairs of pairs in fp64), scale, then the complex epilogue of
+// the DMMA kernel.  The chunks run in
 // lockstep (one __syncthreads each), so nothing with a global-memory latency may sit inside the chunk loop: scales, biases and
 // output weights are staged in shared memory, the factors T (L) of the next chunk are fetched one chunk ahead, and the
-// visible-bias sum is taken while the first tile is still in flight (measured with in-kernel clocks: 4500 -> cycles per chunk).
+// visible-bias sum is taken while the first tile is still in flight, and T / theta go through shared memory so that global
+// memory sees whole 256-byte runs (in-kernel clocks: 4500 cycles per chunk before, of which 2000 were LSU wavefronts of the
+// thread-per-chain T loads and 1500 two dependent L2 round trips for scales and biases).
 // The kernel is launched with programmatic stream serialization: TMEM allocation, barrier setup and the spin tile overlap the
 // tail of ozaki_split_kernel.
 #pragma once
@@ -40,24 +43,29 @@ namespace nqs
 #define NQS_RU_TMEM_COLS 512
 #define NQS_RU_TBUF 256                       // TMEM column stride between the two accumulator buffers
 #define NQS_RU_MAXBUF 6                       // tile buffers in flight
+#define NQS_RU_TPITCH 272                     // bytes per chain in the staged tile of T / theta: 16 hidden units + 16 (LDS.128 conflict-free)
+#define NQS_RU_TTILE (128*NQS_RU_TPITCH)
 
 inline int ru_npad(const int N) { return (N+31)/32*32; }
 inline size_t ru_chunk_bytes(const int N) { return (size_t)NQS_RU_NB*ru_npad(N); }
 inline int ru_nchunks(const int M2) { return (M2+NQS_RU_NC-1)/NQS_RU_NC; }
-// spin tile | nbuf chunk tiles | row sums + visible-bias sums [8][128] | scales [chunks*32] | bias [M] | w1o [M] | barriers
-inline size_t rows_umma_smem(const int N, const int M, const int M2, const int nbuf)
+// spin tile | nbuf chunk tiles | scales [chunks*32] | bias [M] | w1o [M] | 2 staged tiles of T (in) or theta (out), reused for
+// the row sums [8][128] after the chunk loop | barriers
+inline size_t rows_umma_smem(const int N, const int M, const int M2, const int nbuf, const int nt)
 {
-  return (size_t)128*ru_npad(N)+(size_t)nbuf*ru_chunk_bytes(N)+(size_t)8*128*sizeof(cd)+(size_t)ru_nchunks(M2)*NQS_RU_NC*sizeof(double)
-        +(size_t)2*M*sizeof(cd)+128;
+  return (size_t)128*ru_npad(N)+(size_t)nbuf*ru_chunk_bytes(N)+(size_t)ru_nchunks(M2)*NQS_RU_NC*sizeof(double)
+        +(size_t)2*M*sizeof(cd)+(size_t)nt*NQS_RU_TTILE+128;
 }
-// as many tile buffers as fit: the TMA of a chunk is issued several chunks ahead of its MMAs
-inline int rows_umma_nbuf(const int N, const int M, const int M2, const size_t smem_limit)
+// Buffers in flight.  Both streams are consumed in lockstep with the chunks, so each must be issued far enough ahead to cover
+// its latency (about two epilogues for the L2-resident digit planes, three for T from HBM): as many as fit, T first.
+inline void rows_umma_plan(const int N, const int M, const int M2, const bool stream_T, const size_t smem_limit, int & nbuf, int & nt)
 {
-  int nb = NQS_RU_MAXBUF;
-  if (nb > ru_nchunks(M2)) nb = ru_nchunks(M2);
-  if (nb < 2) nb = 2;
-  while (nb > 2 && rows_umma_smem(N, M, M2, nb) > smem_limit) --nb;
-  return nb;
+  const int nch = ru_nchunks(M2);
+  nt = 2; nbuf = 2;
+  if (stream_T)
+    while (nt < 4 && nt < nch && rows_umma_smem(N, M, M2, nbuf, nt+1) <= smem_limit) ++nt;
+  while (nbuf < NQS_RU_MAXBUF && nbuf < nch && rows_umma_smem(N, M, M2, nbuf+1, nt) <= smem_limit) ++nbuf;
+  if (stream_T && nbuf < 3 && nt > 3 && rows_umma_smem(N, M, M2, 3, nt-1) <= smem_limit) { nbuf = 3; --nt; }
 }
 
 // B [N][M2] -> digit planes in the UMMA tile order + scale[c] = 2^(e_c-53) (0 for an all-zero column, NaN for a column holding
@@ -155,7 +163,7 @@ __device__ __forceinline__ void ru_tmem_ld8(const uint32_t taddr, uint32_t (&v)[
 }
 
 template <int MODEL, int EPI>
-__global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const RowsArgs a, const int8_t * __restrict__ Bq, const double * __restrict__ scale, const int nbuf)
+__global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const RowsArgs a, const int8_t * __restrict__ Bq, const double * __restrict__ scale, const int nbuf, const int nt, const int trace_cta)
 {
   if (EPI == ROWS_EPI_Z && a.done != nullptr && *a.done) return;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -165,15 +173,22 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   const uint32_t sbo = (uint32_t)kch*128u, chunk_bytes = (uint32_t)NB*(uint32_t)npad;
   unsigned char * As = smem_raw;                                  // [128][npad] spins, core-matrix order
   unsigned char * Bs = As+(size_t)128*npad;                       // [nbuf] chunk tiles
-  cd * red = reinterpret_cast<cd*>(Bs+(size_t)nbuf*chunk_bytes);  // [2][4 column groups][128 chains]: row sums, visible-bias sums
-  double * scs = reinterpret_cast<double*>(red+8*128);            // [nch*NC] column scales (0 beyond M2)
+  double * scs = reinterpret_cast<double*>(Bs+(size_t)nbuf*chunk_bytes);     // [nch*NC] column scales (0 beyond M2)
   cd * bias_s = reinterpret_cast<cd*>(scs+(size_t)nch*NC);        // [M]
   cd * w1o_s = bias_s+M;                                          // [M] (FFNN)
-  uint64_t * bfull = reinterpret_cast<uint64_t*>(w1o_s+M);        // [NQS_RU_MAXBUF] chunk tile landed
+  unsigned char * Ts = reinterpret_cast<unsigned char*>(w1o_s+M); // [nt][128][NQS_RU_TPITCH]: T of a chunk (Z; nt-1 chunks ahead) / theta of a chunk (THETA, LNPSI; 2)
+  cd * red = reinterpret_cast<cd*>(Ts);                           // [2][4 column groups][128 chains] row sums, visible-bias sums: after the loop
+  uint64_t * bfull = reinterpret_cast<uint64_t*>(Ts+(size_t)nt*NQS_RU_TTILE);   // [NQS_RU_MAXBUF] chunk tile landed
   uint64_t * mdone = bfull+NQS_RU_MAXBUF;                         // [2] MMAs of the chunk complete
   uint32_t * tptr = reinterpret_cast<uint32_t*>(mdone+2);
   const int tid = threadIdx.x, lane = tid&31, w = tid>>5, q = w&3, g = w>>2, row = 32*q+lane;
   const long long kbase = (long long)blockIdx.x*128, k = kbase+row;
+  // NQS_RU_TRACE=<cta>: thread 96 of that CTA prints the clocks of the prologue and of the phases of chunks 4..7
+  const bool trace = (trace_cta >= 0 && (int)blockIdx.x == trace_cta && tid == 96);
+  long long ts[32];
+  int nts = 0;
+#define NQS_RU_STAMP() do { if (trace && nts < 32) ts[nts++] = clock64(); } while (0)
+  NQS_RU_STAMP();
 
   if (w == 0)
   {
@@ -186,6 +201,40 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
     mbar_init(mdone, 1); mbar_init(mdone+1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // T of a chunk ([128 chains][16 hidden units]) / theta of a chunk travel through shared memory so that global memory sees
+  // 256-byte runs per chain (a thread-per-chain access touches 32 cache lines per warp instruction: measured 2000 cycles per
+  // chunk of LSU time).  idx -> (chain, 16-byte piece): 16 consecutive lanes cover one chain's 256 bytes.
+  auto stage_T = [&](const int c)       // always commits a group (empty beyond the last chunk): the waits count groups
+  {
+    if (c < nch)
+    {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+      {
+        const int idx = tid+NQS_RU_THREADS*t, r = idx>>4, j = c*(NC/2)+(idx&15);
+        const bool ok = (kbase+r < a.K && j < M);
+        cp_async16(Ts+(size_t)(c%nt)*NQS_RU_TTILE+r*NQS_RU_TPITCH+(idx&15)*16, ok ? a.T+(kbase+r)*M+j : a.T, ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+  auto wait_T = [&]()                   // all but the newest nt-2 groups have landed
+  {
+    if (nt == 2) cp_async_wait<0>(); else if (nt == 3) cp_async_wait<1>(); else cp_async_wait<2>();
+  };
+  auto flush_theta = [&](const int c)
+  {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+    {
+      const int idx = tid+NQS_RU_THREADS*t, r = idx>>4, j = c*(NC/2)+(idx&15);
+      if (kbase+r < a.K && j < M)
+        a.theta[(kbase+r)*M+j] = *reinterpret_cast<const cd*>(Ts+(size_t)(c&1)*NQS_RU_TTILE+r*NQS_RU_TPITCH+(idx&15)*16);
+    }
+  };
+  const bool store_theta = (!ZF && EPI != ROWS_EPI_SJS && a.theta != nullptr);
+  if (ZF)
+    for (int c = 0; c < nt-1; ++c) stage_T(c);
   { // spin tile: 16-byte pieces, consecutive threads along a chain's row
     const bool vec = (N%16 == 0) && ((reinterpret_cast<size_t>(a.spins)&15) == 0);
     for (int idx = tid; idx < 128*kch; idx += NQS_RU_THREADS)
@@ -218,11 +267,13 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   // read from here on
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int c = tid; c < nch*NC; c += NQS_RU_THREADS) scs[c] = (c < M2) ? scale[c] : 0.0;
+  if (ZF) wait_T();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of A before the tensor core reads them
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tbase = *tptr;
+  NQS_RU_STAMP();
   // instruction descriptor: D = s32, A = B = s8, both K-major, N = 224, M = 128
   constexpr uint32_t idesc = (2u<<4)|(1u<<7)|(1u<<10)|((uint32_t)(NB>>3)<<17)|((128u>>4)<<24);
   const uint64_t adesc = ru_desc(smem_u32(As), 128u, sbo);
@@ -249,19 +300,15 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   // quarter of the sites)
   const unsigned char * arow = As+(size_t)(row>>3)*sbo+(row&7)*16;     // this chain's spins: site i at arow[(i/16) 128 + i%16]
   const bool live = (k < a.K);
-  cd Tn[4], Ln[4];
-  auto fetch_factors = [&](const int c)
+  cd Ln[4];
+  auto fetch_L = [&](const int c)       // FFNN: log cosh theta of the next chunk, thread-per-chain (no room to stage it as well)
   {
     const int j0 = (c*NC+g*8)>>1;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      if (live && j0+t < M)
-      {
-        Tn[t] = a.T[k*M+j0+t];
-        if (MODEL == MODEL_FFNN) Ln[t] = a.L[k*M+j0+t];
-      }
+      if (live && j0+t < M) Ln[t] = a.L[k*M+j0+t];
   };
-  if (ZF) fetch_factors(0);
+  if (ZF && MODEL == MODEL_FFNN) fetch_L(0);
   cd sv = cmake(0.0, 0.0);
   if (MODEL == MODEL_RBM && EPI != ROWS_EPI_SJS && live)
   {
@@ -275,6 +322,7 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   }
   if (tid == 0) issue_mma(0);
   __syncwarp();
+  NQS_RU_STAMP();
   cd rsum = cmake(0.0, 0.0);
   for (int c = 0; c < nch; ++c)
   {
@@ -282,15 +330,22 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
     // __syncthreads that ended the previous iteration
     if (tid == 0 && c+1 < nch) issue_mma(c+1);
     __syncwarp();
-    cd Tv[4], Lv[4];
+    cd Lv[4];
     if (ZF)
     {
+      if (MODEL == MODEL_FFNN)
+      {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) { Tv[t] = Tn[t]; if (MODEL == MODEL_FFNN) Lv[t] = Ln[t]; }
-      if (c+1 < nch) fetch_factors(c+1);       // one chunk ahead: consumed after the next __syncthreads
+        for (int t = 0; t < 4; ++t) Lv[t] = Ln[t];
+        if (c+1 < nch) fetch_L(c+1);
+      }
+      stage_T(c+nt-1);                         // nt-1 chunks ahead, into the buffer chunk c-1 was read from
     }
+    else if (store_theta && c > 0) flush_theta(c-1);
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
     ru_mbar_wait(mdone+(c&1), (uint32_t)((c>>1)&1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
     if (tid == 0 && c+nbuf < nch) issue_tma(c+nbuf);     // the tile buffer of chunk c is free: its MMAs completed
     __syncwarp();
     uint32_t v[NS][8];
@@ -298,15 +353,19 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
 #pragma unroll
     for (int s = 0; s < NS; ++s) ru_tmem_ld8(taddr+(uint32_t)(s*NC), v[s]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
     const int col0 = c*NC+g*8;
+    // sum_s 256^s acc_s: planes are first paired in int32 (|acc| <= 128 N <= 2^16, so acc_s + 256 acc_{s+1} < 2^25: exact), the
+    // four pairs are then combined in fp64 (every term exact, two roundings of the running sum: ~1 ulp of the result)
     double x[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc)
     {
-      long long tot = (long long)(int)v[NS-1][cc];
-#pragma unroll
-      for (int s = NS-2; s >= 0; --s) tot = tot*256+(long long)(int)v[s][cc];
-      x[cc] = (double)tot*scs[col0+cc];
+      const int p0 = (int)v[0][cc]+256*(int)v[1][cc], p1 = (int)v[2][cc]+256*(int)v[3][cc], p2 = (int)v[4][cc]+256*(int)v[5][cc];
+      double tot = fma((double)(int)v[6][cc], 65536.0, (double)p2);      // exact (< 2^33), and so is the next step (< 2^49)
+      tot = fma(tot, 65536.0, (double)p1);
+      tot = fma(tot, 65536.0, (double)p0);
+      x[cc] = tot*scs[col0+cc];
     }
     if (EPI == ROWS_EPI_SJS)
     { // x = (S J)[k][col]: dot with the chain's own spins (0 in the padding)
@@ -330,13 +389,14 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
         const cd val = cmake(x[cc]+bj.x, x[cc+1]+bj.y);
         if (ZF)
         {
-          cd term = cmul(Tv[cc>>1], val);
+          const cd Tkj = *reinterpret_cast<const cd*>(Ts+(size_t)(c%nt)*NQS_RU_TTILE+row*NQS_RU_TPITCH+(g*4+(cc>>1))*16);
+          cd term = cmul(Tkj, val);
           if (MODEL == MODEL_FFNN) term = cadd(term, cmul(Lv[cc>>1], wj));
           rsum = cadd(rsum, term);
         }
         else
         {
-          if (a.theta) a.theta[k*M+j] = val;
+          if (store_theta) *reinterpret_cast<cd*>(Ts+(size_t)(c&1)*NQS_RU_TTILE+row*NQS_RU_TPITCH+(g*4+(cc>>1))*16) = val;
           if (EPI == ROWS_EPI_LNPSI)
           {
             const cd lc = c_logcosh(val);
@@ -345,9 +405,15 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
         }
       }
     }
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
+    if (ZF) wait_T();                          // T of chunk c+1 has landed (this thread's pieces; the barrier covers the rest)
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (c >= 3 && c < 8) NQS_RU_STAMP();
   }
+  NQS_RU_STAMP();
+  if (store_theta) { flush_theta(nch-1); __syncthreads(); }     // red[] lives in the staging tiles
   red[g*128+row] = rsum;
   red[(4+g)*128+row] = sv;
   __syncthreads();
@@ -365,6 +431,15 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
       if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
     }
   }
+  if (trace)
+  {
+    NQS_RU_STAMP();
+    printf("ru trace EPI %d nbuf %d nt %d | prologue %lld first-issue %lld | chunk 3 ends %lld |", EPI, nbuf, nt, ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2]);
+    for (int i = 4; i+5 < nts-1; i += 6)
+      printf(" [top %lld mma-wait %lld ldtm %lld epi %lld T-wait %lld sync %lld]", ts[i]-ts[i-1], ts[i+1]-ts[i], ts[i+2]-ts[i+1], ts[i+3]-ts[i+2], ts[i+4]-ts[i+3], ts[i+5]-ts[i+4]);
+    printf(" | rest of loop %lld tail %lld\n", ts[nts-2]-ts[nts-3], ts[nts-1]-ts[nts-2]);
+  }
+#undef NQS_RU_STAMP
 }
 
 } // namespace nqs
