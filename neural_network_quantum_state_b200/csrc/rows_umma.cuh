@@ -25,8 +25,11 @@
 // lockstep (one __syncthreads each), so nothing with a global-memory latency may sit inside the chunk loop: scales, biases and
 // output weights are staged in shared memory, the factors T (L) of the next chunk are fetched one chunk ahead, and the
 // visible-bias sum is taken while the first tile is still in flight, and T / theta go through shared memory so that global
-// memory sees whole 256-byte runs (in-kernel clocks: 4500 cycles per chunk before, of which 2000 were LSU wavefronts of the
-// thread-per-chain T loads and 1500 two dependent L2 round trips for scales and biases).
+// memory sees whole 256-byte runs.  In-kernel clocks per chunk (cfg3, Z epilogue): 4500 cycles at first -- 2000 of them LSU
+// wavefronts of thread-per-chain T loads, 1500 two dependent L2 round trips for scales and biases -- and 3100 now: 1230 the
+// recombination + complex epilogue (fp64 pipe), 800 issuing the cp.async of the next T tile, 200 tcgen05.ld, 150 waiting for
+// the MMAs; the tensor core itself needs 450.  Next: a dedicated issue warp and mbarrier hand-offs instead of the
+// per-chunk __syncthreads (the 16 epilogue warps then stop running in lockstep).
 // The kernel is launched with programmatic stream serialization: TMEM allocation, barrier setup and the spin tile overlap the
 // tail of ozaki_split_kernel.
 #pragma once
@@ -183,11 +186,16 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   uint32_t * tptr = reinterpret_cast<uint32_t*>(mdone+2);
   const int tid = threadIdx.x, lane = tid&31, w = tid>>5, q = w&3, g = w>>2, row = 32*q+lane;
   const long long kbase = (long long)blockIdx.x*128, k = kbase+row;
-  // NQS_RU_TRACE=<cta>: thread 96 of that CTA prints the clocks of the prologue and of the phases of chunks 4..7
+  // Built with -DNQS_RU_TRACE_BUILD and run with NQS_RU_TRACE=<cta>: thread 96 of that CTA prints the clocks of the prologue and
+  // of the phases of chunks 4..7 (how the numbers in the header were measured; off by default: the stamps cost a stack frame)
+#ifdef NQS_RU_TRACE_BUILD
   const bool trace = (trace_cta >= 0 && (int)blockIdx.x == trace_cta && tid == 96);
-  long long ts[32];
+  long long ts[36];
   int nts = 0;
-#define NQS_RU_STAMP() do { if (trace && nts < 32) ts[nts++] = clock64(); } while (0)
+#define NQS_RU_STAMP() do { if (trace && nts < 36) ts[nts++] = clock64(); } while (0)
+#else
+#define NQS_RU_STAMP() do { } while (0)
+#endif
   NQS_RU_STAMP();
 
   if (w == 0)
@@ -204,6 +212,7 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
   // T of a chunk ([128 chains][16 hidden units]) / theta of a chunk travel through shared memory so that global memory sees
   // 256-byte runs per chain (a thread-per-chain access touches 32 cache lines per warp instruction: measured 2000 cycles per
   // chunk of LSU time).  idx -> (chain, 16-byte piece): 16 consecutive lanes cover one chain's 256 bytes.
+  int tb_next = 0, tb_cur = 0;          // staging buffers of the next chunk to fetch / of the chunk being consumed (c % nt)
   auto stage_T = [&](const int c)       // always commits a group (empty beyond the last chunk): the waits count groups
   {
     if (c < nch)
@@ -213,8 +222,9 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
       {
         const int idx = tid+NQS_RU_THREADS*t, r = idx>>4, j = c*(NC/2)+(idx&15);
         const bool ok = (kbase+r < a.K && j < M);
-        cp_async16(Ts+(size_t)(c%nt)*NQS_RU_TTILE+r*NQS_RU_TPITCH+(idx&15)*16, ok ? a.T+(kbase+r)*M+j : a.T, ok ? 16 : 0);
+        cp_async16(Ts+(size_t)tb_next*NQS_RU_TTILE+r*NQS_RU_TPITCH+(idx&15)*16, ok ? a.T+(kbase+r)*M+j : a.T, ok ? 16 : 0);
       }
+      tb_next = (tb_next+1 == nt) ? 0 : tb_next+1;
     }
     cp_async_commit();
   };
@@ -330,6 +340,7 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
     // __syncthreads that ended the previous iteration
     if (tid == 0 && c+1 < nch) issue_mma(c+1);
     __syncwarp();
+    if (c >= 4 && c < 8) NQS_RU_STAMP();
     cd Lv[4];
     if (ZF)
     {
@@ -355,17 +366,19 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     if (c >= 4 && c < 8) NQS_RU_STAMP();
     const int col0 = c*NC+g*8;
-    // sum_s 256^s acc_s: planes are first paired in int32 (|acc| <= 128 N <= 2^16, so acc_s + 256 acc_{s+1} < 2^25: exact), the
-    // four pairs are then combined in fp64 (every term exact, two roundings of the running sum: ~1 ulp of the result)
+    // sum_s 256^s acc_s with as little fp64-pipe work as possible (the conversions and FMAs of this recombination were the
+    // longest phase of a chunk): planes are paired in int32 (|acc| <= 128 N <= 2^16: acc_s + 256 acc_{s+1} < 2^25), pairs in
+    // int64 (lo = planes 0..3 < 2^41, hi = planes 4..6 < 2^33), both converted by the 2^52+2^51 bias trick (an integer add
+    // and one DADD instead of I2F), then hi 2^32 + lo in one FMA: a single rounding.
     double x[8];
 #pragma unroll
     for (int cc = 0; cc < 8; ++cc)
     {
       const int p0 = (int)v[0][cc]+256*(int)v[1][cc], p1 = (int)v[2][cc]+256*(int)v[3][cc], p2 = (int)v[4][cc]+256*(int)v[5][cc];
-      double tot = fma((double)(int)v[6][cc], 65536.0, (double)p2);      // exact (< 2^33), and so is the next step (< 2^49)
-      tot = fma(tot, 65536.0, (double)p1);
-      tot = fma(tot, 65536.0, (double)p0);
-      x[cc] = tot*scs[col0+cc];
+      const long long lo = (long long)p1*65536+(long long)p0, hi = (long long)(int)v[6][cc]*65536+(long long)p2;
+      const double dlo = __longlong_as_double(0x4338000000000000ll+lo)-6755399441055744.0;
+      const double dhi = __longlong_as_double(0x4338000000000000ll+hi)-6755399441055744.0;
+      x[cc] = fma(dhi, 4294967296.0, dlo)*scs[col0+cc];
     }
     if (EPI == ROWS_EPI_SJS)
     { // x = (S J)[k][col]: dot with the chain's own spins (0 in the padding)
@@ -389,10 +402,10 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
         const cd val = cmake(x[cc]+bj.x, x[cc+1]+bj.y);
         if (ZF)
         {
-          const cd Tkj = *reinterpret_cast<const cd*>(Ts+(size_t)(c%nt)*NQS_RU_TTILE+row*NQS_RU_TPITCH+(g*4+(cc>>1))*16);
-          cd term = cmul(Tkj, val);
-          if (MODEL == MODEL_FFNN) term = cadd(term, cmul(Lv[cc>>1], wj));
-          rsum = cadd(rsum, term);
+          const cd Tkj = *reinterpret_cast<const cd*>(Ts+(size_t)tb_cur*NQS_RU_TTILE+row*NQS_RU_TPITCH+(g*4+(cc>>1))*16);
+          rsum.x = fma(Tkj.x, val.x, rsum.x); rsum.x = fma(-Tkj.y, val.y, rsum.x);
+          rsum.y = fma(Tkj.x, val.y, rsum.y); rsum.y = fma(Tkj.y, val.x, rsum.y);
+          if (MODEL == MODEL_FFNN) rsum = cadd(rsum, cmul(Lv[cc>>1], wj));
         }
         else
         {
@@ -405,6 +418,7 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
         }
       }
     }
+    if (ZF) tb_cur = (tb_cur+1 == nt) ? 0 : tb_cur+1;
     if (c >= 4 && c < 8) NQS_RU_STAMP();
     if (ZF) wait_T();                          // T of chunk c+1 has landed (this thread's pieces; the barrier covers the rest)
     if (c >= 4 && c < 8) NQS_RU_STAMP();
@@ -431,14 +445,17 @@ __global__ void __launch_bounds__(NQS_RU_THREADS, 1) spin_rows_umma_kernel(const
       if (EPI == ROWS_EPI_LNPSI) a.lnpsi[k] = tot;
     }
   }
+#ifdef NQS_RU_TRACE_BUILD
   if (trace)
   {
     NQS_RU_STAMP();
     printf("ru trace EPI %d nbuf %d nt %d | prologue %lld first-issue %lld | chunk 3 ends %lld |", EPI, nbuf, nt, ts[1]-ts[0], ts[2]-ts[1], ts[3]-ts[2]);
-    for (int i = 4; i+5 < nts-1; i += 6)
-      printf(" [top %lld mma-wait %lld ldtm %lld epi %lld T-wait %lld sync %lld]", ts[i]-ts[i-1], ts[i+1]-ts[i], ts[i+2]-ts[i+1], ts[i+3]-ts[i+2], ts[i+4]-ts[i+3], ts[i+5]-ts[i+4]);
+    for (int i = 4; i+6 < nts-1; i += 7)
+      printf(" [issue %lld stage %lld mma-wait %lld ldtm %lld epi %lld T-wait %lld sync %lld]", ts[i]-ts[i-1], ts[i+1]-ts[i], ts[i+2]-ts[i+1], ts[i+3]-ts[i+2],
+             ts[i+4]-ts[i+3], ts[i+5]-ts[i+4], ts[i+6]-ts[i+5]);
     printf(" | rest of loop %lld tail %lld\n", ts[nts-2]-ts[nts-3], ts[nts-1]-ts[nts-2]);
   }
+#endif
 #undef NQS_RU_STAMP
 }
 
