@@ -92,7 +92,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         build_host()
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
+    extra = os.environ.get("NQS_NVCC_EXTRA", "").split()     # e.g. -DNQS_RU_TRACE_BUILD (in-kernel phase clocks of the UMMA kernels)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-Xlinker", "-soname=libnqs_b200.so"]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image exports a wrapper g++ that nvcc must not pick up

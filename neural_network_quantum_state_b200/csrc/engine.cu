@@ -890,6 +890,14 @@ void launch_hidden_values(nqs_handle * h)
     spins_to_double_kernel<<<grid_for((long long)h->K*h->N, 256, 148*8), 256, 0, h->stream>>>((long long)h->K*h->N, h->spins.p, h->Sd.p);
     check_launch(h, "spins_to_double_kernel");
   }
+  if (h->cols_umma)
+  { // per-hidden-unit bound of |T| for the int8 split of conj(T) z (cols_umma.cuh); T is fixed until the next sweep
+    NQS_CUDA(cudaMemsetAsync(h->tmaxb.p, 0, sizeof(unsigned long long)*(size_t)h->M, h->stream));
+    const long long rpb = std::max<long long>(64, (h->K+63)/64);
+    dim3 cg((unsigned)((h->M+31)/32), (unsigned)((h->K+rpb-1)/rpb));
+    colmax_abs_kernel<<<cg, 256, 0, h->stream>>>(h->K, h->M, h->Tm.p, h->tmaxb.p, rpb);
+    check_launch(h, "colmax_abs_kernel");
+  }
   h->hidden_valid = true;
   h->theta_matches_O = true;   // the factors (spins, theta, params) are what S is built from: structured setup sums allowed
 }
@@ -903,6 +911,26 @@ void plan_cols(nqs_handle * h)
 {
   h->cols_ok = false;
   if (h->N > 256 || (h->cfg.flags & NQS_FLAG_NO_DMMA) || h->trsymm) return;    // (tied weights: the rows of O are not outer products)
+  { // tcgen05 int8 kernel (cols_umma.cuh): 128 sites per MMA, one CTA per SM; pays once a rank holds enough chains to give
+    // every CTA several 64-chain blocks.  NQS_COLS_UMMA=0/1 overrides.
+    const char * e = std::getenv("NQS_COLS_UMMA");
+    bool on = (h->K >= 8192);
+    if (e) on = (std::atoi(e) != 0);
+    on = on && h->N <= 128 && cols_umma_smem() <= h->smem_optin;
+    if (on)
+    {
+      const int colgroups = (2*h->M+NQS_CU_NCC-1)/NQS_CU_NCC;
+      long long nchunks = std::max(1, h->sm_count/colgroups);
+      nchunks = std::min<long long>(nchunks, (h->K+NQS_CU_KB-1)/NQS_CU_KB);
+      long long rpc = (h->K+nchunks-1)/nchunks;
+      rpc = (rpc+NQS_CU_KB-1)/NQS_CU_KB*NQS_CU_KB;
+      h->sc_variant = -1; h->sc_colgroups = colgroups; h->sc_rows_per_chunk = rpc; h->sc_nchunks = (int)((h->K+rpc-1)/rpc);
+      h->cols_umma = 1;
+      h->tmaxb.alloc((size_t)h->M);
+      h->cols_ok = true;
+      return;
+    }
+  }
   const int var = cols_variant_for(h->N);
   const int cw = cols_dmma_cw(kColsVariants[var][1], kColsVariants[var][2]);
   const int colgroups = (2*h->M+cw-1)/cw;
@@ -922,6 +950,11 @@ void plan_struct(nqs_handle * h)
     "NQS_FLAG_STRUCTURED_SV excludes NQS_FLAG_SETUP_FROM_O / NQS_FLAG_TWO_PASS_SV / NQS_FLAG_NO_DMMA");
   const int var = h->sc_variant;
   h->struct_sv = true;
+  if (h->cols_umma)
+  {
+    h->variant_sv = "structured_umma_i8_ozaki7_colgroups"+std::to_string(h->sc_colgroups)+"_chunks"+std::to_string(h->sc_nchunks);
+    return;
+  }
   h->variant_sv = "structured_dmma_mtw"+std::to_string(kColsVariants[var][0])+"_ntw"+std::to_string(kColsVariants[var][1])+
     "_wm"+std::to_string(kColsVariants[var][2])+"_colgroups"+std::to_string(h->sc_colgroups)+"_chunks"+std::to_string(h->sc_nchunks);
 }
@@ -937,6 +970,17 @@ void launch_cols_dmma_t(nqs_handle * h, const ColsArgs & a)
 template <int MODEL>
 void launch_cols_dmma(nqs_handle * h, const ColsArgs & a)
 {
+  if (h->cols_umma)
+  {
+    ColsUmmaArgs ua;
+    ua.c = a; ua.tmax = h->tmaxb.p;
+    const size_t smem = cols_umma_smem();
+    set_smem(spin_cols_umma_kernel<MODEL>, smem);
+    dim3 grid((unsigned)h->sc_colgroups, (unsigned)h->sc_nchunks, a.zmode == 1 ? 2u : 1u);
+    spin_cols_umma_kernel<MODEL><<<grid, NQS_CU_THREADS, smem, h->stream>>>(ua);
+    check_launch(h, "spin_cols_umma_kernel");
+  }
+  else
   switch (h->sc_variant)
   {
     case 0: launch_cols_dmma_t<MODEL, 1, 8, 2>(h, a); break;
@@ -1250,6 +1294,9 @@ bool cg_finish_async(nqs_handle * h, double lambda, int max_iter, int fixed_iter
   while (!s.nonfinite && !s.done && enq < n_max)
   {
     more = true;
+    // the update enqueued behind the first batch declined on the device (`done` was not set): parameters, theta and the
+    // hidden-unit factors are still those of this step, whatever do_evolve() recorded on the host
+    if (h->struct_sv) h->hidden_valid = true;
     const int n_here = std::min(2, n_max-enq);
     for (int q = 0; q < n_here; ++q)
     {

@@ -12,6 +12,7 @@
 #include "ffnn_fast_kernels.cuh"
 #include "sweep_f32.cuh"
 #include "rows_umma.cuh"
+#include "cols_umma.cuh"
 
 namespace nqs
 {
@@ -117,6 +118,8 @@ struct nqs_handle
   nqs::DevBuf<nqs::cd> Tm, Lm, vnat;
   nqs::DevBuf<int8_t> bq;                 // rows_umma.cuh: int8 digit planes of the B operand (W, or the W block of v), UMMA tile order
   nqs::DevBuf<double> bscale;             // their per-column power-of-two scales [2M]
+  nqs::DevBuf<unsigned long long> tmaxb;  // cols_umma.cuh: bit patterns of max_k |T_kj|_inf per hidden unit [M]
+  int cols_umma = 0;                      // 1: the O^H z / SR-setup GEMM runs on tcgen05 (int8 UMMA), 0: fp64 DMMA
   int rows_umma = -1;                     // -1 undecided, 0 fp64 DMMA rows kernel, 1 tcgen05 int8 (Ozaki) rows kernel
   nqs::DevBuf<double> Sd;                 // [K][N] spins as doubles: factor rows of the O-generating S*v (sv_fused.cuh, GEN)
   bool gen_ok = false, o_pending = false; // O is written by the first S*v of the CG instead of a separate writer / it still has to be
