@@ -532,16 +532,19 @@ def main():
         u_bufs = [torch.empty((N, K_loc), dtype=torch.float64, pin_memory=True) for _ in range(n_e2e)]
         for ub in u_bufs:
             ub.numpy()[...] = rng.random((N, K_loc))
+        # page-locked result buffers (a user who reads the samples back every step keeps them around)
+        spins_out = torch.empty((K_loc, N), dtype=torch.int8, pin_memory=True).numpy()
+        lnpsi_out = torch.empty((K_loc,), dtype=torch.complex128, pin_memory=True).numpy()
         restart()
         e2e_iters = []
         barrier()
         t0 = time.perf_counter()
         for i in range(n_e2e):
-            e.set_uniforms(u_bufs[i].numpy())   # H2D inside the timed region
+            e.set_uniforms(u_bufs[i].numpy())   # pinned: read in place over PCIe by the sweep (inside the timed region)
             st = step()
             e2e_iters.append(st.cg_iters)
-            spins = e.get_spinStates()          # D2H: what a pynqs user reads back
-            lnpsi = e.get_lnpsi()
+            spins = e.get_spinStates(out=spins_out)          # D2H: what a pynqs user reads back
+            lnpsi = e.get_lnpsi(out=lnpsi_out)
         barrier()
         dt = (time.perf_counter() - t0) / n_e2e
         if world > 1:

@@ -134,13 +134,17 @@ class Engine:
         self._u_keepalive = u
         self._chk(self.lib.nqs_set_uniforms(self._h, _ptr(u), u.shape[0]))
 
-    def get_spinStates(self) -> np.ndarray:
-        s = np.empty((self.K, self.N), dtype=np.int8)
+    def get_spinStates(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """`out`: a caller-owned C-contiguous int8 [K][N] buffer to fill instead of a fresh array (page-locked memory makes the
+        device-to-host copy a single DMA instead of a staged one)."""
+        s = np.empty((self.K, self.N), dtype=np.int8) if out is None else out
+        assert s.dtype == np.int8 and s.shape == (self.K, self.N) and s.flags.c_contiguous
         self._chk(self.lib.nqs_get_spins(self._h, _ptr(s)))
         return s
 
-    def get_lnpsi(self) -> np.ndarray:
-        v = np.empty(self.K, dtype=np.complex128)
+    def get_lnpsi(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        v = np.empty(self.K, dtype=np.complex128) if out is None else out
+        assert v.dtype == np.complex128 and v.shape == (self.K,) and v.flags.c_contiguous
         self._chk(self.lib.nqs_get_lnpsi(self._h, _ptr(v)))
         return v
 
