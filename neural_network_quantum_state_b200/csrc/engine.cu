@@ -885,11 +885,6 @@ void launch_hidden_values(nqs_handle * h)
   else
     hidden_values_kernel<MODEL_FFNN><<<grid, 256, 0, h->stream>>>(h->N, h->M, h->K, h->params.p, h->theta.p, h->Tm.p, h->Lm.p);
   check_launch(h, "hidden_values_kernel");
-  if (h->Sd.p != nullptr)
-  {
-    spins_to_double_kernel<<<grid_for((long long)h->K*h->N, 256, 148*8), 256, 0, h->stream>>>((long long)h->K*h->N, h->spins.p, h->Sd.p);
-    check_launch(h, "spins_to_double_kernel");
-  }
   if (h->cols_umma)
   { // per-hidden-unit bound of |T| for the int8 split of conj(T) z (cols_umma.cuh); T is fixed until the next sweep
     NQS_CUDA(cudaMemsetAsync(h->tmaxb.p, 0, sizeof(unsigned long long)*(size_t)h->M, h->stream));
@@ -1114,7 +1109,7 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
     SvArgs a;
     a.K = K; a.P = P; a.O = h->O.p; a.v = v; a.part = h->part.p; a.done = done; a.pc = h->sv_pc; a.rows_per_cluster = h->sv_rpc;
     a.nslot = h->sv_nslot; a.slot_bytes = (unsigned int)h->sv_slot_bytes; a.depth = h->sv_depth;
-    a.T = h->Tm.p; a.Sd = h->Sd.p; a.Ow = h->O.p; a.N = h->N; a.M = h->M;
+    a.T = h->Tm.p; a.spins8 = h->spins.p; a.Ow = h->O.p; a.N = h->N; a.M = h->M; a.gen_q = 0;
     Span sp(h, TAG_ROWS);
     if (h->o_pending)
     { // first product after the sampling phase: this launch also WRITES O (no separate O writer ran)
@@ -1122,13 +1117,18 @@ int matvec_passes(nqs_handle * h, const cd * v, const int * done)
       a.nslot = NQS_SV_MAX_SLOTS; a.slot_bytes = (unsigned int)sv_gen_slot_bytes(h->N, h->M);
       a.depth = std::min(NQS_SV_MAX_DEPTH, (a.nslot-1)/2);
       const size_t smem = (size_t)a.nslot*a.slot_bytes+NQS_SV_TAIL_BYTES;
-      NQS_CUDA(sv_launch_gen(h->sv_cpt, a, h->sv_cs, h->sv_nclusters, h->sv_nt, smem, h->stream));
+      // its own geometry: a consumer thread count that is a multiple of M makes every element one sign flip of one T value
+      a.pc = h->gen_pc; a.rows_per_cluster = h->gen_rpc; a.gen_q = h->gen_q;
+      NQS_CUDA(sv_launch_gen(h->gen_cpt, a, h->gen_cs, h->gen_nclusters, h->gen_nt, smem, h->stream));
       h->o_pending = false;
+      nparts = h->gen_nclusters;
     }
     else
+    {
       NQS_CUDA(sv_launch(h->sv_cpt, h->sv_defer, a, h->sv_cs, h->sv_nclusters, h->sv_nt, h->sv_smem, h->stream, nullptr));
+      nparts = h->sv_nclusters;
+    }
     check_launch(h, "sv_fused_kernel");
-    nparts = h->sv_nclusters;
   }
   else
   {
@@ -1519,19 +1519,53 @@ void alloc_sr(nqs_handle * h)
   h->nrb = (int)nrb;
   h->rows_per_block = (h->K+nrb-1)/nrb;
   h->nrb = (int)((h->K+h->rows_per_block-1)/h->rows_per_block);
-  // O generated inside the first S*v of the CG (sv_fused_kernel, GEN): RBM, one-pass kernel with the software pipeline, even N
-  // (16-byte TMA rows of the double spins), factors available.  OPT-IN (NQS_SV_GEN=1): measured at cfg3 the generating launch
-  // takes 3.5 ms -- forming 2 x 8 elements per thread and row from their factors makes the kernel issue-bound (~265 instead of
-  // ~100 warp instructions per row) -- against 1.34 ms (writer) + 1.40 ms (read pass) for the two separate kernels, so the
-  // step time does not change (15.09 vs 15.06 ms); the separate O writer stays the default.
+  // O generated inside the first S*v of the CG (sv_fused_kernel, GEN): RBM, one-pass kernel with the software pipeline, N a
+  // multiple of 16 (TMA rows of the int8 spins), factors available.  OPT-IN (NQS_SV_GEN=1), measured twice at cfg3 and slower both
+  // times than writer (1.34 ms) + read pass (1.43 ms): (round 1) with the geometry of the other products every element costs two
+  // shared-memory loads and two multiplications, the launch is issue-bound at 3.5 ms; (round 2) with a consumer thread count that
+  // is a multiple of M (256 threads, 16-CTA clusters, 9 columns per thread) an element is one sign flip of one T value, but a
+  // cluster then handles 1820 rows of only 2072 columns per CTA and the per-row DSMEM exchange dominates: ~4.5 ms (step 25.0 vs
+  // 14.6 ms).  512 consumer threads (the geometry of the other products) do not fit: 17 warps x 120 registers exceed the register
+  // file's allocation unit.  The separate O writer stays the default.
   { const char * ng = std::getenv("NQS_SV_GEN");
-    h->gen_ok = h->sv_ok && h->sv_defer && h->cols_ok && h->model == MODEL_RBM && h->N%2 == 0 && h->M < 65535 && h->N < 32766 &&
+    h->gen_ok = h->sv_ok && h->sv_defer && h->cols_ok && h->model == MODEL_RBM && h->N%16 == 0 && h->M < 65535 && h->N < 32766 &&
       (ng && std::atoi(ng) != 0) &&
       (size_t)NQS_SV_MAX_SLOTS*sv_gen_slot_bytes(h->N, h->M)+NQS_SV_TAIL_BYTES <= h->smem_optin;
-    if (h->gen_ok) h->Sd.alloc((size_t)h->K*h->N); }
+    if (h->gen_ok)
+    { // geometry of the generating launch: by default that of the other products; if a consumer thread count NT <= 480 that is
+      // a multiple of M exists, the cluster size that covers the most SMs with at most 9 columns per thread
+      h->gen_cs = h->sv_cs; h->gen_cpt = h->sv_cpt; h->gen_nt = h->sv_nt; h->gen_nclusters = h->sv_nclusters;
+      h->gen_pc = h->sv_pc; h->gen_rpc = h->sv_rpc; h->gen_q = (h->sv_nt%h->M == 0) ? h->sv_nt/h->M : 0;
+      int step = h->M;
+      while (step%32 != 0) step *= 2;
+      const int nt = (step <= 480) ? 480/step*step : 0;      // (512 + 32 threads would need <= 112 registers: the allocation unit is 512 per warp)
+      const char * g2 = std::getenv("NQS_SV_GEN_PLAN");
+      if (nt > 0 && !(g2 && std::atoi(g2) == 0))
+      {
+        static const int sizes[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16};
+        int best_cs = 0, best_cov = 0, best_cpt = 0;
+        for (int cs : sizes)
+        {
+          const long long pc = (h->P+cs-1)/cs;
+          const int cpt = (int)((pc+nt-1)/nt);
+          if (cpt > 9) continue;
+          const int cov = cs*(h->sm_count/cs)+(cs == h->sv_cs ? 1000 : 0);      // the cluster size of the other products if it fits
+          if (cov > best_cov) { best_cov = cov; best_cs = cs; best_cpt = cpt; }
+        }
+        if (best_cs > 0)
+        {
+          h->gen_cs = best_cs; h->gen_cpt = best_cpt; h->gen_nt = nt; h->gen_pc = (h->P+best_cs-1)/best_cs;
+          const int ncl = std::max(1, std::min<int>(h->sm_count/best_cs, (int)std::min<long long>(h->K, 1<<20)));
+          h->gen_rpc = (h->K+ncl-1)/ncl;
+          h->gen_nclusters = (int)((h->K+h->gen_rpc-1)/h->gen_rpc);
+          h->gen_q = nt/h->M;
+        }
+      }
+    } }
   plan_cgp(h);
   if (h->cgp_ok) h->variant_sv += "_persistentcg";
-  h->part.alloc(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P));
+  h->part.alloc(std::max(std::max(std::max((size_t)h->nrb*5*h->P, (size_t)h->sv_nclusters*2*h->P), (size_t)h->sc_nchunks*4*h->P),
+                         (size_t)h->gen_nclusters*2*h->P));
   h->sums.alloc((size_t)5*h->P+3);
   h->hsall.alloc(4);
   h->traw.alloc((size_t)2*h->P);

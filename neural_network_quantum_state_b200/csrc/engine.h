@@ -121,7 +121,8 @@ struct nqs_handle
   nqs::DevBuf<unsigned long long> tmaxb;  // cols_umma.cuh: bit patterns of max_k |T_kj|_inf per hidden unit [M]
   int cols_umma = 0;                      // 1: the O^H z / SR-setup GEMM runs on tcgen05 (int8 UMMA), 0: fp64 DMMA
   int rows_umma = -1;                     // -1 undecided, 0 fp64 DMMA rows kernel, 1 tcgen05 int8 (Ozaki) rows kernel
-  nqs::DevBuf<double> Sd;                 // [K][N] spins as doubles: factor rows of the O-generating S*v (sv_fused.cuh, GEN)
+  int gen_cs = 0, gen_cpt = 0, gen_nt = 0, gen_nclusters = 0, gen_q = 0;   // launch geometry of the O-generating S*v (sv_fused.cuh, GEN)
+  long long gen_pc = 0, gen_rpc = 0;
   bool gen_ok = false, o_pending = false; // O is written by the first S*v of the CG instead of a separate writer / it still has to be
   nqs::DevBuf<double> abs2;               // [chunks][3M] sums of |T|^2, |L|^2 of the SR setup GEMM
   bool cols_ok = false;                   // spin_cols_dmma_kernel planned (N <= 256): structured S*v and the SR setup GEMM

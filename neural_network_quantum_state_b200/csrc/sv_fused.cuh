@@ -58,16 +58,19 @@ struct SvArgs
   unsigned int slot_bytes; // bytes per slot: >= CPT * consumer threads * 16 (the tail past the slice stays zero)
   int depth;               // DEFER = 1: pass (3) of row k runs after pass (2) of row k+depth (1..NQS_SV_MAX_DEPTH, <= nslot-2)
   // GEN = 1 (RBM): the rows of O do not exist yet.  The producer stages the FACTORS of row k -- T_k = tanh(theta_k) [M] and the
-  // spins as doubles [N] -- and every consumer thread forms its elements O_kp = s_ki T_kj itself, uses them for the product
-  // and WRITES them to O (coalesced 16-byte stores): the O writer (ref RBM::backward, k13 :1426-1449) and the first S*v of the
-  // CG (S x0) cost one HBM write pass instead of a write pass plus a read pass.
+  // spins [N] int8 -- and every consumer thread forms its elements O_kp = s_ki T_kj itself, uses them for the product and
+  // WRITES them to O (coalesced 16-byte stores): the O writer (ref RBM::backward, k13 :1426-1449) and the first S*v of the
+  // CG (S x0) cost one HBM write pass instead of a write pass plus a read pass.  When the consumer thread count is a multiple
+  // of M (gen_q = NT / M > 0) every column of a thread inside the W block has the SAME hidden unit j and sites gen_q apart:
+  // one T load and a sign flip per element (s = +-1) instead of two loads and two multiplications.
   const cd * T;            // [K][M]
-  const double * Sd;       // [K][N]
+  const int8_t * spins8;   // [K][N], N a multiple of 16
   cd * Ow;                 // [K][P] out
   int N, M;
+  int gen_q;
 };
-// GEN slot layout: T row [M] | (1,0) | spins [N] | +1.0 | 0.0   (the three constants serve the a / b blocks and the padding)
-inline size_t sv_gen_slot_bytes(int N, int M) { return (size_t)(M+1)*16+(((size_t)(N+2)*8+15)/16)*16; }
+// GEN slot layout: T row [M] | (1,0) | spins [N] int8 | +1 | 0   (the three constants serve the a / b blocks and the padding)
+inline size_t sv_gen_slot_bytes(int N, int M) { return (size_t)(M+1)*16+(((size_t)(N+2)+15)/16)*16; }
 
 #define NQS_SV_MAX_CLUSTER 16
 #define NQS_SV_MAX_SLOTS 8
@@ -83,11 +86,11 @@ inline size_t sv_gen_slot_bytes(int N, int M) { return (size_t)(M+1)*16+(((size_
 // register budget (16384 registers per SM sub-partition): CPT <= 3 runs up to 992+32 threads (8 warps per sub-partition x 64
 // registers), larger CPT up to 480+32 threads (4 warps per sub-partition x 128 registers)
 #define NQS_SV_MAX_CPT 10
-template <int CPT> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
+template <int CPT, int GEN = 0> struct SvMaxRegs { static const int value = (CPT <= 3) ? 64 : 128; };
 
 // blockDim.x = 32*(NW+1): warps 0..NW-1 consume (NT = 32*NW threads own the columns), warp NW is the TMA producer.
 template <int CPT, int DEFER, int GEN>
-__global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs a)
+__global__ void __maxnreg__((SvMaxRegs<CPT, GEN>::value)) sv_fused_kernel(const SvArgs a)
 {
   if (a.done != nullptr && *a.done) return;   // uniform over the grid
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,7 +131,7 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
     {
       cd * Ts = reinterpret_cast<cd*>(smem_raw+(size_t)s*a.slot_bytes);
       Ts[a.M] = cmake(1.0, 0.0);
-      reinterpret_cast<double*>(Ts+a.M+1)[a.N] = 1.0;
+      reinterpret_cast<int8_t*>(Ts+a.M+1)[a.N] = (int8_t)1;
     }
   }
   if (tid == 0)
@@ -154,9 +157,9 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
         if (GEN)
         {
           unsigned char * dst = smem_raw+(size_t)slot*a.slot_bytes;
-          mbar_expect_tx(full+slot, (uint32_t)a.M*16u+(uint32_t)a.N*8u);
+          mbar_expect_tx(full+slot, (uint32_t)a.M*16u+(uint32_t)a.N);
           tma_load_1d(dst, a.T+(k0+it)*a.M, (uint32_t)a.M*16u, full+slot);
-          tma_load_1d(dst+(size_t)(a.M+1)*16, a.Sd+(k0+it)*a.N, (uint32_t)a.N*8u, full+slot);
+          tma_load_1d(dst+(size_t)(a.M+1)*16, a.spins8+(k0+it)*a.N, (uint32_t)a.N, full+slot);
         }
         else
         {
@@ -181,9 +184,16 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
     const size_t slot_elems = a.slot_bytes/sizeof(cd);
     // GEN: where the two factors of column c sit in a slot, packed (T index | spin index << 16)
     int fac[GEN ? CPT : 1];
+    bool fastp = false;      // all CPT columns of this thread lie in the W block and share their hidden unit
+    int jf = 0, i0 = 0;
     if (GEN)
     {
       const long long NM = (long long)a.N*a.M;
+      if (a.gen_q > 0 && (CPT-1)*NT+tid < n_r && c0+(long long)(CPT-1)*NT+tid < NM)
+      {
+        fastp = true;
+        jf = (int)((c0+tid)%a.M); i0 = (int)((c0+tid)/a.M);
+      }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
       {
@@ -197,14 +207,24 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
         fac[GEN ? c : 0] = tj|(si<<16);
       }
     }
-    auto gen_o = [&](const int c, const int gslot) -> cd
+    // element c of the row staged in slot gslot; trow = T of the thread's hidden unit in that row (fast path)
+    auto gen_o = [&](const int c, const int gslot, const cd trow) -> cd
     {
       const cd * Ts = reinterpret_cast<const cd*>(smem_raw+(size_t)gslot*a.slot_bytes);
-      const double * Sd = reinterpret_cast<const double*>(Ts+a.M+1);
+      const int8_t * sb = reinterpret_cast<const int8_t*>(Ts+a.M+1);
+      if (fastp)
+      { // s = +-1: flip the sign bits
+        const int m = ((int)sb[i0+c*a.gen_q])&0x80000000;
+        return cmake(__hiloint2double(__double2hiint(trow.x)^m, __double2loint(trow.x)), __hiloint2double(__double2hiint(trow.y)^m, __double2loint(trow.y)));
+      }
       const int f = fac[GEN ? c : 0];
       const cd t = Ts[f&0xffff];
-      const double sp = Sd[f>>16];
+      const double sp = (double)sb[f>>16];
       return cmake(t.x*sp, t.y*sp);
+    };
+    auto gen_trow = [&](const int gslot) -> cd
+    {
+      return fastp ? reinterpret_cast<const cd*>(smem_raw+(size_t)gslot*a.slot_bytes)[jf] : cmake(0.0, 0.0);
     };
 
     // (3) for row jt: z_k = sum of the CS partials in rank order, then acc += conj(O_kp) z_k
@@ -227,10 +247,11 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       double zx, zy;
       wait_z(jt, zx, zy);
       const cd * prow = sbase+(size_t)jslot*slot_elems;
+      const cd trow = GEN ? gen_trow(jslot) : cmake(0.0, 0.0);
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
       {
-        const cd q = GEN ? gen_o(c, jslot) : prow[c*NT];
+        const cd q = GEN ? gen_o(c, jslot, trow) : prow[c*NT];
         acc[c].x = fma(q.x, zx, acc[c].x); acc[c].x = fma(q.y, zy, acc[c].x);
         acc[c].y = fma(q.x, zy, acc[c].y); acc[c].y = fma(-q.y, zx, acc[c].y);
       }
@@ -250,11 +271,12 @@ __global__ void __maxnreg__(SvMaxRegs<CPT>::value) sv_fused_kernel(const SvArgs 
       if (GEN)
       {
         cd * orow = a.Ow+(k0+it)*a.P+c0+tid;
+        const cd trow = gen_trow(slot);
 #pragma unroll
         for (int c = 0; c < CPT; ++c)
         {
-          o[c] = gen_o(c, slot);
-          if (c*NT+tid < n_r) orow[c*NT] = o[c];
+          o[c] = gen_o(c, slot, trow);
+          if (fastp || c*NT+tid < n_r) orow[c*NT] = o[c];
         }
       }
       else

@@ -122,8 +122,8 @@ def test_fused_sv_inside_cg_matches_two_pass_trajectory():
 def test_o_generated_inside_first_sv_matches_separate_writer(N, M, K, monkeypatch):
     """nqs_sr_step writes O from inside the first S*v of the CG (sv_fused_kernel GEN: factors staged by TMA, elements formed
     in registers, used and stored; opt-in with NQS_SV_GEN=1, see engine.cu: alloc_sr).  By default the separate writer
-    (oderiv_kernel) runs first.  Both must give the same CG trajectory bit for bit: every later S*v of the step reads the O
-    that the GEN launch wrote."""
+    (oderiv_kernel) runs first.  Both must give the same CG trajectory: every later S*v of the step reads the O that the GEN
+    launch wrote."""
     from neural_network_quantum_state_b200 import Engine
     res = []
     monkeypatch.setenv("NQS_CG_PERSIST", "0")   # the O-generating first product belongs to the launch-per-iteration path: like with like
@@ -139,7 +139,9 @@ def test_o_generated_inside_first_sv_matches_separate_writer(N, M, K, monkeypatc
             steps.append((st.e_mean, dx.copy()))
         res.append((steps, e.get_params()))
         e.close()
+    # (the generating launch has its own cluster geometry, so the partial sums of that one product are grouped differently:
+    # equal to rounding, not bit for bit; every later product of the step reads the O it wrote)
     for (e0, dx0), (e1, dx1) in zip(res[0][0], res[1][0]):
-        assert e0 == e1
-        assert np.array_equal(dx0, dx1), "dx differs between the O-generating S*v and the separate O writer"
-    assert np.array_equal(res[0][1], res[1][1])
+        assert e0 == pytest.approx(e1, rel=1e-13)
+        assert_close(dx0, dx1, rtol=1e-10, what="dx: O-generating S*v vs separate O writer")
+    assert_close(res[0][1], res[1][1], rtol=1e-10, what="params")
