@@ -908,8 +908,10 @@ void plan_cols(nqs_handle * h)
   if (h->N > 256 || (h->cfg.flags & NQS_FLAG_NO_DMMA) || h->trsymm) return;    // (tied weights: the rows of O are not outer products)
   { // tcgen05 int8 kernel (cols_umma.cuh): 128 sites per MMA, one CTA per SM; pays once a rank holds enough chains to give
     // every CTA several 64-chain blocks.  NQS_COLS_UMMA=0/1 overrides.
+    // (FNN: measured slower than the DMMA kernel at cfg4, 0.277 vs 0.214 ms per product -- the FFNN instantiation spills -- so
+    // it is taken for the RBM only unless asked for.)
     const char * e = std::getenv("NQS_COLS_UMMA");
-    bool on = (h->K >= 8192);
+    bool on = (h->K >= 8192 && h->model == MODEL_RBM);
     if (e) on = (std::atoi(e) != 0);
     on = on && h->N <= 128 && cols_umma_smem() <= h->smem_optin;
     if (on)
