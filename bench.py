@@ -686,9 +686,13 @@ def main():
                 "gemm": {"flops_per_launch": flops, "rows_ms": r_ms, "cols_ms": c_ms,
                          "rows_tflops": flops / (r_ms * 1e-3) / 1e12 if r_ms > 0 else None,
                          "cols_tflops": flops / (c_ms * 1e-3) / 1e12 if c_ms > 0 else None,
-                         "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS},
-                "note": "opt-in NQS_FLAG_STRUCTURED_SV: O^H(O v) as two real-by-complex GEMMs on the factors of O (mma.sync m8n8k4 f64); "
-                        "O is never written; same energies as the headline run to rounding"}
+                         "fp64_dmma_peak_tflops": FP64_DMMA_PEAK_TFLOPS,
+                         "tensor_path": "tcgen05 kind::i8 (7 int8 digit planes per fp64 operand: 7x the listed flops as int8 ops)"
+                                        if "umma" in e2.kernel_variant("sv") else "mma.sync m8n8k4 f64 (DMMA)",
+                         "tflops_note": "fp64-EQUIVALENT rate = flops of the fp64 GEMM / time; on the int8 path it may exceed the DMMA peak"},
+                "note": "opt-in NQS_FLAG_STRUCTURED_SV: O^H(O v) as two real-by-complex GEMMs on the factors of O (tcgen05 int8 UMMA with an "
+                        "error-free digit split from 8192 chains per rank, fp64 DMMA below); O is never written; same energies as the "
+                        "headline run to rounding"}
             e2.close()
         except Exception as ex:
             line["structured_sv"] = {"value": None, "error": str(ex)}
