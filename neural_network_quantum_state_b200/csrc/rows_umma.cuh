@@ -20,16 +20,16 @@
 // ozaki_split_kernel and fetched with one 1-D TMA bulk copy per chunk (ring of up to 6 tiles).  One MMA of 128 x 224 x 32 per
 // 32 sites; D = 224 TMEM columns, double-buffered (448 of 512), so the MMAs of chunk c+1 run under the epilogue of chunk c.
 // Epilogue: 16 warps = 4 lane quadrants x 4 column groups; a thread owns one chain and 8 real columns of the chunk:
-// 7 tcgen05.ld (32x32b.x8), the planes recombined (pairs in int32, pairs of pairs in fp64), scale, then the complex epilogue of
-// the DMMA kernel.  The chunks run in
-// lockstep (one __syncthreads each), so nothing with a global-memory latency may sit inside the chunk loop: scales, biases and
-// output weights are staged in shared memory, the factors T (L) of the next chunk are fetched one chunk ahead, and the
-// visible-bias sum is taken while the first tile is still in flight, and T / theta go through shared memory so that global
-// memory sees whole 256-byte runs.  In-kernel clocks per chunk (cfg3, Z epilogue): 4500 cycles at first -- 2000 of them LSU
-// wavefronts of thread-per-chain T loads, 1500 two dependent L2 round trips for scales and biases -- and 3100 now: 1230 the
-// recombination + complex epilogue (fp64 pipe), 800 issuing the cp.async of the next T tile, 200 tcgen05.ld, 150 waiting for
-// the MMAs; the tensor core itself needs 450.  Next: a dedicated issue warp and mbarrier hand-offs instead of the
-// per-chunk __syncthreads (the 16 epilogue warps then stop running in lockstep).
+// 7 tcgen05.ld (32x32b.x8), the planes recombined (pairs in int32, pairs of pairs in int64, one FMA), scale, then the complex
+// epilogue of the DMMA kernel.
+// The chunks run in lockstep (one __syncthreads each), so nothing with a global-memory latency may sit inside the chunk loop:
+// scales, biases and output weights are staged in shared memory once, the visible-bias sum is taken while the first tile is
+// still in flight, and T (in) / theta (out) travel through cp.async-staged shared-memory tiles, fetched chunks ahead, so that
+// global memory sees whole 256-byte runs instead of one cache line per lane.
+// In-kernel clocks per chunk (cfg3, Z epilogue; profiles/r2_umma.md): 4500 cycles at first -- 2000 of them LSU wavefronts of
+// thread-per-chain T loads, 1500 two dependent L2 round trips for scales and biases -- and 3100 now: 1230 recombination +
+// complex epilogue (fp64 pipe), 800 issuing the cp.async of the next T tile, 200 tcgen05.ld, 150 waiting for the MMAs; the
+// tensor core itself needs 450.  Next: a dedicated issue warp and mbarrier hand-offs instead of the per-chunk __syncthreads.
 // The kernel is launched with programmatic stream serialization: TMEM allocation, barrier setup and the spin tile overlap the
 // tail of ozaki_split_kernel.
 #pragma once
