@@ -73,7 +73,7 @@ typedef struct nqs_config {
   double alpha;            /* J_ij = J |i-j|^-alpha */
   int32_t pbc;             /* ref isPBC (distance rule gpu/include/impl_hamiltonians.cuh:146; L must be even) */
   int32_t order;           /* nqs_order */
-  uint64_t seed;           /* key of the internal counter RNG (ref seedNumber; TRNG4 stream itself is not reproduced) */
+  uint64_t seed;           /* ref seedNumber: key of the internal counter RNG, or seed of the yarn2 stream (nqs_set_rng) */
   int32_t device;          /* CUDA ordinal (ref: -dev) */
   int32_t flags;           /* NQS_FLAG_* */
   int64_t max_predrawn_steps; /* capacity (in proposals per chain) of the device buffer for nqs_set_uniforms; 0 -> none */
@@ -119,11 +119,20 @@ nqs_status nqs_sync(nqs_handle * h); /* cudaStreamSynchronize of the handle's st
 /* The reference builds the ansatz first and hands it to the Hamiltonian/sampler and to the optimizer later
  * (gpu/src/LICH-train_rbm.cu:90-101); these three let a host mirror that order on one handle:
  *   nqs_set_hamiltonian  ref: LITFIChain ctor (h, J, alpha, isPBC) gpu/include/impl_hamiltonians.cuh:118-183 (J matrix, site ring)
- *   nqs_set_seed         ref: seedNumber of BaseParallelSampler (impl_mcmc_sampler.cuh:6-15); restarts the proposal counter
+ *   nqs_set_seed         ref: seedNumber of BaseParallelSampler (impl_mcmc_sampler.cuh:6-15); restarts the proposal counter,
+ *                        keeps the generator kind
  *   nqs_enable_sr        ref: StochasticReconfigurationCG ctor (impl_optimizer.cuh:45-64): allocates O [K][P] + CG vectors on a
  *                        handle created with NQS_FLAG_NO_SR (no-op otherwise) */
 nqs_status nqs_set_hamiltonian(nqs_handle * h, double hfield, double J, double alpha, int32_t pbc, int32_t order);
 nqs_status nqs_set_seed(nqs_handle * h, uint64_t seed);
+/* ref: TRNGWrapper<FloatType, trng::yarn2>(seedNumber, seedDistance, nChains) gpu/include/trng4cuda.cuh:41-54 + get_uniformDist
+ * :62-65.  NQS_RNG_YARN2: chain k (GLOBAL id, so the stream does not depend on the number of GPUs) draws the uniforms of
+ * trng::yarn2 after seed(seedNumber); jump(2ul*seedDistance*k), one uniform01_dist<double> draw per proposal -- the published
+ * TRNG4 algorithm restated in csrc/yarn2.cuh (the library itself is absent offline: stream parity is unpinned).
+ * NQS_RNG_PHILOX (default of nqs_create): Philox4x32-10 keyed by (seed, global chain, proposal), seed_distance ignored.
+ * Restarts the proposal counter like nqs_set_seed.  A feed given by nqs_set_uniforms takes precedence over either generator. */
+typedef enum nqs_rng { NQS_RNG_PHILOX = 0, NQS_RNG_YARN2 = 1 } nqs_rng;
+nqs_status nqs_set_rng(nqs_handle * h, int32_t kind, uint64_t seed, uint64_t seed_distance);
 nqs_status nqs_enable_sr(nqs_handle * h);
 /* a NEW optimizer object in the reference starts with bp_ = 1 (lambda schedule) and dx = 0 (CG warm start),
  * gpu/include/impl_optimizer.cuh:45-64 */
@@ -151,7 +160,7 @@ nqs_status nqs_warm_up(nqs_handle * h, int32_t n_sweeps, const int8_t * spins);
 /* ref: do_mcmc_steps(n) :28-39; one sweep = N single-site proposals per chain. */
 nqs_status nqs_do_mcmc_steps(nqs_handle * h, int32_t n_sweeps);
 /* Pre-drawn uniforms u[steps][K_loc] replacing TRNGWrapper::get_uniformDist (gpu/include/trng4cuda.cuh:62-65): proposal t
- * (counted from this call) of chain k uses u[t][k].  u == NULL -> internal Philox4x32-10 keyed by (seed, global chain, step).
+ * (counted from this call) of chain k uses u[t][k].  u == NULL -> the handle's generator (nqs_set_rng; Philox4x32-10 by default).
  * u is consumed asynchronously: it must stay valid and unchanged until the sweeps that use it have completed (any later
  * synchronising call).  Pageable memory is staged through HBM (steps <= nqs_config.max_predrawn_steps); a page-locked
  * buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory) is read in place over PCIe by the sweep kernels, with no

@@ -16,6 +16,7 @@ STATUS_NAMES = ["NQS_OK", "NQS_ERR_INVALID", "NQS_ERR_CUDA", "NQS_ERR_NOMEM", "N
                 "NQS_ERR_NCCL", "NQS_ERR_NONFINITE", "NQS_ERR_UNSUPPORTED"]
 MODEL_RBM, MODEL_FFNN, MODEL_RBMTRSYMM = 0, 1, 2
 ORDER_CHECKERBOARD, ORDER_SEQUENTIAL = 0, 1
+RNG_PHILOX, RNG_YARN2 = 0, 1
 FLAG_NO_SR, FLAG_ACCEPT_LOG, FLAG_FORCE_GENERIC, FLAG_TWO_PASS_SV = 1, 2, 4, 8
 FLAG_SETUP_FROM_O, FLAG_STRUCTURED_SV, FLAG_NO_DMMA = 16, 32, 64
 
@@ -53,6 +54,7 @@ SYMBOLS = {
     "nqs_sync": (_i32, [_vp]),
     "nqs_set_hamiltonian": (_i32, [_vp, _dbl, _dbl, _dbl, _i32, _i32]),
     "nqs_set_seed": (_i32, [_vp, C.c_uint64]),
+    "nqs_set_rng": (_i32, [_vp, _i32, C.c_uint64, C.c_uint64]),
     "nqs_enable_sr": (_i32, [_vp]),
     "nqs_sr_reset": (_i32, [_vp]),
     "nqs_n_variables": (_i32, [_vp, C.POINTER(_i64)]),

@@ -447,6 +447,37 @@ void launch_eloc_fast(nqs_handle * h)
   check_launch(h, "rbm_eloc_sites_kernel");
 }
 
+// ---- trng::yarn2 feed (yarn2.cuh) --------------------------------------------------------------------------------------
+constexpr size_t YARN2_FEED_BYTES = (size_t)256<<20;   // uniforms generated per sweep launch (whole sweeps)
+long long yarn2_steps_per_launch(const nqs_handle * h)
+{
+  const long long sweeps = (long long)(YARN2_FEED_BYTES/sizeof(double))/(h->K*h->N);
+  return std::max(1ll, sweeps)*h->N;
+}
+const double * yarn2_fill(nqs_handle * h, long long nsteps)
+{
+  if (h->yarn_tab.p == nullptr)
+  {
+    h->yarn_tab.alloc((size_t)YARN2_TAB0+YARN2_TAB1);
+    yarn2_table_kernel<<<(YARN2_TAB0+YARN2_TAB1+255)/256, 256, 0, h->stream>>>(h->yarn_tab.p);
+    check_launch(h, "yarn2_table_kernel");
+  }
+  if (h->yarn_state.n < (size_t)h->K) { h->yarn_state.alloc((size_t)h->K); h->yarn_state_at = -1; }
+  if (h->yarn_u.n < (size_t)nsteps*h->K)
+  { // the previous launch may still read the old buffer
+    NQS_CUDA(cudaStreamSynchronize(h->stream));
+    h->yarn_u.alloc((size_t)nsteps*h->K);
+  }
+  Yarn2FillArgs y;
+  y.K = h->K; y.chain_offset = h->koff; y.seed = h->cfg.seed; y.seed_distance = h->seed_distance; y.draws_done = h->step_counter;
+  y.nsteps = nsteps; y.rebuild = (h->yarn_state_at != (long long)h->step_counter) ? 1 : 0;
+  y.tab = h->yarn_tab.p; y.state = h->yarn_state.p; y.u = h->yarn_u.p;
+  yarn2_fill_kernel<<<(unsigned)((h->K+127)/128), 128, 0, h->stream>>>(y);
+  check_launch(h, "yarn2_fill_kernel");
+  h->yarn_state_at = (long long)(h->step_counter+(unsigned long long)nsteps);
+  return h->yarn_u.p;
+}
+
 void launch_sweep(nqs_handle * h, long long nsteps)
 {
   if (nsteps <= 0) return;
@@ -460,6 +491,16 @@ void launch_sweep(nqs_handle * h, long long nsteps)
   {
     NQS_REQUIRE(h->u_used+nsteps <= h->u_steps, NQS_ERR_STATE, "pre-drawn uniform feed exhausted: call nqs_set_uniforms with enough steps");
     a.uniforms = (h->u_zc ? h->u_zc : h->uniforms.p)+(size_t)h->u_used*h->K;
+  }
+  else if (h->rng_kind == NQS_RNG_YARN2)
+  { // the reference's trng::yarn2 stream (yarn2.cuh): the uniforms of this launch are generated into a feed buffer first
+    const long long cap = yarn2_steps_per_launch(h);
+    if (nsteps > cap && !(h->cfg.flags & NQS_FLAG_ACCEPT_LOG))
+    { // bounded buffer: whole sweeps at a time
+      for (long long done = 0; done < nsteps; done += cap) launch_sweep(h, std::min(cap, nsteps-done));
+      return;
+    }
+    a.uniforms = yarn2_fill(h, nsteps);
   }
   a.seed = h->cfg.seed; a.step0 = h->step_counter; a.chain_offset = h->koff;
   a.acc_log = nullptr;
@@ -2202,7 +2243,22 @@ nqs_status nqs_set_seed(nqs_handle * h, uint64_t seed)
   if (!h) return NQS_ERR_INVALID;
   h->cfg.seed = seed;
   h->step_counter = 0;
+  h->yarn_state_at = -1;
   return NQS_OK;
+}
+
+nqs_status nqs_set_rng(nqs_handle * h, int32_t kind, uint64_t seed, uint64_t seed_distance)
+{
+  if (!h) return NQS_ERR_INVALID;
+  return guarded(h, [&]()
+  {
+    NQS_REQUIRE(kind == NQS_RNG_PHILOX || kind == NQS_RNG_YARN2, NQS_ERR_INVALID, "nqs_set_rng: unknown generator kind");
+    h->rng_kind = kind;
+    h->cfg.seed = seed;
+    h->seed_distance = seed_distance;
+    h->step_counter = 0;
+    h->yarn_state_at = -1;
+  });
 }
 
 nqs_status nqs_comm_get_unique_id(char id[NQS_UNIQUE_ID_BYTES])
@@ -2349,13 +2405,15 @@ namespace
 {
 struct CkptHeader
 {
-  char magic[8];            // "NQSCKPT1"
+  char magic[8];            // "NQSCKPT2"
   int32_t model, N, M, trsymm;
   int64_t K, Ktot, koff, P;
   int32_t pos, flip_index, cg_prev_iters, has_sr;
   uint64_t step_counter, seed;
   double bp, hfield, J, alpha;
   int32_t pbc, order;
+  int32_t rng_kind, pad_;
+  uint64_t seed_distance;
 };
 template <typename T>
 void ckpt_write(std::ofstream & f, nqs_handle * h, const T * dev, size_t n)
@@ -2390,12 +2448,13 @@ nqs_status nqs_checkpoint_save(nqs_handle * h, const char * path)
     NQS_REQUIRE(f.is_open(), NQS_ERR_IO, std::string("cannot write ")+path);
     CkptHeader hd;
     std::memset(&hd, 0, sizeof(hd));
-    std::memcpy(hd.magic, "NQSCKPT1", 8);
+    std::memcpy(hd.magic, "NQSCKPT2", 8);
     hd.model = h->model; hd.N = h->N; hd.M = h->M; hd.trsymm = h->trsymm ? 1 : 0;
     hd.K = h->K; hd.Ktot = h->Ktot; hd.koff = h->koff; hd.P = h->P;
     hd.pos = h->pos; hd.flip_index = h->flip_index; hd.cg_prev_iters = h->cg_prev_iters; hd.has_sr = h->aO.p != nullptr ? 1 : 0;
     hd.step_counter = h->step_counter; hd.seed = h->cfg.seed; hd.bp = h->bp;
     hd.hfield = h->cfg.h; hd.J = h->cfg.J; hd.alpha = h->cfg.alpha; hd.pbc = h->cfg.pbc; hd.order = h->cfg.order;
+    hd.rng_kind = h->rng_kind; hd.seed_distance = h->seed_distance;
     f.write(reinterpret_cast<const char*>(&hd), sizeof(hd));
     ckpt_write(f, h, var_ptr(h), (size_t)h->P);
     ckpt_write(f, h, h->spins.p, (size_t)h->K*h->N);
@@ -2419,7 +2478,7 @@ nqs_status nqs_checkpoint_load(nqs_handle * h, const char * path)
     NQS_REQUIRE(f.is_open(), NQS_ERR_IO, std::string("cannot read ")+path);
     CkptHeader hd;
     f.read(reinterpret_cast<char*>(&hd), sizeof(hd));
-    NQS_REQUIRE((size_t)f.gcount() == sizeof(hd) && std::memcmp(hd.magic, "NQSCKPT1", 8) == 0, NQS_ERR_IO, "not a libnqs_b200 checkpoint");
+    NQS_REQUIRE((size_t)f.gcount() == sizeof(hd) && std::memcmp(hd.magic, "NQSCKPT2", 8) == 0, NQS_ERR_IO, "not a libnqs_b200 checkpoint");
     NQS_REQUIRE(hd.model == h->model && hd.N == h->N && hd.M == h->M && (hd.trsymm != 0) == h->trsymm && hd.K == h->K &&
       hd.Ktot == h->Ktot && hd.koff == h->koff && hd.P == h->P, NQS_ERR_INVALID,
       "checkpoint was written by a handle of another shape (model, sizes, chains or chain offset differ)");
@@ -2440,6 +2499,7 @@ nqs_status nqs_checkpoint_load(nqs_handle * h, const char * path)
     }
     h->pos = hd.pos; h->flip_index = hd.flip_index; h->cg_prev_iters = hd.cg_prev_iters;
     h->step_counter = hd.step_counter; h->cfg.seed = hd.seed; h->bp = hd.bp;
+    h->rng_kind = hd.rng_kind; h->seed_distance = hd.seed_distance; h->yarn_state_at = -1;   // the yarn2 state is rebuilt from the counters
     if (hd.hfield != h->cfg.h || hd.J != h->cfg.J || hd.alpha != h->cfg.alpha || hd.pbc != h->cfg.pbc || hd.order != h->cfg.order)
     { // the Hamiltonian travels with the state
       h->cfg.h = hd.hfield; h->cfg.J = hd.J; h->cfg.alpha = hd.alpha; h->cfg.pbc = hd.pbc; h->cfg.order = hd.order;

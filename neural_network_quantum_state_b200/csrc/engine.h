@@ -13,6 +13,7 @@
 #include "sweep_f32.cuh"
 #include "rows_umma.cuh"
 #include "cols_umma.cuh"
+#include "yarn2.cuh"
 
 namespace nqs
 {
@@ -85,6 +86,13 @@ struct nqs_handle
   int pos = 0;                            // next position in the site ring
   int flip_index = 0;                     // the machine's index_ (ref impl_neural_quantum_state.cuh:19)
   unsigned long long step_counter = 0;    // proposals done so far (RNG counter)
+  // trng::yarn2 stream (yarn2.cuh, nqs_set_rng): counter-addressed by (seed, seed_distance, global chain, step_counter)
+  int rng_kind = 0;                       // nqs_rng
+  unsigned long long seed_distance = 0;
+  nqs::DevBuf<uint32_t> yarn_tab;         // g^i tables of the output map
+  nqs::DevBuf<uint2> yarn_state;          // [K] engine state after `yarn_state_at` draws
+  long long yarn_state_at = -1;           // -1: rebuild from the counters at the next fill
+  nqs::DevBuf<double> yarn_u;             // [steps][K] uniforms of the sweep launch in flight
   bool initialized = false;
   bool theta_matches_O = false;           // O was written from the current spins / theta / params (structured SR setup allowed)
 

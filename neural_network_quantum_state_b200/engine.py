@@ -99,6 +99,15 @@ class Engine:
     def init_params_random(self, seed: int):
         self._chk(self.lib.nqs_init_params_random(self._h, int(seed)))
 
+    def set_rng(self, kind: str, seed: int, seed_distance: int = 0):
+        """kind "yarn2": the reference's trng::yarn2 stream, seed(seedNumber) + jump(2*seedDistance*chain) per chain
+        (gpu/include/trng4cuda.cuh:41-54); "philox": the engine's counter generator.  Restarts the proposal counter."""
+        kinds = {"philox": L.RNG_PHILOX, "yarn2": L.RNG_YARN2}
+        if kind not in kinds:
+            raise ValueError("rng kind must be 'philox' or 'yarn2'")
+        mask = (1 << 64) - 1
+        self._chk(self.lib.nqs_set_rng(self._h, kinds[kind], int(seed) & mask, int(seed_distance) & mask))
+
     def load(self, prefix: str):
         self._chk(self.lib.nqs_load_params(self._h, prefix.encode()))
 

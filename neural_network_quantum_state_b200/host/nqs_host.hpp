@@ -11,13 +11,16 @@
 // Differences a caller can see (all forced by the C-ABI boundary):
 //   * pointer arguments are HOST pointers to std::complex<double> (the reference passes device pointers to thrust::complex);
 //   * the device is chosen with nqs_host::set_device(dev) before constructing an ansatz (the reference calls cudaSetDevice);
-//   * the uniform random numbers come from the engine's counter RNG keyed by `seedNumber` (TRNG4's yarn2 stream is not
-//     reproduced; `seedDistance` is accepted and ignored).
+//   * the uniform random numbers are the reference's: one trng::yarn2 engine per chain, seed(seedNumber) + jump(2*seedDistance*k),
+//     restated in csrc/yarn2.cuh (TRNG4 itself is absent offline); NQS_RNG=philox in the environment selects the
+//     engine's counter generator keyed by `seedNumber` instead (`seedDistance` is then ignored).
 #pragma once
 #include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <iomanip>
 #include <iostream>
 #include <stdexcept>
@@ -169,13 +172,15 @@ public:
     const unsigned long seedNumber, const unsigned long seedDistance, const std::string prefix = "./"):
     machine_(machine), kprefix(prefix)
   {
-    (void)seedDistance;
     if (L != machine.get_nInputs())
       throw std::length_error("machine.get_nInputs() is not the same as L!");
     const nqs_status rc = nqs_set_hamiltonian(machine.handle(), h, J, alpha, isPBC ? 1 : 0, NQS_ORDER_CHECKERBOARD);
     if (rc == NQS_ERR_INVALID) throw std::invalid_argument(nqs_last_error(machine.handle()));
     nqs_host::check(machine.handle(), rc, "nqs_set_hamiltonian");
-    nqs_host::check(machine.handle(), nqs_set_seed(machine.handle(), (uint64_t)seedNumber), "nqs_set_seed");
+    // ref: BaseParallelSampler(..., seedNumber, seedDistance) -> TRNGWrapper<FloatType, trng::yarn2> rng_ (mcmc_sampler.cuh:34)
+    const char * env = std::getenv("NQS_RNG");
+    const int kind = (env && !std::strcmp(env, "philox")) ? NQS_RNG_PHILOX : NQS_RNG_YARN2;
+    nqs_host::check(machine.handle(), nqs_set_rng(machine.handle(), kind, (uint64_t)seedNumber, (uint64_t)seedDistance), "nqs_set_rng");
   }
   void warm_up(const int nMCSteps = 100) { nqs_host::check(hd(), nqs_warm_up(hd(), nMCSteps, nullptr), "warm_up"); }
   void do_mcmc_steps(const int nMCSteps = 1) { nqs_host::check(hd(), nqs_do_mcmc_steps(hd(), nMCSteps), "do_mcmc_steps"); }

@@ -33,6 +33,8 @@ class _PySampler:
         mk = lambda: Engine(self._model, self._N, self._M, self._K, 0.0, 0.0, 0.0, order="sequential", seed=self._seed,
                             device=dev, sampler_only=True)
         self._nqs0, self._nqs1 = mk(), mk()
+        # PySampler's smp_(psi, seedNumber, seedDistance) -> TRNGWrapper<T, trng::yarn2> (gpu/src/pywrapping_sampler.cu:29-40)
+        self._nqs0.set_rng("yarn2", self._seed, self._seed_distance)
         # the reference ctor draws clock-seeded random parameters for both instances (load() normally overrides them)
         self._nqs0.init_params_random(self._seed * 2 + 1)
         self._nqs1.init_params_random(self._seed * 2 + 2)

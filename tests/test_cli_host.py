@@ -87,6 +87,8 @@ def test_training_run_matches_python_host_and_writes_reference_files(tmp_path, p
     prefix = str(tmp_path / ("%s-L%dNH%dA2T0.785398V3" % (tag, L, nh)))     # trailing zeros stripped like the reference
     params = reference_init(model, L, nh, np.random.default_rng(4))
     e = Engine(model, L, nh, ns, -math.cos(theta), math.sin(theta), alpha, seed=seed)
+    # the driver's sampler draws trng::yarn2 with seedDistance = niter*nms*L*ns (ref gpu/src/LICH-train_rbm.cu:82,97)
+    e.set_rng("yarn2", seed, niter * 2 * L * ns)
     e.set_params(params)
     e.save(prefix)                      # the driver finds these files and loads them instead of its clock-seeded init
     e.load(prefix)                      # 10 significant digits survive the round trip: start both runs from the same numbers

@@ -104,8 +104,10 @@ def test_cli_driver_prints_the_reference_drivers_table(tmp_path, driver, width):
     ref_bin = ref_cuda.BINARY if driver == "rbm" else ref_cuda.BINARY_TRSYMM
     our_bin = os.path.join(build.BIN_DIR, "LICH-train_rbm-gpu" if driver == "rbm" else "LICH-train_rbmtrsymm-gpu")
     outs = []
+    # this pair of reference binaries draws Philox uniforms (baseline/shim_cuda); the yarn2 pair is tests/test_gpu_yarn2.py
+    env = dict(os.environ, NQS_RNG="philox")
     for b, d in zip((ref_bin, our_bin), dirs):
-        r = subprocess.run([b] + args + ["-path=%s" % d], capture_output=True, text=True, timeout=600)
+        r = subprocess.run([b] + args + ["-path=%s" % d], capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         rows = [ln.split() for ln in r.stdout.splitlines() if re.match(r"^\s*\d+\s+\S+\s+\S+\s*$", ln)]
         outs.append([(int(a), float(b_), float(c)) for a, b_, c in rows])
