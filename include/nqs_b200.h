@@ -223,7 +223,7 @@ const char * nqs_kernel_variant(const nqs_handle * h, const char * stage);
 /* Full-state checkpoint of one handle (one rank's shard) as a binary sidecar file.  The reference saves the parameters only
  * (text, 10 digits: sampler.save() every 100 iterations, gpu/include/optimizer.cuh:154-155,163), so a restarted run re-warms its
  * chains and restarts the lambda schedule; the sidecar carries what that loses: variables (exact doubles), spins, theta, lnpsi0,
- * sa, the per-chain "lnpsi0 is current" flags, site-ring position, the machine's index_, the RNG counter, bp_ of the lambda
+ * sa, the per-chain "lnpsi0 is current" flags, site-ring position, the machine's index_, the generator (kind, seed, seedDistance, draw counter), bp_ of the lambda
  * schedule (optimizer.cuh:176) and the CG warm start dx (impl_optimizer.cuh:55).  A handle of the same (model, N, M, chains,
  * chain offset) that loads it continues BIT-IDENTICALLY.  Errors: NQS_ERR_IO (file), NQS_ERR_INVALID (shape mismatch). */
 nqs_status nqs_checkpoint_save(nqs_handle * h, const char * path);
