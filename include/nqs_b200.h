@@ -50,7 +50,14 @@ typedef enum nqs_status {
  * [w (f*N+i, alpha filters) | a (1) | b (alpha)], P = N*alpha + 1 + alpha; the sampler works on the expanded RBM
  * wf[i][f*N+j] = w[f][(i+j)%N], bf[f*N+j] = b[f], af[i] = a[0].  nqs_config.n_hiddens is the EXPANDED width alpha*N
  * (a multiple of n_inputs); parameter files: ONE file `prefix` holding all P variables (ref :474-482). */
-typedef enum nqs_model { NQS_MODEL_RBM = 0, NQS_MODEL_FFNN = 1, NQS_MODEL_RBMTRSYMM = 2 } nqs_model;
+/* NQS_MODEL_RBMZ2PRSYMM -- ref RBMZ2PrSymm<T> (:106-147, impl :540-745, kernels :1556-1618): Z2- and parity-symmetric RBM,
+ * variables [w (i*alpha+f) | b (alpha)], P = N*alpha + alpha, no visible bias; expanded RBM of n_hiddens = 4*alpha units
+ * wf[i][4f+{0,1,2,3}] = {w[i][f], -w[i][f], w[N-1-i][f], -w[N-1-i][f]}, bf[4f+j] = b[f].
+ * NQS_MODEL_FFNNTRSYMM -- ref FFNNTrSymm<T> (:197-237, impl :1019-1223, kernels :1693-1750): translation-symmetric FNN, variables
+ * [wi1 (f*N+i) | b1 (alpha) | w1o (alpha)], P = N*alpha + 2*alpha; expanded FNN of n_hiddens = alpha*N units
+ * W1[i][f*N+j] = wi1[f][(i+j)%N], b1f[f*N+j] = b1[f], w1of[f*N+j] = w1o[f].  Both: ONE parameter file named by the prefix. */
+typedef enum nqs_model { NQS_MODEL_RBM = 0, NQS_MODEL_FFNN = 1, NQS_MODEL_RBMTRSYMM = 2, NQS_MODEL_RBMZ2PRSYMM = 3,
+                         NQS_MODEL_FFNNTRSYMM = 4 } nqs_model;
 /* site visiting order of one sweep */
 typedef enum nqs_order {
   NQS_ORDER_CHECKERBOARD = 0, /* 2,4,..,1,3,..,0  ref: gpu/include/impl_hamiltonians.cuh:163-180,209-210 (LITFIChain)   */

@@ -14,7 +14,7 @@ IPC_HANDLE_BYTES = 64
 OK, ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_STATE, ERR_NCCL, ERR_NONFINITE, ERR_UNSUPPORTED = range(9)
 STATUS_NAMES = ["NQS_OK", "NQS_ERR_INVALID", "NQS_ERR_CUDA", "NQS_ERR_NOMEM", "NQS_ERR_IO", "NQS_ERR_STATE",
                 "NQS_ERR_NCCL", "NQS_ERR_NONFINITE", "NQS_ERR_UNSUPPORTED"]
-MODEL_RBM, MODEL_FFNN, MODEL_RBMTRSYMM = 0, 1, 2
+MODEL_RBM, MODEL_FFNN, MODEL_RBMTRSYMM, MODEL_RBMZ2PRSYMM, MODEL_FFNNTRSYMM = 0, 1, 2, 3, 4
 ORDER_CHECKERBOARD, ORDER_SEQUENTIAL = 0, 1
 RNG_PHILOX, RNG_YARN2 = 0, 1
 FLAG_NO_SR, FLAG_ACCEPT_LOG, FLAG_FORCE_GENERIC, FLAG_TWO_PASS_SV = 1, 2, 4, 8

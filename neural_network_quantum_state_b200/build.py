@@ -49,6 +49,8 @@ HOST_PROGRAMS = {
     "LICH-train_rbm-gpu": ("LICH-train_rbm.cpp", []),
     "LICH-train_ffnn-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_FFNN"]),
     "LICH-train_rbmtrsymm-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_RBMTRSYMM"]),
+    "LICH-train_rbmz2prsymm-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_RBMZ2PRSYMM"]),
+    "LICH-train_ffnntrsymm-gpu": ("LICH-train_rbm.cpp", ["-DNQS_DRIVER_FFNNTRSYMM"]),
 }
 
 

@@ -169,7 +169,10 @@ cd * var_ptr(nqs_handle * h) { return h->trsymm ? h->vars.p : h->params.p; }
 void expand_vars(nqs_handle * h)
 {
   if (!h->trsymm) return;
-  trsymm_expand_kernel<<<grid_for(h->Pfull, 256, 148*4), 256, 0, h->stream>>>(h->N, h->alpha_f, h->vars.p, h->params.p);
+  const int grid = grid_for(h->Pfull, 256, 148*4);
+  if (h->tied == TIED_RBM_Z2PR) z2pr_expand_kernel<<<grid, 256, 0, h->stream>>>(h->N, h->alpha_f, h->vars.p, h->params.p);
+  else if (h->tied == TIED_FFNN_TR) ffnntr_expand_kernel<<<grid, 256, 0, h->stream>>>(h->N, h->alpha_f, h->vars.p, h->params.p);
+  else trsymm_expand_kernel<<<grid, 256, 0, h->stream>>>(h->N, h->alpha_f, h->vars.p, h->params.p);
   check_launch(h, "trsymm_expand_kernel");
 }
 
@@ -668,7 +671,18 @@ void launch_oderiv(nqs_handle * h, cudaStream_t stream = nullptr)
   if (stream == nullptr) stream = h->stream;
   const size_t smem = (size_t)(h->model == MODEL_FFNN ? 2 : 1)*h->M*sizeof(cd)+(size_t)h->N*sizeof(double);
   NQS_REQUIRE(smem <= h->smem_optin, NQS_ERR_UNSUPPORTED, "n_hiddens too large for oderiv_kernel shared memory");
-  if (h->trsymm)
+  if (h->tied == TIED_RBM_Z2PR)
+  {
+    set_smem(oderiv_z2pr_kernel, smem);
+    oderiv_z2pr_kernel<<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->alpha_f, h->K, h->spins.p, h->theta.p, h->O.p);
+  }
+  else if (h->tied == TIED_FFNN_TR)
+  { // w1of = the third block of the expanded FFNN parameters
+    set_smem(oderiv_ffnntr_kernel, smem);
+    oderiv_ffnntr_kernel<<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->alpha_f, h->K, h->params.p+(size_t)h->N*h->M+h->M,
+      h->spins.p, h->theta.p, h->O.p);
+  }
+  else if (h->trsymm)
   {
     set_smem(oderiv_trsymm_kernel, smem);
     oderiv_trsymm_kernel<<<(unsigned)h->K, 256, smem, stream>>>(h->N, h->alpha_f, h->K, h->spins.p, h->theta.p, h->O.p);
@@ -1440,7 +1454,7 @@ void do_evolve(nqs_handle * h, const cd * dx_dev, double lr, const CgScalars * s
 {
   h->theta_matches_O = false; h->hidden_valid = false; h->o_pending = false;
   invalidate_tables(h);
-  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->model, h->P, dx_dev, lr, var_ptr(h), sc, need_done);
+  update_params_kernel<<<grid_for(h->P, 256, 148*4), 256, 0, h->stream>>>(h->N, h->M, h->trsymm ? -1 : h->model, h->P, dx_dev, lr, var_ptr(h), sc, need_done);   // tied variables: plain update (ref update_parameters)
   check_launch(h, "update_params_kernel");
   expand_vars(h);
   build_tables_async(h);   // the next sweep needs them anyway; their bound rides on the caller's final read-back
@@ -1666,10 +1680,11 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
   {
     NQS_REQUIRE(cfg && out, NQS_ERR_INVALID, "nqs_create: null argument");
     NQS_REQUIRE(cfg->abi_version == NQS_B200_ABI_VERSION, NQS_ERR_INVALID, "nqs_create: abi_version mismatch");
-    NQS_REQUIRE(cfg->model == NQS_MODEL_RBM || cfg->model == NQS_MODEL_FFNN || cfg->model == NQS_MODEL_RBMTRSYMM, NQS_ERR_INVALID,
-      "nqs_create: unknown model");
-    NQS_REQUIRE(cfg->model != NQS_MODEL_RBMTRSYMM || cfg->n_hiddens%cfg->n_inputs == 0, NQS_ERR_INVALID,
-      "nqs_create: translation-symmetric RBM needs n_hiddens = alpha * n_inputs (the expanded width)");
+    NQS_REQUIRE(cfg->model >= NQS_MODEL_RBM && cfg->model <= NQS_MODEL_FFNNTRSYMM, NQS_ERR_INVALID, "nqs_create: unknown model");
+    NQS_REQUIRE((cfg->model != NQS_MODEL_RBMTRSYMM && cfg->model != NQS_MODEL_FFNNTRSYMM) || cfg->n_hiddens%cfg->n_inputs == 0, NQS_ERR_INVALID,
+      "nqs_create: a translation-symmetric ansatz needs n_hiddens = alpha * n_inputs (the expanded width)");
+    NQS_REQUIRE(cfg->model != NQS_MODEL_RBMZ2PRSYMM || cfg->n_hiddens%4 == 0, NQS_ERR_INVALID,
+      "nqs_create: the Z2/parity-symmetric RBM needs n_hiddens = 4 * alpha (the expanded width)");
     NQS_REQUIRE(cfg->n_inputs >= 1 && cfg->n_hiddens >= 1 && cfg->n_chains >= 1, NQS_ERR_INVALID, "nqs_create: sizes must be >= 1");
     NQS_REQUIRE(!(cfg->pbc && cfg->n_inputs%2 == 1), NQS_ERR_INVALID, "kL%2 == 1 (set \"isPBC\" to \"false\".)"); // ref :141-142
     NQS_REQUIRE(cfg->order == NQS_ORDER_CHECKERBOARD || cfg->order == NQS_ORDER_SEQUENTIAL, NQS_ERR_INVALID, "nqs_create: unknown order");
@@ -1688,12 +1703,16 @@ nqs_status nqs_create(const nqs_config * cfg, nqs_handle ** out)
         h->cfg.flags |= NQS_FLAG_STRUCTURED_SV;
     }
     h->N = cfg->n_inputs; h->M = cfg->n_hiddens; h->model = cfg->model;
-    if (cfg->model == NQS_MODEL_RBMTRSYMM) { h->model = MODEL_RBM; h->trsymm = true; h->alpha_f = h->M/h->N; }
+    if (cfg->model == NQS_MODEL_RBMTRSYMM) { h->model = MODEL_RBM; h->trsymm = true; h->tied = TIED_RBM_TR; h->alpha_f = h->M/h->N; }
+    if (cfg->model == NQS_MODEL_RBMZ2PRSYMM) { h->model = MODEL_RBM; h->trsymm = true; h->tied = TIED_RBM_Z2PR; h->alpha_f = h->M/4; }
+    if (cfg->model == NQS_MODEL_FFNNTRSYMM) { h->model = MODEL_FFNN; h->trsymm = true; h->tied = TIED_FFNN_TR; h->alpha_f = h->M/h->N; }
     h->K = cfg->n_chains; h->Ktot = cfg->n_chains_total > 0 ? cfg->n_chains_total : cfg->n_chains; h->koff = cfg->chain_offset;
     NQS_REQUIRE(h->Ktot >= h->K, NQS_ERR_INVALID, "n_chains_total < n_chains");
     h->P = (h->model == MODEL_RBM) ? (long long)h->N*h->M+h->N+h->M : (long long)h->N*h->M+2*h->M;
     h->Pfull = h->P;
-    if (h->trsymm) h->P = (long long)h->N*h->alpha_f+1+h->alpha_f;
+    if (h->tied == TIED_RBM_TR) h->P = (long long)h->N*h->alpha_f+1+h->alpha_f;
+    if (h->tied == TIED_RBM_Z2PR) h->P = (long long)h->N*h->alpha_f+h->alpha_f;
+    if (h->tied == TIED_FFNN_TR) h->P = (long long)h->N*h->alpha_f+2*h->alpha_f;
     std::memset(&h->timing, 0, sizeof(h->timing));
     cudaDeviceProp prop;
     NQS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1811,7 +1830,22 @@ nqs_status nqs_init_params_random(nqs_handle * h, uint64_t seed)
     const int N = h->N, M = h->M;
     std::vector<std::complex<double> > v((size_t)h->P);
     const long long NM = (long long)N*M;
-    if (h->trsymm)
+    if (h->tied == TIED_RBM_Z2PR)
+    { // ref ctor impl_neural_quantum_state.cuh:562-579
+      const int al = h->alpha_f;
+      std::normal_distribution<double> randw(0, std::sqrt(1.0/(4*al+N))), randb(0, std::sqrt(1.0/(4*al)));
+      for (long long i = 0; i < (long long)N*al; ++i) { const double re = 1e-1*randw(ran), im = 1e-1*randw(ran); v[i] = {re, im}; }
+      for (int j = 0; j < al; ++j) { const double re = 1e-1*randb(ran), im = 1e-1*randb(ran); v[(size_t)N*al+j] = {re, im}; }
+    }
+    else if (h->tied == TIED_FFNN_TR)
+    { // ref ctor impl_neural_quantum_state.cuh:1041-1061
+      const int al = h->alpha_f;
+      std::normal_distribution<double> randwi1(0, std::sqrt(1.0/((1+al)*N))), randw1o(0, std::sqrt(1.0/(al*N)));
+      for (long long i = 0; i < (long long)N*al; ++i) { const double re = randwi1(ran), im = 1e-1*randwi1(ran); v[i] = {re, im}; }
+      for (int j = 0; j < al; ++j) v[(size_t)N*al+j] = {0.0, 0.0};
+      for (int j = 0; j < al; ++j) { const double re = randw1o(ran), im = 1e-1*randw1o(ran); v[(size_t)N*al+al+j] = {re, im}; }
+    }
+    else if (h->trsymm)
     { // ref ctor impl_neural_quantum_state.cuh:325-345
       const int al = h->alpha_f;
       std::normal_distribution<double> randw(0, std::sqrt(1.0/((1+al)*N))), randb(0, std::sqrt(1.0/(N*al)));
@@ -2449,7 +2483,7 @@ nqs_status nqs_checkpoint_save(nqs_handle * h, const char * path)
     CkptHeader hd;
     std::memset(&hd, 0, sizeof(hd));
     std::memcpy(hd.magic, "NQSCKPT2", 8);
-    hd.model = h->model; hd.N = h->N; hd.M = h->M; hd.trsymm = h->trsymm ? 1 : 0;
+    hd.model = h->model; hd.N = h->N; hd.M = h->M; hd.trsymm = h->tied;
     hd.K = h->K; hd.Ktot = h->Ktot; hd.koff = h->koff; hd.P = h->P;
     hd.pos = h->pos; hd.flip_index = h->flip_index; hd.cg_prev_iters = h->cg_prev_iters; hd.has_sr = h->aO.p != nullptr ? 1 : 0;
     hd.step_counter = h->step_counter; hd.seed = h->cfg.seed; hd.bp = h->bp;
@@ -2479,7 +2513,7 @@ nqs_status nqs_checkpoint_load(nqs_handle * h, const char * path)
     CkptHeader hd;
     f.read(reinterpret_cast<char*>(&hd), sizeof(hd));
     NQS_REQUIRE((size_t)f.gcount() == sizeof(hd) && std::memcmp(hd.magic, "NQSCKPT2", 8) == 0, NQS_ERR_IO, "not a libnqs_b200 checkpoint");
-    NQS_REQUIRE(hd.model == h->model && hd.N == h->N && hd.M == h->M && (hd.trsymm != 0) == h->trsymm && hd.K == h->K &&
+    NQS_REQUIRE(hd.model == h->model && hd.N == h->N && hd.M == h->M && hd.trsymm == h->tied && hd.K == h->K &&
       hd.Ktot == h->Ktot && hd.koff == h->koff && hd.P == h->P, NQS_ERR_INVALID,
       "checkpoint was written by a handle of another shape (model, sizes, chains or chain offset differ)");
     NQS_CUDA(cudaStreamSynchronize(h->stream));

@@ -28,6 +28,8 @@ struct Error: public std::runtime_error
 #define NQS_REQUIRE(cond, code, msg) do { if (!(cond)) throw nqs::Error(code, msg); } while (0)
 
 struct CgScalars;
+// tied-variable (symmetric) ansaetze: sampled as their expanded plain network, optimised in the tied variables
+enum { TIED_NONE = 0, TIED_RBM_TR = 1, TIED_RBM_Z2PR = 2, TIED_FFNN_TR = 3 };
 
 template <typename T>
 struct DevBuf
@@ -55,7 +57,8 @@ struct nqs_handle
   long long K = 0, Ktot = 0, koff = 0, P = 0;
   // translation-symmetric RBM (NQS_MODEL_RBMTRSYMM): `model` is MODEL_RBM for every sampler kernel, `params` holds the EXPANDED
   // network [wf | af | bf] (Pfull entries), `vars` the P = N*alpha+1+alpha variables the optimiser moves
-  bool trsymm = false;
+  bool trsymm = false;                    // any tied-variable ansatz (the name is the first one built)
+  int tied = 0;                           // TIED_*: which one
   int alpha_f = 0;
   long long Pfull = 0;
   nqs::DevBuf<nqs::cd> vars;

@@ -138,6 +138,124 @@ __global__ void __launch_bounds__(256) oderiv_trsymm_kernel(const int N, const i
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Z2- and parity-symmetric RBM (ref RBMZ2PrSymm, impl_neural_quantum_state.cuh:540-745; driver gpu/src/LICH-train_rbmz2prsymm.cu).
+// Variables [w (i*alpha+f) | b (alpha)], P = N*alpha + alpha; four hidden units per filter.
+// expand (ref RBMZ2PrSymm__ConstructWeightAndBias__, :1588-1618) into the plain-RBM layout [wf (i*M+c) | af = 0 | bf], M = 4 alpha:
+//   wf[i][4f+0] = w[i][f], wf[i][4f+1] = -w[i][f], wf[i][4f+2] = w[N-1-i][f], wf[i][4f+3] = -w[N-1-i][f], bf[4f+j] = b[f]
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void z2pr_expand_kernel(const int N, const int alpha, const cd * __restrict__ vars, cd * __restrict__ full)
+{
+  const int M = 4*alpha;
+  const cd * w = vars;
+  const cd * b = vars+(size_t)N*alpha;
+  const long long NM = (long long)N*M;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < NM+N+M; idx += (long long)gridDim.x*blockDim.x)
+  {
+    if (idx < NM)
+    {
+      const int i = (int)(idx/M), c = (int)(idx-(long long)i*M), f = c>>2, j = c&3;
+      const cd v = w[(size_t)((j&2) ? N-1-i : i)*alpha+f];
+      full[idx] = (j&1) ? cmake(-v.x, -v.y) : v;
+    }
+    else if (idx < NM+N) full[idx] = cmake(0.0, 0.0);
+    else full[idx] = b[(idx-NM-N)>>2];
+  }
+}
+
+// O writer (ref RBMZ2PrSymm__GetGradientsOfParameters__, :1556-1585): with T = tanh(theta) of the four units of filter f,
+//   d_w[i*alpha+f] = (T[4f] - T[4f+1]) s_i + (T[4f+2] - T[4f+3]) s_{N-1-i} ,  d_b[f] = T[4f] + T[4f+1] + T[4f+2] + T[4f+3]
+__global__ void __launch_bounds__(256) oderiv_z2pr_kernel(const int N, const int alpha, const long long K,
+  const int8_t * __restrict__ spins, const cd * __restrict__ theta, cd * __restrict__ O)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = 4*alpha;
+  cd * T = reinterpret_cast<cd*>(smem_raw);             // [M]
+  double * s = reinterpret_cast<double*>(T+M);         // [N]
+  const long long k = blockIdx.x;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) T[j] = c_tanh(theta[k*M+j]);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s[i] = (double)spins[k*N+i];
+  __syncthreads();
+  const long long P = (long long)N*alpha+alpha;
+  cd * row = O+k*P;
+  const int NA = N*alpha;
+  for (int q = threadIdx.x; q < NA; q += blockDim.x)
+  {
+    const int i = q/alpha, f = q-i*alpha;
+    const cd d0 = csub(T[4*f], T[4*f+1]), d1 = csub(T[4*f+2], T[4*f+3]);
+    st_stream(row+q, cadd(cscale(d0, s[i]), cscale(d1, s[N-1-i])));
+  }
+  for (int f = threadIdx.x; f < alpha; f += blockDim.x)
+    st_stream(row+NA+f, cadd(cadd(T[4*f], T[4*f+1]), cadd(T[4*f+2], T[4*f+3])));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Translation-symmetric FNN (ref FFNNTrSymm, impl_neural_quantum_state.cuh:1019-1223; driver gpu/src/LICH-train_ffnntrsymm.cu).
+// Variables [wi1 (f*N+i) | b1 (alpha) | w1o (alpha)], P = N*alpha + 2 alpha.
+// expand (ref FFNNTrSymm__ConstructWeightAndBias__, :1693-1717) into the plain-FFNN layout [W1 (i*M+c) | b1f | w1of], M = alpha*N:
+//   W1[i][f*N+j] = wi1[f][(i+j)%N], b1f[f*N+j] = b1[f], w1of[f*N+j] = w1o[f]
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void ffnntr_expand_kernel(const int N, const int alpha, const cd * __restrict__ vars, cd * __restrict__ full)
+{
+  const int M = alpha*N;
+  const cd * w = vars;
+  const cd * b1 = vars+(size_t)N*alpha;
+  const cd * w1o = b1+alpha;
+  const long long NM = (long long)N*M;
+  for (long long idx = (long long)blockIdx.x*blockDim.x+threadIdx.x; idx < NM+2*M; idx += (long long)gridDim.x*blockDim.x)
+  {
+    if (idx < NM)
+    {
+      const int i = (int)(idx/M), c = (int)(idx-(long long)i*M), f = c/N, j = c-f*N;
+      full[idx] = w[(size_t)f*N+(i+j)%N];
+    }
+    else if (idx < NM+M) full[idx] = b1[(idx-NM)/N];
+    else full[idx] = w1o[(idx-NM-M)/N];
+  }
+}
+
+// O writer (ref FFNNTrSymm__GetGradientsOfParameters__, :1720-1750): with T' = tanh(theta) w1of and L = log cosh(theta),
+//   d_wi1[f*N+i] = sum_j T'[f*N+j] s[(N+i-j)%N] ,  d_b1[f] = sum_j T'[f*N+j] ,  d_w1o[f] = sum_j L[f*N+j]
+__global__ void __launch_bounds__(256) oderiv_ffnntr_kernel(const int N, const int alpha, const long long K, const cd * __restrict__ w1of,
+  const int8_t * __restrict__ spins, const cd * __restrict__ theta, cd * __restrict__ O)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int M = alpha*N;
+  cd * T = reinterpret_cast<cd*>(smem_raw);             // [M] tanh(theta_c) w1of_c
+  cd * L = T+M;                                         // [M] log cosh(theta_c)
+  double * s = reinterpret_cast<double*>(L+M);         // [N]
+  const long long k = blockIdx.x;
+  for (int j = threadIdx.x; j < M; j += blockDim.x)
+  {
+    const cd th = theta[k*M+j];
+    T[j] = cmul(c_tanh(th), w1of[j]);
+    L[j] = c_logcosh(th);
+  }
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s[i] = (double)spins[k*N+i];
+  __syncthreads();
+  const long long P = (long long)N*alpha+2*alpha;
+  cd * row = O+k*P;
+  for (int q = threadIdx.x; q < M; q += blockDim.x)
+  {
+    const int f = q/N, i = q-f*N;
+    cd acc = cmake(0.0, 0.0);
+    for (int j = 0; j < N; ++j)
+    {
+      const cd t = T[f*N+j];
+      const double sv = s[(N+i-j)%N];
+      acc.x += t.x*sv; acc.y += t.y*sv;
+    }
+    st_stream(row+q, acc);
+  }
+  for (int f = threadIdx.x; f < 2*alpha; f += blockDim.x)
+  {
+    const cd * src = (f < alpha) ? T+(size_t)f*N : L+(size_t)(f-alpha)*N;
+    cd acc = cmake(0.0, 0.0);
+    for (int j = 0; j < N; ++j) acc = cadd(acc, src[j]);
+    st_stream(row+M+f, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Column-direction passes over O.  Grid = (column tiles, row blocks); one thread owns ONE column p of its tile and walks the
 // rows of its row block, so a warp reads 32 consecutive complex numbers (512 B) per row: fully coalesced.  Row-block
 // partials go to part[rb][...][P] and are summed in fixed order by colsum_reduce_kernel.

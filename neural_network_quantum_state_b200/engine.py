@@ -48,7 +48,9 @@ class Engine:
         self.N, self.M, self.K = int(n_inputs), int(n_hiddens), int(n_chains)
         cfg = L.Config()
         cfg.abi_version = L.ABI_VERSION
-        cfg.model = {"rbm": L.MODEL_RBM, "ffnn": L.MODEL_FFNN, "rbmtrsymm": L.MODEL_RBMTRSYMM}[model]   # rbmtrsymm: n_hiddens = alpha*N
+        # tied ansaetze take the EXPANDED width: rbmtrsymm / ffnntrsymm n_hiddens = alpha*N, rbmz2prsymm n_hiddens = 4*alpha
+        cfg.model = {"rbm": L.MODEL_RBM, "ffnn": L.MODEL_FFNN, "rbmtrsymm": L.MODEL_RBMTRSYMM,
+                     "rbmz2prsymm": L.MODEL_RBMZ2PRSYMM, "ffnntrsymm": L.MODEL_FFNNTRSYMM}[model]
         cfg.n_inputs, cfg.n_hiddens, cfg.n_chains = self.N, self.M, self.K
         cfg.n_chains_total, cfg.chain_offset = int(n_chains_total), int(chain_offset)
         cfg.h, cfg.J, cfg.alpha, cfg.pbc = float(h), float(J), float(alpha), int(bool(pbc))

@@ -3,7 +3,8 @@
 // same parameter-file prefix  <path>/RBMLICH-L{L}NH{nh}A{alpha}T{theta}V{ver}D{w,a,b}.dat, same stdout table.
 // The hot path runs in libnqs_b200.so (hand-written sm_100a kernels) through the classes of nqs_host.hpp.
 // -DNQS_DRIVER_RBMTRSYMM builds LICH-train_rbmtrsymm-gpu (ref gpu/src/LICH-train_rbmtrsymm.cu: the translation-symmetric RBM on
-// the periodic chain, the CMake default target of the reference).  -DNQS_DRIVER_FFNN builds LICH-train_ffnn-gpu: the same driver for the one-hidden-layer FNN (the reference ships the
+// the periodic chain, the CMake default target of the reference); -DNQS_DRIVER_RBMZ2PRSYMM / -DNQS_DRIVER_FFNNTRSYMM build the drivers of
+// the other two tied ansaetze (ref gpu/src/LICH-train_rbmz2prsymm.cu, gpu/src/LICH-train_ffnntrsymm.cu).  -DNQS_DRIVER_FFNN builds LICH-train_ffnn-gpu: the same driver for the one-hidden-layer FNN (the reference ships the
 // ansatz, gpu/src/CH-train_ffnn.cu:75, but no LICH driver for it; prefix FFNNLICH-..., files Dw1/Dw2/Db1).
 #include <chrono>
 #include <cmath>
@@ -32,6 +33,15 @@ int main(int argc, char * argv[])
   // ONE variables file <path>/RBMTrSymmLICH-L{L}NF{nf}A{alpha}T{theta}V{ver}
   using Machine = RBMTrSymm<double>;
   const std::string tag = "RBMTrSymmLICH-L", what = "RBMTrSymm";
+#elif defined(NQS_DRIVER_RBMZ2PRSYMM)
+  // ref gpu/src/LICH-train_rbmz2prsymm.cu:14-113: -nf filters, OPEN chain, nwarm 100 / rsd 1e-3 by default, ONE variables file
+  // <path>/RBMZ2PrSymmLICH-L{L}NF{nf}A{alpha}T{theta}V{ver}  (its help text says "RBMTrSymm", :21)
+  using Machine = RBMZ2PrSymm<double>;
+  const std::string tag = "RBMZ2PrSymmLICH-L", what = "RBMTrSymm";
+#elif defined(NQS_DRIVER_FFNNTRSYMM)
+  // ref gpu/src/LICH-train_ffnntrsymm.cu:14-113: -nf filters, periodic chain, nwarm 100 / rsd 1e-3 by default, ONE variables file
+  using Machine = FFNNTrSymm<double>;
+  const std::string tag = "FFNNTrSymmLICH-L", what = "FFNNTrSymm";
 #elif defined(NQS_DRIVER_FFNN)
   using Machine = FFNN<double>;
   const std::string tag = "FFNNLICH-L", what = "FFNN";
@@ -40,7 +50,7 @@ int main(int argc, char * argv[])
   const std::string tag = "RBMLICH-L", what = "RBM";
 #endif
   const std::vector<pair_t> options = {
-#if defined(NQS_DRIVER_RBMTRSYMM)
+#if defined(NQS_DRIVER_RBMTRSYMM) || defined(NQS_DRIVER_RBMZ2PRSYMM) || defined(NQS_DRIVER_FFNNTRSYMM)
     {"L", "# of lattice sites"}, {"nf", "# of filters"}, {"ns", "# of spin samples for parallel Monte-Carlo"},
 #else
     {"L", "# of lattice sites"}, {"nh", "# of hidden nodes"}, {"ns", "# of spin samples for parallel Monte-Carlo"},
@@ -51,12 +61,21 @@ int main(int argc, char * argv[])
     {"rsd", "cutoff value of the energy deviation per energy (convergence criterion)"},
     {"path", "directory to load and save files"}, {"seed", "seed of the parallel random number generator"},
     {"ifprefix", "prefix of the file to load data"}};
-#if defined(NQS_DRIVER_RBMTRSYMM)
+#if defined(NQS_DRIVER_RBMTRSYMM) || defined(NQS_DRIVER_RBMZ2PRSYMM) || defined(NQS_DRIVER_FFNNTRSYMM)
   const std::vector<pair_t> defaults = {
-    {"nwarm", "500"}, {"nms", "1"}, {"lr", "1e-2"}, {"rsd", "1e-3"}, {"path", "."}, {"seed", "0"}, {"ifprefix", "None"}};
+#if defined(NQS_DRIVER_RBMTRSYMM)
+    {"nwarm", "500"},
+#else
+    {"nwarm", "100"},
+#endif
+    {"nms", "1"}, {"lr", "1e-2"}, {"rsd", "1e-3"}, {"path", "."}, {"seed", "0"}, {"ifprefix", "None"}};
   const char * width_opt = "nf";
   const std::string width_tag = "NF";
+#if defined(NQS_DRIVER_RBMZ2PRSYMM)
+  const bool isPBC = false;
+#else
   const bool isPBC = true;
+#endif
 #else
   const std::vector<pair_t> defaults = {
     {"nwarm", "100"}, {"nms", "1"}, {"lr", "1e-2"}, {"path", "."}, {"seed", "0"}, {"ifprefix", "None"}};

@@ -5,6 +5,7 @@
 //
 //   spinhalf::RBM<double>, spinhalf::FFNN<double>      ref gpu/include/neural_quantum_state.cuh:17-59,151-194
 //   spinhalf::RBMTrSymm<double>                         ref gpu/include/neural_quantum_state.cuh:62-105
+//   spinhalf::RBMZ2PrSymm<double>, FFNNTrSymm<double>   ref gpu/include/neural_quantum_state.cuh:106-147,197-237
 //   spinhalf::LITFIChain<Traits>                        ref gpu/include/hamiltonians.cuh:43-75 + mcmc_sampler.cuh:16-37
 //   StochasticReconfigurationCG<double>                 ref gpu/include/optimizer.cuh:112-181
 //
@@ -156,6 +157,34 @@ class RBMTrSymm: public nqs_host::Ansatz
 public:
   RBMTrSymm(const int nInputs, const int alpha, const int nChains):
     nqs_host::Ansatz(NQS_MODEL_RBMTRSYMM, nInputs, alpha*nInputs, nChains), kAlpha(alpha) {}
+  int get_alpha() const { return kAlpha; }
+private:
+  const int kAlpha;
+};
+
+// ref: RBMZ2PrSymm<T>(nInputs, alpha, nChains), gpu/include/neural_quantum_state.cuh:106-147: Z2- and parity-symmetric RBM,
+// nVariables = N*alpha + alpha (4 hidden units per filter); save / load take the FILE path (impl :680-722)
+template <typename FloatType>
+class RBMZ2PrSymm: public nqs_host::Ansatz
+{
+  static_assert(sizeof(FloatType) == sizeof(double), "libnqs_b200 computes in fp64 only");
+public:
+  RBMZ2PrSymm(const int nInputs, const int alpha, const int nChains):
+    nqs_host::Ansatz(NQS_MODEL_RBMZ2PRSYMM, nInputs, 4*alpha, nChains), kAlpha(alpha) {}
+  int get_alpha() const { return kAlpha; }
+private:
+  const int kAlpha;
+};
+
+// ref: FFNNTrSymm<T>(nInputs, alpha, nChains), gpu/include/neural_quantum_state.cuh:197-237: translation-symmetric FNN,
+// nVariables = N*alpha + 2*alpha; save / load take the FILE path (impl :1167-1209)
+template <typename FloatType>
+class FFNNTrSymm: public nqs_host::Ansatz
+{
+  static_assert(sizeof(FloatType) == sizeof(double), "libnqs_b200 computes in fp64 only");
+public:
+  FFNNTrSymm(const int nInputs, const int alpha, const int nChains):
+    nqs_host::Ansatz(NQS_MODEL_FFNNTRSYMM, nInputs, alpha*nInputs, nChains), kAlpha(alpha) {}
   int get_alpha() const { return kAlpha; }
 private:
   const int kAlpha;

@@ -10,8 +10,9 @@ nqs1's own spin register is never set (all zero, as the reference's zero-initial
 visible-bias term -- computed from the MEMBER spins, ref impl_neural_quantum_state.cuh:119-120 -- contributes nothing there;
 that reference quirk is kept bit for bit.
 
-In scope natively: dRBMSampler, dFFNNSampler, dRBMTrSymmSampler (fp64, the arithmetic type of the engine).  The float32 and the
-other symmetric variants exist as names and raise NotImplementedError.
+Native: every double-precision class of the module -- dRBMSampler, dFFNNSampler, dRBMTrSymmSampler, dRBMZ2PrSymmSampler,
+dFFNNTrSymmSampler (fp64 is the arithmetic type of the engine).  The float32 instantiations exist as names and raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -25,8 +26,10 @@ class _PySampler:
 
     def __init__(self, kwargs: dict):
         self._N, self._M, self._K = int(kwargs["nInputs"]), int(kwargs["nHiddens"]), int(kwargs["nChains"])
-        if self._model == "rbmtrsymm":
-            self._M *= self._N     # RBMTrSymm(nInputs, alpha, nChains): "nHiddens" is the number of filters; the engine takes alpha*N
+        if self._model in ("rbmtrsymm", "ffnntrsymm"):
+            self._M *= self._N     # RBMTrSymm / FFNNTrSymm(nInputs, alpha, nChains): "nHiddens" is the number of filters; the engine takes alpha*N
+        elif self._model == "rbmz2prsymm":
+            self._M *= 4           # RBMZ2PrSymm(nInputs, alpha, nChains): four hidden units per filter
         self._seed, self._seed_distance = int(kwargs["seedNumber"]), int(kwargs["seedDistance"])
         dev = int(kwargs.get("device", 0))
         # Sampler4SpinHalf has no Hamiltonian: h = J = 0; sequential order; O / CG buffers are not allocated
@@ -78,6 +81,17 @@ class dRBMTrSymmSampler(_PySampler):
     _model = "rbmtrsymm"
 
 
+class dRBMZ2PrSymmSampler(_PySampler):
+    """ref MAKE_PYSAMPLER_MODULE(m, "dRBMZ2PrSymmSampler", spinhalf::RBMZ2PrSymm, double), pywrapping_sampler.cu:127; kwargs["nHiddens"]
+    is the number of filters alpha, load(path) reads the single variables file (impl_neural_quantum_state.cuh:691-722)."""
+    _model = "rbmz2prsymm"
+
+
+class dFFNNTrSymmSampler(_PySampler):
+    """ref MAKE_PYSAMPLER_MODULE(m, "dFFNNTrSymmSampler", spinhalf::FFNNTrSymm, double), pywrapping_sampler.cu:131."""
+    _model = "ffnntrsymm"
+
+
 def _unsupported(name: str, why: str):
     class _U:
         def __init__(self, *a, **k):
@@ -87,11 +101,8 @@ def _unsupported(name: str, why: str):
 
 
 _FP32 = "libnqs_b200 computes in fp64 only (the reference's float32 instantiation is out of scope)"
-_SYMM = "this symmetric ansatz is out of scope of the B200 hot path (SURVEY 8f; the translation-symmetric RBM is dRBMTrSymmSampler)"
 sRBMSampler = _unsupported("sRBMSampler", _FP32)
 sFFNNSampler = _unsupported("sFFNNSampler", _FP32)
-sRBMTrSymmSampler = _unsupported("sRBMTrSymmSampler", _SYMM)
-sRBMZ2PrSymmSampler = _unsupported("sRBMZ2PrSymmSampler", _SYMM)
-dRBMZ2PrSymmSampler = _unsupported("dRBMZ2PrSymmSampler", _SYMM)
-sFFNNTrSymmSampler = _unsupported("sFFNNTrSymmSampler", _SYMM)
-dFFNNTrSymmSampler = _unsupported("dFFNNTrSymmSampler", _SYMM)
+sRBMTrSymmSampler = _unsupported("sRBMTrSymmSampler", _FP32)
+sRBMZ2PrSymmSampler = _unsupported("sRBMZ2PrSymmSampler", _FP32)
+sFFNNTrSymmSampler = _unsupported("sFFNNTrSymmSampler", _FP32)

@@ -558,6 +558,218 @@ class RBMTrSymm:
             print(" check parameter size... ")
 
 
+class RBMZ2PrSymm:
+    """Z2- and parity-symmetric complex RBM, GPU semantics.  gpu/include/impl_neural_quantum_state.cuh:540-745, kernels
+    :1556-1618 (the ansatz of gpu/src/LICH-train_rbmz2prsymm.cu).
+
+    variables = [w (N*alpha, index i*alpha+f) | b (alpha)], P = N*alpha + alpha, NO visible bias.  symmetrize_variables_
+    (:740-745, kernel :1588-1618) expands them to 4 hidden units per filter: wf[i][4f+0] = w[i][f], wf[i][4f+1] = -w[i][f],
+    wf[i][4f+2] = w[N-1-i][f], wf[i][4f+3] = -w[N-1-i][f], bf[4f+j] = b[f]; every sampler operation (:589-637, 670-678) is the
+    plain RBM's on (wf, 0, bf) with M = 4 alpha.  backward (:639-646, kernel :1556-1585):
+    d_w[i*alpha+f] = (tanh y[4f] - tanh y[4f+1]) s_i + (tanh y[4f+2] - tanh y[4f+3]) s_{N-1-i},  d_b[f] = sum of the 4 tanh."""
+
+    kind = "rbmz2prsymm"
+
+    def __init__(self, n_inputs: int, alpha: int, n_chains: int, rng: Optional[np.random.Generator] = None):
+        self.N, self.alpha, self.K = n_inputs, alpha, n_chains
+        self.M = 4 * alpha
+        self.P = n_inputs * alpha + alpha
+        self.variables = np.zeros(self.P, dtype=np.complex128)
+        self.spins = np.ones((n_chains, n_inputs), dtype=np.float64)
+        self.y = np.zeros((n_chains, self.M), dtype=np.complex128)
+        self.sa = np.zeros(n_chains, dtype=np.complex128)
+        self.index_ = 0
+        if rng is not None:
+            self.random_init(rng)
+
+    def random_init(self, rng: np.random.Generator):
+        """ctor :562-579: w = 0.1 (g + i g'), g ~ N(0, 1/(4 alpha + N)); b = 0.1 (g + i g'), g ~ N(0, 1/(4 alpha))."""
+        N, al = self.N, self.alpha
+        sw, sb = math.sqrt(1.0 / (4 * al + N)), math.sqrt(1.0 / (4 * al))
+        self.variables[: N * al] = 0.1 * (rng.normal(0, sw, N * al) + 1j * rng.normal(0, sw, N * al))
+        self.variables[N * al:] = 0.1 * (rng.normal(0, sb, al) + 1j * rng.normal(0, sb, al))
+
+    @property
+    def W(self):
+        N, al = self.N, self.alpha
+        w = self.variables[: N * al].reshape(N, al)
+        wr = w[::-1]                                            # w[N-1-i][f]
+        return np.stack([w, -w, wr, -wr], axis=2).reshape(N, 4 * al)   # wf[i][4f+j]
+
+    @property
+    def a(self):
+        return np.zeros(self.N, dtype=np.complex128)
+
+    @property
+    def b(self):
+        return np.repeat(self.variables[self.N * self.alpha:], 4)
+
+    def _theta(self, spins):
+        return spins @ self.W + self.b[None, :]
+
+    def initialize(self, spins: np.ndarray) -> np.ndarray:
+        self.spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(self.spins)
+        return logcosh(self.y).sum(axis=1)
+
+    def forward_flip(self, idx: int) -> np.ndarray:
+        self.index_ = idx
+        s = self.spins[:, idx]
+        return logcosh(self.y - self.W[idx][None, :] * (2.0 * s)[:, None]).sum(axis=1)
+
+    def forward_spins(self, spins: np.ndarray, save: bool = True) -> np.ndarray:
+        spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(spins)
+        out = logcosh(self.y).sum(axis=1)
+        if save:
+            self.spins = spins.copy()
+        return out
+
+    def spin_flip(self, mask: np.ndarray, idx: int = -1):
+        if idx != -1:
+            self.index_ = idx
+        i = self.index_
+        two_delta = np.where(mask, 2.0, 0.0)
+        s = self.spins[:, i]
+        self.y = self.y - self.W[i][None, :] * (two_delta * s)[:, None]
+        self.spins[:, i] = (1.0 - two_delta) * s
+
+    def backward(self) -> np.ndarray:
+        N, al = self.N, self.alpha
+        t = np.tanh(self.y).reshape(self.K, al, 4)              # [k][f][j]
+        d0, d1 = t[:, :, 0] - t[:, :, 1], t[:, :, 2] - t[:, :, 3]
+        O = np.empty((self.K, self.P), dtype=np.complex128)
+        O[:, : N * al] = (d0[:, None, :] * self.spins[:, :, None] + d1[:, None, :] * self.spins[:, ::-1, None]).reshape(self.K, N * al)
+        O[:, N * al:] = t.sum(axis=2)
+        return O
+
+    def update_variables(self, dx: np.ndarray, lr: float):
+        """:648-661: variables -= lr*dx, symmetrize, y re-derived for the current spins."""
+        self.variables = self.variables - lr * np.asarray(dx, dtype=np.complex128)
+        self.y = self._theta(self.spins)
+
+    def save(self, path: str, prec: int = 10):
+        """:680-689: every variable, blank separated, in one file."""
+        _write_rows(path, [self.variables], prec, False)
+
+    def load(self, path: str):
+        raw = _read_complex_tokens(path)
+        if raw is None:
+            print("# --- file-path: %s is not exist..." % path)
+        elif raw.size == self.variables.size:
+            self.variables[...] = raw
+        else:
+            print(" check parameter size... ")
+
+
+class FFNNTrSymm:
+    """Translation-symmetric one-hidden-layer complex FNN, GPU semantics.  gpu/include/impl_neural_quantum_state.cuh:1019-1223,
+    kernels :1693-1750 (the ansatz of gpu/src/LICH-train_ffnntrsymm.cu).
+
+    variables = [wi1 (alpha*N, index f*N+i) | b1 (alpha) | w1o (alpha)], P = N*alpha + 2 alpha.  symmetrize_variables_ (:1217-1223,
+    kernel :1693-1717): W1[i][f*N+j] = wi1[f][(i+j)%N], b1f[f*N+j] = b1[f], w1of[f*N+j] = w1o[f]; sampler operations
+    (:1081-1131, 1157-1165) are the plain FFNN's on the expansion with M = alpha*N.  backward (:1133-1141, kernel :1720-1750):
+    d_wi1[f*N+i] = sum_j w1of[fN+j] tanh(y[fN+j]) s[(N+i-j)%N],  d_b1[f] = sum_j w1of tanh(y),  d_w1o[f] = sum_j logcosh(y[fN+j])."""
+
+    kind = "ffnntrsymm"
+
+    def __init__(self, n_inputs: int, alpha: int, n_chains: int, rng: Optional[np.random.Generator] = None):
+        self.N, self.alpha, self.K = n_inputs, alpha, n_chains
+        self.M = alpha * n_inputs
+        self.P = n_inputs * alpha + 2 * alpha
+        self.variables = np.zeros(self.P, dtype=np.complex128)
+        self.spins = np.ones((n_chains, n_inputs), dtype=np.float64)
+        self.y = np.zeros((n_chains, self.M), dtype=np.complex128)
+        self.index_ = 0
+        if rng is not None:
+            self.random_init(rng)
+
+    def random_init(self, rng: np.random.Generator):
+        """ctor :1041-1061: wi1 = g + 0.1 i g', g ~ N(0, 1/((1+alpha) N)); b1 = 0; w1o = g + 0.1 i g', g ~ N(0, 1/(alpha N))."""
+        N, al = self.N, self.alpha
+        sw, so = math.sqrt(1.0 / ((1 + al) * N)), math.sqrt(1.0 / (al * N))
+        self.variables[: N * al] = rng.normal(0, sw, N * al) + 0.1j * rng.normal(0, sw, N * al)
+        self.variables[N * al: N * al + al] = 0.0
+        self.variables[N * al + al:] = rng.normal(0, so, al) + 0.1j * rng.normal(0, so, al)
+
+    @property
+    def W(self):
+        N, al = self.N, self.alpha
+        w = self.variables[: N * al].reshape(al, N)
+        i = np.arange(N)[:, None, None]
+        f = np.arange(al)[None, :, None]
+        j = np.arange(N)[None, None, :]
+        return w[f, (i + j) % N].reshape(N, al * N)
+
+    @property
+    def b(self):
+        return np.repeat(self.variables[self.N * self.alpha: self.N * self.alpha + self.alpha], self.N)
+
+    @property
+    def w1o(self):
+        return np.repeat(self.variables[self.N * self.alpha + self.alpha:], self.N)
+
+    def _theta(self, spins):
+        return spins @ self.W + self.b[None, :]
+
+    def initialize(self, spins: np.ndarray) -> np.ndarray:
+        self.spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(self.spins)
+        return logcosh(self.y) @ self.w1o
+
+    def forward_flip(self, idx: int) -> np.ndarray:
+        self.index_ = idx
+        s = self.spins[:, idx]
+        return logcosh(self.y - self.W[idx][None, :] * (2.0 * s)[:, None]) @ self.w1o
+
+    def forward_spins(self, spins: np.ndarray, save: bool = True) -> np.ndarray:
+        spins = np.array(spins, dtype=np.float64).reshape(self.K, self.N)
+        self.y = self._theta(spins)
+        out = logcosh(self.y) @ self.w1o
+        if save:
+            self.spins = spins.copy()
+        return out
+
+    def spin_flip(self, mask: np.ndarray, idx: int = -1):
+        if idx != -1:
+            self.index_ = idx
+        i = self.index_
+        two_delta = np.where(mask, 2.0, 0.0)
+        s = self.spins[:, i]
+        self.y = self.y - self.W[i][None, :] * (two_delta * s)[:, None]
+        self.spins[:, i] = (1.0 - two_delta) * s
+
+    def backward(self) -> np.ndarray:
+        N, al = self.N, self.alpha
+        t = (np.tanh(self.y) * self.w1o[None, :]).reshape(self.K, al, N)      # [k][f][j]
+        O = np.empty((self.K, self.P), dtype=np.complex128)
+        i = np.arange(N)[:, None]
+        j = np.arange(N)[None, :]
+        sh = self.spins[:, (N + i - j) % N]                                  # [k][i][j] = s[(N+i-j)%N]
+        O[:, : N * al] = np.einsum("kfj,kij->kfi", t, sh).reshape(self.K, N * al)
+        O[:, N * al: N * al + al] = t.sum(axis=2)
+        O[:, N * al + al:] = logcosh(self.y).reshape(self.K, al, N).sum(axis=2)
+        return O
+
+    def update_variables(self, dx: np.ndarray, lr: float):
+        """:1143-1155: variables -= lr*dx (no transposition: the tied block is f*N+i on both sides), symmetrize, y re-derived."""
+        self.variables = self.variables - lr * np.asarray(dx, dtype=np.complex128)
+        self.y = self._theta(self.spins)
+
+    def save(self, path: str, prec: int = 10):
+        """:1167-1176: every variable, blank separated, in one file."""
+        _write_rows(path, [self.variables], prec, False)
+
+    def load(self, path: str):
+        raw = _read_complex_tokens(path)
+        if raw is None:
+            print("# --- file-path: %s is not exist..." % path)
+        elif raw.size == self.variables.size:
+            self.variables[...] = raw
+        else:
+            print(" check parameter size... ")
+
+
 def make_ansatz(kind: str, N: int, M: int, K: int, rng=None):
     if kind == "rbm":
         return RBM(N, M, K, rng)
@@ -566,6 +778,12 @@ def make_ansatz(kind: str, N: int, M: int, K: int, rng=None):
     if kind == "rbmtrsymm":          # M = the expanded width alpha*N (as in nqs_config.n_hiddens)
         assert M % N == 0
         return RBMTrSymm(N, M // N, K, rng)
+    if kind == "rbmz2prsymm":        # M = 4*alpha
+        assert M % 4 == 0
+        return RBMZ2PrSymm(N, M // 4, K, rng)
+    if kind == "ffnntrsymm":         # M = alpha*N
+        assert M % N == 0
+        return FFNNTrSymm(N, M // N, K, rng)
     raise ValueError(kind)
 
 
