@@ -10,9 +10,11 @@ nqs1's own spin register is never set (all zero, as the reference's zero-initial
 visible-bias term -- computed from the MEMBER spins, ref impl_neural_quantum_state.cuh:119-120 -- contributes nothing there;
 that reference quirk is kept bit for bit.
 
-Native: every double-precision class of the module -- dRBMSampler, dFFNNSampler, dRBMTrSymmSampler, dRBMZ2PrSymmSampler,
-dFFNNTrSymmSampler (fp64 is the arithmetic type of the engine).  The float32 instantiations exist as names and raise
-NotImplementedError.
+All ten classes of the module are served.  The engine computes in fp64 only: the d* classes are the reference's double
+instantiations; the s* classes (what the reference's own python/meas_*.py scripts select, floatType = 'float32') keep the
+float32 surface -- get_spinStates -> float32, get_lnpsi / get_lnpsi_for_fixed_spins -> complex64 -- on the same fp64
+arithmetic, i.e. they are MORE precise than the reference's float instantiation and not bit-comparable to it (a float32 Markov
+chain follows another path anyway: the reference draws uniform01_dist<float> there).
 """
 from __future__ import annotations
 
@@ -23,6 +25,7 @@ from ..engine import Engine
 
 class _PySampler:
     _model = "rbm"
+    _real, _complex = np.float64, np.complex128      # dtypes of the returned arrays (py::array_t<T> / std::complex<T> upstream)
 
     def __init__(self, kwargs: dict):
         self._N, self._M, self._K = int(kwargs["nInputs"]), int(kwargs["nHiddens"]), int(kwargs["nChains"])
@@ -57,14 +60,14 @@ class _PySampler:
         self._nqs0.do_mcmc_steps(int(nMCSteps))
 
     def get_spinStates(self) -> np.ndarray:
-        return self._nqs0.get_spinStates().astype(np.float64).reshape(-1)   # flat [K*N] reals like py::array_t<T>(size)
+        return self._nqs0.get_spinStates().astype(self._real).reshape(-1)   # flat [K*N] reals like py::array_t<T>(size)
 
     def get_lnpsi(self) -> np.ndarray:
-        return self._nqs0.get_lnpsi()
+        return self._nqs0.get_lnpsi().astype(self._complex, copy=False)
 
     def get_lnpsi_for_fixed_spins(self, spinStates) -> np.ndarray:
         s = np.asarray(spinStates).reshape(self._K, self._N)
-        return self._nqs1.get_lnpsi_for_fixed_spins(np.rint(s).astype(np.int8))
+        return self._nqs1.get_lnpsi_for_fixed_spins(np.rint(s).astype(np.int8)).astype(self._complex, copy=False)
 
 
 class dRBMSampler(_PySampler):
@@ -92,17 +95,13 @@ class dFFNNTrSymmSampler(_PySampler):
     _model = "ffnntrsymm"
 
 
-def _unsupported(name: str, why: str):
-    class _U:
-        def __init__(self, *a, **k):
-            raise NotImplementedError("%s: %s" % (name, why))
-    _U.__name__ = name
-    return _U
+def _single(cls):
+    """the float instantiation of MAKE_PYSAMPLER_MODULE (pywrapping_sampler.cu:120-131): float32 / complex64 arrays out"""
+    return type("s" + cls.__name__[1:], (cls,), {"_real": np.float32, "_complex": np.complex64, "__doc__": cls.__doc__})
 
 
-_FP32 = "libnqs_b200 computes in fp64 only (the reference's float32 instantiation is out of scope)"
-sRBMSampler = _unsupported("sRBMSampler", _FP32)
-sFFNNSampler = _unsupported("sFFNNSampler", _FP32)
-sRBMTrSymmSampler = _unsupported("sRBMTrSymmSampler", _FP32)
-sRBMZ2PrSymmSampler = _unsupported("sRBMZ2PrSymmSampler", _FP32)
-sFFNNTrSymmSampler = _unsupported("sFFNNTrSymmSampler", _FP32)
+sRBMSampler = _single(dRBMSampler)
+sFFNNSampler = _single(dFFNNSampler)
+sRBMTrSymmSampler = _single(dRBMTrSymmSampler)
+sRBMZ2PrSymmSampler = _single(dRBMZ2PrSymmSampler)
+sFFNNTrSymmSampler = _single(dFFNNTrSymmSampler)

@@ -22,9 +22,11 @@ def test_surface_and_argument_checks_cpu():
     r = sampler.RBM(floatType="float64", symmType="None")
     with pytest.raises(Exception):
         r.init(nInputs=4, nHiddens=4, nChains=4)           # essential arguments omitted
-    with pytest.raises(NotImplementedError):
-        sampler.RBM(floatType="float32", symmType="None").init(nInputs=4, nHiddens=4, nChains=4, seedNumber=0, seedDistance=1,
-                                                               path_to_load="x", init_mcmc_steps=1)
+    # the float instantiations keep the float32 / complex64 surface (the engine computes in fp64)
+    for name in ("RBM", "FFNN", "RBMTrSymm", "RBMZ2PrSymm", "FFNNTrSymm"):
+        s_cls, d_cls = getattr(_pynqs_gpu, "s%sSampler" % name), getattr(_pynqs_gpu, "d%sSampler" % name)
+        assert issubclass(s_cls, d_cls) and s_cls._real is np.float32 and s_cls._complex is np.complex64
+        assert d_cls._real is np.float64 and d_cls._complex is np.complex128 and s_cls._model == d_cls._model
 
 
 @pytest.mark.gpu
