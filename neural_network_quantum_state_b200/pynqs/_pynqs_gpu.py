@@ -20,7 +20,15 @@ from __future__ import annotations
 
 import numpy as np
 
-from ..engine import Engine
+try:
+    from ..engine import Engine
+except ImportError:
+    # imported as the TOP-LEVEL package `pynqs` -- PYTHONPATH=<repo>/neural_network_quantum_state_b200, the way the reference's
+    # scripts find python/pynqs (README.md:20-22, python/meas_*.py: `from pynqs import sampler`)
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from neural_network_quantum_state_b200.engine import Engine
 
 
 class _PySampler:

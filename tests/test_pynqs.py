@@ -29,6 +29,21 @@ def test_surface_and_argument_checks_cpu():
         assert d_cls._real is np.float64 and d_cls._complex is np.complex128 and s_cls._model == d_cls._model
 
 
+def test_reference_scripts_import_path_cpu():
+    """python/meas_*.py do `from pynqs import sampler` with the directory that holds pynqs/ on PYTHONPATH (ref README.md:20-22);
+    the drop-in must resolve the same way, with the arguments those scripts pass (floatType 'float32', symmType 'tr')."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "neural_network_quantum_state_b200"))
+    code = ("from pynqs import sampler\n"
+            "r = sampler.RBM(floatType='float32', symmType='tr')\n"
+            "print(r._sampler.__name__, r._sampler._model)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split() == ["sRBMTrSymmSampler", "rbmtrsymm"]
+
+
 @pytest.mark.gpu
 def test_pynqs_sampler_against_oracle(tmp_path):
     from neural_network_quantum_state_b200 import Engine
