@@ -11,6 +11,8 @@ import os
 import re
 import subprocess
 import tempfile
+import threading
+import time
 from typing import Optional
 
 import numpy as np
@@ -42,20 +44,32 @@ def run(L: int, nh: int, ns: int, niter: int, nwarm: int, seed: int, path: str, 
     opts = {"L": L, ("nh" if driver == "rbm" else "nf"): nh, "ns": ns, "niter": niter, "alpha": "2", "theta": THETA_STR, "ver": 0, "nwarm": nwarm, "nms": nms,
             "dev": device, "lr": repr(lr), "rsd": "1e-30", "seed": seed, "path": path}
     cmd = [BINARY if driver == "rbm" else BINARY_TRSYMM] + ["-%s=%s" % (k, v) for k, v in opts.items()]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-    if r.returncode != 0:
-        raise RuntimeError("reference CUDA driver failed (%d): %s" % (r.returncode, (r.stderr or r.stdout)[-2000:]))
-    energies, rsd = [], []
+    # The driver prints one row per SR iteration and flushes it (`<< std::endl << std::flush`, gpu/include/optimizer.cuh:156-159), so
+    # the arrival time of each row on the pipe is the end of that iteration: per-iteration wall times without touching the program.
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, bufsize=1)
+    killer = threading.Timer(timeout, proc.kill)
+    killer.start()
+    energies, rsd, row_times, lines = [], [], [], []
     elapsed = None
-    for ln in r.stdout.splitlines():
-        m = re.match(r"^\s*(\d+)\s+(\S+)\s+(\S+)\s*$", ln)
-        if m and not ln.lstrip().startswith("#"):
-            energies.append(float(m.group(2)))
-            rsd.append(float(m.group(3)))
-        m = re.match(r"^# elapsed time:\s*(\S+)\(sec\)", ln)
-        if m:
-            elapsed = float(m.group(1))
-    return {"energies": energies, "rsd": rsd, "elapsed_s": elapsed, "stdout_tail": r.stdout[-400:]}
+    try:
+        for ln in proc.stdout:
+            now = time.perf_counter()
+            lines.append(ln)
+            m = re.match(r"^\s*(\d+)\s+(\S+)\s+(\S+)\s*$", ln)
+            if m and not ln.lstrip().startswith("#"):
+                energies.append(float(m.group(2)))
+                rsd.append(float(m.group(3)))
+                row_times.append(now)
+            m = re.match(r"^# elapsed time:\s*(\S+)\(sec\)", ln)
+            if m:
+                elapsed = float(m.group(1))
+        rc = proc.wait()
+    finally:
+        killer.cancel()
+    out = "".join(lines)
+    if rc != 0:
+        raise RuntimeError("reference CUDA driver failed (%d): %s" % (rc, out[-2000:]))
+    return {"energies": energies, "rsd": rsd, "elapsed_s": elapsed, "row_times_s": row_times, "stdout_tail": out[-400:]}
 
 
 def load_vars(path: str) -> np.ndarray:

@@ -180,8 +180,8 @@ def multi_gpu_parity(world: int, rank: int, local_rank: int) -> dict:
 
 def gpu_reference_leg(model: str, N: int, M: int, K: int, cfg_id: int, device: int) -> dict:
     """The reference's OWN CUDA driver (gpu/src/LICH-train_rbm.cu, unmodified, compiled for sm_100 by baseline/Makefile) on this
-    GPU, same parameter files, same uniforms (Philox TRNG shim), next to this engine: ms per SR step from two runs (3 and 8
-    iterations after 100 warm-up sweeps) and the energy trajectories side by side.  A second leg next to the CPU reference arm,
+    GPU, same parameter files, same uniforms (Philox TRNG shim), next to this engine: ms per SR step from the arrival times of the
+    rows it prints (8 iterations after 100 warm-up sweeps, the first 3 left out) and the energy trajectories side by side.  A second leg next to the CPU reference arm,
     not a replacement for it."""
     import tempfile
     from baseline import ref_cuda
@@ -201,18 +201,24 @@ def gpu_reference_leg(model: str, N: int, M: int, K: int, cfg_id: int, device: i
         e.set_params(synthetic_params(model, N, M, cfg_id))
         e.save(prefix, 17)
         e.load(prefix)
-        ra = ref_cuda.run(N, M, K, n_a, nwarm, seed, tmp, device=device)
-        e.save(prefix, 17)                     # the driver overwrote the files with its final parameters: restore the start
         rb = ref_cuda.run(N, M, K, n_b, nwarm, seed, tmp, device=device)
         e.warm_up(nwarm)
         ours = [e.sr_step(n_mc_steps=1, lr=1e-2).e_mean.real for _ in range(n_b)]
         e.close()
-    ms = (rb["elapsed_s"] - ra["elapsed_s"]) / (n_b - n_a) * 1e3
+    # the driver flushes one row per iteration: the time between the arrival of row n_a and row n_b spans iterations n_a+1..n_b
+    # (the first n_a are left out as its warm-up: cuBLAS / Thrust first-use costs)
+    t = rb["row_times_s"]
+    per_iter = [(t[i] - t[i - 1]) * 1e3 for i in range(1, len(t))]
+    if len(t) < n_b:
+        return {"unavailable": "the reference driver printed %d of %d iteration rows: %s" % (len(t), n_b, rb["stdout_tail"][-200:])}
+    ms = (t[n_b - 1] - t[n_a - 1]) / (n_b - n_a) * 1e3
     diff = max(abs(a - b) / max(abs(b), 1e-300) for a, b in zip(ours, rb["energies"])) if rb["energies"] else None
     return {"ms_per_step": ms, "value": K / (ms * 1e-3), "unit": UNIT, "steps_timed": n_b - n_a,
+            "ms_per_iteration": [round(x, 3) for x in per_iter],
             "energies_reference": rb["energies"], "energies_engine": ours, "energy_max_rel_diff": diff,
             "how": "unmodified gpu/src/LICH-train_rbm.cu, nvcc -arch=sm_100, TRNG4 -> Philox shim (same uniforms as the engine); "
-                   "(elapsed of 8 iterations - elapsed of 3) / 5, 100 warm-up sweeps each; energies printed with 7 digits"}
+                   "one run of 8 iterations after 100 warm-up sweeps, each iteration timed by the arrival of the row the driver "
+                   "prints and flushes at its end; ms_per_step = mean of iterations 4..8; energies printed with 7 digits"}
 
 
 def sweep_roofline(model, N, M, K_loc, sweep_ms, hbm_peak_gbs, variant):
