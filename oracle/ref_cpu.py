@@ -82,7 +82,7 @@ def _p(a: np.ndarray):
 class RefSampler:
     """Reference CPU RBM/FFNN + sampler + long-range TFI shim + SR-CG, driven with pre-drawn uniforms.
 
-    model: "rbm" | "ffnn";  order: "checkerboard" (LITFIChain) | "sequential" (Sampler4SpinHalf).
+    model: "rbm" | "ffnn" | "rbmtrsymm" | "ffnntrsymm";  order: "checkerboard" (LITFIChain) | "sequential" (Sampler4SpinHalf).
     NOTE for "ffnn": the CPU tree emits the W-block of O in natural (i*M+j) layout; the GPU tree transposes.
     """
 
@@ -90,7 +90,10 @@ class RefSampler:
                  order: str = "checkerboard"):
         self.L = lib()
         self.model, self.N, self.M, self.K = model, N, M, K
-        self.h = self.L.ref_create({"rbm": 0, "ffnn": 1}[model], N, M, K, h, J, alpha, int(pbc),
+        # the tied ansaetze (cpu/include/neural_quantum_state.hpp:68-102, 184-217) are constructed with the number of filters;
+        # M here is the expanded width alpha*N (the shape of theta), as in nqs_config.n_hiddens
+        width = M // N if model in ("rbmtrsymm", "ffnntrsymm") else M
+        self.h = self.L.ref_create({"rbm": 0, "ffnn": 1, "rbmtrsymm": 2, "ffnntrsymm": 4}[model], N, width, K, h, J, alpha, int(pbc),
                                    {"checkerboard": 0, "sequential": 1}[order])
         if not self.h:
             raise RuntimeError("ref_create failed")

@@ -2,7 +2,8 @@
 //
 // This translation unit #includes the reference headers where they lie under /root/reference/cpu/include
 // (nothing is copied into this repository) and instantiates, unmodified:
-//   spinhalf::RBM<double>, spinhalf::FFNN<double>      cpu/include/neural_quantum_state.hpp, impl_neural_quantum_state.hpp
+//   spinhalf::RBM<double>, spinhalf::FFNN<double>,     cpu/include/neural_quantum_state.hpp, impl_neural_quantum_state.hpp
+//   spinhalf::RBMTrSymm<double>, spinhalf::FFNNTrSymm<double>
 //   BaseParallelSampler<...>                            cpu/include/mcmc_sampler.hpp, impl_mcmc_sampler.hpp
 //   SMatrixForCG<double>, ConjugateGradient<double>     cpu/include/functor_for_CG.hpp, conjugate_gradient.hpp
 // What the CPU tree does NOT have is written here as a thin shim that restates the GPU tree:
@@ -325,19 +326,29 @@ template <> void Ctx<spinhalf::FFNN<double> >::save(const char * prefix, int pre
   machine->save(spinhalf::FFNNDataType::W2, p+"Dw2.dat", prec);
   machine->save(spinhalf::FFNNDataType::B1, p+"Db1.dat", prec);
 }
+// the tied-variable ansaetze of the CPU tree keep every variable in ONE file named by the path itself
+// (cpu/include/impl_neural_quantum_state.hpp:515-548, 1159-1192), like their GPU counterparts
+template <> void Ctx<spinhalf::RBMTrSymm<double> >::load(const char * prefix) { machine->load(std::string(prefix)); }
+template <> void Ctx<spinhalf::RBMTrSymm<double> >::save(const char * prefix, int prec) { machine->save(std::string(prefix), prec); }
+template <> void Ctx<spinhalf::FFNNTrSymm<double> >::load(const char * prefix) { machine->load(std::string(prefix)); }
+template <> void Ctx<spinhalf::FFNNTrSymm<double> >::save(const char * prefix, int prec) { machine->save(std::string(prefix), prec); }
 } // namespace
 
 #define REF_TRY(stmt) try { stmt; return 0; } catch (const std::exception & e) { std::cerr << "# ref_harness: " << e.what() << std::endl; return 1; }
 
 extern "C"
 {
-// model: 0 = RBM, 1 = FFNN (CPU gradient layout is natural i*M+j).  order: 0 = checkerboard, 1 = sequential.
+// model: 0 = RBM, 1 = FFNN (CPU gradient layout is natural i*M+j), 2 = RBMTrSymm, 4 = FFNNTrSymm (for these two
+// M is the number of filters alpha; numbering as nqs_model of include/nqs_b200.h -- the CPU tree has no RBMZ2PrSymm).
+// order: 0 = checkerboard, 1 = sequential.
 void * ref_create(int model, int N, int M, int K, double h, double J, double alpha, int pbc, int order)
 {
   try
   {
     if (model == 0) return new Ctx<spinhalf::RBM<double> >(N, M, K, h, J, alpha, pbc, order);
     if (model == 1) return new Ctx<spinhalf::FFNN<double> >(N, M, K, h, J, alpha, pbc, order);
+    if (model == 2) return new Ctx<spinhalf::RBMTrSymm<double> >(N, M, K, h, J, alpha, pbc, order);
+    if (model == 4) return new Ctx<spinhalf::FFNNTrSymm<double> >(N, M, K, h, J, alpha, pbc, order);
   }
   catch (const std::exception & e) { std::cerr << "# ref_harness: " << e.what() << std::endl; }
   return nullptr;

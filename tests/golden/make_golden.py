@@ -28,6 +28,17 @@ def synth_params(model, N, M, rng):
         a = 0.3 * (rng.normal(size=N) + 1j * rng.normal(size=N))
         b = 0.5 * math.sqrt(1.0 / M) * (rng.normal(size=M) + 1j * rng.normal(size=M))
         return np.concatenate([W.ravel(), a, b])
+    if model == "rbmtrsymm":       # [w (f*N+i) | a | b (alpha)], M = alpha*N
+        al = M // N
+        w = 0.8 * (rng.normal(0, 0.35, N * al) + 1j * rng.normal(0, 0.35, N * al))
+        b = 0.3 * (rng.normal(size=al) + 1j * rng.normal(size=al))
+        return np.concatenate([w, [0.2 - 0.1j], b])
+    if model == "ffnntrsymm":      # [wi1 (f*N+i) | b1 (alpha) | w1o (alpha)], M = alpha*N
+        al = M // N
+        w = rng.normal(0, 0.3, N * al) + 0.1j * rng.normal(0, 0.3, N * al)
+        b1 = 0.3 * (rng.normal(size=al) + 1j * rng.normal(size=al))
+        w1o = rng.normal(0, 0.5, al) + 0.1j * rng.normal(0, 0.5, al)
+        return np.concatenate([w, b1, w1o])
     W = rng.normal(0, sw, (N, M)) + 0.1j * rng.normal(0, sw, (N, M))
     b1 = 0.3 * (rng.normal(size=M) + 1j * rng.normal(size=M))
     w1o = rng.normal(0, math.sqrt(1.0 / M), M) + 0.1j * rng.normal(0, math.sqrt(1.0 / M), M)
@@ -85,6 +96,13 @@ def make_case(name, model, N, M, K, pbc, order, seed, n_warm, n_sr, lr, custom_i
 if __name__ == "__main__":
     if not ref_cpu.available():
         raise SystemExit("build oracle/_ref first: make -C oracle")
+    if "--tied" in sys.argv:
+        # the tied-variable ansaetze the CPU tree has (cpu/include/neural_quantum_state.hpp:68-102, 184-217); added in round 2
+        # without regenerating the four cases below.  M = expanded width alpha*N; random initial spins (a symmetric start leaves
+        # zero-variance columns in the few-parameter O)
+        make_case("rbmtrsymm_pbc", "rbmtrsymm", 10, 20, 64, True, "checkerboard", 201, 10, 3, 0.03, custom_init=True)
+        make_case("ffnntrsymm_pbc", "ffnntrsymm", 8, 24, 64, True, "checkerboard", 202, 10, 3, 0.03, custom_init=True)
+        raise SystemExit(0)
     make_case("rbm_obc", "rbm", 10, 16, 48, False, "checkerboard", 101, 12, 3, 0.05)
     make_case("rbm_pbc_odd_m", "rbm", 8, 13, 40, True, "checkerboard", 112, 14, 2, 0.05)
     make_case("rbm_seq_custom", "rbm", 9, 12, 50, False, "sequential", 103, 10, 2, 0.02, custom_init=True)

@@ -200,3 +200,31 @@ def test_cli_driver_prints_the_reference_drivers_table(tmp_path, driver, kind, n
     want, have = ref_cuda.load_vars(names[0]), ref_cuda.load_vars(names[1])
     assert want.size == have.size == L * nf + (1 if driver == "rbmz2prsymm" else 2) * nf
     assert np.abs(have - want).max() <= 3e-9 * max(1.0, np.abs(want).max())
+
+
+# ---- against the reference's own CPU code (cpu/include/neural_quantum_state.hpp:68-102, 184-217 compiled in place; vectors by
+# `python tests/golden/make_golden.py --tied`): RBMTrSymm and FFNNTrSymm on the periodic chain ------------------------------------
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_golden_tied_sampler_energy_gradients(golden_tied, force_generic):
+    import test_gpu_parity as tp
+    tp.test_golden_sampler_energy_gradients(golden_tied, force_generic)
+
+
+@pytest.mark.parametrize("force_generic", [False, True])
+def test_golden_tied_sr_trajectory(golden_tied, force_generic):
+    import test_gpu_parity as tp
+    tp.test_golden_sr_trajectory(golden_tied, force_generic)
+
+
+def test_golden_tied_variables_file(golden_tied, tmp_path):
+    from neural_network_quantum_state_b200 import Engine
+    g = golden_tied
+    e = Engine(g["model"], g["N"], g["M"], 4, g["h"], g["J"], g["alpha"], pbc=True, sampler_only=True)
+    want = os.path.join(os.path.dirname(__file__), "golden", "files", g["name"] + "_")
+    e.load(want)
+    assert_close(e.get_params(), g["params"], rtol=2e-10, what="loaded variables")
+    e.set_params(g["params"])
+    out = str(tmp_path / "vars")
+    e.save(out, 10)
+    assert open(out).read() == open(want).read()
+    e.close()

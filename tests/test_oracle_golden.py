@@ -118,3 +118,26 @@ def test_structured_factorisation_of_S_dot_v(golden):
     assert_close(aO, to_gpu(g, g["sm_aO"]), what="<O> from the factors")
     assert_close(diag, to_gpu(g, g["sm_diag"]), atol=1e-11, what="diag S from the factors")
     assert_close(Sv, to_gpu(g, g["sm_Sv"]), what="S v from the factors")
+
+
+# ---- the tied-variable ansaetze of the reference's CPU tree (cpu/include/neural_quantum_state.hpp:68-102, 184-217; vectors by
+# `python tests/golden/make_golden.py --tied`): pins oracle.RBMTrSymm / oracle.FFNNTrSymm to the reference's own code --------------
+def test_tied_sweep_energy_gradients(golden_tied):
+    test_sweep_energy_gradients(golden_tied)
+
+
+def test_tied_sr_trajectory(golden_tied):
+    test_sr_trajectory(golden_tied)
+
+
+def test_tied_variables_file_is_byte_identical(golden_tied, tmp_path):
+    g = golden_tied
+    m = o.make_ansatz(g["model"], g["N"], g["M"], g["K"])
+    m.variables = g["params"].copy()
+    out = str(tmp_path / "vars")
+    m.save(out, 10)
+    want = os.path.join(os.path.dirname(__file__), "golden", "files", g["name"] + "_")
+    assert open(out).read() == open(want).read()
+    m2 = o.make_ansatz(g["model"], g["N"], g["M"], g["K"])
+    m2.load(want)
+    assert_close(m2.variables, g["params"], rtol=2e-10, what="10-digit file")
