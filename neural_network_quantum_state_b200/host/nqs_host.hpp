@@ -7,6 +7,7 @@
 //   spinhalf::RBMTrSymm<double>                         ref gpu/include/neural_quantum_state.cuh:62-105
 //   spinhalf::RBMZ2PrSymm<double>, FFNNTrSymm<double>   ref gpu/include/neural_quantum_state.cuh:106-147,197-237
 //   spinhalf::LITFIChain<Traits>                        ref gpu/include/hamiltonians.cuh:43-75 + mcmc_sampler.cuh:16-37
+//   Sampler4SpinHalf<Traits>                            ref gpu/include/meas.cuh:11-28, impl_meas.cuh:5-41
 //   StochasticReconfigurationCG<double>                 ref gpu/include/optimizer.cuh:112-181
 //
 // Differences a caller can see (all forced by the C-ABI boundary):
@@ -24,6 +25,7 @@
 #include <cstring>
 #include <iomanip>
 #include <iostream>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -231,6 +233,45 @@ private:
   const std::string kprefix;
 };
 } // namespace spinhalf
+
+// ref: Sampler4SpinHalf<TraitsClass> (gpu/include/meas.cuh:11-28, impl_meas.cuh:5-41): the Hamiltonian-free sampler behind the
+// measurement programs and pynqs' PySampler -- sequential site ring 1,2,..,N-1,0, random +-1 initial spins (the reference draws
+// them inside psi.initialize(lnpsi) from a clock-seeded generator, neural_quantum_state.cuh:239-249; here from seedNumber so that
+// a run is reproducible), the BaseParallelSampler interface otherwise.
+template <typename TraitsClass>
+class Sampler4SpinHalf
+{
+  using AnsatzType = typename TraitsClass::AnsatzType;
+public:
+  Sampler4SpinHalf(AnsatzType & psi, const unsigned long seedNumber, const unsigned long seedDistance): psi_(psi), seed_(seedNumber)
+  {
+    nqs_host::check(psi.handle(), nqs_set_hamiltonian(psi.handle(), 0.0, 0.0, 0.0, 0, NQS_ORDER_SEQUENTIAL), "nqs_set_hamiltonian");
+    const char * env = std::getenv("NQS_RNG");
+    const int kind = (env && !std::strcmp(env, "philox")) ? NQS_RNG_PHILOX : NQS_RNG_YARN2;
+    nqs_host::check(psi.handle(), nqs_set_rng(psi.handle(), kind, (uint64_t)seedNumber, (uint64_t)seedDistance), "nqs_set_rng");
+  }
+  void warm_up(const int nMCSteps = 100)
+  {
+    std::mt19937_64 ran(seed_*0x9E3779B97F4A7C15ull+0x5EEDull);
+    std::vector<int8_t> spins((size_t)psi_.get_nChains()*psi_.get_nInputs());
+    for (auto & s : spins) s = (ran()&1ull) ? 1 : -1;
+    nqs_host::check(hd(), nqs_warm_up(hd(), nMCSteps, spins.data()), "warm_up");
+  }
+  void do_mcmc_steps(const int nMCSteps = 1) { nqs_host::check(hd(), nqs_do_mcmc_steps(hd(), nMCSteps), "do_mcmc_steps"); }
+  std::vector<std::complex<double> > get_lnpsi()
+  {
+    std::vector<std::complex<double> > v((size_t)psi_.get_nChains());
+    nqs_host::check(hd(), nqs_get_lnpsi(hd(), nqs_host::cptr(v.data())), "get_lnpsi");
+    return v;
+  }
+  std::vector<int8_t> get_quantumStates() const { return psi_.get_spinStates(); }
+  int get_nInputs() const { return psi_.get_nInputs(); }
+  int get_nChains() const { return psi_.get_nChains(); }
+private:
+  nqs_handle * hd() const { return psi_.handle(); }
+  AnsatzType & psi_;
+  const unsigned long seed_;
+};
 
 // ref: StochasticReconfigurationCG<FloatType> (gpu/include/optimizer.cuh:112-181): the whole iteration body runs on the device
 // inside nqs_sr_step; this class keeps the reference's loop, stop rules and stdout.

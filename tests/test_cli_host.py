@@ -129,3 +129,39 @@ def test_missing_parameter_file_is_not_an_error(tmp_path):
 def test_bad_device_number(tmp_path):
     r = run([exe()] + [a for a in REQUIRED if not a.startswith("-dev")] + ["-dev=99"])
     assert r.returncode == 1 and "# error ---> dev(99) >= # of devices" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_sampler4spinhalf(tmp_path):
+    """The C++ host mirror of Sampler4SpinHalf (ref gpu/include/meas.cuh:11-28, impl_meas.cuh:5-41) driven the way the reference's
+    measurement programs drive it: tracked lnpsi == amplitude of the sampled configuration == forward(spins) of a second instance
+    == the numpy oracle's amplitude."""
+    import shutil
+    import subprocess
+    from neural_network_quantum_state_b200 import build
+    from oracle import nqs_oracle as o
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not found")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe_path = str(tmp_path / "sampler4spinhalf_check")
+    env = {k: v for k, v in os.environ.items() if k not in ("CXX", "CC")}
+    r = subprocess.run([gxx, "-O2", "-std=c++17", "-o", exe_path, os.path.join(root, "tests", "sampler4spinhalf_check.cpp"),
+                        "-L" + build.PKG_DIR, "-lnqs_b200", "-Wl,-rpath," + build.PKG_DIR], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    N, al, K = 12, 2, 48
+    m = o.RBMTrSymm(N, al, K, np.random.default_rng(6))
+    m.variables *= 5.0
+    m.variables[N * al] = 0.1 - 0.05j
+    path = str(tmp_path / "vars")
+    m.save(path, 17)
+    r = subprocess.run([exe_path, path, str(N), str(al), str(K)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    rows = np.array([[float(t) for t in ln.split()] for ln in r.stdout.splitlines()])
+    assert rows.shape == (K, N + 4)
+    spins = rows[:, :N]
+    assert set(np.unique(spins)) <= {-1.0, 1.0} and 0 < np.abs(spins.mean(axis=1)).mean() < 1
+    tracked, fixed = rows[:, N] + 1j * rows[:, N + 1], rows[:, N + 2] + 1j * rows[:, N + 3]
+    want = m.forward_spins(spins, save=False)
+    np.testing.assert_allclose(fixed, want, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(tracked, want, rtol=1e-10, atol=1e-12)
