@@ -96,3 +96,41 @@ def test_product_header_and_reference_shim_agree_with_the_oracle(tmp_path):
         want = np.array([e.uniform01() for _ in range(40)])
         assert np.array_equal(got[:, 0], want), "csrc/yarn2.cuh"
         assert np.array_equal(got[:, 1], want), "baseline/shim_yarn2"
+
+
+def test_committed_known_answers_of_the_restatement():
+    """tests/golden/yarn2_kat.json: regression vectors of the RESTATEMENT (not of TRNG4) together with the 6-line program that
+    would pin it against the library once TRNG4 v4.22 can be obtained."""
+    import json
+    kat = json.load(open(os.path.join(ROOT, "tests", "golden", "yarn2_kat.json")))
+    c0, c1, c2 = kat["cases"]
+    e = y.Yarn2()
+    assert [e.next_int() for _ in range(8)] == c0["ints"]
+    e = y.Yarn2(12345)
+    e.jump(2 * 1000 * 7)
+    assert [float.hex(e.uniform01()) for _ in range(8)] == c1["hex"]
+    e = y.Yarn2(2**64 - 1)
+    assert (e.r0, e.r1) == (y.M - 1, 1)                     # int64(2^64-1) = -1 -> m-1
+    e.jump(1 << 40)
+    assert [e.next_int() for _ in range(4)] == c2["ints"]
+    assert "trng/yarn2.hpp" in kat["check_program"]
+
+
+def test_jump_properties_hypothesis():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 2**64 - 1), st.integers(0, 2**63), st.integers(0, 2**63 - 1))
+    def prop(seed, a, b):
+        e1, e2, e3 = y.Yarn2(seed), y.Yarn2(seed), y.Yarn2(seed)
+        e1.jump(a)
+        e1.jump(b)
+        e2.jump(b)
+        e2.jump(a)
+        e3.jump((a + b) % 2**64)                             # a + b < 2^64 here: no wrap
+        assert (e1.r0, e1.r1) == (e2.r0, e2.r1) == (e3.r0, e3.r1)
+        assert 0 <= e1.r0 < y.M and 0 <= e1.r1 < y.M
+        u = e1.uniform01()
+        assert 0.0 <= u < 1.0
+
+    prop()
