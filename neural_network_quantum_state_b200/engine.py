@@ -8,6 +8,7 @@ All arrays are numpy on the host; device memory is owned by the library.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -61,7 +62,14 @@ class Engine:
                     (L.FLAG_STRUCTURED_SV if structured_sv else 0) | (L.FLAG_NO_DMMA if no_dmma else 0)
         cfg.max_predrawn_steps = int(max_predrawn_steps)
         self._h = C.c_void_p()
-        rc = self.lib.nqs_create(C.byref(cfg), C.byref(self._h))
+        # the environment opt-in of the structured S*v is for plain RBM / FNN handles: hidden from the library while a tied-variable
+        # handle is made (the library reads the C environment: putenv / unsetenv through os.environ reach it)
+        hide = os.environ.pop("NQS_STRUCTURED_SV", None) if model not in ("rbm", "ffnn") else None
+        try:
+            rc = self.lib.nqs_create(C.byref(cfg), C.byref(self._h))
+        finally:
+            if hide is not None:
+                os.environ["NQS_STRUCTURED_SV"] = hide
         if rc != L.OK:
             raise NQSError(rc, (self.lib.nqs_last_error(None) or b"").decode())
         p = C.c_int64()

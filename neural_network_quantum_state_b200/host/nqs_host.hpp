@@ -67,7 +67,14 @@ public:
     cfg.seed = 0; cfg.device = current_device();
     cfg.flags = NQS_FLAG_NO_SR;          // O and the CG vectors are allocated when an optimizer first uses the sampler
     cfg.max_predrawn_steps = 0;
+    // NQS_STRUCTURED_SV=1 in the environment opts plain RBM / FNN handles into the structured S*v; the tied-variable ansaetze have
+    // no such form (their rows of O are not outer products), so the switch is hidden from the library while such a handle is made
+    const bool tied = model != NQS_MODEL_RBM && model != NQS_MODEL_FFNN;
+    const char * envs = tied ? std::getenv("NQS_STRUCTURED_SV") : nullptr;
+    const std::string saved = envs ? envs : "";
+    if (envs) unsetenv("NQS_STRUCTURED_SV");
     const nqs_status rc = nqs_create(&cfg, &h_);
+    if (envs) setenv("NQS_STRUCTURED_SV", saved.c_str(), 1);
     if (rc != NQS_OK)
     {
       const char * msg = nqs_last_error(nullptr);

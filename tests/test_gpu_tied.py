@@ -228,3 +228,23 @@ def test_golden_tied_variables_file(golden_tied, tmp_path):
     e.save(out, 10)
     assert open(out).read() == open(want).read()
     e.close()
+
+
+def test_structured_sv_environment_switch_does_not_reach_tied_handles(tmp_path, monkeypatch):
+    """NQS_STRUCTURED_SV=1 (the opt-in of callers that cannot pass flags) is for plain RBM / FNN handles; a tied-variable handle made
+    under it -- Python host or command-line program -- must run its explicit-O path, not fail."""
+    from neural_network_quantum_state_b200 import Engine, build
+    monkeypatch.setenv("NQS_STRUCTURED_SV", "1")
+    e = Engine("rbmz2prsymm", 12, 8, 128, H, J, ALPHA, seed=3)
+    e.init_params_random(4)
+    e.warm_up(5)
+    st = e.sr_step(n_mc_steps=1, lr=0.02)
+    assert st.finite and st.cg_iters >= 1
+    e.close()
+    assert os.environ["NQS_STRUCTURED_SV"] == "1"
+    args = ["-L=12", "-nf=2", "-ns=256", "-niter=3", "-alpha=2", "-theta=0.785398", "-ver=0", "-nwarm=10", "-dev=0", "-lr=0.02",
+            "-rsd=1e-30", "-seed=5", "-path=%s" % tmp_path]
+    exe = os.path.join(build.BIN_DIR, "LICH-train_ffnntrsymm-gpu")
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len([ln for ln in r.stdout.splitlines() if re.match(r"^\s*\d+\s+\S+\s+\S+\s*$", ln)]) == 3
